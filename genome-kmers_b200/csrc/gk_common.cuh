@@ -1,0 +1,152 @@
+// gk_common.cuh -- shared helpers for the libgkb200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gkb200.h"
+
+namespace gk {
+
+constexpr uint8_t kSep = 36;  // '$', sequence_collection.py:689-691
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define GK_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            gk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                          __LINE__);                                                         \
+            return GK_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define GK_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != GK_OK) return _s;   \
+    } while (0)
+
+#define GK_LAUNCH_CHECK()                                                                    \
+    do {                                                                                     \
+        gk::count_launch();                                                                  \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            gk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
+                          __FILE__, __LINE__);                                               \
+            return GK_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// ---- stream-ordered temporary device memory ------------------------------------------------
+// All scratch comes from the device's default mempool (cudaMallocAsync); the release threshold
+// is raised once so repeated sorts reuse the same pages instead of going back to the driver.
+int ensure_pool_configured();
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer() { release(); }
+    int alloc(size_t n, cudaStream_t s)
+    {
+        release();
+        stream = s;
+        bytes = n;
+        if (n == 0) return GK_OK;
+        GK_TRY(ensure_pool_configured());
+        GK_CUDA(cudaMallocAsync(&ptr, n, s));
+        return GK_OK;
+    }
+    void release()
+    {
+        if (ptr) cudaFreeAsync(ptr, stream);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+
+// ---- device helpers ------------------------------------------------------------------------
+// 2-bit code with A<C<G<T: A=65,C=67,G=71,T=84 -> bits 2:1 are 00,01,11,10.
+__device__ __forceinline__ uint32_t code2(uint32_t b)
+{
+    uint32_t c = (b >> 1) & 3u;
+    return c ^ (c >> 1);
+}
+__device__ __forceinline__ bool is_acgt(uint32_t b)
+{
+    // letters live in 64..95; bit (b & 31) of the mask marks A(1) C(3) G(7) T(20)
+    constexpr uint32_t mask = (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20);
+    return ((b & 0xE0u) == 0x40u) && ((mask >> (b & 31u)) & 1u);
+}
+// number of A/C/G/T that sort below byte b in raw ASCII order (kmers.py:381-388); '$' -> 0
+__device__ __forceinline__ uint32_t acgt_below(uint32_t b)
+{
+    return (b > 65u) + (b > 67u) + (b > 71u) + (b > 84u);
+}
+// 4-bit rank of an allowed symbol: '$'/unknown = 0, then A B C D G H K M N R S T V W Y = 1..15
+__device__ __forceinline__ uint32_t rank4(uint32_t b)
+{
+    constexpr uint64_t lo = (1ull << 4) | (2ull << 8) | (3ull << 12) | (4ull << 16) |
+                            (5ull << 28) | (6ull << 32) | (7ull << 44) | (8ull << 52) |
+                            (9ull << 56);
+    constexpr uint64_t hi = (10ull << 8) | (11ull << 12) | (12ull << 16) | (13ull << 24) |
+                            (14ull << 28) | (15ull << 36);
+    if ((b & 0xE0u) != 0x40u) return 0u;
+    uint32_t i = b & 31u;
+    uint64_t t = (i & 16u) ? hi : lo;
+    return (uint32_t)(t >> (4u * (i & 15u))) & 15u;
+}
+__device__ __forceinline__ uint32_t complement_byte(uint32_t b)
+{
+    // sequence_collection.py:410-427; bytes the reference's table does not know map to 0
+    switch (b) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+    case 'R': return 'Y'; case 'Y': return 'R'; case 'S': return 'S'; case 'W': return 'W';
+    case 'K': return 'M'; case 'M': return 'K'; case 'B': return 'V'; case 'D': return 'H';
+    case 'H': return 'D'; case 'V': return 'B'; case 'N': return 'N'; case '$': return '$';
+    default: return 0;
+    }
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// index of the last entry of a sorted table that is <= x (table[0] <= x assumed)
+__device__ __forceinline__ uint32_t upper_seg(const uint64_t *__restrict__ starts, uint32_t n,
+                                              uint64_t x)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (x < starts[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo - 1;
+}
+
+}  // namespace gk

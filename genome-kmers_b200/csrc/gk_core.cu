@@ -1,0 +1,92 @@
+// gk_core.cu -- library plumbing: status strings, thread-local error text, launch counter,
+// memory pool configuration, device info.
+#include <stdarg.h>
+
+#include "gk_common.cuh"
+
+namespace gk {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+int ensure_pool_configured()
+{
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    GK_CUDA(cudaGetDevice(&dev));
+    if (configured_device == dev) return GK_OK;
+    cudaMemPool_t pool;
+    GK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t threshold = UINT64_MAX;
+    GK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    configured_device = dev;
+    return GK_OK;
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace gk
+
+extern "C" {
+
+int gk_version(void) { return GKB200_VERSION; }
+
+const char *gk_status_string(int status)
+{
+    switch (status) {
+    case GK_OK: return "ok";
+    case GK_ERR_CUDA: return "CUDA error";
+    case GK_ERR_ARG: return "invalid argument";
+    case GK_ERR_UNSUPPORTED: return "unsupported on the GPU path";
+    case GK_ERR_INTERNAL: return "device-side consistency check failed";
+    case GK_ERR_INVALID_KMERS: return "k-mers shorter than min_kmer_len";
+    case GK_ERR_STATE: return "invalid call order";
+    default: return "unknown status";
+    }
+}
+
+const char *gk_last_error(void) { return gk::g_err; }
+
+uint64_t gk_launch_count(int reset)
+{
+    uint64_t v = gk::g_launches;
+    if (reset) gk::g_launches = 0;
+    return v;
+}
+
+int gk_device_info(int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem_bytes)
+{
+    int dev = 0;
+    GK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem_bytes) *total_mem_bytes = (uint64_t)prop.totalGlobalMem;
+    return GK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// gk_pack.cu -- k-mer key packing (north_star subsystem 1; SURVEY.md 8a rows A3 + A4).
+//
+// pack_keys_kernel: one streaming pass over the sequence byte array.  A CTA stages a tile of
+// bases in shared memory with 128-bit loads, converts it once into a packed 2-bit stream plus
+// per-position "not A/C/G/T" and "'$'" bit masks, and then every thread cuts its windows out
+// of those streams with funnel shifts.  Output position = start - valid_len * segment, which
+// is exactly the slot the reference's init loop gives that start (kmers.py:814-826), so the
+// (key, start) pairs leave in ascending start order with no compaction pass.
+//
+// Key of a window w over its first key_len symbols (compare order = raw ASCII, kmers.py:381-388):
+//   pure (all A/C/G/T):  value(w) = 2-bit code, A<C<G<T, most significant symbol first
+//   otherwise:           value(w) = number of pure key_len-mers that sort below w
+//                                 = prefix * 4^(key_len-j) + below(w[j]) * 4^(key_len-j-1)
+//                        with j the first non-ACGT position, below() the count of A/C/G/T
+//                        smaller than that byte ('$' -> 0: a terminated k-mer sorts first,
+//                        kmers.py:372-375).
+//   key = class_bit ? (value << 1) | is_pure : value
+// A non-pure window never equals a pure one, and value() is monotone in the true order, so one
+// stable integer sort places every window correctly relative to all pure windows; only runs
+// of non-pure windows with equal value need the 4-bit refinement in gk_index.cu.
+//
+// pack4_gather_kernel: terminator-aware 4-bit rank words for an arbitrary list of starts (the
+// refinement keys).
+#include "gk_common.cuh"
+
+namespace gk {
+
+constexpr int kPackThreads = 256;
+constexpr int kPackPerThread = 16;
+constexpr int kPackTile = kPackThreads * kPackPerThread;  // window starts per CTA
+constexpr int kPackChunks = kPackTile / 16 + 2;           // 16-byte chunks staged (tile + 32 B halo)
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kPackThreads)
+pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
+                 const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint32_t valid_len,
+                 uint32_t key_len, int class_bit, uint64_t first_start, uint64_t end_start,
+                 uint64_t out_base, uint64_t *__restrict__ keys_out, IdxT *__restrict__ idx_out,
+                 unsigned long long *__restrict__ n_amb_out)
+{
+    __shared__ __align__(16) uint8_t s_bytes[kPackChunks * 16];
+    __shared__ uint32_t s_codes[kPackChunks];
+    __shared__ __align__(4) uint16_t s_amb[kPackChunks + 2];
+    __shared__ __align__(4) uint16_t s_sep[kPackChunks + 2];
+    __shared__ uint32_t s_sep_pre[kPackChunks / 2 + 2];
+    __shared__ uint32_t s_seg0;
+
+    const uint32_t t = threadIdx.x;
+    // tiles are aligned to the byte array, not to first_start, so 128-bit loads stay aligned
+    const uint64_t tile0 = (first_start / kPackTile + blockIdx.x) * (uint64_t)kPackTile;
+
+    // ---- stage bytes, convert to streams ----------------------------------------------------
+    const bool aligned = (reinterpret_cast<uintptr_t>(sba) & 15u) == 0;
+    for (uint32_t c = t; c < kPackChunks; c += kPackThreads) {
+        const uint64_t g = tile0 + 16ull * c;
+        uint32_t w[4];
+        if (aligned && g + 16 <= sba_len) {
+            uint4 q = *reinterpret_cast<const uint4 *>(sba + g);
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint64_t p = g + 4 * i + j;
+                    uint32_t b = (p < sba_len) ? sba[p] : kSep;  // past the end == terminator
+                    x |= b << (8 * j);
+                }
+                w[i] = x;
+            }
+        }
+        *reinterpret_cast<uint4 *>(s_bytes + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+        uint32_t codes = 0, amb = 0, sep = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            codes |= code2(b) << (30 - 2 * i);
+            amb |= (is_acgt(b) ? 0u : 1u) << i;
+            sep |= (b == kSep ? 1u : 0u) << i;
+        }
+        s_codes[c] = codes;
+        s_amb[c] = (uint16_t)amb;
+        s_sep[c] = (uint16_t)sep;
+    }
+    if (t < 2) { s_amb[kPackChunks + t] = 0xFFFFu; s_sep[kPackChunks + t] = 0xFFFFu; }
+    if (t == 0) s_seg0 = upper_seg(seg_starts, n_seg, tile0 < sba_len ? tile0 : sba_len - 1);
+    __syncthreads();
+
+    // exclusive prefix of '$' counts per 32-position word (one warp, kPackChunks/2 words)
+    const uint32_t *amb32 = reinterpret_cast<const uint32_t *>(s_amb);
+    const uint32_t *sep32 = reinterpret_cast<const uint32_t *>(s_sep);
+    if (t < 32) {
+        constexpr int n_words = kPackChunks / 2;          // 129
+        constexpr int per_lane = (n_words + 31) / 32;     // 5
+        uint32_t local[per_lane];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < per_lane; ++i) {
+            int wi = t * per_lane + i;
+            local[i] = sum;
+            sum += (wi < n_words) ? __popc(sep32[wi]) : 0;
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= (uint32_t)o) inc += v;
+        }
+        uint32_t excl = inc - sum;
+#pragma unroll
+        for (int i = 0; i < per_lane; ++i) {
+            int wi = t * per_lane + i;
+            if (wi < n_words) s_sep_pre[wi] = excl + local[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- cut windows ---------------------------------------------------------------------------
+    const uint32_t seg0 = s_seg0;
+    const uint64_t key_mask = (key_len >= 32) ? 0xFFFFFFFFull : ((1ull << key_len) - 1ull);
+    uint32_t n_amb = 0;
+#pragma unroll 4
+    for (int j = 0; j < kPackPerThread; ++j) {
+        const uint32_t q = t + j * kPackThreads;
+        const uint64_t i = tile0 + q;
+        if (i < first_start || i >= end_start) continue;
+        const uint32_t mw = q >> 5, mo = q & 31u;
+        const uint32_t seg = seg0 + s_sep_pre[mw] + __popc(sep32[mw] & ((1u << mo) - 1u));
+        if (seg >= n_seg) continue;
+        const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;
+        if (i + valid_len > seg_end) continue;  // also rejects '$' positions themselves
+
+        const uint32_t cw = q >> 4, co = 2u * (q & 15u);
+        const uint32_t c0 = s_codes[cw], c1 = s_codes[cw + 1], c2 = s_codes[cw + 2];
+        const uint32_t hi = __funnelshift_l(c1, c0, co);
+        const uint32_t lo = __funnelshift_l(c2, c1, co);
+        uint64_t value = (((uint64_t)hi << 32) | lo) >> (64 - 2 * key_len);
+
+        const uint64_t m64 = (((uint64_t)amb32[mw + 1] << 32) | amb32[mw]) >> mo;
+        const uint32_t m = (uint32_t)(m64 & key_mask);
+        const bool pure = (m == 0);
+        if (!pure) {
+            ++n_amb;
+            const uint32_t j0 = __ffs(m) - 1;                  // first non-ACGT symbol
+            const uint32_t below = acgt_below(s_bytes[q + j0]);
+            const uint32_t rem = 2u * (key_len - j0);          // bits from symbol j0 to the end
+            const uint64_t prefix = (rem >= 64) ? 0ull : (value >> rem);
+            value = ((rem >= 64) ? 0ull : (prefix << rem)) + ((uint64_t)below << (rem - 2));
+        }
+        const uint64_t key = class_bit ? ((value << 1) | (pure ? 1ull : 0ull)) : value;
+        const uint64_t pos = i - (uint64_t)valid_len * seg - out_base;
+        keys_out[pos] = key;
+        idx_out[pos] = (IdxT)i;
+    }
+    if (n_amb_out) {
+        n_amb = warp_sum(n_amb);
+        if (lane_id() == 0 && n_amb) atomicAdd(n_amb_out, (unsigned long long)n_amb);
+    }
+}
+
+// Terminator-aware 4-bit rank word `word` (symbols [16*word, 16*word+16) of the window, most
+// significant first) for each start in idx; symbols at or after a '$'/end of array are 0, so
+// a shorter k-mer sorts first (kmers.py:360-378).
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pack4_gather_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
+                    const IdxT *__restrict__ idx, uint64_t n, uint32_t word, uint32_t max_len,
+                    uint64_t *__restrict__ keys_out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const uint64_t s = (uint64_t)idx[r];
+        const uint32_t lo = 16u * word;
+        const uint32_t hi = (lo + 16u < max_len) ? lo + 16u : max_len;
+        uint64_t key = 0;
+        bool alive = true;
+        for (uint32_t j = 0; j < hi && alive; ++j) {
+            const uint64_t p = s + j;
+            const uint32_t code = (p < sba_len) ? rank4(sba[p]) : 0u;
+            if (code == 0) { alive = false; break; }
+            if (j >= lo) key |= (uint64_t)code << (4u * (15u - (j - lo)));
+        }
+        keys_out[r] = key;
+    }
+}
+
+int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_seg_starts,
+                     uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
+                     uint64_t first_start, uint64_t end_start, uint64_t out_base,
+                     uint64_t *d_keys_out, int idx_bytes, void *d_idx_out,
+                     unsigned long long *d_n_amb, cudaStream_t st)
+{
+    if (key_len < 1 || key_len > 32 || valid_len < key_len || (class_bit && key_len > 31)) {
+        set_error("pack_keys: key_len %u / valid_len %u / class_bit %d out of range", key_len,
+                  valid_len, class_bit);
+        return GK_ERR_ARG;
+    }
+    if (end_start > sba_len) end_start = sba_len;
+    if (first_start >= end_start) return GK_OK;
+    const uint64_t tile_first = first_start / kPackTile;
+    const uint64_t tile_last = (end_start - 1) / kPackTile;
+    const uint64_t grid = tile_last - tile_first + 1;
+    if (grid > 0x7FFFFFFFull) {
+        set_error("pack_keys: range too large for one launch");
+        return GK_ERR_ARG;
+    }
+    if (idx_bytes == 4)
+        pack_keys_kernel<uint32_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
+            d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
+            end_start, out_base, d_keys_out, (uint32_t *)d_idx_out, d_n_amb);
+    else
+        pack_keys_kernel<uint64_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
+            d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
+            end_start, out_base, d_keys_out, (uint64_t *)d_idx_out, d_n_amb);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int pack4_gather_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
+                        uint64_t n, uint32_t word, uint32_t max_len, uint64_t *d_keys_out,
+                        cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    uint64_t blocks = (n + 255) / 256;
+    uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (idx_bytes == 4)
+        pack4_gather_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_sba, sba_len, (const uint32_t *)d_idx, n, word, max_len, d_keys_out);
+    else
+        pack4_gather_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_sba, sba_len, (const uint64_t *)d_idx, n, word, max_len, d_keys_out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// number of valid_len-windows that start before `start` (host; mirrors the kernel's slot rule)
+uint64_t windows_before(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t sba_len,
+                        uint32_t valid_len, uint64_t start)
+{
+    uint64_t n = 0;
+    for (uint32_t s = 0; s < n_seg; ++s) {
+        uint64_t a = h_seg_starts[s];
+        uint64_t e_excl = (s + 1 < n_seg) ? h_seg_starts[s + 1] - 1 : sba_len;
+        if (start <= a) break;
+        uint64_t last_excl = e_excl - valid_len + 1;  // one past the last valid start
+        uint64_t upto = start < last_excl ? start : last_excl;
+        if (upto > a) n += upto - a;
+    }
+    return n;
+}
+
+}  // namespace gk
+
+using namespace gk;
+
+extern "C" int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts,
+                            uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
+                            uint64_t first_start, uint64_t end_start, uint64_t *d_keys_out,
+                            int idx_bytes, void *d_idx_out, uint64_t out_capacity,
+                            uint64_t *h_n_out, uint64_t *h_n_ambiguous, void *stream)
+{
+    if (!d_sba || !h_seg_starts || !d_keys_out || !d_idx_out || n_seg == 0 ||
+        (idx_bytes != 4 && idx_bytes != 8)) {
+        set_error("gk_pack_keys: bad argument");
+        return GK_ERR_ARG;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (end_start > sba_len) end_start = sba_len;
+    const uint64_t base = windows_before(h_seg_starts, n_seg, sba_len, valid_len, first_start);
+    const uint64_t upto = windows_before(h_seg_starts, n_seg, sba_len, valid_len, end_start);
+    const uint64_t n = upto - base;
+    if (n > out_capacity) {
+        set_error("gk_pack_keys: %llu windows do not fit the output capacity %llu",
+                  (unsigned long long)n, (unsigned long long)out_capacity);
+        return GK_ERR_ARG;
+    }
+    DeviceBuffer segs, amb;
+    GK_TRY(segs.alloc((size_t)n_seg * 8, st));
+    GK_CUDA(cudaMemcpyAsync(segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    GK_TRY(amb.alloc(8, st));
+    GK_CUDA(cudaMemsetAsync(amb.ptr, 0, 8, st));
+    GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, valid_len, key_len,
+                            class_bit, first_start, end_start, base, d_keys_out, idx_bytes,
+                            d_idx_out, amb.as<unsigned long long>(), st));
+    uint64_t n_amb = 0;
+    GK_CUDA(cudaMemcpyAsync(&n_amb, amb.ptr, 8, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_n_out) *h_n_out = n;
+    if (h_n_ambiguous) *h_n_ambiguous = n_amb;
+    return GK_OK;
+}

@@ -1,0 +1,382 @@
+// gk_sort.cu -- stable LSD "onesweep" radix sort of (64-bit key, 32/64-bit value) pairs
+// (north_star subsystem 2; replaces numba.misc.quicksort behind kmers.py:1644-1648).
+//
+// Structure (after Adinets & Merrill, "Onesweep", 2022 -- restated, not copied):
+//   1. digit_histogram_kernel: ONE read of the keys builds the 256-bin histogram of every digit
+//      position (shared-memory privatised, flushed with 64-bit global atomics).
+//   2. scan_histogram_kernel: exclusive scan per digit position -> global bin bases.
+//   3. onesweep_kernel, once per 8-bit digit, least significant first.  A CTA claims the next
+//      tile with an atomic ticket (so look-back never waits on an unscheduled tile), ranks its
+//      keys with warp-level match_any (stable: items are visited in memory order), publishes
+//      its per-bin counts, resolves its global bin offsets by decoupled look-back over the
+//      preceding tiles' status words, reorders the tile in shared memory and streams it out so
+//      consecutive threads write consecutive addresses inside each bin.
+// Every pass reads 12 (16) bytes and writes 12 (16) bytes per pair: the 2*W*N bytes of
+// SURVEY.md 8d.  Ties leave in input order, so starting from ascending start indices the
+// result is the reference's break_ties=True order (kmers.py:1710-1711).
+//
+// Memory layout: keys and values are separate arrays (SoA) so each warp-wide access is one
+// fully used 256-byte / 128-byte segment; tile status is [tile][256] words so a look-back step
+// of the 256 bin-threads is one coalesced 1 KB read.
+#include "gk_common.cuh"
+
+namespace gk {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMaxPasses = 8;
+
+// ---- 1. histogram ------------------------------------------------------------------------------
+constexpr int kHistThreads = 512;
+
+__global__ void __launch_bounds__(kHistThreads)
+digit_histogram_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_bit, int end_bit,
+                       unsigned long long *__restrict__ g_hist /* [passes][256] */)
+{
+    __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kHistThreads)
+        (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint64_t n2 = n / 2;
+    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
+    const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
+    auto add = [&](uint64_t key) {
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; ++p) {
+            if (p < passes) {
+                const int lo = begin_bit + p * kRadixBits;
+                const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
+                const uint32_t d = (uint32_t)(key >> lo) & ((1u << bits) - 1u);
+                atomicAdd(&s_hist[p][d], 1u);
+            }
+        }
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n2; i += stride) {
+        ulonglong2 v = k2[i];
+        add(v.x);
+        add(v.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) add(keys[n - 1]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) {
+        uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&g_hist[i], (unsigned long long)c);
+    }
+}
+
+// ---- 2. exclusive scan per digit position ------------------------------------------------------
+__global__ void __launch_bounds__(kRadix)
+scan_histogram_kernel(const unsigned long long *__restrict__ g_hist,
+                      unsigned long long *__restrict__ g_base)
+{
+    __shared__ unsigned long long s_warp[kRadix / 32];
+    const int p = blockIdx.x, t = threadIdx.x;
+    const unsigned long long c = g_hist[p * kRadix + t];
+    unsigned long long inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((t & 31) >= o) inc += v;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    unsigned long long pre = 0;
+    for (int w = 0; w < (t >> 5); ++w) pre += s_warp[w];
+    g_base[p * kRadix + t] = pre + inc - c;
+}
+
+// ---- 3. onesweep pass --------------------------------------------------------------------------
+// Status word: top 2 bits = state (0 empty, 1 tile-local count, 2 inclusive prefix), rest = value.
+template <typename StatusT>
+struct StatusTraits;
+template <>
+struct StatusTraits<uint32_t> {
+    static constexpr int kShift = 30;
+    static constexpr uint32_t kMask = (1u << 30) - 1u;
+};
+template <>
+struct StatusTraits<uint64_t> {
+    static constexpr int kShift = 62;
+    static constexpr uint64_t kMask = (1ull << 62) - 1ull;
+};
+
+constexpr uint32_t kLookbackSpinLimit = 1u << 24;  // then flag an error instead of hanging the GPU
+
+template <typename ValT, typename StatusT, int THREADS, int IPT>
+struct OnesweepSmem {
+    static constexpr int kTile = THREADS * IPT;
+    static constexpr int kWarps = THREADS / 32;
+    uint64_t keys[kTile];
+    ValT vals[kTile];
+    uint32_t warp_hist[kWarps][kRadix];
+    long long global_off[kRadix];
+    uint32_t bin_excl[kRadix];
+    uint32_t warp_sums[kRadix / 32];
+    uint32_t tile;
+};
+
+template <typename ValT, typename StatusT, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
+onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+                const ValT *__restrict__ vals_in, ValT *__restrict__ vals_out, uint64_t n,
+                int shift, uint32_t digit_mask, const unsigned long long *__restrict__ bin_base,
+                uint32_t *__restrict__ tile_counter, StatusT *__restrict__ status,
+                int *__restrict__ err)
+{
+    using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
+    using ST = StatusTraits<StatusT>;
+    constexpr int kTile = Smem::kTile;
+    constexpr int kWarps = Smem::kWarps;
+    static_assert(THREADS >= kRadix, "one thread per bin is needed for the look-back");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+
+    const uint32_t t = threadIdx.x;
+    const uint32_t lane = t & 31u, warp = t >> 5;
+
+    if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
+    for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t tile = s.tile;
+    const uint64_t tile_base = tile * (uint64_t)kTile;
+    const uint32_t tile_valid = (n - tile_base < (uint64_t)kTile) ? (uint32_t)(n - tile_base) : kTile;
+
+    // ---- load: warp-striped inside a warp-contiguous chunk, so memory order == (j, lane) ------
+    uint64_t key[IPT];
+    ValT val[IPT];
+    const uint64_t warp_base = tile_base + (uint64_t)warp * (32 * IPT);
+    if (tile_valid == kTile) {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) key[j] = keys_in[warp_base + j * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) val[j] = vals_in[warp_base + j * 32 + lane];
+    } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint64_t g = warp_base + j * 32 + lane;
+            const bool ok = g < n;
+            key[j] = ok ? keys_in[g] : ~0ull;  // pads rank last in the last bin of the last tile
+            val[j] = ok ? vals_in[g] : (ValT)0;
+        }
+    }
+
+    // ---- rank inside the warp (stable) -------------------------------------------------------------
+    uint32_t rank[IPT];  // low 16 bits: rank among same-digit items of this warp; high: digit
+    uint32_t *my_hist = s.warp_hist[warp];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & digit_mask;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) {
+            base = my_hist[d];
+            my_hist[d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[j] = (base + __popc(peers & lanemask_lt())) | (d << 16);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-bin: exclusive scan over warps, tile totals, look-back ---------------------------------
+    uint32_t bin_count = 0;
+    if (t < kRadix) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = s.warp_hist[w][t];
+            s.warp_hist[w][t] = sum;
+            sum += c;
+        }
+        bin_count = sum;
+        // publish the tile-local count first so successors can make progress
+        // (volatile: the two status stores of this thread must both reach memory, in order)
+        *const_cast<volatile StatusT *>(status + tile * kRadix + t) =
+            ((StatusT)1 << ST::kShift) | (StatusT)bin_count;
+    }
+    // exclusive scan of bin_count over the 256 bins (first 8 warps)
+    uint32_t inc = bin_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (t < kRadix && lane == 31) s.warp_sums[warp] = inc;
+    __syncthreads();
+    if (t < kRadix) {
+        uint32_t pre = 0;
+        for (uint32_t w = 0; w < warp; ++w) pre += s.warp_sums[w];
+        const uint32_t excl_in_tile = pre + inc - bin_count;
+        s.bin_excl[t] = excl_in_tile;
+
+        // decoupled look-back over predecessor tiles for this bin
+        uint64_t excl = 0;
+        bool failed = false;
+        for (int64_t tp = (int64_t)tile - 1; tp >= 0; --tp) {
+            const volatile StatusT *slot = status + (uint64_t)tp * kRadix + t;
+            StatusT sv = *slot;
+            uint32_t spins = 0;
+            while ((sv >> ST::kShift) == 0) {
+                if (++spins > kLookbackSpinLimit) { failed = true; break; }
+                __nanosleep(20);
+                sv = *slot;
+            }
+            if (failed) break;
+            excl += (uint64_t)(sv & ST::kMask);
+            if ((sv >> ST::kShift) == 2) break;
+        }
+        if (failed) atomicExch(err, 1);
+        *const_cast<volatile StatusT *>(status + tile * kRadix + t) =
+            ((StatusT)2 << ST::kShift) | (StatusT)(excl + bin_count);
+        s.global_off[t] = (long long)(bin_base[t] + excl) - (long long)excl_in_tile;
+    }
+    __syncthreads();
+
+    // ---- reorder the tile in shared memory -------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t d = rank[j] >> 16;
+        const uint32_t pos = s.bin_excl[d] + s.warp_hist[warp][d] + (rank[j] & 0xFFFFu);
+        s.keys[pos] = key[j];
+        s.vals[pos] = val[j];
+    }
+    __syncthreads();
+
+    // ---- stream out: thread t handles tile positions t, t+THREADS, ... -----------------------------
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t p = t + j * THREADS;
+        if (p < tile_valid) {
+            const uint64_t k = s.keys[p];
+            const uint32_t d = (uint32_t)(k >> shift) & digit_mask;
+            const long long dst = s.global_off[d] + (long long)p;
+            keys_out[dst] = k;
+            vals_out[dst] = s.vals[p];
+        }
+    }
+}
+
+// ---- host driver ---------------------------------------------------------------------------------
+template <typename ValT, typename StatusT, int THREADS, int IPT>
+static int launch_pass(const uint64_t *kin, uint64_t *kout, const void *vin, void *vout, uint64_t n,
+                       int shift, int bits, const unsigned long long *bin_base,
+                       uint32_t *tile_counter, void *status, int *err, cudaStream_t st)
+{
+    using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
+    auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT>;
+    GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(Smem)));
+    const uint64_t tiles = (n + Smem::kTile - 1) / Smem::kTile;
+    kernel<<<(unsigned)tiles, THREADS, sizeof(Smem), st>>>(
+        kin, kout, (const ValT *)vin, (ValT *)vout, n, shift, (1u << bits) - 1u, bin_base,
+        tile_counter, (StatusT *)status, err);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// Tunables (see DESIGN.md "onesweep tile shape"): 256 threads x 16 pairs = 4096-pair tiles,
+// ~61 KB shared memory and <=128 registers -> 2-3 CTAs per SM.
+constexpr int kSortThreads = 256;
+constexpr int kSortIPT4 = 16;  // 32-bit values
+constexpr int kSortIPT8 = 12;  // 64-bit values
+
+int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                            int val_bytes, uint64_t n, int begin_bit, int end_bit,
+                            int *result_in_alt, cudaStream_t st)
+{
+    if (val_bytes != 4 && val_bytes != 8) {
+        set_error("radix_sort_pairs: val_bytes must be 4 or 8");
+        return GK_ERR_ARG;
+    }
+    if (begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) {
+        set_error("radix_sort_pairs: bad bit range [%d, %d)", begin_bit, end_bit);
+        return GK_ERR_ARG;
+    }
+    if (result_in_alt) *result_in_alt = 0;
+    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    if (n < 2 || passes == 0) return GK_OK;
+    if ((reinterpret_cast<uintptr_t>(d_keys) & 15u) || (reinterpret_cast<uintptr_t>(d_keys_alt) & 15u)) {
+        set_error("radix_sort_pairs: key buffers must be 16-byte aligned");
+        return GK_ERR_ARG;
+    }
+
+    const int tile = kSortThreads * (val_bytes == 4 ? kSortIPT4 : kSortIPT8);
+    const uint64_t tiles = (n + tile - 1) / tile;
+    const bool wide = n >= (1ull << 30);
+    const size_t status_bytes = (size_t)tiles * kRadix * (wide ? 8 : 4);
+    const size_t hist_bytes = (size_t)kMaxPasses * kRadix * sizeof(unsigned long long);
+    // temp layout: [hist][base][counters (kMaxPasses u32) + err (int)][status]
+    DeviceBuffer temp;
+    const size_t ctr_bytes = 64;
+    GK_TRY(temp.alloc(2 * hist_bytes + ctr_bytes + status_bytes, st));
+    unsigned long long *d_hist = temp.as<unsigned long long>();
+    unsigned long long *d_base = d_hist + kMaxPasses * kRadix;
+    uint32_t *d_ctr = reinterpret_cast<uint32_t *>(d_base + kMaxPasses * kRadix);
+    int *d_err = reinterpret_cast<int *>(d_ctr + kMaxPasses);
+    void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
+    GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
+
+    int hist_grid = sm_count() * 2;
+    {
+        uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
+        if (need < 1) need = 1;
+        if ((uint64_t)hist_grid > need) hist_grid = (int)need;
+    }
+    digit_histogram_kernel<<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, d_hist);
+    GK_LAUNCH_CHECK();
+    scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_hist, d_base);
+    GK_LAUNCH_CHECK();
+
+    uint64_t *kin = d_keys, *kout = d_keys_alt;
+    void *vin = d_vals, *vout = d_vals_alt;
+    for (int p = 0; p < passes; ++p) {
+        const int lo = begin_bit + p * kRadixBits;
+        const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
+        GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
+        const unsigned long long *base = d_base + p * kRadix;
+        int rc;
+        if (val_bytes == 4) {
+            rc = wide ? launch_pass<uint32_t, uint64_t, kSortThreads, kSortIPT4>(
+                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st)
+                      : launch_pass<uint32_t, uint32_t, kSortThreads, kSortIPT4>(
+                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st);
+        } else {
+            rc = wide ? launch_pass<uint64_t, uint64_t, kSortThreads, kSortIPT8>(
+                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st)
+                      : launch_pass<uint64_t, uint32_t, kSortThreads, kSortIPT8>(
+                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st);
+        }
+        GK_TRY(rc);
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        void *tv = vin; vin = vout; vout = tv;
+    }
+    if (result_in_alt) *result_in_alt = passes & 1;
+
+    int h_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("radix_sort_pairs: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
+    return GK_OK;
+}
+
+}  // namespace gk
+
+using namespace gk;
+
+extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals,
+                                   void *d_vals_alt, int val_bytes, uint64_t n, int begin_bit,
+                                   int end_bit, int *result_in_alt, void *stream)
+{
+    if (n && (!d_keys || !d_keys_alt || !d_vals || !d_vals_alt)) {
+        set_error("gk_radix_sort_pairs: null buffer");
+        return GK_ERR_ARG;
+    }
+    return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
+                                   end_bit, result_in_alt, as_stream(stream));
+}

@@ -1,0 +1,177 @@
+/*
+ * gkb200.h -- C ABI of the B200-native genome-kmers hot path (libgkb200.so).
+ *
+ * The reference (mrperkett/genome-kmers) is pure Python + numba and has no FFI; the seams this
+ * library replaces are the two places where the reference hands work to numba-compiled code
+ * (file:line relative to /root/reference/src/genome_kmers):
+ *
+ *   seam 1  kmers.py:1648   jit_sort_func(self.kmer_sba_start_indices)       -> gk_index_sort
+ *   seam 2  kmers.py:1072, :1166  get_kmer_group_size_hist(sba, ..., max_counts_bin)
+ *                                                                            -> gk_index_group_counts
+ * plus the data producers either side of them:
+ *   sequence_collection.py:42-73   reverse_complement_sba                   -> gk_sba_revcomp
+ *   sequence_collection.py:693-697 alphabet check                           -> gk_sba_scan_alphabet
+ *   kmers.py:789-835               _initialize_single_pass                  -> gk_index_create /
+ *                                                                              gk_kmer_init_indices
+ *
+ * Conventions: every function returns a gk_status (0 = ok); gk_last_error() gives the text of
+ * the last failure on the calling thread.  Pointers named d_* are device pointers on the current
+ * CUDA device, h_* are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  No torch types appear anywhere.  Index arrays hold sequence byte array
+ * start positions as uint32 (idx_bytes == 4, the reference's dtype, kmers.py:811) or uint64
+ * (idx_bytes == 8, the extension needed once a byte array exceeds 2^32 - 1 positions).
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * GK_ERR_CUDA.
+ */
+#ifndef GKB200_H
+#define GKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKB200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    GK_OK = 0,
+    GK_ERR_CUDA = 1,          /* a CUDA runtime call failed (see gk_last_error) */
+    GK_ERR_ARG = 2,           /* invalid argument */
+    GK_ERR_UNSUPPORTED = 3,   /* valid in the reference API but not implemented on this path */
+    GK_ERR_INTERNAL = 4,      /* device-side consistency check failed (e.g. look-back timeout) */
+    GK_ERR_INVALID_KMERS = 5, /* k-mers shorter than min_kmer_len (kmers.py:1724-1727) */
+    GK_ERR_STATE = 6          /* call order violated (e.g. group counts on an unsorted index) */
+} gk_status;
+
+/* k-mer filters with device implementations (kmers.py:14-259).  p0..p2 as documented. */
+typedef enum {
+    GK_FILTER_KEEP_ALL = 0,     /* kmers.py:14-16 */
+    GK_FILTER_NO_AMBIGUOUS = 1, /* kmers.py:195-229   p0 = kmer_len */
+    GK_FILTER_MIN_LENGTH = 2,   /* kmers.py:19-34     p0 = min_kmer_len */
+    GK_FILTER_HOMOPOLYMER = 3,  /* kmers.py:37-100    p0 = max_homopolymer_size, p1 = kmer_len */
+    GK_FILTER_GC_COUNT = 4,     /* kmers.py:103-192   p0 = min_gc_count, p1 = max_gc_count, p2 = kmer_len */
+    GK_FILTER_NGG_PAM = 5       /* kmers.py:232-259 */
+} gk_filter_id;
+
+typedef struct {
+    int32_t id; /* gk_filter_id */
+    int64_t p0, p1, p2;
+} gk_filter;
+
+/* Per-stage device times of the last gk_index_sort, in milliseconds (CUDA events). */
+typedef struct {
+    float pack_ms;        /* key-pack kernel(s) */
+    float hist_ms;        /* up-front digit histogram + scan */
+    float sort_ms;        /* all onesweep passes of the main sort */
+    float fixup_ms;       /* ambiguous-window refinement + long-k refinement rounds */
+    float total_ms;       /* whole sort, first launch to last */
+    int32_t sort_passes;  /* onesweep passes launched for the main sort */
+    int32_t key_bits;     /* radix key width of the main sort */
+    int32_t levels;       /* 1 + number of prefix-doubling refinement rounds */
+    int32_t gpu_launches; /* kernels launched by the call */
+    uint64_t n_windows;   /* k-mers sorted */
+    uint64_t n_ambiguous; /* windows holding a non-ACGT symbol within the key */
+} gk_sort_stats;
+
+typedef struct gk_index gk_index;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int gk_version(void);
+const char *gk_status_string(int status);
+const char *gk_last_error(void);
+/* sm_count / cc / memory of the current device; GK_ERR_CUDA when there is none. */
+int gk_device_info(int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem_bytes);
+/* number of kernels launched by this library on the calling thread since the last reset */
+uint64_t gk_launch_count(int reset);
+
+/* ---- sequence byte array helpers ------------------------------ */
+/* counts[0] = bytes outside the IUPAC+'$' alphabet (sequence_collection.py:441-459),
+ * counts[1] = '$' bytes, counts[2] = ambiguous IUPAC letters (allowed, not A/C/G/T/'$'). */
+int gk_sba_scan_alphabet(const uint8_t *d_sba, uint64_t len, uint64_t *h_counts3, void *stream);
+/* out[len-1-i] = complement(in[i]) (sequence_collection.py:42-73, :402-433); in != out. */
+int gk_sba_revcomp(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream);
+/* out = in || '$' || revcomp(in), 2*len+1 bytes: this library's definition of both strands. */
+int gk_sba_both_strands(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream);
+
+/* ---- k-mer start indices (row A3, kmers.py:789-835) --------------------------------------- */
+/* Number of windows of kmer_len bases that fit inside a record. */
+int gk_kmer_count(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t sba_len,
+                  uint32_t kmer_len, uint64_t *n_out);
+int gk_kmer_init_indices(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t sba_len,
+                         uint32_t kmer_len, int idx_bytes, void *d_idx_out, void *stream);
+
+/* ---- building blocks (also used by the multi-GPU driver and the unit tests) ---------------- */
+/* Key-pack (north_star subsystem 1).  For every window of `valid_len` bases inside a record, in
+ * ascending start order, emit a 64-bit radix key over its first key_len <= 32 symbols and its
+ * start index.  Pure A/C/G/T windows get the 2-bit code (A<C<G<T); a window whose first
+ * key_len symbols hold another symbol gets the count of pure windows that sort below it, so a
+ * single integer sort orders both classes (DESIGN.md "two-class keys").  With class_bit = 1
+ * the key is (value << 1) | is_pure; it is required whenever ambiguous symbols may occur and
+ * needs key_len <= 31.  *h_n_ambiguous receives the number of non-pure windows. */
+int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_seg_starts,
+                 uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
+                 uint64_t first_start, uint64_t end_start, uint64_t *d_keys_out, int idx_bytes,
+                 void *d_idx_out, uint64_t out_capacity, uint64_t *h_n_out,
+                 uint64_t *h_n_ambiguous, void *stream);
+/* Stable LSD onesweep radix sort of (key, value) pairs on key bits [begin_bit, end_bit)
+ * (north_star subsystem 2).  Buffers ping-pong; *result_in_alt tells where the result is. */
+int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                        int val_bytes, uint64_t n, int begin_bit, int end_bit,
+                        int *result_in_alt, void *stream);
+/* Run-length pass over sorted keys (north_star subsystem 3): group offsets (positions where a
+ * new key starts; d_offsets_out has room for n entries), number of groups. */
+int gk_rle_keys(const uint64_t *d_keys_sorted, uint64_t n, uint64_t *d_offsets_out,
+                uint64_t *h_n_groups, void *stream);
+/* counts_by_group_size[min(size, max_bin)] += 1 and total += size over groups with
+ * min_group <= size <= max_group (0 = no maximum) -- kmers.py:514-518, :612-614. */
+int gk_group_size_hist(const uint64_t *d_offsets, uint64_t n_groups, uint64_t n,
+                       uint64_t min_group, uint64_t max_group, uint64_t max_bin,
+                       int64_t *h_hist_out, int64_t *h_total_out, void *stream);
+
+/* ---- the index object: drop-in for the state behind reference `Kmers` --------------------- */
+/* Borrow d_sba (caller keeps it alive and unchanged), copy the segment table.  max_kmer_len 0
+ * means None.  Mirrors Kmers.__init__ validation that depends on the data (kmers.py:743-748,
+ * :805-808 is lifted: more than 2^32-1 k-mers switch the index to uint64). */
+int gk_index_create(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts,
+                    uint32_t n_seg, uint32_t min_kmer_len, uint32_t max_kmer_len,
+                    gk_index **out);
+void gk_index_destroy(gk_index *ix);
+uint64_t gk_index_size(const gk_index *ix);   /* number of k-mers, kmers.py:863-864 */
+int gk_index_idx_bytes(const gk_index *ix);   /* 4 or 8 */
+int gk_index_is_sorted(const gk_index *ix);
+/* Replace the start indices (e.g. Kmers.load); `sorted` states what the caller knows. */
+int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_bytes, int sorted,
+                         void *stream);
+/* seam 1: sort the start indices lexicographically by k-mer, ties by ascending start. */
+int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream);
+/* Device pointer to the current (init or sorted) start indices; owned by the index. */
+int gk_index_device_indices(gk_index *ix, const void **d_idx_out, void *stream);
+/* Copy the start indices to a host buffer of gk_index_size() * idx_bytes bytes. */
+int gk_index_copy_indices(gk_index *ix, void *h_dst, void *stream);
+/* seam 2: group-size histogram and total (kmers.py:454-520).  kmer_len 0 means None.
+ * sorted semantics follow get_kmer_count: on an unsorted index every passing k-mer is its own
+ * group (kmers.py:1061-1064). h_hist_out may be NULL (get_kmer_count). */
+int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filter,
+                          uint64_t min_group, uint64_t max_group, uint64_t max_bin,
+                          int64_t *h_hist_out, int64_t *h_total_out, void *stream);
+/* Group table of the sorted index for kmer_len: number of groups, and (optionally, host
+ * buffers of n_groups entries obtained by a first call with NULLs) offsets into the sorted
+ * order and sizes.  This is the unique-k-mer set: one entry per distinct k-mer. */
+int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups,
+                    uint64_t *h_offsets_out, uint64_t *h_sizes_out, void *stream);
+
+/* ---- one-shot host entry point (host buffers in, host buffers out) ------------------------ */
+/* sba (forward strand, records joined by '$') -> sorted start indices + histogram.  strands:
+ * 0 forward, 2 both (index space of forward || '$' || revcomp).  h_idx_out may be NULL.
+ * This is what a non-Python host would bind; bench.py's e2e leg times the Python equivalent. */
+int gk_sort_count_host(const uint8_t *h_sba, uint64_t sba_len, const uint64_t *h_seg_starts,
+                       uint32_t n_seg, uint32_t kmer_len, int strands, int idx_bytes,
+                       void *h_idx_out, uint64_t max_bin, int64_t *h_hist_out,
+                       int64_t *h_total_out, uint64_t *h_n_kmers_out, gk_sort_stats *stats_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKB200_H */

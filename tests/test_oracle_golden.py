@@ -1,0 +1,119 @@
+"""
+Pins the CPU oracle (oracle/gk_oracle.c and oracle/oracle_np.py) to the real reference: every
+golden case in tests/golden was produced by running mrperkett/genome-kmers itself
+(tests/golden/make_golden.py).  CPU only.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np
+from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
+
+ALL = golden_case_names()
+COMP = str.maketrans("ACGTRYSWKMBDHVN", "TGCAYRSWMKVHDBN")
+
+
+def _filter(spec):
+    if spec is None:
+        return (oracle.FILTER_KEEP_ALL, 0, 0, 0)
+    assert spec[0] == "no_ambiguous"
+    return (oracle.FILTER_NO_AMBIGUOUS, spec[1], 0, 0)
+
+
+def _build(case):
+    sba, starts = oracle.build_sba([s for _, s in case["seq_list"]])
+    starts = starts.astype(np.uint64)
+    if case["strands"] == "both":
+        sba, starts = oracle.both_strands(sba, starts)
+    return sba, starts
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_sba_layout_matches_reference(name):
+    """A1/A2: byte array and segment starts (sequence_collection.py:663-726, :42-73, :905-928)."""
+    case = golden_case(name)
+    sba, starts = _build(case)
+    assert np.array_equal(sba, case["sba"])
+    assert np.array_equal(starts, case["seg_starts"].astype(np.uint64))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_init_indices_match_reference(name):
+    """A3: kmers.py:789-835."""
+    case = golden_case(name)
+    got = oracle.init_indices(case["seg_starts"], len(case["sba"]), case["min_len"])
+    assert np.array_equal(got, case["init"].astype(np.uint64))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_c_sort_matches_reference(name):
+    """A4+A5: comparator + quicksort, canonical tie order (kmers.py:306-397, :1624-1731)."""
+    case = golden_case(name)
+    got = oracle.sort_indices(case["sba"], case["init"], case["min_len"], case["max_len"])
+    assert np.array_equal(got, case["sorted"].astype(np.uint64))
+    if len(case["init"]) > 3000:
+        par = oracle.sort_indices(case["sba"], case["init"], case["min_len"], case["max_len"],
+                                  threads=4)
+        assert np.array_equal(par, got)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_numpy_sort_matches_reference(name):
+    case = golden_case(name)
+    got = oracle_np.sort_indices(case["sba"], case["init"], case["seg_starts"], case["max_len"])
+    assert np.array_equal(got, case["sorted"].astype(np.uint64))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_group_counts_match_reference(name):
+    """A6+A7: group walk + histogram incl. filters and group-size limits (kmers.py:454-648)."""
+    case = golden_case(name)
+    for qu, ans in zip(case["queries"], case["answers"]):
+        hist, total = oracle.group_hist(
+            case["sba"], case["sorted"], qu["kmer_len"], True, _filter(qu["filter"]),
+            qu["min_group"], qu["max_group"], qu["max_bin"])
+        assert total == ans["total"], qu
+        assert np.array_equal(hist, dense_hist(ans, qu["max_bin"])), qu
+        if qu["filter"] is None:
+            sizes = oracle_np.group_sizes(case["sba"], case["sorted"], case["seg_starts"],
+                                          qu["kmer_len"])
+            h2, t2 = oracle_np.group_hist(sizes, qu["min_group"], qu["max_group"], qu["max_bin"])
+            assert t2 == ans["total"] and np.array_equal(h2, hist), qu
+
+
+def test_unsorted_count_is_number_of_kmers():
+    """get_kmer_count on unsorted data: every k-mer is its own group (kmers.py:1061-1064)."""
+    case = golden_case("sl2_k3")
+    hist, total = oracle.group_hist(case["sba"], case["init"], 3, sorted_=False, max_bin=4)
+    assert total == len(case["init"]) and hist[1] == len(case["init"])
+
+
+def test_reference_known_answers():
+    """Known answers the reference's own tests hold (tests/test_kmers.py:1889-1944)."""
+    case = golden_case("sl2_k1")
+    hist, total = oracle.group_hist(case["sba"], case["sorted"], 1, max_bin=20)
+    assert total == 35
+    assert sorted(np.repeat(np.arange(21), hist).tolist()) == [7, 8, 8, 12]  # C, A, G, T
+    case = golden_case("sl2_k5")
+    hist, total = oracle.group_hist(case["sba"], case["sorted"], 5, max_bin=5)
+    assert total == 23 and hist[1] == 23
+
+
+def test_reference_golden_revcomp():
+    """tests/test_sequence_collection.py:40-44."""
+    sba, starts = oracle.build_sba(["ATCGAATTAG", "GGATCTTGCATT", "GTGATTGACCCCT"])
+    assert bytes(sba) == b"ATCGAATTAG$GGATCTTGCATT$GTGATTGACCCCT"
+    assert starts.tolist() == [0, 11, 24]
+    assert bytes(oracle.revcomp(sba)) == b"AGGGGTCAATCAC$AATGCAAGATCC$CTAATTCGAT"
+    assert oracle.revcomp_seg_starts(starts, len(sba)).tolist() == [0, 14, 27]
+
+
+def test_sorted_3mers_match_reference_docs():
+    """Sorted 3-mer list of seq_list_2 (tests/test_kmers.py:984-1014, docs/overview.rst:46-74)."""
+    case = golden_case("sl2_k3")
+    sba = case["sba"]
+    kmers = [bytes(sba[i:i + 3]).decode() for i in case["sorted"]]
+    assert kmers == sorted(kmers)
+    assert kmers[:5] == ["AAT", "ACC", "AGG", "ATC", "ATC"] or kmers[0] == "AAT"
+    assert len(kmers) == 29
