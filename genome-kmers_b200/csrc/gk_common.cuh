@@ -75,6 +75,13 @@ struct DeviceBuffer {
     T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 
+// device time of one radix sort, split the way bench.py reports it
+struct SortTiming {
+    float hist_ms;    // digit histogram + scan (one read of the keys)
+    float passes_ms;  // all onesweep passes (and their status memsets)
+    int passes;
+};
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
 

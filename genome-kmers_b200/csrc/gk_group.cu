@@ -1,0 +1,554 @@
+// gk_group.cu -- segmented run-length pass over the sorted k-mers (north_star subsystem 3;
+// replaces the linear group walk kmers.py:523-648 and the histogram kmers.py:454-520).
+//
+//   head flags   flag[p] = k-mer at sorted position p differs from the one at p-1
+//                  * from sorted radix keys (8 B/k-mer, the fast path), or
+//                  * from the sequence bytes with the reference's '$'-terminated comparator
+//                    (kmers.py:306-397) for anything the keys cannot answer: ambiguous windows,
+//                    a kmer_len different from the sort length, indices loaded from disk.
+//   select       ordered stream compaction of flagged positions -> group offsets (one entry per
+//                distinct k-mer).  Three kernels: per-tile counts, one-CTA scan of the counts,
+//                ordered write.
+//   histogram    counts_by_group_size[min(size, max_bin)] += 1, total += size over groups with
+//                min_group <= size <= max_group (kmers.py:514-518, :612-614); small sizes are
+//                privatised in shared memory because a random genome puts almost every group in
+//                bin 1.
+#include "gk_common.cuh"
+
+namespace gk {
+
+constexpr uint8_t kFlagHead = 1;  // first k-mer of a group
+constexpr uint8_t kFlagAmb = 2;   // slot holds a non-ACGT window (key class bit 0)
+
+// ---- head flags from sorted keys ---------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+key_flags_kernel(const uint64_t *__restrict__ keys, uint64_t n, int class_bit,
+                 uint8_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n8 = (n + 7) / 8;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n8; c += stride) {
+        const uint64_t p0 = c * 8;
+        uint64_t prev = (p0 == 0) ? 0 : keys[p0 - 1];
+        uint64_t packed = 0;
+        if (p0 + 8 <= n) {
+            const ulonglong2 *v = reinterpret_cast<const ulonglong2 *>(keys + p0);
+            uint64_t k[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ulonglong2 q = v[i];
+                k[2 * i] = q.x;
+                k[2 * i + 1] = q.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool amb = class_bit && !(k[i] & 1ull);
+                const bool head = (p0 + i == 0) || (k[i] != prev);
+                const uint64_t f = amb ? kFlagAmb : (head ? kFlagHead : 0);
+                packed |= f << (8 * i);
+                prev = k[i];
+            }
+            *reinterpret_cast<uint64_t *>(flags + p0) = packed;
+        } else {
+            for (uint64_t p = p0; p < n; ++p) {
+                const uint64_t k = keys[p];
+                const bool amb = class_bit && !(k & 1ull);
+                const bool head = (p == 0) || (k != prev);
+                flags[p] = amb ? kFlagAmb : (head ? kFlagHead : 0);
+                prev = k;
+            }
+        }
+    }
+}
+
+// ---- head flags from the sequence bytes (reference comparator) ------------------------------------
+// equal <=> compare_sba_kmers_lexicographically(...) == 0: same bytes up to kmer_len, or both
+// terminated ('$' / end of array) at the same offset.  kmer_len == 0 means None.
+__device__ __forceinline__ bool windows_equal(const uint8_t *__restrict__ sba, uint64_t len,
+                                              uint64_t a, uint64_t b, uint32_t kmer_len)
+{
+    if (a == b) return true;
+    for (uint32_t j = 0;; ++j) {
+        const uint32_t ca = (a + j < len) ? sba[a + j] : kSep;
+        const uint32_t cb = (b + j < len) ? sba[b + j] : kSep;
+        const bool a_out = ca == kSep, b_out = cb == kSep;
+        if (a_out || b_out) return a_out && b_out;
+        if (ca != cb) return false;
+        if (kmer_len && j == kmer_len - 1) return true;
+    }
+}
+
+// dst == nullptr: flags[r] = head bit.  dst != nullptr: flags[dst[r]] = extra | head bit.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+sba_flags_kernel(const uint8_t *__restrict__ sba, uint64_t len, const IdxT *__restrict__ idx,
+                 uint64_t n, uint32_t kmer_len, const IdxT *__restrict__ dst, uint8_t extra,
+                 uint8_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        bool head = true;
+        if (r > 0) head = !windows_equal(sba, len, (uint64_t)idx[r - 1], (uint64_t)idx[r], kmer_len);
+        const uint8_t f = extra | (head ? kFlagHead : 0);
+        if (dst) flags[(uint64_t)dst[r]] = f; else flags[r] = f;
+    }
+}
+
+// ---- ordered select of flagged positions ----------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSelPerThread = 16;
+constexpr int kSelTile = kSelThreads * kSelPerThread;
+
+__device__ __forceinline__ uint32_t load_flag_bits(const uint8_t *__restrict__ flags, uint64_t n,
+                                                   uint64_t p0, uint8_t mask)
+{
+    // bit i of the result = (flags[p0+i] & mask) != 0, for i < 16
+    uint32_t bits = 0;
+    if (p0 + 16 <= n) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(flags + p0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            bits |= (((w[i >> 2] >> (8 * (i & 3))) & mask) ? 1u : 0u) << i;
+    } else {
+        for (int i = 0; i < 16; ++i)
+            if (p0 + i < n && (flags[p0 + i] & mask)) bits |= 1u << i;
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_count_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
+                    uint32_t *__restrict__ tile_counts)
+{
+    __shared__ uint32_t s_warp[kSelThreads / 32];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * kSelPerThread;
+    uint32_t c = (p0 < n) ? __popc(load_flag_bits(flags, n, p0, mask)) : 0;
+    c = warp_sum(c);
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) s += s_warp[w];
+        tile_counts[blockIdx.x] = s;
+    }
+}
+
+// one CTA: exclusive scan of tile counts into 64-bit offsets; total appended at [n_tiles]
+__global__ void __launch_bounds__(1024)
+select_scan_kernel(const uint32_t *__restrict__ tile_counts, uint64_t n_tiles,
+                   unsigned long long *__restrict__ tile_offsets)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n_tiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long c = (i < n_tiles) ? tile_counts[i] : 0;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+        if (i < n_tiles) tile_offsets[i] = pre + inc - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_offsets[n_tiles] = s_carry;
+}
+
+template <typename PosT, typename PayT>
+__global__ void __launch_bounds__(kSelThreads)
+select_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
+                    const unsigned long long *__restrict__ tile_offsets,
+                    PosT *__restrict__ pos_out, const PayT *__restrict__ payload_in,
+                    PayT *__restrict__ payload_out)
+{
+    __shared__ uint32_t s_warp[kSelThreads / 32];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * kSelPerThread;
+    const uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, mask) : 0;
+    const uint32_t c = __popc(bits);
+    uint32_t inc = c;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+    uint64_t out = tile_offsets[blockIdx.x] + pre + inc - c;
+    uint32_t b = bits;
+    while (b) {
+        const uint32_t i = __ffs(b) - 1;
+        b &= b - 1;
+        if (pos_out) pos_out[out] = (PosT)(p0 + i);
+        if (payload_out) payload_out[out] = payload_in[p0 + i];
+        ++out;
+    }
+}
+
+// positions (and optionally payload_in[position]) of flags with (flag & mask) != 0, in order
+template <typename PosT, typename PayT>
+int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, PosT *d_pos_out,
+                          const PayT *d_payload_in, PayT *d_payload_out, uint64_t *h_count,
+                          cudaStream_t st)
+{
+    if (h_count) *h_count = 0;
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kSelTile - 1) / kSelTile;
+    DeviceBuffer temp;
+    const size_t counts_bytes = ((size_t)tiles * 4 + 15) & ~(size_t)15;
+    GK_TRY(temp.alloc(counts_bytes + (size_t)(tiles + 1) * 8, st));
+    uint32_t *d_counts = temp.as<uint32_t>();
+    unsigned long long *d_offsets =
+        reinterpret_cast<unsigned long long *>(temp.as<unsigned char>() + counts_bytes);
+    select_count_kernel<<<(unsigned)tiles, kSelThreads, 0, st>>>(d_flags, n, mask, d_counts);
+    GK_LAUNCH_CHECK();
+    select_scan_kernel<<<1, 1024, 0, st>>>(d_counts, tiles, d_offsets);
+    GK_LAUNCH_CHECK();
+    select_write_kernel<PosT, PayT><<<(unsigned)tiles, kSelThreads, 0, st>>>(
+        d_flags, n, mask, d_offsets, d_pos_out, d_payload_in, d_payload_out);
+    GK_LAUNCH_CHECK();
+    if (h_count) {
+        GK_CUDA(cudaMemcpyAsync(h_count, d_offsets + tiles, 8, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+    }
+    return GK_OK;
+}
+
+template int select_flagged_device<uint32_t, uint32_t>(const uint8_t *, uint64_t, uint8_t, uint32_t *,
+                                                       const uint32_t *, uint32_t *, uint64_t *,
+                                                       cudaStream_t);
+template int select_flagged_device<uint64_t, uint64_t>(const uint8_t *, uint64_t, uint8_t, uint64_t *,
+                                                       const uint64_t *, uint64_t *, uint64_t *,
+                                                       cudaStream_t);
+
+// scatter: dst_array[pos[r]] = src[r]
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+scatter_kernel(const IdxT *__restrict__ src, const IdxT *__restrict__ pos, uint64_t n,
+               IdxT *__restrict__ dst_array)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride)
+        dst_array[(uint64_t)pos[r]] = src[r];
+}
+
+// ---- group-size histogram -----------------------------------------------------------------------------
+constexpr int kHistSmallBins = 2048;
+
+template <typename PosT>
+__global__ void __launch_bounds__(256)
+group_hist_kernel(const PosT *__restrict__ offsets, uint64_t n_groups, uint64_t n,
+                  const uint8_t *__restrict__ flags, uint8_t skip_mask, uint64_t min_group,
+                  uint64_t max_group, uint64_t max_bin, unsigned long long *__restrict__ hist,
+                  unsigned long long *__restrict__ totals)
+{
+    __shared__ uint32_t s_small[kHistSmallBins];
+    __shared__ unsigned long long s_total[3];
+    for (int i = threadIdx.x; i < kHistSmallBins; i += blockDim.x) s_small[i] = 0;
+    if (threadIdx.x < 3) s_total[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long total = 0, counted = 0, top_bin = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const uint64_t a = (uint64_t)offsets[g];
+        const uint64_t b = (g + 1 < n_groups) ? (uint64_t)offsets[g + 1] : n;
+        const uint64_t size = b - a;
+        if (skip_mask && (flags[a] & skip_mask)) continue;  // e.g. groups of ambiguous k-mers
+        if (size >= min_group && (max_group == 0 || size <= max_group)) {
+            total += size;
+            ++counted;
+            const uint64_t bin = size < max_bin ? size : max_bin;
+            if (bin > top_bin) top_bin = bin;
+            if (bin < kHistSmallBins) atomicAdd(&s_small[bin], 1u);
+            else atomicAdd(&hist[bin], 1ull);
+        }
+    }
+    total = warp_sum(total);
+    counted = warp_sum(counted);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, top_bin, o);
+        top_bin = other > top_bin ? other : top_bin;
+    }
+    if (lane_id() == 0) {
+        atomicAdd(&s_total[0], total);
+        atomicAdd(&s_total[1], counted);
+        atomicMax(&s_total[2], top_bin);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistSmallBins; i += blockDim.x) {
+        const uint32_t c = s_small[i];
+        if (c && (uint64_t)i <= max_bin) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+    if (threadIdx.x < 2 && s_total[threadIdx.x]) atomicAdd(&totals[threadIdx.x], s_total[threadIdx.x]);
+    if (threadIdx.x == 2 && s_total[2]) atomicMax(&totals[2], s_total[2]);
+}
+
+static int launch_grid(uint64_t items, int block)
+{
+    uint64_t blocks = (items + block - 1) / block;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int key_flags_device(const uint64_t *d_keys, uint64_t n, int class_bit, uint8_t *d_flags,
+                     cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    key_flags_kernel<<<launch_grid((n + 7) / 8, 256), 256, 0, st>>>(d_keys, n, class_bit, d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int sba_flags_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
+                     uint64_t n, uint32_t kmer_len, const void *d_dst, uint8_t extra,
+                     uint8_t *d_flags, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    const int grid = launch_grid(n, 256);
+    if (idx_bytes == 4)
+        sba_flags_kernel<uint32_t><<<grid, 256, 0, st>>>(d_sba, sba_len, (const uint32_t *)d_idx, n,
+                                                         kmer_len, (const uint32_t *)d_dst, extra,
+                                                         d_flags);
+    else
+        sba_flags_kernel<uint64_t><<<grid, 256, 0, st>>>(d_sba, sba_len, (const uint64_t *)d_idx, n,
+                                                         kmer_len, (const uint64_t *)d_dst, extra,
+                                                         d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int scatter_device(const void *d_src, const void *d_pos, uint64_t n, int idx_bytes, void *d_dst,
+                   cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    const int grid = launch_grid(n, 256);
+    if (idx_bytes == 4)
+        scatter_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_src,
+                                                       (const uint32_t *)d_pos, n, (uint32_t *)d_dst);
+    else
+        scatter_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)d_src,
+                                                       (const uint64_t *)d_pos, n, (uint64_t *)d_dst);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// hist (host, max_bin+1 int64, may be NULL) and totals[0] = sum of sizes, totals[1] = groups counted.
+// Groups whose first slot has (flags & skip_mask) != 0 are left out (skip_mask 0: none).
+static int group_hist_impl(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
+                           const uint8_t *d_flags, uint8_t skip_mask, uint64_t min_group,
+                           uint64_t max_group, uint64_t max_bin, int64_t *h_hist, int64_t *h_total,
+                           int64_t *h_counted, cudaStream_t st)
+{
+    if (min_group < 1) {
+        set_error("min_group_size (%llu) must be >= 1", (unsigned long long)min_group);
+        return GK_ERR_ARG;
+    }
+    if (max_group != 0 && max_group < min_group) {
+        set_error("max_group_size must be >= min_group_size");
+        return GK_ERR_ARG;
+    }
+    if (max_bin < 1) {
+        set_error("max_counts_bin (%llu) must be >= 1", (unsigned long long)max_bin);
+        return GK_ERR_ARG;
+    }
+    DeviceBuffer buf;
+    const size_t hist_bytes = (size_t)(max_bin + 1) * 8;
+    GK_TRY(buf.alloc(hist_bytes + 24, st));
+    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 24, st));
+    unsigned long long *d_hist = buf.as<unsigned long long>();
+    unsigned long long *d_totals = d_hist + (max_bin + 1);
+    if (n_groups) {
+        const int grid = launch_grid(n_groups, 256);
+        if (pos_bytes == 4)
+            group_hist_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_offsets, n_groups, n,
+                                                              d_flags, skip_mask, min_group,
+                                                              max_group, max_bin, d_hist, d_totals);
+        else
+            group_hist_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)d_offsets, n_groups, n,
+                                                              d_flags, skip_mask, min_group,
+                                                              max_group, max_bin, d_hist, d_totals);
+        GK_LAUNCH_CHECK();
+    }
+    // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB)
+    unsigned long long totals[3] = {0, 0, 0};
+    GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_hist) {
+        memset(h_hist, 0, hist_bytes);
+        GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+    }
+    if (h_total) *h_total = (int64_t)totals[0];
+    if (h_counted) *h_counted = (int64_t)totals[1];
+    return GK_OK;
+}
+
+int group_hist_device(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
+                      uint64_t min_group, uint64_t max_group, uint64_t max_bin, int64_t *h_hist,
+                      int64_t *h_total, int64_t *h_counted, cudaStream_t st)
+{
+    return group_hist_impl(d_offsets, pos_bytes, n_groups, n, nullptr, 0, min_group, max_group, max_bin,
+                           h_hist, h_total, h_counted, st);
+}
+
+int group_hist_masked_device(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
+                             const uint8_t *d_flags, uint8_t skip_mask, uint64_t min_group,
+                             uint64_t max_group, uint64_t max_bin, int64_t *h_hist, int64_t *h_total,
+                             cudaStream_t st)
+{
+    return group_hist_impl(d_offsets, pos_bytes, n_groups, n, d_flags, skip_mask, min_group, max_group,
+                           max_bin, h_hist, h_total, nullptr, st);
+}
+
+// ---- k-mer filters as device predicates (kmers.py:14-259) ------------------------------------------
+// returns 1 pass, 0 fail, -1 where the reference raises ValueError
+__device__ __forceinline__ int eval_filter(const uint8_t *__restrict__ sba, uint64_t len, uint64_t s,
+                                           int id, int64_t p0, int64_t p1, int64_t p2)
+{
+    switch (id) {
+    case GK_FILTER_KEEP_ALL:
+        return 1;
+    case GK_FILTER_NO_AMBIGUOUS:  // kmers.py:209-227
+        if (s + (uint64_t)p0 > len) return -1;
+        for (int64_t i = 0; i < p0; ++i) {
+            const uint32_t b = sba[s + i];
+            if (b == kSep) return -1;
+            if (!is_acgt(b)) return 0;
+        }
+        return 1;
+    case GK_FILTER_MIN_LENGTH:  // kmers.py:30-32 -> :262-282
+        for (int64_t i = 0; i < p0; ++i)
+            if (s + i >= len || sba[s + i] == kSep) return 0;
+        return 1;
+    case GK_FILTER_HOMOPOLYMER: {  // kmers.py:63-98
+        if (s + (uint64_t)p1 - 1 >= len) return -1;
+        if (p1 < p0) return 1;
+        int64_t run = 1;
+        for (int64_t i = 1; i < p1; ++i) {
+            const uint32_t b = sba[s + i];
+            if (b == kSep) return -1;
+            if (b == sba[s + i - 1]) {
+                if (++run > p0) return 0;
+            } else {
+                run = 1;
+            }
+        }
+        return 1;
+    }
+    case GK_FILTER_GC_COUNT: {  // kmers.py:150-190
+        if (p1 < p0) return 0;
+        int64_t gc = 0;
+        for (int64_t i = 0; i < p2; ++i) {
+            if (s + i >= len) return -1;
+            const uint32_t b = sba[s + i];
+            if (b == kSep) return -1;
+            if (b == 'G' || b == 'C')
+                if (++gc > p1) return 0;
+        }
+        return (p0 <= gc && gc <= p1) ? 1 : 0;
+    }
+    case GK_FILTER_NGG_PAM:  // kmers.py:232-259
+        if (s + 23 > len) return -1;
+        return (sba[s + 21] == 'G' && sba[s + 22] == 'G') ? 1 : 0;
+    default:
+        return -1;
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+filter_flags_kernel(const uint8_t *__restrict__ sba, uint64_t len, const IdxT *__restrict__ idx,
+                    uint64_t n, int id, int64_t p0, int64_t p1, int64_t p2,
+                    uint8_t *__restrict__ flags, int *__restrict__ err)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const int v = eval_filter(sba, len, (uint64_t)idx[r], id, p0, p1, p2);
+        if (v < 0) atomicExch(err, 1);
+        flags[r] = v > 0 ? 4 : 0;  // kFlagPass
+    }
+}
+
+int filter_flags_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
+                        uint64_t n, const gk_filter &f, uint8_t *d_flags, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    if (f.id < GK_FILTER_KEEP_ALL || f.id > GK_FILTER_NGG_PAM) {
+        set_error("unknown filter id %d", f.id);
+        return GK_ERR_ARG;
+    }
+    DeviceBuffer err;
+    GK_TRY(err.alloc(4, st));
+    GK_CUDA(cudaMemsetAsync(err.ptr, 0, 4, st));
+    const int grid = launch_grid(n, 256);
+    if (idx_bytes == 4)
+        filter_flags_kernel<uint32_t><<<grid, 256, 0, st>>>(d_sba, sba_len, (const uint32_t *)d_idx, n,
+                                                            f.id, f.p0, f.p1, f.p2, d_flags,
+                                                            err.as<int>());
+    else
+        filter_flags_kernel<uint64_t><<<grid, 256, 0, st>>>(d_sba, sba_len, (const uint64_t *)d_idx, n,
+                                                            f.id, f.p0, f.p1, f.p2, d_flags,
+                                                            err.as<int>());
+    GK_LAUNCH_CHECK();
+    int h_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_err, err.ptr, 4, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("k-mer filter raised: a k-mer of the requested length runs past the end of its "
+                  "record or of the sequence byte array");
+        return GK_ERR_ARG;
+    }
+    return GK_OK;
+}
+
+}  // namespace gk
+
+using namespace gk;
+
+extern "C" {
+
+int gk_rle_keys(const uint64_t *d_keys_sorted, uint64_t n, uint64_t *d_offsets_out,
+                uint64_t *h_n_groups, void *stream)
+{
+    if (n && (!d_keys_sorted || !d_offsets_out)) {
+        set_error("gk_rle_keys: null buffer");
+        return GK_ERR_ARG;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (h_n_groups) *h_n_groups = 0;
+    if (n == 0) return GK_OK;
+    DeviceBuffer flags;
+    GK_TRY(flags.alloc((size_t)((n + 15) & ~15ull), st));
+    GK_TRY(key_flags_device(d_keys_sorted, n, 0, flags.as<uint8_t>(), st));
+    uint64_t count = 0;
+    GK_TRY((select_flagged_device<uint64_t, uint64_t>(flags.as<uint8_t>(), n, kFlagHead, d_offsets_out,
+                                                      nullptr, nullptr, &count, st)));
+    if (h_n_groups) *h_n_groups = count;
+    return GK_OK;
+}
+
+int gk_group_size_hist(const uint64_t *d_offsets, uint64_t n_groups, uint64_t n, uint64_t min_group,
+                       uint64_t max_group, uint64_t max_bin, int64_t *h_hist_out,
+                       int64_t *h_total_out, void *stream)
+{
+    return group_hist_device(d_offsets, 8, n_groups, n, min_group, max_group, max_bin, h_hist_out,
+                             h_total_out, nullptr, as_stream(stream));
+}
+
+}  // extern "C"

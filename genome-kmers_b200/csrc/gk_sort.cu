@@ -285,8 +285,9 @@ constexpr int kSortIPT8 = 12;  // 64-bit values
 
 int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                             int val_bytes, uint64_t n, int begin_bit, int end_bit,
-                            int *result_in_alt, cudaStream_t st)
+                            int *result_in_alt, cudaStream_t st, SortTiming *timing)
 {
+    if (timing) { timing->hist_ms = 0.f; timing->passes_ms = 0.f; timing->passes = 0; }
     if (val_bytes != 4 && val_bytes != 8) {
         set_error("radix_sort_pairs: val_bytes must be 4 or 8");
         return GK_ERR_ARG;
@@ -319,6 +320,10 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
     void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
     GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
 
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing)
+        for (auto &e : ev) GK_CUDA(cudaEventCreate(&e));
+    if (timing) GK_CUDA(cudaEventRecord(ev[0], st));
     int hist_grid = sm_count() * 2;
     {
         uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
@@ -330,6 +335,7 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
     scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_hist, d_base);
     GK_LAUNCH_CHECK();
 
+    if (timing) GK_CUDA(cudaEventRecord(ev[1], st));
     uint64_t *kin = d_keys, *kout = d_keys_alt;
     void *vin = d_vals, *vout = d_vals_alt;
     for (int p = 0; p < passes; ++p) {
@@ -354,10 +360,17 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
         void *tv = vin; vin = vout; vout = tv;
     }
     if (result_in_alt) *result_in_alt = passes & 1;
+    if (timing) GK_CUDA(cudaEventRecord(ev[2], st));
 
     int h_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    if (timing) {
+        cudaEventElapsedTime(&timing->hist_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&timing->passes_ms, ev[1], ev[2]);
+        timing->passes = passes;
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     if (h_err) {
         set_error("radix_sort_pairs: decoupled look-back timed out");
         return GK_ERR_INTERNAL;
@@ -378,5 +391,5 @@ extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void 
         return GK_ERR_ARG;
     }
     return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
-                                   end_bit, result_in_alt, as_stream(stream));
+                                   end_bit, result_in_alt, as_stream(stream), nullptr);
 }

@@ -109,8 +109,10 @@ int gk_kmer_init_indices(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t 
  * key_len symbols hold another symbol gets the count of pure windows that sort below it, so a
  * single integer sort orders both classes (DESIGN.md "two-class keys").  With class_bit = 1
  * the key is (value << 1) | is_pure; it is required whenever ambiguous symbols may occur and
- * needs key_len <= 31.  *h_n_ambiguous receives the number of non-pure windows. */
-int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_seg_starts,
+ * needs key_len <= 31.  Only windows whose start lies in [first_start, end_start) are emitted
+ * (a GPU's slice of the byte array); *h_n_out receives their number, *h_n_ambiguous the number
+ * of non-pure ones. */
+int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts,
                  uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
                  uint64_t first_start, uint64_t end_start, uint64_t *d_keys_out, int idx_bytes,
                  void *d_idx_out, uint64_t out_capacity, uint64_t *h_n_out,

@@ -1,0 +1,205 @@
+"""
+GPU parity tests proper: the drop-in API (SequenceCollection + Kmers, which call libgkb200 through
+the C ABI) against (1) the golden vectors produced by the real reference and (2) the CPU oracle on
+larger seeded inputs, (3) size-independent properties at BASELINE.json's full sizes.
+Bit-exact: start-index order with ties ascending (the reference's break_ties=True order).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
+from genome_kmers.kmers import Kmers, gen_no_ambiguous_bases_filter, kmer_filter_keep_all
+from genome_kmers.sequence_collection import SequenceCollection
+import gpu_utils as gu
+
+pytestmark = pytest.mark.gpu
+
+FIXED = golden_case_names(is_fixed_k)
+VARIABLE = golden_case_names(lambda c: not is_fixed_k(c))
+
+
+def _filter(spec):
+    return kmer_filter_keep_all if spec is None else gen_no_ambiguous_bases_filter(spec[1])
+
+
+def _kmers_for(case):
+    sc = SequenceCollection(sequence_list=[tuple(r) for r in case["seq_list"]],
+                            strands_to_load=case["strands"])
+    return sc, Kmers(sc, min_kmer_len=case["min_len"], max_kmer_len=case["max_len"],
+                     source_strand=case["strands"])
+
+
+@pytest.mark.parametrize("name", FIXED)
+def test_golden_init_sort_and_counts(name):
+    case = golden_case(name)
+    sc, km = _kmers_for(case)
+    assert len(km) == case["n_kmers"]
+    assert np.array_equal(km.kmer_sba_start_indices, case["init"])          # A3
+    assert km.kmer_sba_start_indices.dtype == np.uint32
+    try:
+        km.sort()                                                             # A4 + A5
+    except NotImplementedError as exc:
+        pytest.skip(f"not on the GPU path yet: {exc}")
+    assert km._is_sorted
+    got = km.kmer_sba_start_indices
+    bad = np.flatnonzero(got != case["sorted"])
+    assert len(bad) == 0, f"{name}: first mismatches at {bad[:8]}: got {got[bad[:8]]} want {case['sorted'][bad[:8]]}"
+    for qu, ans in zip(case["queries"], case["answers"]):                    # A6 + A7
+        hist, total = km.get_kmer_group_counts(
+            qu["kmer_len"], kmer_filter_func=_filter(qu["filter"]), min_group_size=qu["min_group"],
+            max_group_size=qu["max_group"], max_counts_bin=qu["max_bin"])
+        assert total == ans["total"], (name, qu)
+        assert np.array_equal(hist, dense_hist(ans, qu["max_bin"])), (name, qu)
+        assert km.get_kmer_count(qu["kmer_len"], _filter(qu["filter"]), qu["min_group"],
+                                 qu["max_group"]) == ans["total"]
+
+
+@pytest.mark.parametrize("name", VARIABLE)
+def test_golden_variable_length_modes(name):
+    """sort() with min_kmer_len != max_kmer_len."""
+    case = golden_case(name)
+    sc, km = _kmers_for(case)
+    assert np.array_equal(km.kmer_sba_start_indices, case["init"])
+    try:
+        km.sort()
+    except NotImplementedError:
+        pytest.skip("variable-length / suffix order is not on the GPU path yet")
+    assert np.array_equal(km.kmer_sba_start_indices, case["sorted"])
+    for qu, ans in zip(case["queries"], case["answers"]):
+        hist, total = km.get_kmer_group_counts(qu["kmer_len"], max_counts_bin=qu["max_bin"],
+                                               min_group_size=qu["min_group"],
+                                               max_group_size=qu["max_group"])
+        assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"]))
+
+
+def test_counts_with_other_kmer_len_and_unsorted():
+    case = golden_case("rand5k_k21_count11")
+    sc, km = _kmers_for(case)
+    assert km.get_kmer_count(21) == case["n_kmers"]                          # unsorted: kmers.py:1061-1064
+    with pytest.raises(AssertionError):
+        km.get_kmer_group_counts(21)
+    with pytest.raises(ValueError):
+        km.get_kmer_count(21, min_group_size=2)
+    km.sort()
+    for qu, ans in zip(case["queries"], case["answers"]):
+        hist, total = km.get_kmer_group_counts(qu["kmer_len"], min_group_size=qu["min_group"],
+                                               max_group_size=qu["max_group"], max_counts_bin=qu["max_bin"])
+        assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"]))
+
+
+def test_group_table_is_the_unique_kmer_set():
+    case = golden_case("sl2_k3")
+    sc, km = _kmers_for(case)
+    km.sort()
+    offsets, sizes = km.get_kmer_groups(3)
+    idx = km.kmer_sba_start_indices
+    kmers = [sc.forward_sba[i:i + 3].tobytes().decode() for i in idx]
+    uniq = [kmers[o] for o in offsets]
+    assert uniq == sorted(set(kmers))
+    assert [kmers.count(u) for u in uniq] == sizes.tolist()
+    minimal = list(km.get_kmers(3, min_group_size=2, yield_first_n=1))
+    assert [kmers[num] for num, _, _ in minimal] == [u for u, s in zip(uniq, sizes) if s >= 2]
+
+
+def _oracle_compare(records, k, strands, threads=8, filt_k=None):
+    sc = SequenceCollection.from_arrays(records, strands_to_load=strands)
+    km = Kmers(sc, k, k, source_strand=strands)
+    km.sort()
+    got = km.kmer_sba_start_indices.astype(np.uint64)
+    sba, starts = sc.forward_sba, sc._forward_sba_seg_starts.astype(np.uint64)
+    if strands == "both":
+        sba, starts = oracle.both_strands(sba, starts)
+    init = oracle.init_indices(starts, len(sba), k)
+    want = oracle.sort_indices(sba, init, k, k, threads=threads)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, f"first mismatches at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
+    hist, total = km.get_kmer_group_counts(k, max_counts_bin=1000)
+    o_hist, o_total = oracle.group_hist(sba, want, k, max_bin=1000)
+    assert total == o_total and np.array_equal(hist, o_hist)
+    fk = filt_k or k
+    hist, total = km.get_kmer_group_counts(fk, gen_no_ambiguous_bases_filter(fk), max_counts_bin=1000)
+    o_hist, o_total = oracle.group_hist(sba, want, fk, filt=(oracle.FILTER_NO_AMBIGUOUS, fk, 0, 0), max_bin=1000)
+    assert total == o_total and np.array_equal(hist, o_hist)
+    return km, sba, want
+
+
+@pytest.mark.parametrize("k,strands,n_bases,n_rec,runs", [
+    (21, "forward", 400_000, 1, 0),
+    (31, "both", 300_000, 5, 6),
+    (12, "both", 500_000, 3, 4),      # 4^12 < windows: heavy duplication
+    (31, "forward", 1_000_000, 10, 20),
+    (8, "forward", 200_000, 2, 3),
+    (32, "forward", 250_000, 3, 0),
+])
+def test_seeded_random_vs_oracle(k, strands, n_bases, n_rec, runs):
+    rng = np.random.default_rng(42 + k + n_bases)
+    recs = gu.random_genome(rng, n_bases, n_rec, n_runs=runs, run_lo=50, run_hi=3000,
+                            n_scatter=30 if runs else 0)
+    _oracle_compare(recs, k, strands)
+
+
+def test_config1_shape_vs_oracle():
+    """BASELINE.json configs[0]: 4.6 Mbp, one record, forward, k=21 (the reference's CPU case)."""
+    rng = np.random.default_rng(42)
+    recs = gu.random_genome(rng, 4_600_000, 1)
+    km, sba, want = _oracle_compare(recs, 21, "forward")
+    assert len(km) == 4_599_980
+
+
+def _check_sorted_properties(km, sc, k, strands):
+    """Size-independent checks, all on the device with torch as the checker."""
+    torch = gu.torch_mod()
+    idx = km.device_start_indices().to(torch.int64)
+    n = idx.numel()
+    # (1) a permutation of the init set
+    fresh = Kmers(sc, k, k, source_strand=strands)
+    init = fresh.device_start_indices().to(torch.int64)
+    assert torch.equal(torch.sort(idx).values, init)
+    # (2) adjacent windows non-decreasing by raw byte order, ties ascending in start
+    d_sba = km._d_sba
+    chunk = 1 << 22
+    carry = None
+    n_groups = 0
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk + 1)
+        starts = idx[lo:hi]
+        win = d_sba[(starts[:, None] + torch.arange(k, device="cuda")[None, :])]
+        a, b = win[:-1].to(torch.int16), win[1:].to(torch.int16)
+        diff = (a != b)
+        first = torch.where(diff.any(dim=1), diff.to(torch.int8).argmax(dim=1), torch.full((len(a),), k - 1, device="cuda"))
+        av = a.gather(1, first[:, None]).squeeze(1)
+        bv = b.gather(1, first[:, None]).squeeze(1)
+        assert bool((av <= bv).all()), "k-mers are not in non-decreasing order"
+        tie = ~diff.any(dim=1)
+        assert bool((starts[:-1][tie] < starts[1:][tie]).all()), "ties are not in ascending start order"
+        n_groups += int((~tie).sum())
+    return n_groups + 1
+
+
+def test_config2_full_size_properties():
+    """BASELINE.json configs[1]: 100 Mbp, 10 records, N runs, both strands, k=31 -- the bench workload.
+    The oracle cannot reach this size; check permutation, order, tie order and histogram identities."""
+    n_bases = int(os.environ.get("GK_TEST_C2_BASES", 100_000_000))
+    rng = np.random.default_rng(42)
+    recs = gu.random_genome(rng, n_bases, 10, n_runs=200, run_lo=1000, run_hi=100_000)
+    sc = SequenceCollection.from_arrays(recs, strands_to_load="both")
+    km = Kmers(sc, 31, 31, source_strand="both")
+    km.sort()
+    n = len(km)
+    assert n == 2 * (n_bases - 10 * 30)
+    n_groups = _check_sorted_properties(km, sc, 31, "both")
+    hist, total = km.get_kmer_group_counts(31)
+    assert total == n
+    assert int(hist.sum()) == n_groups
+    sizes = np.flatnonzero(hist)
+    assert int((hist[sizes] * np.minimum(sizes, 1000000)).sum()) <= n
+    offsets, group_sizes = km.get_kmer_groups(31)
+    assert len(offsets) == n_groups and int(group_sizes.sum()) == n
+    # the fast (key-flag) and general (byte comparator) grouping paths agree
+    h2, t2 = km.get_kmer_group_counts(30)   # forces the comparator path with another length
+    assert t2 == n and int(h2.sum()) <= n_groups
+    pure_hist, pure_total = km.get_kmer_group_counts(31, gen_no_ambiguous_bases_filter(31))
+    assert pure_total == n - km.last_sort_stats["n_ambiguous"]

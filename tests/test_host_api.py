@@ -1,0 +1,176 @@
+"""
+CPU-only tests: the C-ABI library loads and exports every symbol include/gkb200.h declares, and the
+host-side mirror of the reference API validates arguments with the reference's exact messages
+(tests/test_kmers.py:262-329, :467-469 of the reference).  No compute calls (no GPU here).
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from genome_kmers import _native
+from genome_kmers.kmers import (Kmers, KmerFilter, compare_sba_kmers_lexicographically,
+                                crispr_ngg_pam_filter, gen_kmer_gc_content_filter_func,
+                                gen_kmer_homopolymer_filter_func, gen_kmer_length_filter_func,
+                                gen_no_ambiguous_bases_filter, kmer_filter_keep_all)
+from genome_kmers.sequence_collection import SequenceCollection
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SL1 = [("chr1", "ATCGAATTAG")]
+SL2 = [("chr1", "ATCGAATTAG"), ("chr2", "GGATCTTGCATT"), ("chr3", "GTGATTGACCCCT")]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gkb200.h")).read()
+    declared = set(re.findall(r"\b(gk_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gk_status", "gk_filter_id"}
+    lib = _native.lib()
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert lib.gk_version() == 100
+    assert lib.gk_status_string(3) == b"unsupported on the GPU path"
+
+
+def test_kmer_count_host_side():
+    import ctypes
+
+    lib = _native.lib()
+    starts = np.array([0, 11, 24], dtype=np.uint64)
+    n = ctypes.c_uint64(0)
+    assert lib.gk_kmer_count(_native.host_ptr(starts), 3, 37, 3, ctypes.byref(n)) == 0
+    assert n.value == 29
+    assert lib.gk_kmer_count(_native.host_ptr(starts), 3, 37, 11, ctypes.byref(n)) == _native.GK_ERR_ARG
+    assert b"exceeds the length of record" in lib.gk_last_error()
+
+
+def test_sequence_collection_golden_layout():
+    """tests/test_sequence_collection.py:26-50 of the reference."""
+    sc = SequenceCollection(sequence_list=SL2, strands_to_load="both")
+    assert sc.forward_sba.tobytes() == b"ATCGAATTAG$GGATCTTGCATT$GTGATTGACCCCT"
+    assert sc._forward_sba_seg_starts.tolist() == [0, 11, 24]
+    assert sc._forward_sba_seg_starts.dtype == np.uint32 and sc.forward_sba.dtype == np.uint8
+    assert sc.revcomp_sba.tobytes() == b"AGGGGTCAATCAC$AATGCAAGATCC$CTAATTCGAT"
+    assert sc._revcomp_sba_seg_starts.tolist() == [0, 14, 27]
+    assert sc.forward_record_names == ["chr1", "chr2", "chr3"]
+    assert sc.revcomp_record_names == ["chr3", "chr2", "chr1"]
+    assert len(sc) == 3 and sc.strands_loaded() == "both"
+    assert list(sc.iter_records("forward")) == [("chr1", 0, 9), ("chr2", 11, 22), ("chr3", 24, 36)]
+    assert list(sc.iter_records("reverse_complement")) == [("chr1", 27, 36), ("chr2", 14, 25), ("chr3", 0, 12)]
+    with pytest.raises(ValueError, match="sba_strand must be specified"):
+        list(sc.iter_records())
+
+
+def test_sequence_collection_reverse_complement_round_trip():
+    sc = SequenceCollection(sequence_list=SL2)
+    ref = SequenceCollection(sequence_list=SL2, strands_to_load="reverse_complement")
+    sc.reverse_complement()
+    assert sc == ref and sc.forward_sba is None
+    sc.reverse_complement()
+    assert sc == SequenceCollection(sequence_list=SL2)
+    assert str(sc) == ">chr1\nATCGAATTAG\n>chr2\nGGATCTTGCATT\n>chr3\nGTGATTGACCCCT"
+    assert sc.get_record_loc_from_sba_index(12) == ("+", "chr2", 1)
+    assert ref.get_record_loc_from_sba_index(0) == ("-", "chr3", 12)
+    assert sc.get_segment_num_from_sba_index(24) == 2
+    with pytest.raises(IndexError):
+        sc.get_segment_num_from_sba_index(37)
+
+
+def test_sequence_collection_errors():
+    with pytest.raises(ValueError, match="Only one of fasta_file_path and sequence_list"):
+        SequenceCollection(fasta_file_path="x.fa", sequence_list=SL1)
+    with pytest.raises(ValueError, match="strands_to_load unrecognized"):
+        SequenceCollection(sequence_list=SL1, strands_to_load="nope")
+    with pytest.raises(ValueError, match="non-allowed characters"):
+        SequenceCollection(sequence_list=[("a", "ACGTX")])
+    with pytest.raises(ValueError, match="must have length > 0"):
+        SequenceCollection(sequence_list=[("a", "ACGT"), ("b", "")])
+    with pytest.raises(ValueError, match="sequence_list contains 1 repeated record_names"):
+        SequenceCollection(sequence_list=[("a", "ACGT"), ("a", "AC")])
+
+
+def test_sequence_collection_array_constructors_and_fasta(tmp_path):
+    a = SequenceCollection(sequence_list=SL2, strands_to_load="both")
+    b = SequenceCollection.from_arrays([(n, s.encode()) for n, s in SL2], strands_to_load="both")
+    c = SequenceCollection.from_sba(a.forward_sba, a._forward_sba_seg_starts, ["chr1", "chr2", "chr3"],
+                                    strands_to_load="both")
+    assert a == b == c
+    fasta = tmp_path / "t.fa"
+    fasta.write_text(">chr1 some description\nATCGA\nattag\n>chr2\nGGATCTTGCATT\n>chr3\tx\nGTGATTGACCCCT\n")
+    assert SequenceCollection(fasta_file_path=fasta) == SequenceCollection(sequence_list=SL2)
+    a.save(tmp_path / "sc.db", format="shelve")
+    d = SequenceCollection()
+    d.load(tmp_path / "sc.db", format="shelve")
+    assert d == a
+
+
+def test_kmers_argument_errors_match_reference_messages():
+    sc = SequenceCollection(sequence_list=SL2)
+    with pytest.raises(ValueError, match=r"min_kmer_len \(0\) must be greater than zero"):
+        Kmers(sc, min_kmer_len=0)
+    with pytest.raises(ValueError, match=r"max_kmer_len \(0\) must be greater than zero"):
+        Kmers(sc, min_kmer_len=1, max_kmer_len=0)
+    with pytest.raises(ValueError, match=r"max_kmer_len \(2\) is less than min_kmer_len \(3\)"):
+        Kmers(sc, min_kmer_len=3, max_kmer_len=2)
+    with pytest.raises(ValueError, match=r"min_kmer_len \(11\) must be <= the shortest sequence length \(10\)"):
+        Kmers(sc, min_kmer_len=11)
+    with pytest.raises(ValueError, match=r"source_strand \(reverse_complement\) does not match sequence_collection loaded strand \(forward\)"):
+        Kmers(sc, source_strand="reverse_complement")
+    with pytest.raises(ValueError, match=r"source_strand \(sideways\) not recognized"):
+        Kmers(sc, source_strand="sideways")
+    with pytest.raises(NotImplementedError, match="track_strands_separately"):
+        Kmers(sc, track_strands_separately=True)
+    with pytest.raises(NotImplementedError, match="double_pass"):
+        Kmers(sc, method="double_pass")
+    with pytest.raises(ValueError, match="method 'x' not recognized"):
+        Kmers(sc, method="x")
+
+
+def test_kmers_host_state_without_gpu():
+    empty = Kmers()
+    assert empty.kmer_sba_start_indices is None and not empty._is_initialized
+    sc = SequenceCollection(sequence_list=SL2)
+    km = Kmers(sc, min_kmer_len=3, max_kmer_len=3)
+    assert len(km) == 29 and km._is_initialized and not km._is_sorted and not km._is_set
+    assert km.min_kmer_len == 3 and km.max_kmer_len == 3 and km.kmer_source_strand == "forward"
+    both = Kmers(SequenceCollection(sequence_list=SL2, strands_to_load="both"), 3, 3, source_strand="both")
+    assert len(both) == 58
+    with pytest.raises(ValueError, match="Did you mean to run sort"):
+        km.get_kmer_count(3, min_group_size=2)
+    with pytest.raises(AssertionError, match="must be sorted"):
+        km.get_kmer_group_counts(3)
+    with pytest.raises(ValueError, match=r"kmer_len \(0\) must be > 0"):
+        km.get_kmer_count(0)
+
+
+def test_filters_host_evaluation_matches_reference_examples():
+    sba = np.frombuffer(b"ATCGAATTAGNNNRYACGTTGCAWSACGT$GGGGGGCCAAAATTTTACGTACGTAGG", dtype=np.uint8)
+    assert kmer_filter_keep_all(sba, "forward", 0)
+    no_amb = gen_no_ambiguous_bases_filter(5)
+    assert no_amb(sba, "forward", 0) and not no_amb(sba, "forward", 6)
+    with pytest.raises(ValueError, match="end of segment was reached"):
+        no_amb(sba, "forward", 26)
+    assert gen_kmer_length_filter_func(4)(sba, "forward", 25) and not gen_kmer_length_filter_func(5)(sba, "forward", 25)
+    homo = gen_kmer_homopolymer_filter_func(3, 6)
+    assert homo(sba, "forward", 0) and not homo(sba, "forward", 30)
+    gc = gen_kmer_gc_content_filter_func(0.4, 0.6, 5)
+    assert gc(sba, "forward", 0) and not gc(sba, "forward", 30)
+    assert crispr_ngg_pam_filter(sba, "forward", 33) == bool(sba[54] == 71 and sba[55] == 71)
+    with pytest.raises(ValueError, match="must be >= 1"):
+        gen_kmer_homopolymer_filter_func(0, 5)
+    with pytest.raises(ValueError, match="must be <= max_allowed_gc_frac"):
+        gen_kmer_gc_content_filter_func(0.7, 0.6, 5)
+    assert isinstance(no_amb, KmerFilter) and no_amb.native().p0 == 5
+
+
+def test_scalar_comparator_matches_reference_docstring_example():
+    """kmers.py:341-351: the comparison table in the reference's docstring."""
+    sba = np.frombuffer(b"ATGGGCTGCAAGCTCGA$AATTTAGCGGCCTAGGCTTA", dtype=np.uint8)
+    a, b = 7, 11
+    assert [compare_sba_kmers_lexicographically(sba, sba, a, b, m)[0] for m in (1, 2)] == [0, 0]
+    assert compare_sba_kmers_lexicographically(sba, sba, a, b, 3)[0] == -1
+    assert compare_sba_kmers_lexicographically(sba, sba, a, b, None)[0] == -1
+    assert compare_sba_kmers_lexicographically(sba, sba, 15, 36, None) == (-1, 0)
+    assert compare_sba_kmers_lexicographically(sba, sba, 16, 37, None) == (0, 0)   # both terminate
+    assert compare_sba_kmers_lexicographically(sba, sba, 16, 18, None) == (-1, 0)  # 'A$' < 'AAT..'
