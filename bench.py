@@ -310,20 +310,23 @@ def run_single_gpu(args):
         assert total == n and len(idx) == n
         return idx, h
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        idx, h = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": n / e2e_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
-           "h2d_bytes_per_step": int(total_len), "d2h_bytes_per_step": int(idx.nbytes + 8 * (int(np.flatnonzero(h).max()) + 1)),
-           "api": "Kmers(seq_coll, 31, 31, 'both'); sort(); get_kmer_group_counts(31); kmer_sba_start_indices"}
-    assert np.array_equal(h, hist)
-    del idx
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            idx, h = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": n / e2e_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+               "h2d_bytes_per_step": int(total_len),
+               "d2h_bytes_per_step": int(idx.nbytes + 8 * (int(np.flatnonzero(h).max()) + 1)),
+               "api": "Kmers(seq_coll, 31, 31, 'both'); sort(); get_kmer_group_counts(31); kmer_sba_start_indices"}
+        assert np.array_equal(h, hist)
+        del idx
 
     # ---- CPU baseline on a bounded sample -----------------------------------------------------------
     cpu = None
@@ -369,6 +372,7 @@ def main():
     ap.add_argument("--cpu-sample-bases", type=int, default=2_000_000)
     ap.add_argument("--ref-sample-bases", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rules: at least 3 warm-up steps

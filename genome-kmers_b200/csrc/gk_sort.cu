@@ -26,23 +26,43 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 
+// A "digit" is normally 8 key bits; the multi-GPU partition step reuses the same kernels with
+// digit = destination rank = number of splitters <= key (splitters sorted, at most 255).
+
+__device__ __forceinline__ uint32_t splitter_digit(const uint64_t *s_split, uint32_t n_split, uint64_t key)
+{
+    uint32_t lo = 0, hi = n_split;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key < s_split[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 // ---- 1. histogram ------------------------------------------------------------------------------
 constexpr int kHistThreads = 512;
 
 __global__ void __launch_bounds__(kHistThreads)
 digit_histogram_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_bit, int end_bit,
+                       const uint64_t *__restrict__ splitters, uint32_t n_split,
                        unsigned long long *__restrict__ g_hist /* [passes][256] */)
 {
     __shared__ uint32_t s_hist[kMaxPasses][kRadix];
-    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    __shared__ uint64_t s_split[kRadix];
+    const int passes = splitters ? 1 : (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kHistThreads)
         (&s_hist[0][0])[i] = 0;
+    if (splitters && threadIdx.x < n_split) s_split[threadIdx.x] = splitters[threadIdx.x];
     __syncthreads();
 
     const uint64_t n2 = n / 2;
     const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
     const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
     auto add = [&](uint64_t key) {
+        if (splitters) {
+            atomicAdd(&s_hist[0][splitter_digit(s_split, n_split, key)], 1u);
+            return;
+        }
 #pragma unroll
         for (int p = 0; p < kMaxPasses; ++p) {
             if (p < passes) {
@@ -112,6 +132,7 @@ struct OnesweepSmem {
     ValT vals[kTile];
     uint32_t warp_hist[kWarps][kRadix];
     long long global_off[kRadix];
+    uint64_t splitters[kRadix];
     uint32_t bin_excl[kRadix];
     uint32_t warp_sums[kRadix / 32];
     uint32_t tile;
@@ -121,9 +142,9 @@ template <typename ValT, typename StatusT, int THREADS, int IPT>
 __global__ void __launch_bounds__(THREADS)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                 const ValT *__restrict__ vals_in, ValT *__restrict__ vals_out, uint64_t n,
-                int shift, uint32_t digit_mask, const unsigned long long *__restrict__ bin_base,
-                uint32_t *__restrict__ tile_counter, StatusT *__restrict__ status,
-                int *__restrict__ err)
+                int shift, uint32_t digit_mask, const uint64_t *__restrict__ splitters, uint32_t n_split,
+                const unsigned long long *__restrict__ bin_base, uint32_t *__restrict__ tile_counter,
+                StatusT *__restrict__ status, int *__restrict__ err)
 {
     using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
     using ST = StatusTraits<StatusT>;
@@ -138,7 +159,11 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
 
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
     for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
+    if (splitters && t < n_split) s.splitters[t] = splitters[t];
     __syncthreads();
+    auto digit_of = [&](uint64_t k) -> uint32_t {
+        return splitters ? splitter_digit(s.splitters, n_split, k) : ((uint32_t)(k >> shift) & digit_mask);
+    };
     const uint64_t tile = s.tile;
     const uint64_t tile_base = tile * (uint64_t)kTile;
     const uint32_t tile_valid = (n - tile_base < (uint64_t)kTile) ? (uint32_t)(n - tile_base) : kTile;
@@ -167,7 +192,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     uint32_t *my_hist = s.warp_hist[warp];
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & digit_mask;
+        const uint32_t d = digit_of(key[j]);
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t leader = __ffs(peers) - 1;
         uint32_t base = 0;
@@ -251,7 +276,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         const uint32_t p = t + j * THREADS;
         if (p < tile_valid) {
             const uint64_t k = s.keys[p];
-            const uint32_t d = (uint32_t)(k >> shift) & digit_mask;
+            const uint32_t d = digit_of(k);
             const long long dst = s.global_off[d] + (long long)p;
             keys_out[dst] = k;
             vals_out[dst] = s.vals[p];
@@ -262,8 +287,9 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
 // ---- host driver ---------------------------------------------------------------------------------
 template <typename ValT, typename StatusT, int THREADS, int IPT>
 static int launch_pass(const uint64_t *kin, uint64_t *kout, const void *vin, void *vout, uint64_t n,
-                       int shift, int bits, const unsigned long long *bin_base,
-                       uint32_t *tile_counter, void *status, int *err, cudaStream_t st)
+                       int shift, int bits, const uint64_t *splitters, uint32_t n_split,
+                       const unsigned long long *bin_base, uint32_t *tile_counter, void *status, int *err,
+                       cudaStream_t st)
 {
     using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
     auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT>;
@@ -271,8 +297,8 @@ static int launch_pass(const uint64_t *kin, uint64_t *kout, const void *vin, voi
                                  (int)sizeof(Smem)));
     const uint64_t tiles = (n + Smem::kTile - 1) / Smem::kTile;
     kernel<<<(unsigned)tiles, THREADS, sizeof(Smem), st>>>(
-        kin, kout, (const ValT *)vin, (ValT *)vout, n, shift, (1u << bits) - 1u, bin_base,
-        tile_counter, (StatusT *)status, err);
+        kin, kout, (const ValT *)vin, (ValT *)vout, n, shift, (1u << bits) - 1u, splitters, n_split,
+        bin_base, tile_counter, (StatusT *)status, err);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -283,9 +309,13 @@ constexpr int kSortThreads = 256;
 constexpr int kSortIPT4 = 16;  // 32-bit values
 constexpr int kSortIPT8 = 12;  // 64-bit values
 
-int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
-                            int val_bytes, uint64_t n, int begin_bit, int end_bit,
-                            int *result_in_alt, cudaStream_t st, SortTiming *timing)
+// Shared driver: histogram(s) + scan + `passes` onesweep launches.  splitters != nullptr selects
+// the single partition pass (digit = destination rank); h_bin_counts (256 entries, optional)
+// receives the first pass's histogram.
+static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                        int val_bytes, uint64_t n, int begin_bit, int end_bit,
+                        const uint64_t *d_splitters, uint32_t n_split, int *result_in_alt,
+                        unsigned long long *h_bin_counts, cudaStream_t st, SortTiming *timing)
 {
     if (timing) { timing->hist_ms = 0.f; timing->passes_ms = 0.f; timing->passes = 0; }
     if (val_bytes != 4 && val_bytes != 8) {
@@ -297,8 +327,10 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
         return GK_ERR_ARG;
     }
     if (result_in_alt) *result_in_alt = 0;
-    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
-    if (n < 2 || passes == 0) return GK_OK;
+    if (h_bin_counts) memset(h_bin_counts, 0, kRadix * sizeof(unsigned long long));
+    const int passes = d_splitters ? 1 : (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    if (n == 0 || passes == 0) return GK_OK;
+    if (n == 1 && !d_splitters) return GK_OK;
     if ((reinterpret_cast<uintptr_t>(d_keys) & 15u) || (reinterpret_cast<uintptr_t>(d_keys_alt) & 15u)) {
         set_error("radix_sort_pairs: key buffers must be 16-byte aligned");
         return GK_ERR_ARG;
@@ -330,30 +362,35 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
         if (need < 1) need = 1;
         if ((uint64_t)hist_grid > need) hist_grid = (int)need;
     }
-    digit_histogram_kernel<<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, d_hist);
+    digit_histogram_kernel<<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, d_splitters,
+                                                              n_split, d_hist);
     GK_LAUNCH_CHECK();
     scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_hist, d_base);
     GK_LAUNCH_CHECK();
-
     if (timing) GK_CUDA(cudaEventRecord(ev[1], st));
+
     uint64_t *kin = d_keys, *kout = d_keys_alt;
     void *vin = d_vals, *vout = d_vals_alt;
     for (int p = 0; p < passes; ++p) {
         const int lo = begin_bit + p * kRadixBits;
-        const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
+        const int bits = d_splitters ? kRadixBits : ((end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits);
         GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
         const unsigned long long *base = d_base + p * kRadix;
         int rc;
         if (val_bytes == 4) {
             rc = wide ? launch_pass<uint32_t, uint64_t, kSortThreads, kSortIPT4>(
-                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st)
+                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
+                            d_status, d_err, st)
                       : launch_pass<uint32_t, uint32_t, kSortThreads, kSortIPT4>(
-                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st);
+                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
+                            d_status, d_err, st);
         } else {
             rc = wide ? launch_pass<uint64_t, uint64_t, kSortThreads, kSortIPT8>(
-                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st)
+                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
+                            d_status, d_err, st)
                       : launch_pass<uint64_t, uint32_t, kSortThreads, kSortIPT8>(
-                            kin, kout, vin, vout, n, lo, bits, base, d_ctr + p, d_status, d_err, st);
+                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
+                            d_status, d_err, st);
         }
         GK_TRY(rc);
         uint64_t *tk = kin; kin = kout; kout = tk;
@@ -364,6 +401,9 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
 
     int h_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_bin_counts)
+        GK_CUDA(cudaMemcpyAsync(h_bin_counts, d_hist, kRadix * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     if (timing) {
         cudaEventElapsedTime(&timing->hist_ms, ev[0], ev[1]);
@@ -375,6 +415,32 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
         set_error("radix_sort_pairs: decoupled look-back timed out");
         return GK_ERR_INTERNAL;
     }
+    return GK_OK;
+}
+
+int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                            int val_bytes, uint64_t n, int begin_bit, int end_bit,
+                            int *result_in_alt, cudaStream_t st, SortTiming *timing)
+{
+    return run_onesweep(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit, end_bit, nullptr,
+                        0, result_in_alt, nullptr, st, timing);
+}
+
+// Stable partition of the pairs by destination = number of splitters <= key.  Output always lands
+// in the *_out buffers; h_counts[d] = pairs sent to destination d (n_parts entries).
+int partition_pairs_device(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,
+                           int val_bytes, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                           uint64_t *h_counts, cudaStream_t st)
+{
+    if (n_parts < 1 || n_parts > (uint32_t)kRadix) {
+        set_error("partition_pairs: n_parts must be in [1, 256]");
+        return GK_ERR_ARG;
+    }
+    unsigned long long bins[kRadix];
+    int in_alt = 0;
+    GK_TRY(run_onesweep(d_keys, d_keys_out, d_vals, d_vals_out, val_bytes, n, 0, 8, d_splitters, n_parts - 1,
+                        &in_alt, bins, st, nullptr));
+    for (uint32_t d = 0; d < n_parts; ++d) h_counts[d] = (n == 0) ? 0 : (uint64_t)bins[d];
     return GK_OK;
 }
 
@@ -392,4 +458,19 @@ extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void 
     }
     return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
                                    end_bit, result_in_alt, as_stream(stream), nullptr);
+}
+
+extern "C" int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,
+                                  int val_bytes, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                                  uint64_t *h_counts_out, void *stream)
+{
+    if (!h_counts_out || (n && (!d_keys || !d_keys_out || !d_vals || !d_vals_out)) ||
+        (n_parts > 1 && !d_splitters)) {
+        set_error("gk_partition_pairs: null buffer");
+        return GK_ERR_ARG;
+    }
+    // with a single destination the splitter list is empty: pass a non-null dummy to select the mode
+    return partition_pairs_device(d_keys, d_keys_out, d_vals, d_vals_out, val_bytes, n,
+                                  d_splitters ? d_splitters : d_keys, n_parts, h_counts_out,
+                                  as_stream(stream));
 }
