@@ -165,12 +165,12 @@ select_scan_kernel(const uint32_t *__restrict__ tile_counts, uint64_t n_tiles,
     if (threadIdx.x == 0) tile_offsets[n_tiles] = s_carry;
 }
 
-template <typename PosT, typename PayT>
+template <typename T>
 __global__ void __launch_bounds__(kSelThreads)
 select_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
-                    const unsigned long long *__restrict__ tile_offsets,
-                    PosT *__restrict__ pos_out, const PayT *__restrict__ payload_in,
-                    PayT *__restrict__ payload_out)
+                    const unsigned long long *__restrict__ tile_offsets, T *__restrict__ pos_out,
+                    const T *__restrict__ pay_in, T *__restrict__ pay_out,
+                    const T *__restrict__ pay2_in, T *__restrict__ pay2_out)
 {
     __shared__ uint32_t s_warp[kSelThreads / 32];
     const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * kSelPerThread;
@@ -192,17 +192,19 @@ select_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
     while (b) {
         const uint32_t i = __ffs(b) - 1;
         b &= b - 1;
-        if (pos_out) pos_out[out] = (PosT)(p0 + i);
-        if (payload_out) payload_out[out] = payload_in[p0 + i];
+        if (pos_out) pos_out[out] = (T)(p0 + i);
+        if (pay_out) pay_out[out] = pay_in[p0 + i];
+        if (pay2_out) pay2_out[out] = pay2_in[p0 + i];
         ++out;
     }
 }
 
-// positions (and optionally payload_in[position]) of flags with (flag & mask) != 0, in order
-template <typename PosT, typename PayT>
-int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, PosT *d_pos_out,
-                          const PayT *d_payload_in, PayT *d_payload_out, uint64_t *h_count,
-                          cudaStream_t st)
+// Ordered selection of the positions p with (flags[p] & mask) != 0: optionally the positions
+// themselves and up to two payload arrays gathered at those positions.
+template <typename T>
+int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, T *d_pos_out,
+                          const T *d_pay_in, T *d_pay_out, const T *d_pay2_in, T *d_pay2_out,
+                          uint64_t *h_count, cudaStream_t st)
 {
     if (h_count) *h_count = 0;
     if (n == 0) return GK_OK;
@@ -217,8 +219,8 @@ int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, PosT
     GK_LAUNCH_CHECK();
     select_scan_kernel<<<1, 1024, 0, st>>>(d_counts, tiles, d_offsets);
     GK_LAUNCH_CHECK();
-    select_write_kernel<PosT, PayT><<<(unsigned)tiles, kSelThreads, 0, st>>>(
-        d_flags, n, mask, d_offsets, d_pos_out, d_payload_in, d_payload_out);
+    select_write_kernel<T><<<(unsigned)tiles, kSelThreads, 0, st>>>(
+        d_flags, n, mask, d_offsets, d_pos_out, d_pay_in, d_pay_out, d_pay2_in, d_pay2_out);
     GK_LAUNCH_CHECK();
     if (h_count) {
         GK_CUDA(cudaMemcpyAsync(h_count, d_offsets + tiles, 8, cudaMemcpyDeviceToHost, st));
@@ -227,12 +229,26 @@ int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, PosT
     return GK_OK;
 }
 
-template int select_flagged_device<uint32_t, uint32_t>(const uint8_t *, uint64_t, uint8_t, uint32_t *,
-                                                       const uint32_t *, uint32_t *, uint64_t *,
-                                                       cudaStream_t);
-template int select_flagged_device<uint64_t, uint64_t>(const uint8_t *, uint64_t, uint8_t, uint64_t *,
-                                                       const uint64_t *, uint64_t *, uint64_t *,
-                                                       cudaStream_t);
+template int select_flagged_device<uint32_t>(const uint8_t *, uint64_t, uint8_t, uint32_t *, const uint32_t *,
+                                             uint32_t *, const uint32_t *, uint32_t *, uint64_t *,
+                                             cudaStream_t);
+template int select_flagged_device<uint64_t>(const uint8_t *, uint64_t, uint8_t, uint64_t *, const uint64_t *,
+                                             uint64_t *, const uint64_t *, uint64_t *, uint64_t *,
+                                             cudaStream_t);
+
+// type-erased front end (elem_bytes 4 or 8)
+int select_flagged(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_bytes, void *d_pos_out,
+                   const void *d_pay_in, void *d_pay_out, const void *d_pay2_in, void *d_pay2_out,
+                   uint64_t *h_count, cudaStream_t st)
+{
+    if (elem_bytes == 4)
+        return select_flagged_device<uint32_t>(d_flags, n, mask, (uint32_t *)d_pos_out,
+                                               (const uint32_t *)d_pay_in, (uint32_t *)d_pay_out,
+                                               (const uint32_t *)d_pay2_in, (uint32_t *)d_pay2_out, h_count, st);
+    return select_flagged_device<uint64_t>(d_flags, n, mask, (uint64_t *)d_pos_out,
+                                           (const uint64_t *)d_pay_in, (uint64_t *)d_pay_out,
+                                           (const uint64_t *)d_pay2_in, (uint64_t *)d_pay2_out, h_count, st);
+}
 
 // scatter: dst_array[pos[r]] = src[r]
 template <typename IdxT>
@@ -537,8 +553,8 @@ int gk_rle_keys(const uint64_t *d_keys_sorted, uint64_t n, uint64_t *d_offsets_o
     GK_TRY(flags.alloc((size_t)((n + 15) & ~15ull), st));
     GK_TRY(key_flags_device(d_keys_sorted, n, 0, flags.as<uint8_t>(), st));
     uint64_t count = 0;
-    GK_TRY((select_flagged_device<uint64_t, uint64_t>(flags.as<uint8_t>(), n, kFlagHead, d_offsets_out,
-                                                      nullptr, nullptr, &count, st)));
+    GK_TRY(select_flagged(flags.as<uint8_t>(), n, kFlagHead, 8, d_offsets_out, nullptr, nullptr, nullptr,
+                          nullptr, &count, st));
     if (h_n_groups) *h_n_groups = count;
     return GK_OK;
 }

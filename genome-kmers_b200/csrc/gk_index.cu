@@ -29,13 +29,21 @@ int group_hist_masked_device(const void *, int, uint64_t, uint64_t, const uint8_
                              uint64_t, uint64_t, int64_t *, int64_t *, cudaStream_t);
 int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, const gk_filter &,
                         uint8_t *, cudaStream_t);
-template <typename PosT, typename PayT>
-int select_flagged_device(const uint8_t *, uint64_t, uint8_t, PosT *, const PayT *, PayT *,
-                          uint64_t *, cudaStream_t);
+int select_flagged(const uint8_t *, uint64_t, uint8_t, int, void *, const void *, void *, const void *,
+                   void *, uint64_t *, cudaStream_t);
+int head_positions_device(const uint8_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
+int valid_flags_device(const uint32_t *, uint64_t, const uint64_t *, uint32_t, uint64_t, uint32_t, uint8_t *,
+                       cudaStream_t);
+int gid_flags_device(const uint32_t *, uint64_t, uint8_t *, cudaStream_t);
+int pair_keys_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, uint64_t *,
+                     cudaStream_t);
+int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint8_t *,
+                        cudaStream_t);
 
 constexpr uint8_t kFlagHead = 1;
 constexpr uint8_t kFlagAmb = 2;
 constexpr uint8_t kFlagPass = 4;
+constexpr uint8_t kFlagMulti = 8;
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
 // destroying an index per query does not pay a device-wide synchronising cudaFree
@@ -107,6 +115,7 @@ struct gk_index {
     bool sorted = false;
     Owned d_flags;                      // head/amb flags of the sorted order for flags_kmer_len
     bool flags_valid = false;
+    bool flags_mark_amb = false;        // kFlagAmb bits are meaningful (single-level sort only)
     uint32_t flags_kmer_len = 0;
     bool alphabet_known = false;
     uint64_t n_bad = 0, n_sep = 0, n_amb_letters = 0;
@@ -134,96 +143,151 @@ static int ensure_indices(gk_index *ix, cudaStream_t st)
     return GK_OK;
 }
 
-// Single-word sort: key over key_len <= 32 symbols, all windows of valid_len.
-static int sort_single_level(gk_index *ix, uint32_t key_len, bool has_amb, gk_sort_stats *stats,
-                             EventTimer &tm, cudaStream_t st)
+// Stage timing marks of one sort; turned into milliseconds after the final synchronise.
+struct StageMarks {
+    int pack0 = -1, pack1 = -1, fix0 = -1, fix1 = -1;
+    SortTiming main_sort = {0.f, 0.f, 0};
+    uint64_t n_amb = 0;
+    int key_bits = 0;
+    int levels = 1;
+};
+
+// After the main radix sort: head flags from the sorted keys, then the ambiguous windows (which
+// already sit in the right slots as a set) are ordered among themselves by their full 4-bit keys,
+// 16 symbols per word, least significant word first, stable; their head flags come from the
+// byte comparator.  d_idx holds the sorted starts and is updated in place.
+static int finish_sorted(gk_index *ix, const uint64_t *keys_sorted, void *d_idx, uint8_t *d_flags,
+                         uint64_t n, int class_bit, uint32_t key_len, uint64_t n_amb, cudaStream_t st)
 {
-    const uint64_t n = ix->n;
+    const int ib = ix->idx_bytes;
+    GK_TRY(key_flags_device(keys_sorted, n, class_bit, d_flags, st));
+    if (n_amb == 0) return GK_OK;
+    DeviceBuffer slot_pos, amb_a, amb_b, akeys_a, akeys_b;
+    GK_TRY(slot_pos.alloc((size_t)n_amb * ib, st));
+    GK_TRY(amb_a.alloc((size_t)n_amb * ib, st));
+    GK_TRY(amb_b.alloc((size_t)n_amb * ib, st));
+    GK_TRY(akeys_a.alloc((size_t)n_amb * 8, st));
+    GK_TRY(akeys_b.alloc((size_t)n_amb * 8, st));
+    uint64_t found = 0;
+    GK_TRY(select_flagged(d_flags, n, kFlagAmb, ib, slot_pos.ptr, d_idx, amb_a.ptr, nullptr, nullptr,
+                          &found, st));
+    if (found != n_amb) {
+        set_error("ambiguous window count mismatch: packed %llu, selected %llu",
+                  (unsigned long long)n_amb, (unsigned long long)found);
+        return GK_ERR_INTERNAL;
+    }
+    void *cur = amb_a.ptr, *alt = amb_b.ptr;
+    const int words = ((int)key_len + 15) / 16;
+    for (int w = words - 1; w >= 0; --w) {
+        const int syms = ((int)key_len - 16 * w < 16) ? (int)key_len - 16 * w : 16;
+        GK_TRY(pack4_gather_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, (uint32_t)w, key_len,
+                                   akeys_a.as<uint64_t>(), st));
+        int alt_has = 0;
+        GK_TRY(radix_sort_pairs_device(akeys_a.as<uint64_t>(), akeys_b.as<uint64_t>(), cur, alt, ib, n_amb,
+                                       64 - 4 * syms, 64, &alt_has, st, nullptr));
+        if (alt_has) { void *t = cur; cur = alt; alt = t; }
+    }
+    GK_TRY(scatter_device(cur, slot_pos.ptr, n_amb, ib, d_idx, st));
+    GK_TRY(sba_flags_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, key_len, slot_pos.ptr, kFlagAmb,
+                            d_flags, st));
+    return GK_OK;
+}
+
+// Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
+// Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags.
+static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool has_amb, uint64_t n,
+                       Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm,
+                       cudaStream_t st)
+{
     const int ib = ix->idx_bytes;
     const int class_bit = has_amb ? 1 : 0;
+    // value <= 4^key_len needs 2*key_len+1 bits when ambiguous windows exist, plus the class bit
     const int key_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
+    marks.key_bits = key_bits;
 
     DeviceBuffer keys_a, keys_b, n_amb_dev;
     Owned idx_b;
     GK_TRY(keys_a.alloc((size_t)n * 8, st));
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
     GK_TRY(idx_b.alloc((size_t)n * ib, st));
-    GK_TRY(ix->d_idx.alloc((size_t)n * ib, st));
+    GK_TRY(out_idx.alloc((size_t)n * ib, st));
     GK_TRY(n_amb_dev.alloc(8, st));
     GK_CUDA(cudaMemsetAsync(n_amb_dev.ptr, 0, 8, st));
 
-    const int e0 = tm.mark();
+    marks.pack0 = tm.mark();
     GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
-                            (uint32_t)ix->h_segs.size(), ix->min_len, key_len, class_bit, 0,
-                            ix->sba_len, 0, keys_a.as<uint64_t>(), ib, ix->d_idx.ptr,
-                            n_amb_dev.as<unsigned long long>(), st));
-    const int e1 = tm.mark();
+                            (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
+                            keys_a.as<uint64_t>(), ib, out_idx.ptr, n_amb_dev.as<unsigned long long>(), st));
+    marks.pack1 = tm.mark();
     int in_alt = 0;
-    SortTiming timing;
-    GK_TRY(radix_sort_pairs_device(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), ix->d_idx.ptr,
-                                   idx_b.ptr, ib, n, 0, key_bits, &in_alt, st, &timing));
-    const int e2 = tm.mark();
-    uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
-    if (in_alt) ix->d_idx.swap(idx_b);
+    GK_TRY(radix_sort_pairs_device(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib,
+                                   n, 0, key_bits, &in_alt, st, &marks.main_sort));
+    const uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
+    if (in_alt) out_idx.swap(idx_b);
     idx_b.reset();
 
     uint64_t n_amb = 0;
     GK_CUDA(cudaMemcpyAsync(&n_amb, n_amb_dev.ptr, 8, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    marks.n_amb = n_amb;
 
-    // head flags of the sorted order; ambiguous slots are refined below
-    GK_TRY(ix->d_flags.alloc((size_t)((n + 15) & ~15ull), st));
-    GK_TRY(key_flags_device(keys_sorted, n, class_bit, (uint8_t *)ix->d_flags.ptr, st));
+    marks.fix0 = tm.mark();
+    GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
+    GK_TRY(finish_sorted(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len,
+                         n_amb, st));
+    marks.fix1 = tm.mark();
+    return GK_OK;
+}
 
-    if (n_amb > 0) {
-        // ambiguous windows sit in the right slots as a set; order them among themselves by
-        // their full 4-bit keys (16 symbols per word, least significant word first, stable)
-        DeviceBuffer slot_pos, amb_a, amb_b, akeys_a, akeys_b;
-        GK_TRY(slot_pos.alloc((size_t)n_amb * ib, st));
-        GK_TRY(amb_a.alloc((size_t)n_amb * ib, st));
-        GK_TRY(amb_b.alloc((size_t)n_amb * ib, st));
-        GK_TRY(akeys_a.alloc((size_t)n_amb * 8, st));
-        GK_TRY(akeys_b.alloc((size_t)n_amb * 8, st));
-        uint64_t found = 0;
-        if (ib == 4)
-            GK_TRY((select_flagged_device<uint32_t, uint32_t>(
-                (const uint8_t *)ix->d_flags.ptr, n, kFlagAmb, slot_pos.as<uint32_t>(),
-                (const uint32_t *)ix->d_idx.ptr, amb_a.as<uint32_t>(), &found, st)));
-        else
-            GK_TRY((select_flagged_device<uint64_t, uint64_t>(
-                (const uint8_t *)ix->d_flags.ptr, n, kFlagAmb, slot_pos.as<uint64_t>(),
-                (const uint64_t *)ix->d_idx.ptr, amb_a.as<uint64_t>(), &found, st)));
-        if (found != n_amb) {
-            set_error("ambiguous window count mismatch: packed %llu, selected %llu",
-                      (unsigned long long)n_amb, (unsigned long long)found);
-            return GK_ERR_INTERNAL;
-        }
-        void *cur = amb_a.ptr, *alt = amb_b.ptr;
-        const int words = ((int)key_len + 15) / 16;
-        for (int w = words - 1; w >= 0; --w) {
-            const int syms = ((int)key_len - 16 * w < 16) ? (int)key_len - 16 * w : 16;
-            GK_TRY(pack4_gather_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, (uint32_t)w, key_len,
-                                       akeys_a.as<uint64_t>(), st));
-            int alt_has = 0;
-            GK_TRY(radix_sort_pairs_device(akeys_a.as<uint64_t>(), akeys_b.as<uint64_t>(), cur, alt,
-                                           ib, n_amb, 64 - 4 * syms, 64, &alt_has, st, nullptr));
-            if (alt_has) { void *t = cur; cur = alt; alt = t; }
-        }
-        GK_TRY(scatter_device(cur, slot_pos.ptr, n_amb, ib, ix->d_idx.ptr, st));
-        GK_TRY(sba_flags_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, key_len, slot_pos.ptr,
-                                kFlagAmb, (uint8_t *)ix->d_flags.ptr, st));
+// One prefix-doubling round: cur (sorted by the first h symbols, flags = h-groups) -> windows of
+// h2 <= 2h symbols.  See gk_refine.cu.  32-bit indices only.
+static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, Owned &cur_idx, Owned &cur_flags,
+                        uint64_t &n_cur, uint32_t *d_rank, cudaStream_t st)
+{
+    const uint32_t delta = h2 - h;
+    DeviceBuffer gid, vflags;
+    GK_TRY(gid.alloc((size_t)n_cur * 4, st));
+    GK_TRY(head_positions_device((const uint8_t *)cur_flags.ptr, (const uint32_t *)cur_idx.ptr, n_cur,
+                                 gid.as<uint32_t>(), d_rank, st));
+    // keep the windows that still fit their record at length h2 (order preserved)
+    GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
+    GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
+                              (uint32_t)ix->h_segs.size(), ix->sba_len, h2, vflags.as<uint8_t>(), st));
+    Owned new_idx, new_flags;
+    DeviceBuffer new_gid;
+    GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
+    GK_TRY(new_gid.alloc((size_t)n_cur * 4, st));
+    uint64_t n_new = 0;
+    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, nullptr, cur_idx.ptr, new_idx.ptr,
+                          gid.ptr, new_gid.ptr, &n_new, st));
+    GK_TRY(new_flags.alloc((size_t)((n_new + 15) & ~15ull), st));
+    GK_TRY(gid_flags_device(new_gid.as<uint32_t>(), n_new, (uint8_t *)new_flags.ptr, st));
+    // members of groups with more than one element are the only ones that can move
+    DeviceBuffer slots, sub_idx, sub_idx_alt, sub_gid, keys, keys_alt;
+    GK_TRY(slots.alloc((size_t)n_new * 4, st));
+    GK_TRY(sub_idx.alloc((size_t)n_new * 4, st));
+    GK_TRY(sub_gid.alloc((size_t)n_new * 4, st));
+    uint64_t m = 0;
+    GK_TRY(select_flagged((const uint8_t *)new_flags.ptr, n_new, kFlagMulti, 4, slots.ptr, new_idx.ptr,
+                          sub_idx.ptr, new_gid.ptr, sub_gid.ptr, &m, st));
+    if (m > 0) {
+        GK_TRY(sub_idx_alt.alloc((size_t)m * 4, st));
+        GK_TRY(keys.alloc((size_t)m * 8, st));
+        GK_TRY(keys_alt.alloc((size_t)m * 8, st));
+        GK_TRY(pair_keys_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
+                                keys.as<uint64_t>(), st));
+        int in_alt = 0;
+        GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr,
+                                       sub_idx_alt.ptr, 4, m, 0, 64, &in_alt, st, nullptr));
+        GK_TRY(key2_scatter_device(in_alt ? keys_alt.as<uint64_t>() : keys.as<uint64_t>(),
+                                   in_alt ? sub_idx_alt.as<uint32_t>() : sub_idx.as<uint32_t>(),
+                                   slots.as<uint32_t>(), m, (uint32_t *)new_idx.ptr,
+                                   (uint8_t *)new_flags.ptr, st));
     }
-    const int e3 = tm.mark();
-    if (stats) {
-        stats->pack_ms = tm.ms(e0, e1);
-        stats->hist_ms = timing.hist_ms;
-        stats->sort_ms = timing.passes_ms;
-        stats->fixup_ms = tm.ms(e2, e3);
-        stats->sort_passes = timing.passes;
-        stats->key_bits = key_bits;
-        stats->levels = 1;
-        stats->n_ambiguous = n_amb;
-    }
+    GK_CUDA(cudaStreamSynchronize(st));  // scratch above is released in stream order after this
+    cur_idx.swap(new_idx);
+    cur_flags.swap(new_flags);
+    n_cur = n_new;
     return GK_OK;
 }
 
@@ -292,6 +356,7 @@ int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_by
     ix->idx_ready = true;
     ix->sorted = sorted != 0;
     ix->flags_valid = false;
+    ix->flags_mark_amb = false;
     return GK_OK;
 }
 
@@ -303,6 +368,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     memset(&stats, 0, sizeof(stats));
     const uint64_t launches0 = gk_launch_count(0);
     EventTimer tm(st);
+    StageMarks marks;
     const int t0 = tm.mark();
 
     GK_TRY(ensure_alphabet(ix, st));
@@ -321,20 +387,124 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     const bool has_amb = ix->n_amb_letters > 0 || ix->n_bad > 0;
     const uint32_t k = ix->min_len;
     stats.n_windows = ix->n;
+    int t_ref0 = -1, t_ref1 = -1;
     if (ix->n == 0) {
         ix->sorted = true;
     } else if (k <= 31 || (k == 32 && !has_amb)) {
-        GK_TRY(sort_single_level(ix, k, has_amb, &stats, tm, st));
-        ix->idx_ready = true;
-        ix->flags_valid = true;
-        ix->flags_kmer_len = k;
-        ix->sorted = true;
+        GK_TRY(sort_level1(ix, k, k, has_amb, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
+        ix->flags_mark_amb = true;
     } else {
-        set_error("kmer_len %u needs multi-word keys (prefix-doubling), not available yet", k);
-        return GK_ERR_UNSUPPORTED;
+        ix->flags_mark_amb = false;
+        // multi-word k-mers: exact order of the first k1 symbols, then prefix doubling on ranks
+        if (ix->idx_bytes != 4) {
+            set_error("kmer_len %u on a byte array of 2^32 or more positions is not available yet", k);
+            return GK_ERR_UNSUPPORTED;
+        }
+        const uint32_t k1 = has_amb ? 31 : 32;
+        uint64_t n_cur = 0;
+        GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, k1, &n_cur));
+        Owned cur_idx, cur_flags;
+        GK_TRY(sort_level1(ix, k1, k1, has_amb, n_cur, cur_idx, cur_flags, marks, tm, st));
+        DeviceBuffer rank;
+        GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
+        t_ref0 = tm.mark();
+        uint32_t h = k1;
+        while (h < k) {
+            const uint32_t h2 = (2 * h < k) ? 2 * h : k;
+            GK_TRY(refine_level(ix, h, h2, cur_idx, cur_flags, n_cur, rank.as<uint32_t>(), st));
+            h = h2;
+            ++marks.levels;
+        }
+        t_ref1 = tm.mark();
+        if (n_cur != ix->n) {
+            set_error("refinement kept %llu windows, expected %llu", (unsigned long long)n_cur,
+                      (unsigned long long)ix->n);
+            return GK_ERR_INTERNAL;
+        }
+        ix->d_idx.swap(cur_idx);
+        ix->d_flags.swap(cur_flags);
     }
+    ix->idx_ready = true;
+    ix->flags_valid = ix->n > 0;
+    ix->flags_kmer_len = k;
+    ix->sorted = true;
     const int t1 = tm.mark();
     GK_CUDA(cudaStreamSynchronize(st));
+    stats.pack_ms = tm.ms(marks.pack0, marks.pack1);
+    stats.hist_ms = marks.main_sort.hist_ms;
+    stats.sort_ms = marks.main_sort.passes_ms;
+    stats.sort_passes = marks.main_sort.passes;
+    stats.fixup_ms = tm.ms(marks.fix0, marks.fix1) + tm.ms(t_ref0, t_ref1);
+    stats.key_bits = marks.key_bits;
+    stats.levels = marks.levels;
+    stats.n_ambiguous = marks.n_amb;
+    stats.total_ms = tm.ms(t0, t1);
+    stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
+    if (stats_out) *stats_out = stats;
+    return GK_OK;
+}
+
+// Multi-GPU shard: adopt (key, start) pairs that the caller received from the exchange (keys made by
+// gk_pack_keys with the same key_len / class_bit), sort them and build the same state gk_index_sort
+// leaves behind, for this rank's key range only.  The pair buffers are scratch (ping-pong).
+int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
+                        uint64_t n_local, int class_bit, gk_sort_stats *stats_out, void *stream)
+{
+    if (!ix || (n_local && (!d_keys || !d_keys_alt || !d_idx || !d_idx_alt))) {
+        set_error("gk_index_sort_pairs: null buffer");
+        return GK_ERR_ARG;
+    }
+    const uint32_t k = ix->min_len;
+    if (!(ix->max_len == ix->min_len && (k <= 31 || (k == 32 && !class_bit)))) {
+        set_error("gk_index_sort_pairs: only single-word k-mers (k <= 31, or 32 without ambiguous bases)");
+        return GK_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    gk_sort_stats stats;
+    memset(&stats, 0, sizeof(stats));
+    const uint64_t launches0 = gk_launch_count(0);
+    EventTimer tm(st);
+    const int t0 = tm.mark();
+    const int ib = ix->idx_bytes;
+    const int key_bits = 2 * (int)k + (class_bit ? 2 : 0);
+    SortTiming timing = {0.f, 0.f, 0};
+    int in_alt = 0;
+    GK_TRY(radix_sort_pairs_device(d_keys, d_keys_alt, d_idx, d_idx_alt, ib, n_local, 0, key_bits, &in_alt, st,
+                                   &timing));
+    const uint64_t *keys_sorted = in_alt ? d_keys_alt : d_keys;
+    const void *idx_sorted = in_alt ? d_idx_alt : d_idx;
+    ix->n = n_local;
+    GK_TRY(ix->d_idx.alloc((size_t)n_local * ib, st));
+    GK_TRY(ix->d_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
+    if (n_local)
+        GK_CUDA(cudaMemcpyAsync(ix->d_idx.ptr, idx_sorted, (size_t)n_local * ib, cudaMemcpyDeviceToDevice, st));
+    const int f0 = tm.mark();
+    uint64_t n_amb = 0;
+    if (class_bit && n_local) {
+        // count the slots whose class bit is 0 (the flags pass marks them)
+        GK_TRY(key_flags_device(keys_sorted, n_local, class_bit, (uint8_t *)ix->d_flags.ptr, st));
+        GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n_local, kFlagAmb, ib, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, &n_amb, st));
+    }
+    if (n_local)
+        GK_TRY(finish_sorted(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
+                             n_amb, st));
+    const int f1 = tm.mark();
+    ix->idx_ready = true;
+    ix->flags_mark_amb = true;
+    ix->flags_valid = n_local > 0;
+    ix->flags_kmer_len = k;
+    ix->sorted = true;
+    const int t1 = tm.mark();
+    GK_CUDA(cudaStreamSynchronize(st));
+    stats.hist_ms = timing.hist_ms;
+    stats.sort_ms = timing.passes_ms;
+    stats.sort_passes = timing.passes;
+    stats.fixup_ms = tm.ms(f0, f1);
+    stats.key_bits = key_bits;
+    stats.levels = 1;
+    stats.n_windows = n_local;
+    stats.n_ambiguous = n_amb;
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;
@@ -393,19 +563,14 @@ int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filt
 
     // fast path: sorted, same kmer_len as the sort, filter uniform over a group of equal k-mers
     const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
-    const bool no_amb_same_len = f.id == GK_FILTER_NO_AMBIGUOUS && (uint64_t)f.p0 == kmer_len;
+    const bool no_amb_same_len =
+        f.id == GK_FILTER_NO_AMBIGUOUS && (uint64_t)f.p0 == kmer_len && ix->flags_mark_amb;
     if (cached && (f.id == GK_FILTER_KEEP_ALL || no_amb_same_len)) {
         DeviceBuffer offsets;
         GK_TRY(offsets.alloc((size_t)n * ib, st));
         uint64_t n_groups = 0;
-        if (ib == 4)
-            GK_TRY((select_flagged_device<uint32_t, uint32_t>((const uint8_t *)ix->d_flags.ptr, n, kFlagHead,
-                                                              offsets.as<uint32_t>(), nullptr, nullptr,
-                                                              &n_groups, st)));
-        else
-            GK_TRY((select_flagged_device<uint64_t, uint64_t>((const uint8_t *)ix->d_flags.ptr, n, kFlagHead,
-                                                              offsets.as<uint64_t>(), nullptr, nullptr,
-                                                              &n_groups, st)));
+        GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n, kFlagHead, ib, offsets.ptr, nullptr, nullptr,
+                              nullptr, nullptr, &n_groups, st));
         return group_hist_masked_device(offsets.ptr, ib, n_groups, n, (const uint8_t *)ix->d_flags.ptr,
                                         no_amb_same_len ? kFlagAmb : 0, min_group, max_group, max_bin,
                                         h_hist_out, h_total_out, st);
@@ -421,14 +586,8 @@ int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filt
         GK_TRY(filter_flags_device(ix->d_sba, ix->sba_len, ix->d_idx.ptr, ib, n, f,
                                    pass_flags.as<uint8_t>(), st));
         GK_TRY(kept.alloc((size_t)n * ib, st));
-        if (ib == 4)
-            GK_TRY((select_flagged_device<uint32_t, uint32_t>(pass_flags.as<uint8_t>(), n, kFlagPass, nullptr,
-                                                              (const uint32_t *)ix->d_idx.ptr,
-                                                              kept.as<uint32_t>(), &m, st)));
-        else
-            GK_TRY((select_flagged_device<uint64_t, uint64_t>(pass_flags.as<uint8_t>(), n, kFlagPass, nullptr,
-                                                              (const uint64_t *)ix->d_idx.ptr,
-                                                              kept.as<uint64_t>(), &m, st)));
+        GK_TRY(select_flagged(pass_flags.as<uint8_t>(), n, kFlagPass, ib, nullptr, ix->d_idx.ptr, kept.ptr,
+                              nullptr, nullptr, &m, st));
         d_list = kept.ptr;
     }
     if (m == 0) return GK_OK;
@@ -445,14 +604,8 @@ int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filt
                             flags.as<uint8_t>(), st));
     GK_TRY(offsets.alloc((size_t)m * ib, st));
     uint64_t n_groups = 0;
-    if (ib == 4)
-        GK_TRY((select_flagged_device<uint32_t, uint32_t>(flags.as<uint8_t>(), m, kFlagHead,
-                                                          offsets.as<uint32_t>(), nullptr, nullptr,
-                                                          &n_groups, st)));
-    else
-        GK_TRY((select_flagged_device<uint64_t, uint64_t>(flags.as<uint8_t>(), m, kFlagHead,
-                                                          offsets.as<uint64_t>(), nullptr, nullptr,
-                                                          &n_groups, st)));
+    GK_TRY(select_flagged(flags.as<uint8_t>(), m, kFlagHead, ib, offsets.ptr, nullptr, nullptr, nullptr,
+                          nullptr, &n_groups, st));
     return group_hist_device(offsets.ptr, ib, n_groups, m, min_group, max_group, max_bin, h_hist_out,
                              h_total_out, nullptr, st);
 }
@@ -474,8 +627,8 @@ int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups, uint6
     GK_TRY(flags_for(ix, kmer_len, &d_flags, scratch, st));
     GK_TRY(offsets.alloc((size_t)n * 8, st));
     uint64_t n_groups = 0;
-    GK_TRY((select_flagged_device<uint64_t, uint64_t>(d_flags, n, kFlagHead, offsets.as<uint64_t>(), nullptr,
-                                                      nullptr, &n_groups, st)));
+    GK_TRY(select_flagged(d_flags, n, kFlagHead, 8, offsets.ptr, nullptr, nullptr, nullptr, nullptr,
+                          &n_groups, st));
     *h_n_groups = n_groups;
     if (h_offsets_out && n_groups) {
         GK_CUDA(cudaMemcpyAsync(h_offsets_out, offsets.ptr, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,8 @@
 // Memory layout: keys and values are separate arrays (SoA) so each warp-wide access is one
 // fully used 256-byte / 128-byte segment; tile status is [tile][256] words so a look-back step
 // of the 256 bin-threads is one coalesced 1 KB read.
+#include <stdlib.h>
+
 #include "gk_common.cuh"
 
 namespace gk {
@@ -123,14 +125,16 @@ struct StatusTraits<uint64_t> {
 };
 
 constexpr uint32_t kLookbackSpinLimit = 1u << 24;  // then flag an error instead of hanging the GPU
+constexpr int kLookbackBatch = 4;                  // predecessor status words loaded per round trip
 
-template <typename ValT, typename StatusT, int THREADS, int IPT>
+template <typename ValT, int THREADS, int IPT>
 struct OnesweepSmem {
     static constexpr int kTile = THREADS * IPT;
     static constexpr int kWarps = THREADS / 32;
     uint64_t keys[kTile];
     ValT vals[kTile];
-    uint32_t warp_hist[kWarps][kRadix];
+    uint32_t warp_cnt[kWarps][kRadix];  // per-warp digit counts, then running tile positions
+    uint32_t match[kWarps][kRadix];     // per-warp peer masks (atomicOr), zero between rounds
     long long global_off[kRadix];
     uint64_t splitters[kRadix];
     uint32_t bin_excl[kRadix];
@@ -138,15 +142,30 @@ struct OnesweepSmem {
     uint32_t tile;
 };
 
-template <typename ValT, typename StatusT, int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS)
+template <typename StatusT>
+__device__ __forceinline__ StatusT load_status(const StatusT *p)
+{
+    return *reinterpret_cast<const volatile StatusT *>(p);
+}
+
+// One pass.  Phases (profiles/r01_onesweep.md explains the choices):
+//   A  claim a tile, load its pairs, count digits per warp with shared-memory atomics
+//   B  bin threads: per-warp exclusive offsets, tile totals -> publish the tile-local counts EARLY
+//   C  stable ranking: the lanes of a warp that hold the same digit find each other by OR-ing their lane
+//      bit into a per-warp mask word (one ATOMS per item; MATCH.ANY issues once per ~180 cycles on
+//      sm_100a and eight ballots cost ~40 instructions per item), then drop their pair straight into its
+//      tile-sorted slot in shared memory
+//   D  bin threads: decoupled look-back, several predecessor status words per round trip
+//   E  stream the tile out; consecutive threads write consecutive addresses inside each bin
+template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
+__global__ void __launch_bounds__(THREADS, MINB)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                 const ValT *__restrict__ vals_in, ValT *__restrict__ vals_out, uint64_t n,
                 int shift, uint32_t digit_mask, const uint64_t *__restrict__ splitters, uint32_t n_split,
                 const unsigned long long *__restrict__ bin_base, uint32_t *__restrict__ tile_counter,
                 StatusT *__restrict__ status, int *__restrict__ err)
 {
-    using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
+    using Smem = OnesweepSmem<ValT, THREADS, IPT>;
     using ST = StatusTraits<StatusT>;
     constexpr int kTile = Smem::kTile;
     constexpr int kWarps = Smem::kWarps;
@@ -157,26 +176,29 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     const uint32_t t = threadIdx.x;
     const uint32_t lane = t & 31u, warp = t >> 5;
 
+    // ---- A ------------------------------------------------------------------------------------------
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
-    if (splitters && t < n_split) s.splitters[t] = splitters[t];
+    for (int i = t; i < 2 * kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;  // warp_cnt + match
+    if (PARTITION && t < n_split) s.splitters[t] = splitters[t];
     __syncthreads();
     auto digit_of = [&](uint64_t k) -> uint32_t {
-        return splitters ? splitter_digit(s.splitters, n_split, k) : ((uint32_t)(k >> shift) & digit_mask);
+        if (PARTITION) return splitter_digit(s.splitters, n_split, k);
+        return (uint32_t)(k >> shift) & digit_mask;
     };
     const uint64_t tile = s.tile;
     const uint64_t tile_base = tile * (uint64_t)kTile;
-    const uint32_t tile_valid = (n - tile_base < (uint64_t)kTile) ? (uint32_t)(n - tile_base) : kTile;
+    const bool full_tile = (n - tile_base) >= (uint64_t)kTile;
+    const uint32_t tile_valid = full_tile ? (uint32_t)kTile : (uint32_t)(n - tile_base);
 
-    // ---- load: warp-striped inside a warp-contiguous chunk, so memory order == (j, lane) ------
+    // warp-striped inside a warp-contiguous chunk, so memory order == (j, lane)
     uint64_t key[IPT];
     ValT val[IPT];
     const uint64_t warp_base = tile_base + (uint64_t)warp * (32 * IPT);
-    if (tile_valid == kTile) {
+    if (full_tile) {
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) key[j] = keys_in[warp_base + j * 32 + lane];
+        for (int j = 0; j < IPT; ++j) key[j] = __ldcs(keys_in + warp_base + j * 32 + lane);
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) val[j] = vals_in[warp_base + j * 32 + lane];
+        for (int j = 0; j < IPT; ++j) val[j] = __ldcs(vals_in + warp_base + j * 32 + lane);
     } else {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -186,44 +208,28 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
             val[j] = ok ? vals_in[g] : (ValT)0;
         }
     }
-
-    // ---- rank inside the warp (stable) -------------------------------------------------------------
-    uint32_t rank[IPT];  // low 16 bits: rank among same-digit items of this warp; high: digit
-    uint32_t *my_hist = s.warp_hist[warp];
+    uint32_t *my_cnt = s.warp_cnt[warp];
+    uint32_t *my_match = s.match[warp];
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint32_t d = digit_of(key[j]);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader) {
-            base = my_hist[d];
-            my_hist[d] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        rank[j] = (base + __popc(peers & lanemask_lt())) | (d << 16);
-        __syncwarp();
-    }
+    for (int j = 0; j < IPT; ++j) atomicAdd(&my_cnt[digit_of(key[j])], 1u);
     __syncthreads();
 
-    // ---- per-bin: exclusive scan over warps, tile totals, look-back ---------------------------------
+    // ---- B ------------------------------------------------------------------------------------------
     uint32_t bin_count = 0;
     if (t < kRadix) {
         uint32_t sum = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = s.warp_hist[w][t];
-            s.warp_hist[w][t] = sum;
+            const uint32_t c = s.warp_cnt[w][t];
+            s.warp_cnt[w][t] = sum;
             sum += c;
         }
         bin_count = sum;
-        // publish the tile-local count first so successors can make progress
         // (volatile: the two status stores of this thread must both reach memory, in order)
         *const_cast<volatile StatusT *>(status + tile * kRadix + t) =
             ((StatusT)1 << ST::kShift) | (StatusT)bin_count;
     }
-    // exclusive scan of bin_count over the 256 bins (first 8 warps)
-    uint32_t inc = bin_count;
+    uint32_t inc = bin_count;  // exclusive scan of the tile totals over the 256 bins
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
@@ -231,27 +237,66 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     }
     if (t < kRadix && lane == 31) s.warp_sums[warp] = inc;
     __syncthreads();
+    uint32_t excl_in_tile = 0;
     if (t < kRadix) {
         uint32_t pre = 0;
         for (uint32_t w = 0; w < warp; ++w) pre += s.warp_sums[w];
-        const uint32_t excl_in_tile = pre + inc - bin_count;
+        excl_in_tile = pre + inc - bin_count;
         s.bin_excl[t] = excl_in_tile;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s.warp_cnt[w][t] += excl_in_tile;  // -> running tile positions
+    }
+    __syncthreads();
 
-        // decoupled look-back over predecessor tiles for this bin
+    // ---- C ------------------------------------------------------------------------------------------
+    const uint32_t lane_bit = 1u << lane;
+    const uint32_t lt_mask = lane_bit - 1u;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t d = digit_of(key[j]);
+        atomicOr(&my_match[d], lane_bit);
+        __syncwarp();
+        const uint32_t peers = my_match[d];
+        const uint32_t base = my_cnt[d];
+        __syncwarp();
+        const uint32_t before = peers & lt_mask;
+        if (before == 0) {  // lowest peer lane: advance the running position, clear the mask word
+            my_cnt[d] = base + __popc(peers);
+            my_match[d] = 0;
+        }
+        __syncwarp();
+        const uint32_t pos = base + __popc(before);
+        s.keys[pos] = key[j];
+        s.vals[pos] = val[j];
+    }
+
+    // ---- D ------------------------------------------------------------------------------------------
+    if (t < kRadix) {
+        // a tile completes chip-wide every few dozen cycles while one L2 round trip takes hundreds, so
+        // a one-at-a-time walk never catches up with the inclusive frontier: batch the status loads
         uint64_t excl = 0;
-        bool failed = false;
-        for (int64_t tp = (int64_t)tile - 1; tp >= 0; --tp) {
-            const volatile StatusT *slot = status + (uint64_t)tp * kRadix + t;
-            StatusT sv = *slot;
-            uint32_t spins = 0;
-            while ((sv >> ST::kShift) == 0) {
-                if (++spins > kLookbackSpinLimit) { failed = true; break; }
-                __nanosleep(20);
-                sv = *slot;
+        bool failed = false, done = (tile == 0);
+        int64_t tp = (int64_t)tile - 1;
+        while (!done) {
+            StatusT sv[kLookbackBatch];
+#pragma unroll
+            for (int u = 0; u < kLookbackBatch; ++u)
+                sv[u] = (tp - u >= 0) ? load_status(status + (uint64_t)(tp - u) * kRadix + t)
+                                      : ((StatusT)2 << ST::kShift);  // before tile 0: inclusive 0
+#pragma unroll
+            for (int u = 0; u < kLookbackBatch; ++u) {
+                if (done) break;
+                uint32_t spins = 0;
+                while ((sv[u] >> ST::kShift) == 0) {
+                    if (++spins > kLookbackSpinLimit) { failed = true; break; }
+                    __nanosleep(64);
+                    sv[u] = load_status(status + (uint64_t)(tp - u) * kRadix + t);
+                }
+                if (failed) { done = true; break; }
+                excl += (uint64_t)(sv[u] & ST::kMask);
+                if ((sv[u] >> ST::kShift) == 2) done = true;
             }
-            if (failed) break;
-            excl += (uint64_t)(sv & ST::kMask);
-            if ((sv >> ST::kShift) == 2) break;
+            tp -= kLookbackBatch;
         }
         if (failed) atomicExch(err, 1);
         *const_cast<volatile StatusT *>(status + tile * kRadix + t) =
@@ -260,54 +305,100 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     }
     __syncthreads();
 
-    // ---- reorder the tile in shared memory -------------------------------------------------------
+    // ---- E ------------------------------------------------------------------------------------------
+    if (full_tile) {
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint32_t d = rank[j] >> 16;
-        const uint32_t pos = s.bin_excl[d] + s.warp_hist[warp][d] + (rank[j] & 0xFFFFu);
-        s.keys[pos] = key[j];
-        s.vals[pos] = val[j];
-    }
-    __syncthreads();
-
-    // ---- stream out: thread t handles tile positions t, t+THREADS, ... -----------------------------
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint32_t p = t + j * THREADS;
-        if (p < tile_valid) {
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = t + j * THREADS;
             const uint64_t k = s.keys[p];
-            const uint32_t d = digit_of(k);
-            const long long dst = s.global_off[d] + (long long)p;
-            keys_out[dst] = k;
-            vals_out[dst] = s.vals[p];
+            const long long dst = s.global_off[digit_of(k)] + (long long)p;
+            __stcs(keys_out + dst, k);
+            __stcs(vals_out + dst, s.vals[p]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = t + j * THREADS;
+            if (p < tile_valid) {
+                const uint64_t k = s.keys[p];
+                const long long dst = s.global_off[digit_of(k)] + (long long)p;
+                keys_out[dst] = k;
+                vals_out[dst] = s.vals[p];
+            }
         }
     }
 }
 
 // ---- host driver ---------------------------------------------------------------------------------
-template <typename ValT, typename StatusT, int THREADS, int IPT>
-static int launch_pass(const uint64_t *kin, uint64_t *kout, const void *vin, void *vout, uint64_t n,
-                       int shift, int bits, const uint64_t *splitters, uint32_t n_split,
-                       const unsigned long long *bin_base, uint32_t *tile_counter, void *status, int *err,
-                       cudaStream_t st)
+struct PassArgs {
+    const uint64_t *kin; uint64_t *kout; const void *vin; void *vout; uint64_t n;
+    int shift, bits; const uint64_t *splitters; uint32_t n_split;
+    const unsigned long long *bin_base; uint32_t *tile_counter; void *status; int *err;
+};
+
+template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
+static int launch_pass_impl(const PassArgs &a, cudaStream_t st)
 {
-    using Smem = OnesweepSmem<ValT, StatusT, THREADS, IPT>;
-    auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT>;
-    GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(Smem)));
-    const uint64_t tiles = (n + Smem::kTile - 1) / Smem::kTile;
+    using Smem = OnesweepSmem<ValT, THREADS, IPT>;
+    auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT, MINB, PARTITION>;
+    GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
+    const uint64_t tiles = (a.n + Smem::kTile - 1) / Smem::kTile;
     kernel<<<(unsigned)tiles, THREADS, sizeof(Smem), st>>>(
-        kin, kout, (const ValT *)vin, (ValT *)vout, n, shift, (1u << bits) - 1u, splitters, n_split,
-        bin_base, tile_counter, (StatusT *)status, err);
+        a.kin, a.kout, (const ValT *)a.vin, (ValT *)a.vout, a.n, a.shift, (1u << a.bits) - 1u, a.splitters,
+        a.n_split, a.bin_base, a.tile_counter, (StatusT *)a.status, a.err);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
 
-// Tunables (see DESIGN.md "onesweep tile shape"): 256 threads x 16 pairs = 4096-pair tiles,
-// ~61 KB shared memory and <=128 registers -> 2-3 CTAs per SM.
-constexpr int kSortThreads = 256;
-constexpr int kSortIPT4 = 16;  // 32-bit values
-constexpr int kSortIPT8 = 12;  // 64-bit values
+template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB>
+static int launch_pass(const PassArgs &a, cudaStream_t st)
+{
+    if (a.splitters) return launch_pass_impl<ValT, StatusT, THREADS, IPT, MINB, true>(a, st);
+    return launch_pass_impl<ValT, StatusT, THREADS, IPT, MINB, false>(a, st);
+}
+
+// Tile shapes (threads, pairs per thread, CTAs per SM the register budget is compiled for).
+// Selected once per process; GK_SORT_CFG overrides the default for tuning runs.
+struct SortConfig { int threads, ipt, minb; };
+constexpr SortConfig kSortConfigs[] = {
+    {256, 16, 3},  // 0: 4096-pair tiles, 61 KB smem, <=80 regs
+    {512, 8, 2},   // 1: 4096-pair tiles, 69 KB smem, <=64 regs
+    {384, 12, 2},  // 2: 4608-pair tiles
+    {256, 24, 2},  // 3: 6144-pair tiles
+    {512, 12, 1},  // 4: 6144-pair tiles
+    {512, 16, 1},  // 5: 8192-pair tiles
+};
+constexpr int kNumSortConfigs = (int)(sizeof(kSortConfigs) / sizeof(kSortConfigs[0]));
+constexpr int kDefaultSortConfig = 0;
+
+static int sort_config_id()
+{
+    static int id = -1;
+    if (id < 0) {
+        id = kDefaultSortConfig;
+        const char *e = getenv("GK_SORT_CFG");
+        if (e && *e) {
+            const int v = atoi(e);
+            if (v >= 0 && v < kNumSortConfigs) id = v;
+        }
+    }
+    return id;
+}
+
+template <typename ValT, typename StatusT>
+static int dispatch_pass(int cfg, const PassArgs &a, cudaStream_t st)
+{
+    switch (cfg) {
+    case 1: return launch_pass<ValT, StatusT, 512, 8, 2>(a, st);
+    case 2: return launch_pass<ValT, StatusT, 384, 12, 2>(a, st);
+    case 3: return launch_pass<ValT, StatusT, 256, 24, 2>(a, st);
+    case 4: return launch_pass<ValT, StatusT, 512, 12, 1>(a, st);
+    case 5: return launch_pass<ValT, StatusT, 512, 16, 1>(a, st);
+    default: return launch_pass<ValT, StatusT, 256, 16, 3>(a, st);
+    }
+}
 
 // Shared driver: histogram(s) + scan + `passes` onesweep launches.  splitters != nullptr selects
 // the single partition pass (digit = destination rank); h_bin_counts (256 entries, optional)
@@ -336,7 +427,8 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         return GK_ERR_ARG;
     }
 
-    const int tile = kSortThreads * (val_bytes == 4 ? kSortIPT4 : kSortIPT8);
+    const int cfg = sort_config_id();
+    const int tile = kSortConfigs[cfg].threads * kSortConfigs[cfg].ipt;
     const uint64_t tiles = (n + tile - 1) / tile;
     const bool wide = n >= (1ull << 30);
     const size_t status_bytes = (size_t)tiles * kRadix * (wide ? 8 : 4);
@@ -375,23 +467,13 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         const int lo = begin_bit + p * kRadixBits;
         const int bits = d_splitters ? kRadixBits : ((end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits);
         GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
-        const unsigned long long *base = d_base + p * kRadix;
+        PassArgs pa = {kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, d_base + p * kRadix,
+                       d_ctr + p, d_status, d_err};
         int rc;
-        if (val_bytes == 4) {
-            rc = wide ? launch_pass<uint32_t, uint64_t, kSortThreads, kSortIPT4>(
-                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
-                            d_status, d_err, st)
-                      : launch_pass<uint32_t, uint32_t, kSortThreads, kSortIPT4>(
-                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
-                            d_status, d_err, st);
-        } else {
-            rc = wide ? launch_pass<uint64_t, uint64_t, kSortThreads, kSortIPT8>(
-                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
-                            d_status, d_err, st)
-                      : launch_pass<uint64_t, uint32_t, kSortThreads, kSortIPT8>(
-                            kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, base, d_ctr + p,
-                            d_status, d_err, st);
-        }
+        if (val_bytes == 4)
+            rc = wide ? dispatch_pass<uint32_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint32_t, uint32_t>(cfg, pa, st);
+        else
+            rc = wide ? dispatch_pass<uint64_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint64_t, uint32_t>(cfg, pa, st);
         GK_TRY(rc);
         uint64_t *tk = kin; kin = kout; kout = tk;
         void *tv = vin; vin = vout; vout = tv;

@@ -69,6 +69,7 @@ SIGNATURES = {
     "gk_pack_keys": (_int, [_vp, _u64, _vp, _u32, _u32, _u32, _int, _u64, _u64, _vp, _int, _vp,
                             _u64, _p(_u64), _p(_u64), _vp]),
     "gk_radix_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _int, _int, _p(_int), _vp]),
+    "gk_partition_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _vp, _u32, _vp, _vp]),
     "gk_rle_keys": (_int, [_vp, _u64, _vp, _p(_u64), _vp]),
     "gk_group_size_hist": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp, _p(ctypes.c_int64), _vp]),
     "gk_index_create": (_int, [_vp, _u64, _vp, _u32, _u32, _u32, _p(_vp)]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "gk_index_is_sorted": (_int, [_vp]),
     "gk_index_set_indices": (_int, [_vp, _vp, _u64, _int, _int, _vp]),
     "gk_index_sort": (_int, [_vp, _p(GkSortStats), _vp]),
+    "gk_index_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _int, _p(GkSortStats), _vp]),
     "gk_index_device_indices": (_int, [_vp, _p(_vp), _vp]),
     "gk_index_copy_indices": (_int, [_vp, _vp, _vp]),
     "gk_index_group_counts": (_int, [_vp, _u32, _p(GkFilter), _u64, _u64, _u64, _vp,

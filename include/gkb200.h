@@ -122,6 +122,12 @@ int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_s
 int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                         int val_bytes, uint64_t n, int begin_bit, int end_bit,
                         int *result_in_alt, void *stream);
+/* Multi-GPU partition step: stable split of the pairs by destination rank = number of splitters
+ * (sorted, n_parts-1 of them, device memory) that are <= key.  One onesweep pass whose "digit" is
+ * the destination.  Output in the *_out buffers; h_counts_out[d] = pairs for destination d. */
+int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,
+                       int val_bytes, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                       uint64_t *h_counts_out, void *stream);
 /* Run-length pass over sorted keys (north_star subsystem 3): group offsets (positions where a
  * new key starts; d_offsets_out has room for n entries), number of groups. */
 int gk_rle_keys(const uint64_t *d_keys_sorted, uint64_t n, uint64_t *d_offsets_out,
@@ -148,6 +154,13 @@ int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_by
                          void *stream);
 /* seam 1: sort the start indices lexicographically by k-mer, ties by ascending start. */
 int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream);
+/* Multi-GPU shard of seam 1: adopt the (key, start) pairs this rank received from the exchange
+ * (made by gk_pack_keys with key_len = valid_len = min_kmer_len and the same class_bit), sort them
+ * and leave the index describing this rank's key range only (gk_index_size() == n_local).  The
+ * pair buffers are scratch. */
+int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx,
+                        void *d_idx_alt, uint64_t n_local, int class_bit, gk_sort_stats *stats_out,
+                        void *stream);
 /* Device pointer to the current (init or sorted) start indices; owned by the index. */
 int gk_index_device_indices(gk_index *ix, const void **d_idx_out, void *stream);
 /* Copy the start indices to a host buffer of gk_index_size() * idx_bytes bytes. */

@@ -1,0 +1,84 @@
+"""
+World-size-2 (and 3) gloo tests of the multi-GPU orchestration on CPU: slicing, splitter
+choice, count + pair exchange, shard concatenation, histogram all-reduce.  The compute steps are served by
+tests/numpy_engine.py (a test double); the GPU kernels behind the same calls are covered by the gpu tests.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, strands, k, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "genome-kmers_b200"), HERE]
+    import torch.distributed as dist
+
+    import oracle
+    from genome_kmers.distributed import ShardedKmers
+    from numpy_engine import NumpyEngine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        recs = []
+        for n in (700, 900, 650):
+            seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+            seq[100:140] = ord("N")
+            seq[rng.integers(0, n, 3)] = ord("R")
+            recs.append(seq)
+        recs.append(np.frombuffer(b"ACAC" * 60, dtype=np.uint8))     # a low-complexity record: big groups
+        sba, starts = oracle.build_sba(recs)
+        sk = ShardedKmers(sba, starts, k, strands, engine=NumpyEngine())
+        sk.sort()
+        hist, total = sk.get_kmer_group_counts(k, max_counts_bin=50)
+        everything = sk.gather_start_indices(0)
+        shard = sk.local_start_indices()
+        np.save(os.path.join(out_dir, f"shard{rank}.npy"), shard)
+        if rank == 0:
+            full_sba, full_starts = (oracle.both_strands(sba, starts.astype(np.uint64)) if strands == "both"
+                                     else (sba, starts.astype(np.uint64)))
+            want = oracle.sort_indices(full_sba, oracle.init_indices(full_starts, len(full_sba), k), k, k)
+            o_hist, o_total = oracle.group_hist(full_sba, want, k, max_bin=50)
+            assert np.array_equal(everything.astype(np.uint64), want), "concatenated shards != global order"
+            assert total == o_total and np.array_equal(hist, o_hist)
+            np.save(os.path.join(out_dir, "ok.npy"), np.array([len(want)]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,strands,k", [(2, "forward", 11), (2, "both", 21), (3, "both", 5)])
+def test_sharded_sort_count_matches_oracle(tmp_path, world, strands, k):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, strands, k, str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok.npy")
+    sizes = [len(np.load(tmp_path / f"shard{r}.npy")) for r in range(world)]
+    assert sum(sizes) == int(np.load(tmp_path / "ok.npy")[0])
+    assert min(sizes) > 0, f"a rank received nothing: {sizes}"
+
+
+def test_splitters_and_slices():
+    sys.path[:0] = [os.path.join(ROOT, "genome-kmers_b200")]
+    from genome_kmers.distributed import choose_splitters, slice_bounds
+
+    samples = np.arange(100, dtype=np.uint64) * np.uint64(7)
+    sp = choose_splitters(samples, 4)
+    assert sp.tolist() == [175, 350, 525]
+    assert choose_splitters(samples, 1).size == 0
+    bounds = [slice_bounds(1001, 4, r) for r in range(4)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 1001
+    assert all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
