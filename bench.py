@@ -87,50 +87,71 @@ def n_kmers(n_bases, n_records, k, strands=2):
 # clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, through NVML in a background thread (the
+    recipe's nvidia-smi line, without spawning a process that competes for the driver while we time)."""
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_s=0.02):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.path = None
+        self.period_s = period_s
+        self.samples = []
+        self.thread = None
+        self.stop_flag = False
+        self.nvml = None
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu_index)],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import threading
+
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+
+    def _run(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, reasons, power))
+            except Exception:
+                pass
+            time.sleep(self.period_s)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        if self.thread is None:
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
-            if sm:
-                out["sm_mhz"] = float(np.median(sm))
-                out["sm_max_mhz"] = float(rows[0][2])
-                out["samples"] = len(sm)
-                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for i, nm in enumerate(names):
-                    if any(r[5 + i].strip().lower().startswith("active") for r in rows if len(r) >= 9):
-                        out["reasons"].append(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nvml
+        if self.samples:
+            out["sm_mhz"] = float(np.median([s[0] for s in self.samples]))
+            out["sm_max_mhz"] = float(self.max_sm)
+            out["samples"] = len(self.samples)
+            out["power_w_max"] = float(max(s[2] for s in self.samples))
+            bits = 0
+            for s in self.samples:
+                bits |= int(s[1])
+            names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown",
+                     "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                     "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown",
+                     "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+            alt = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown",
+                   "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                   "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown",
+                   "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+            for key in names:
+                mask = getattr(nv, names[key], None) or getattr(nv, alt[key], 0)
+                if bits & int(mask):
+                    out["reasons"].append(key)
         return out
 
 
@@ -269,8 +290,11 @@ def run_single_gpu(args):
     _native.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    step_wall_ms = []
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         per_step_stats.append(device_step())
+        step_wall_ms.append(1e3 * (time.perf_counter() - t_step))
     ev1.record(stream)
     torch.cuda.synchronize()
     launches = _native.launch_count()
@@ -302,12 +326,21 @@ def run_single_gpu(args):
     sc = SequenceCollection.from_sba(host_sba, starts.astype(np.uint32), names, strands_to_load="both",
                                      validate=False)
 
+    e2e_phases = []
+
     def e2e_step():
+        t = [time.perf_counter()]
         km = Kmers(sc, K, K, source_strand="both")
+        km._ensure_device()                  # H2D of the forward byte array, both-strand layout
+        t.append(time.perf_counter())
         km.sort()
+        t.append(time.perf_counter())
         h, total = km.get_kmer_group_counts(K, max_counts_bin=MAX_BIN)
+        t.append(time.perf_counter())
         idx = km.kmer_sba_start_indices      # D2H of the sorted start indices
+        t.append(time.perf_counter())
         assert total == n and len(idx) == n
+        e2e_phases.append([round(1e3 * (b - a), 3) for a, b in zip(t[:-1], t[1:])])
         return idx, h
 
     e2e = None
@@ -318,13 +351,15 @@ def run_single_gpu(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            idx = h = None                   # release the previous result before the next step
             idx, h = e2e_step()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": n / e2e_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
                "h2d_bytes_per_step": int(total_len),
                "d2h_bytes_per_step": int(idx.nbytes + 8 * (int(np.flatnonzero(h).max()) + 1)),
-               "api": "Kmers(seq_coll, 31, 31, 'both'); sort(); get_kmer_group_counts(31); kmer_sba_start_indices"}
+               "api": "Kmers(seq_coll, 31, 31, 'both'); sort(); get_kmer_group_counts(31); kmer_sba_start_indices",
+               "phase_ms_upload_sort_count_download": e2e_phases[-e2e_steps:]}
         assert np.array_equal(h, hist)
         del idx
 
@@ -347,6 +382,7 @@ def run_single_gpu(args):
         "result": {"kmers": int(n), "distinct_kmers": n_distinct,
                    "ambiguous_windows": int(per_step_stats[-1]["n_ambiguous"]),
                    "key_bits": per_step_stats[-1]["key_bits"]},
+        "step_wall_ms": [round(v, 3) for v in step_wall_ms],
     }
     if args.bases != BASES_PER_GPU:
         line["config"]["workload"] += f" [REDUCED to {args.bases} bp: not a valid bench number]"

@@ -134,8 +134,8 @@ struct OnesweepSmem {
     uint64_t keys[kTile];
     ValT vals[kTile];
     uint32_t warp_cnt[kWarps][kRadix];  // per-warp digit counts, then running tile positions
-    uint32_t match[kWarps][kRadix];     // per-warp peer masks (atomicOr), zero between rounds
-    long long global_off[kRadix];
+    unsigned long long global_off[kRadix];  // bin's global start minus its start inside the tile
+    uint32_t global_off32[kRadix];          // the same modulo 2^32 (enough when n < 2^32)
     uint64_t splitters[kRadix];
     uint32_t bin_excl[kRadix];
     uint32_t warp_sums[kRadix / 32];
@@ -148,13 +148,38 @@ __device__ __forceinline__ StatusT load_status(const StatusT *p)
     return *reinterpret_cast<const volatile StatusT *>(p);
 }
 
+// peers = lanes of this warp whose 8-bit digit equals mine, from eight ballots (about 3 SASS
+// instructions per bit).  No shared memory is touched: that pipe is the scarce resource here.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d)
+{
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+        uint32_t m;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+            "@!p not.b32 %0, %0;\n\t"
+            "}"
+            : "=r"(m)
+            : "r"(d), "r"(1u << b));
+        peers &= m;
+    }
+    return peers;
+}
+
 // One pass.  Phases (profiles/r01_onesweep.md explains the choices):
 //   A  claim a tile, load its pairs, count digits per warp with shared-memory atomics
 //   B  bin threads: per-warp exclusive offsets, tile totals -> publish the tile-local counts EARLY
-//   C  stable ranking: the lanes of a warp that hold the same digit find each other by OR-ing their lane
-//      bit into a per-warp mask word (one ATOMS per item; MATCH.ANY issues once per ~180 cycles on
-//      sm_100a and eight ballots cost ~40 instructions per item), then drop their pair straight into its
-//      tile-sorted slot in shared memory
+//   C  stable ranking: the lanes of a warp that hold the same digit find each other with eight ballots
+//      (MATCH.ANY issues once per ~180 cycles on sm_100a; a shared-memory atomicOr mask costs three more
+//      bank-conflicted shared accesses per item, and the shared-memory pipe is what bounds this kernel),
+//      read the warp's running position for the digit, and drop their pair straight into its tile-sorted
+//      slot in shared memory
 //   D  bin threads: decoupled look-back, several predecessor status words per round trip
 //   E  stream the tile out; consecutive threads write consecutive addresses inside each bin
 template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
@@ -178,7 +203,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
 
     // ---- A ------------------------------------------------------------------------------------------
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = t; i < 2 * kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;  // warp_cnt + match
+    for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;
     if (PARTITION && t < n_split) s.splitters[t] = splitters[t];
     __syncthreads();
     auto digit_of = [&](uint64_t k) -> uint32_t {
@@ -209,7 +234,6 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         }
     }
     uint32_t *my_cnt = s.warp_cnt[warp];
-    uint32_t *my_match = s.match[warp];
 #pragma unroll
     for (int j = 0; j < IPT; ++j) atomicAdd(&my_cnt[digit_of(key[j])], 1u);
     __syncthreads();
@@ -249,21 +273,15 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     __syncthreads();
 
     // ---- C ------------------------------------------------------------------------------------------
-    const uint32_t lane_bit = 1u << lane;
-    const uint32_t lt_mask = lane_bit - 1u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
         const uint32_t d = digit_of(key[j]);
-        atomicOr(&my_match[d], lane_bit);
-        __syncwarp();
-        const uint32_t peers = my_match[d];
-        const uint32_t base = my_cnt[d];
-        __syncwarp();
+        const uint32_t peers = digit_peers(d);
         const uint32_t before = peers & lt_mask;
-        if (before == 0) {  // lowest peer lane: advance the running position, clear the mask word
-            my_cnt[d] = base + __popc(peers);
-            my_match[d] = 0;
-        }
+        const uint32_t base = my_cnt[d];                       // peers read the same word (broadcast)
+        __syncwarp();
+        if (before == 0) my_cnt[d] = base + __popc(peers);     // lowest peer lane advances the position
         __syncwarp();
         const uint32_t pos = base + __popc(before);
         s.keys[pos] = key[j];
@@ -301,17 +319,23 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         if (failed) atomicExch(err, 1);
         *const_cast<volatile StatusT *>(status + tile * kRadix + t) =
             ((StatusT)2 << ST::kShift) | (StatusT)(excl + bin_count);
-        s.global_off[t] = (long long)(bin_base[t] + excl) - (long long)excl_in_tile;
+        const unsigned long long off = bin_base[t] + excl - (unsigned long long)excl_in_tile;
+        s.global_off[t] = off;
+        s.global_off32[t] = (uint32_t)off;
     }
     __syncthreads();
 
     // ---- E ------------------------------------------------------------------------------------------
+    // 32-bit offsets when every destination index fits (StatusT is 32-bit exactly when n < 2^30)
+    constexpr bool kNarrow = sizeof(StatusT) == 4;
     if (full_tile) {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const uint32_t p = t + j * THREADS;
             const uint64_t k = s.keys[p];
-            const long long dst = s.global_off[digit_of(k)] + (long long)p;
+            const uint32_t d = digit_of(k);
+            const uint64_t dst = kNarrow ? (uint64_t)(uint32_t)(s.global_off32[d] + p)
+                                         : (uint64_t)(s.global_off[d] + p);
             __stcs(keys_out + dst, k);
             __stcs(vals_out + dst, s.vals[p]);
         }
@@ -321,7 +345,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
             const uint32_t p = t + j * THREADS;
             if (p < tile_valid) {
                 const uint64_t k = s.keys[p];
-                const long long dst = s.global_off[digit_of(k)] + (long long)p;
+                const uint64_t dst = (uint64_t)(s.global_off[digit_of(k)] + p);
                 keys_out[dst] = k;
                 vals_out[dst] = s.vals[p];
             }
