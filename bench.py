@@ -87,18 +87,25 @@ def n_kmers(n_bases, n_records, k, strands=2):
 # clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, through NVML in a background thread (the
-    recipe's nvidia-smi line, without spawning a process that competes for the driver while we time)."""
+    """SM clock and throttle reasons DURING the timed region, through NVML.
 
-    def __init__(self, gpu_index=0, period_s=0.02):
+    mode "inline": sample() is called by the timing loop between steps (no second thread touching the
+    driver while kernels are being launched); mode "thread": a background thread polls every period_s.
+    `queries` selects what is read ("c" clock, "r" throttle reasons, "p" power)."""
+
+    def __init__(self, gpu_index=0, period_s=0.02, mode="inline", queries="crp"):
         self.gpu_index = gpu_index
         self.period_s = period_s
+        self.mode = mode
+        self.queries = queries
         self.samples = []
         self.thread = None
         self.stop_flag = False
         self.nvml = None
 
     def start(self):
+        if self.mode == "off":
+            return
         try:
             import threading
 
@@ -108,35 +115,44 @@ class ClockSampler:
             self.nvml = pynvml
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
+            self.sample()
+            if self.mode == "thread":
+                self.thread = threading.Thread(target=self._run, daemon=True)
+                self.thread.start()
         except Exception:
-            self.thread = None
+            self.nvml = None
+
+    def sample(self):
+        nv = self.nvml
+        if nv is None:
+            return
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM) if "c" in self.queries else 0
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if "r" in self.queries else 0
+            power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if "p" in self.queries else 0.0
+            self.samples.append((sm, reasons, power))
+        except Exception:
+            pass
 
     def _run(self):
-        nv = self.nvml
         while not self.stop_flag:
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                self.samples.append((sm, reasons, power))
-            except Exception:
-                pass
+            self.sample()
             time.sleep(self.period_s)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.thread is None:
+        if self.nvml is None:
             return out
-        self.stop_flag = True
-        self.thread.join(timeout=2)
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
         nv = self.nvml
         if self.samples:
             out["sm_mhz"] = float(np.median([s[0] for s in self.samples]))
             out["sm_max_mhz"] = float(self.max_sm)
             out["samples"] = len(self.samples)
             out["power_w_max"] = float(max(s[2] for s in self.samples))
+            out["sampler"] = self.mode
             bits = 0
             for s in self.samples:
                 bits |= int(s[1])
@@ -285,7 +301,7 @@ def run_single_gpu(args):
     for _ in range(args.warmup):
         device_step()
     torch.cuda.synchronize()
-    clocks = ClockSampler(0)
+    clocks = ClockSampler(0, period_s=args.clock_period, mode=args.clock_mode, queries=args.clock_queries)
     clocks.start()
     _native.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,6 +310,8 @@ def run_single_gpu(args):
     for _ in range(args.steps):
         t_step = time.perf_counter()
         per_step_stats.append(device_step())
+        if args.clock_mode == "inline":
+            clocks.sample()                  # GPU still draining the step's last kernels
         step_wall_ms.append(1e3 * (time.perf_counter() - t_step))
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -408,6 +426,9 @@ def main():
     ap.add_argument("--cpu-sample-bases", type=int, default=2_000_000)
     ap.add_argument("--ref-sample-bases", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="NVML sampling period in s (thread mode)")
+    ap.add_argument("--clock-mode", default="inline", choices=["inline", "thread", "off"])
+    ap.add_argument("--clock-queries", default="crp")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

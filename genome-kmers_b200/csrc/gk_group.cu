@@ -432,6 +432,203 @@ int group_hist_masked_device(const void *d_offsets, int pos_bytes, uint64_t n_gr
                            max_bin, h_hist, h_total, nullptr, st);
 }
 
+// ---- group-size histogram straight from the head flags (no offsets array) ---------------------------
+// The cached-flags fast path of gk_index_group_counts.  A group is closed when the NEXT head is met:
+// its size is the distance between the two heads, so every thread only needs the position of the
+// latest head before its 16 flags.  Three launches: last head per tile, one-CTA running max over
+// the tiles, then the histogram pass.  Reads the flags twice (2 B per k-mer) and writes nothing per
+// k-mer, instead of materialising 4-8 B per distinct k-mer and reading them back.
+constexpr int kGfThreads = 256;
+constexpr int kGfPerThread = 16;
+constexpr int kGfTile = kGfThreads * kGfPerThread;
+
+// last head position + 1 inside each tile (0 = none)
+__global__ void __launch_bounds__(kGfThreads)
+flag_tile_last_head_kernel(const uint8_t *__restrict__ flags, uint64_t n,
+                           unsigned long long *__restrict__ tile_last)
+{
+    __shared__ unsigned long long s_max[kGfThreads / 32];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kGfTile + (uint64_t)threadIdx.x * kGfPerThread;
+    const uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, kFlagHead) : 0u;
+    unsigned long long last = bits ? p0 + (31 - __clz(bits)) + 1 : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, last, o);
+        last = v > last ? v : last;
+    }
+    if (lane_id() == 0) s_max[threadIdx.x >> 5] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = 0;
+        for (int w = 0; w < kGfThreads / 32; ++w) m = s_max[w] > m ? s_max[w] : m;
+        tile_last[blockIdx.x] = m;
+    }
+}
+
+// one CTA: carry[t] = max of tile_last over tiles < t (exclusive running max)
+__global__ void __launch_bounds__(1024)
+flag_tile_carry_kernel(const unsigned long long *__restrict__ tile_last, uint64_t n_tiles,
+                       unsigned long long *__restrict__ carry)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n_tiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = (i < n_tiles) ? tile_last[i] : 0;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc = u > inc ? u : inc;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre = s_warp[w] > pre ? s_warp[w] : pre;
+        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        excl = excl > pre ? excl : pre;
+        if (i < n_tiles) carry[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = inc > pre ? inc : pre;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kGfThreads)
+flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n_tiles,
+                       const unsigned long long *__restrict__ carry, uint8_t skip_mask,
+                       uint64_t min_group, uint64_t max_group, uint64_t max_bin,
+                       unsigned long long *__restrict__ hist, unsigned long long *__restrict__ totals)
+{
+    __shared__ uint32_t s_small[kHistSmallBins];
+    __shared__ unsigned long long s_total[3];
+    __shared__ unsigned long long s_warp[kGfThreads / 32];
+    for (int i = threadIdx.x; i < kHistSmallBins; i += kGfThreads) s_small[i] = 0;
+    if (threadIdx.x < 3) s_total[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long total = 0, counted = 0, top_bin = 0;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+
+    auto close_group = [&](uint64_t head, uint64_t size) {
+        if (skip_mask && (flags[head] & skip_mask)) return;  // e.g. groups of ambiguous k-mers
+        if (size >= min_group && (max_group == 0 || size <= max_group)) {
+            total += size;
+            ++counted;
+            const uint64_t bin = size < max_bin ? size : max_bin;
+            if (bin > top_bin) top_bin = bin;
+            if (bin < kHistSmallBins) atomicAdd(&s_small[bin], 1u);
+            else atomicAdd(&hist[bin], 1ull);
+        }
+    };
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t p0 = tile * kGfTile + (uint64_t)threadIdx.x * kGfPerThread;
+        uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, kFlagHead) : 0u;
+        const unsigned long long last = bits ? p0 + (31 - __clz(bits)) + 1 : 0ull;
+        unsigned long long inc = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc = u > inc ? u : inc;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = carry[tile];
+        for (uint32_t w = 0; w < warp; ++w) pre = s_warp[w] > pre ? s_warp[w] : pre;
+        unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) prev = 0;
+        prev = prev > pre ? prev : pre;  // position + 1 of the latest head before this thread's flags
+        while (bits) {
+            const uint32_t i = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint64_t p = p0 + i;
+            if (prev) close_group(prev - 1, p - (prev - 1));
+            prev = p + 1;
+        }
+        // the thread that owns the last position also closes the last group
+        if (p0 < n && n - 1 < p0 + kGfPerThread && prev) close_group(prev - 1, n - (prev - 1));
+        __syncthreads();
+    }
+
+    total = warp_sum(total);
+    counted = warp_sum(counted);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, top_bin, o);
+        top_bin = other > top_bin ? other : top_bin;
+    }
+    if (lane == 0) {
+        atomicAdd(&s_total[0], total);
+        atomicAdd(&s_total[1], counted);
+        atomicMax(&s_total[2], top_bin);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistSmallBins; i += kGfThreads) {
+        const uint32_t c = s_small[i];
+        if (c && (uint64_t)i <= max_bin) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+    if (threadIdx.x < 2 && s_total[threadIdx.x]) atomicAdd(&totals[threadIdx.x], s_total[threadIdx.x]);
+    if (threadIdx.x == 2 && s_total[2]) atomicMax(&totals[2], s_total[2]);
+}
+
+// hist (host, max_bin+1 int64, may be NULL), total and number of groups counted, straight from flags
+int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask, uint64_t min_group,
+                           uint64_t max_group, uint64_t max_bin, int64_t *h_hist, int64_t *h_total,
+                           int64_t *h_counted, cudaStream_t st)
+{
+    if (min_group < 1) {
+        set_error("min_group_size (%llu) must be >= 1", (unsigned long long)min_group);
+        return GK_ERR_ARG;
+    }
+    if (max_group != 0 && max_group < min_group) {
+        set_error("max_group_size must be >= min_group_size");
+        return GK_ERR_ARG;
+    }
+    if (max_bin < 1) {
+        set_error("max_counts_bin (%llu) must be >= 1", (unsigned long long)max_bin);
+        return GK_ERR_ARG;
+    }
+    const size_t hist_bytes = (size_t)(max_bin + 1) * 8;
+    if (h_hist) memset(h_hist, 0, hist_bytes);
+    if (h_total) *h_total = 0;
+    if (h_counted) *h_counted = 0;
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kGfTile - 1) / kGfTile;
+    DeviceBuffer buf;
+    // [hist][totals x3][tile_last][carry]
+    GK_TRY(buf.alloc(hist_bytes + 24 + (size_t)tiles * 16, st));
+    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 24, st));
+    unsigned long long *d_hist = buf.as<unsigned long long>();
+    unsigned long long *d_totals = d_hist + (max_bin + 1);
+    unsigned long long *d_last = d_totals + 3;
+    unsigned long long *d_carry = d_last + tiles;
+    flag_tile_last_head_kernel<<<(unsigned)tiles, kGfThreads, 0, st>>>(d_flags, n, d_last);
+    GK_LAUNCH_CHECK();
+    flag_tile_carry_kernel<<<1, 1024, 0, st>>>(d_last, tiles, d_carry);
+    GK_LAUNCH_CHECK();
+    uint64_t grid = (uint64_t)sm_count() * 8;
+    if (grid > tiles) grid = tiles;
+    flag_group_hist_kernel<<<(unsigned)grid, kGfThreads, 0, st>>>(d_flags, n, tiles, d_carry, skip_mask,
+                                                                   min_group, max_group, max_bin, d_hist,
+                                                                   d_totals);
+    GK_LAUNCH_CHECK();
+    unsigned long long totals[3] = {0, 0, 0};
+    GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_hist) {
+        // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB)
+        GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+    }
+    if (h_total) *h_total = (int64_t)totals[0];
+    if (h_counted) *h_counted = (int64_t)totals[1];
+    return GK_OK;
+}
+
 // ---- k-mer filters as device predicates (kmers.py:14-259) ------------------------------------------
 // returns 1 pass, 0 fail, -1 where the reference raises ValueError
 __device__ __forceinline__ int eval_filter(const uint8_t *__restrict__ sba, uint64_t len, uint64_t s,

@@ -27,6 +27,8 @@ int group_hist_device(const void *, int, uint64_t, uint64_t, uint64_t, uint64_t,
                       int64_t *, int64_t *, cudaStream_t);
 int group_hist_masked_device(const void *, int, uint64_t, uint64_t, const uint8_t *, uint8_t, uint64_t,
                              uint64_t, uint64_t, int64_t *, int64_t *, cudaStream_t);
+int flag_group_hist_device(const uint8_t *, uint64_t, uint8_t, uint64_t, uint64_t, uint64_t, int64_t *,
+                           int64_t *, int64_t *, cudaStream_t);
 int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, const gk_filter &,
                         uint8_t *, cudaStream_t);
 int select_flagged(const uint8_t *, uint64_t, uint8_t, int, void *, const void *, void *, const void *,
@@ -565,16 +567,9 @@ int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filt
     const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
     const bool no_amb_same_len =
         f.id == GK_FILTER_NO_AMBIGUOUS && (uint64_t)f.p0 == kmer_len && ix->flags_mark_amb;
-    if (cached && (f.id == GK_FILTER_KEEP_ALL || no_amb_same_len)) {
-        DeviceBuffer offsets;
-        GK_TRY(offsets.alloc((size_t)n * ib, st));
-        uint64_t n_groups = 0;
-        GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n, kFlagHead, ib, offsets.ptr, nullptr, nullptr,
-                              nullptr, nullptr, &n_groups, st));
-        return group_hist_masked_device(offsets.ptr, ib, n_groups, n, (const uint8_t *)ix->d_flags.ptr,
-                                        no_amb_same_len ? kFlagAmb : 0, min_group, max_group, max_bin,
-                                        h_hist_out, h_total_out, st);
-    }
+    if (cached && (f.id == GK_FILTER_KEEP_ALL || no_amb_same_len))
+        return flag_group_hist_device((const uint8_t *)ix->d_flags.ptr, n, no_amb_same_len ? kFlagAmb : 0,
+                                      min_group, max_group, max_bin, h_hist_out, h_total_out, nullptr, st);
 
     // general path: the reference's walk, data-parallel.  Drop k-mers that fail the filter
     // (order preserved), then compare neighbours with the '$'-terminated comparator.

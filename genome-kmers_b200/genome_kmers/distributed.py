@@ -394,6 +394,8 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
     per_step = []
     for _ in range(args.steps):
         hist, stats, sent = step(d_fwd)
+        if rank == 0:
+            clocks.sample()
         per_step.append((stats, sent))
     ev1.record(stream)
     torch.cuda.synchronize()
