@@ -278,9 +278,9 @@ def run_single_gpu(args):
     d_both = torch.empty(both_len, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
     sp = int(stream.cuda_stream)
-    hist = np.zeros(MAX_BIN + 1, dtype=np.int64)
     stats = _native.GkSortStats()
     per_step_stats = []
+    last_hist = [None]
 
     def device_step():
         """inputs (forward byte array) resident in HBM; outputs stay on the device except the histogram"""
@@ -290,10 +290,12 @@ def run_single_gpu(args):
                                           len(both_starts), K, K, ctypes.byref(handle)))
         try:
             _native.check(lib.gk_index_sort(handle, ctypes.byref(stats), sp))
-            total = ctypes.c_int64(0)
-            _native.check(lib.gk_index_group_counts(handle, K, None, 1, 0, MAX_BIN, _native.host_ptr(hist),
-                                                    ctypes.byref(total), sp))
+            hist = np.zeros(MAX_BIN + 1, dtype=np.int64)   # fresh zero pages, as Kmers.get_kmer_group_counts does
+            total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
+            _native.check(lib.gk_index_group_counts_zeroed(handle, K, None, 1, 0, MAX_BIN, _native.host_ptr(hist),
+                                                           ctypes.byref(total), ctypes.byref(top), sp))
             assert total.value == n, (total.value, n)
+            last_hist[0] = hist
         finally:
             lib.gk_index_destroy(handle)
         return stats.as_dict()
@@ -320,6 +322,7 @@ def run_single_gpu(args):
     clock_info = clocks.stop()
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3) / 1e9
+    hist = last_hist[0]
     n_distinct = int(hist.sum())
 
     # ---- roofline of the dominant kernel: one onesweep pass moves 2*W*N bytes ----

@@ -11,6 +11,13 @@ namespace gk {
 
 constexpr uint8_t kSep = 36;  // '$', sequence_collection.py:689-691
 
+// per-slot flag bits of a sorted order (one byte per k-mer)
+constexpr uint8_t kFlagHead = 1;   // first k-mer of a group of equal k-mers
+constexpr uint8_t kFlagAmb = 2;    // slot holds a non-ACGT window (key class bit 0)
+constexpr uint8_t kFlagPass = 4;   // element passes a filter / validity test (scratch arrays)
+constexpr uint8_t kFlagMulti = 8;  // member of a group with more than one element (scratch arrays)
+constexpr uint8_t kFlagLong = 16;  // member of a prefix run too long for the in-place tie repair
+
 // ---- error plumbing ------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

@@ -17,8 +17,6 @@
 
 namespace gk {
 
-constexpr uint8_t kFlagHead = 1;  // first k-mer of a group
-constexpr uint8_t kFlagAmb = 2;   // slot holds a non-ACGT window (key class bit 0)
 
 // ---- head flags from sorted keys ---------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -56,6 +54,153 @@ key_flags_kernel(const uint64_t *__restrict__ keys, uint64_t n, int class_bit,
                 const bool head = (p == 0) || (k != prev);
                 flags[p] = amb ? kFlagAmb : (head ? kFlagHead : 0);
                 prev = k;
+            }
+        }
+    }
+}
+
+// ---- head flags + tie repair after a PREFIX sort ------------------------------------------------------
+// gk_index.cu sorts only the top bits of the keys (enough that almost every k-mer is alone in its
+// prefix bucket) and leaves the rest to this pass, which reads the keys once -- the read the flags
+// pass needs anyway.  For every run of equal prefixes:
+//   * one element: nothing to do;
+//   * up to kTieMaxRun elements: the thread of the run's first element loads the run, ranks it
+//     stably by the full key in registers and writes keys, values and flags back in place.  Other
+//     threads only ever compare PREFIXES of these slots, and the prefix of a slot never changes;
+//   * longer runs (giant groups: N runs, exact repeats, low complexity) are left untouched and
+//     marked kFlagLong.  Their members write their own flags and report a descent (key smaller than
+//     its predecessor) through *descent; only then does the host sort those runs with full LSD
+//     passes.  A long run without a descent is already in final order.
+constexpr int kTieMaxRun = 8;
+constexpr int kTieThreads = 256;
+constexpr int kTiePerThread = 8;
+constexpr int kTieTile = kTieThreads * kTiePerThread;  // slots per CTA
+constexpr int kTieHalo = kTieMaxRun;                   // keys staged either side of the tile
+
+// A CTA stages its tile of keys (plus a halo) in shared memory, so that every neighbour look-up is a
+// shared-memory read.  Pass 1 classifies every slot (alone / member of a short run / member of a long
+// run), writes the flags nobody else will write and queues the first slot of every short run; pass 2
+// hands the queued runs to consecutive threads, so the ranking code runs on full warps instead of on
+// the one or two lanes per warp that happen to hold a run head.
+template <typename ValT>
+__global__ void __launch_bounds__(kTieThreads)
+tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
+                     int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent)
+{
+    __shared__ uint64_t s_key[kTieTile + 2 * kTieHalo];
+    __shared__ uint16_t s_queue[kTieTile / 2];
+    __shared__ uint32_t s_count;
+    const uint32_t t = threadIdx.x;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kTieTile;
+    if (t == 0) s_count = 0;
+    // slot p lives at s_key[p - tile0 + kTieHalo]; slots outside [0, n) are never looked at
+#pragma unroll
+    for (int j = 0; j < kTiePerThread; ++j) {
+        const uint64_t p = tile0 + (uint64_t)j * kTieThreads + t;
+        if (p < n) s_key[kTieHalo + j * kTieThreads + t] = keys[p];
+    }
+    if (t < 2 * kTieHalo) {
+        const bool before = t < kTieHalo;
+        const uint64_t p = before ? tile0 - kTieHalo + t : tile0 + kTieTile + (t - kTieHalo);
+        const bool ok = before ? (tile0 >= (uint64_t)kTieHalo - t) : (p < n);
+        if (ok) s_key[before ? t : kTieHalo + kTieTile + (t - kTieHalo)] = keys[p];
+    }
+    __syncthreads();
+
+    auto pre_at = [&](int64_t i) -> uint64_t { return s_key[i + kTieHalo] >> lo_bits; };  // i = p - tile0
+    auto valid = [&](int64_t i) -> bool { return (int64_t)tile0 + i >= 0 && tile0 + (uint64_t)i < n; };
+
+#pragma unroll
+    for (int j = 0; j < kTiePerThread; ++j) {
+        const int64_t i = (int64_t)j * kTieThreads + t;
+        const uint64_t p = tile0 + (uint64_t)i;
+        if (p >= n) continue;
+        const uint64_t k = s_key[i + kTieHalo];
+        const uint64_t pre = k >> lo_bits;
+        const bool ph = !valid(i - 1) || pre_at(i - 1) != pre;
+        const bool nh = !valid(i + 1) || pre_at(i + 1) != pre;
+        const bool amb = class_bit && !(k & 1ull);
+        if (ph && nh) {
+            flags[p] = amb ? kFlagAmb : kFlagHead;
+            continue;
+        }
+        // bounded search for the run's first and last slot (all inside the staged window)
+        int64_t h = i, e = i;
+        bool is_long = false;
+        if (!ph) {
+            int back = 1;
+            for (; back < kTieMaxRun; ++back) {
+                const int64_t q = i - back;
+                if (!valid(q - 1) || pre_at(q - 1) != pre) break;
+            }
+            if (back == kTieMaxRun) is_long = true; else h = i - back;
+        }
+        if (!is_long && !nh) {
+            const int64_t limit = h + kTieMaxRun;  // first slot that must NOT belong to the run
+            int64_t q = i + 1;
+            for (;; ++q) {
+                if (!valid(q + 1) || pre_at(q + 1) != pre) break;
+                if (q + 1 >= limit) { is_long = true; break; }
+            }
+            e = q;
+            if (e >= limit) is_long = true;
+        }
+        if (is_long) {
+            const uint64_t kp = ph ? 0 : s_key[i - 1 + kTieHalo];
+            const bool head = ph || kp != k;
+            if (!ph && k < kp) atomicOr(descent, 1u);
+            flags[p] = (amb ? kFlagAmb : (head ? kFlagHead : 0)) | kFlagLong;
+            continue;
+        }
+        if (i == h) s_queue[atomicAdd(&s_count, 1u)] = (uint16_t)i;  // runs that start in this tile
+    }
+    __syncthreads();
+
+    const uint32_t n_runs = s_count;
+    for (uint32_t r = t; r < n_runs; r += kTieThreads) {
+        const int64_t h = s_queue[r];
+        const uint64_t pre = pre_at(h);
+        int len = 1;
+        while (len < kTieMaxRun && valid(h + len) && pre_at(h + len) == pre) ++len;
+        uint64_t kk[kTieMaxRun];
+#pragma unroll
+        for (int i = 0; i < kTieMaxRun; ++i) kk[i] = (i < len) ? s_key[h + i + kTieHalo] : ~0ull;
+        bool sorted = true;
+#pragma unroll
+        for (int i = 1; i < kTieMaxRun; ++i) sorted = sorted && (i >= len || kk[i - 1] <= kk[i]);
+        const uint64_t g = tile0 + (uint64_t)h;
+        if (sorted) {  // about half of the two-element runs: only the flags are missing
+#pragma unroll
+            for (int i = 0; i < kTieMaxRun; ++i) {
+                if (i < len) {
+                    const bool a = class_bit && !(kk[i] & 1ull);
+                    const bool first = (i == 0) || kk[i - 1] != kk[i];
+                    flags[g + i] = a ? kFlagAmb : (first ? kFlagHead : 0);
+                }
+            }
+            continue;
+        }
+        ValT vv[kTieMaxRun];
+#pragma unroll
+        for (int i = 0; i < kTieMaxRun; ++i) vv[i] = (i < len) ? vals[g + i] : (ValT)0;
+#pragma unroll
+        for (int i = 0; i < kTieMaxRun; ++i) {
+            int rank = 0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < kTieMaxRun; ++j) {
+                if (j < i) {
+                    rank += (kk[j] <= kk[i]) ? 1 : 0;
+                    first = first && (kk[j] != kk[i]);
+                } else if (j > i) {
+                    rank += (kk[j] < kk[i]) ? 1 : 0;
+                }
+            }
+            if (i < len) {
+                const bool a = class_bit && !(kk[i] & 1ull);
+                flags[g + rank] = a ? kFlagAmb : (first ? kFlagHead : 0);
+                keys[g + rank] = kk[i];  // in place is safe: every source value is in registers
+                vals[g + rank] = vv[i];
             }
         }
     }
@@ -236,6 +381,118 @@ template int select_flagged_device<uint64_t>(const uint8_t *, uint64_t, uint8_t,
                                              uint64_t *, const uint64_t *, uint64_t *, uint64_t *,
                                              cudaStream_t);
 
+// ordered selection of (key, value) pairs at flagged positions, with the positions themselves
+template <typename T>
+__global__ void __launch_bounds__(kSelThreads)
+select_pairs_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
+                          const unsigned long long *__restrict__ tile_offsets, T *__restrict__ pos_out,
+                          const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+                          const T *__restrict__ vals_in, T *__restrict__ vals_out)
+{
+    __shared__ uint32_t s_warp[kSelThreads / 32];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * kSelPerThread;
+    const uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, mask) : 0;
+    const uint32_t c = __popc(bits);
+    uint32_t inc = c;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+    uint64_t out = tile_offsets[blockIdx.x] + pre + inc - c;
+    uint32_t b = bits;
+    while (b) {
+        const uint32_t i = __ffs(b) - 1;
+        b &= b - 1;
+        pos_out[out] = (T)(p0 + i);
+        keys_out[out] = keys_in[p0 + i];
+        vals_out[out] = vals_in[p0 + i];
+        ++out;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+scatter_pairs_kernel(const uint64_t *__restrict__ keys_src, const T *__restrict__ vals_src,
+                     const T *__restrict__ pos, uint64_t m, uint64_t *__restrict__ keys_dst,
+                     T *__restrict__ vals_dst)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const uint64_t d = (uint64_t)pos[r];
+        keys_dst[d] = keys_src[r];
+        vals_dst[d] = vals_src[r];
+    }
+}
+
+// Two-step ordered selection of (key, value) pairs: select_pairs_count leaves the tile offsets in
+// `temp` and returns the number of flagged positions (synchronises), so that the caller can size the
+// outputs; select_pairs_write then fills them.
+int select_pairs_count(const uint8_t *d_flags, uint64_t n, uint8_t mask, DeviceBuffer &temp, uint64_t *h_count,
+                       cudaStream_t st)
+{
+    *h_count = 0;
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kSelTile - 1) / kSelTile;
+    const size_t counts_bytes = ((size_t)tiles * 4 + 15) & ~(size_t)15;
+    GK_TRY(temp.alloc(counts_bytes + (size_t)(tiles + 1) * 8, st));
+    uint32_t *d_counts = temp.as<uint32_t>();
+    unsigned long long *d_offsets =
+        reinterpret_cast<unsigned long long *>(temp.as<unsigned char>() + counts_bytes);
+    select_count_kernel<<<(unsigned)tiles, kSelThreads, 0, st>>>(d_flags, n, mask, d_counts);
+    GK_LAUNCH_CHECK();
+    select_scan_kernel<<<1, 1024, 0, st>>>(d_counts, tiles, d_offsets);
+    GK_LAUNCH_CHECK();
+    GK_CUDA(cudaMemcpyAsync(h_count, d_offsets + tiles, 8, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    return GK_OK;
+}
+
+int select_pairs_write(const uint8_t *d_flags, uint64_t n, uint8_t mask, const DeviceBuffer &temp, int val_bytes,
+                       void *d_pos_out, const uint64_t *d_keys_in, uint64_t *d_keys_out, const void *d_vals_in,
+                       void *d_vals_out, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kSelTile - 1) / kSelTile;
+    const size_t counts_bytes = ((size_t)tiles * 4 + 15) & ~(size_t)15;
+    const unsigned long long *d_offsets =
+        reinterpret_cast<const unsigned long long *>(temp.as<unsigned char>() + counts_bytes);
+    if (val_bytes == 4)
+        select_pairs_write_kernel<uint32_t><<<(unsigned)tiles, kSelThreads, 0, st>>>(
+            d_flags, n, mask, d_offsets, (uint32_t *)d_pos_out, d_keys_in, d_keys_out,
+            (const uint32_t *)d_vals_in, (uint32_t *)d_vals_out);
+    else
+        select_pairs_write_kernel<uint64_t><<<(unsigned)tiles, kSelThreads, 0, st>>>(
+            d_flags, n, mask, d_offsets, (uint64_t *)d_pos_out, d_keys_in, d_keys_out,
+            (const uint64_t *)d_vals_in, (uint64_t *)d_vals_out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int scatter_pairs_device(const uint64_t *d_keys_src, const void *d_vals_src, const void *d_pos, uint64_t m,
+                         int val_bytes, uint64_t *d_keys_dst, void *d_vals_dst, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    uint64_t blocks = (m + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (val_bytes == 4)
+        scatter_pairs_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_keys_src, (const uint32_t *)d_vals_src, (const uint32_t *)d_pos, m, d_keys_dst,
+            (uint32_t *)d_vals_dst);
+    else
+        scatter_pairs_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_keys_src, (const uint64_t *)d_vals_src, (const uint64_t *)d_pos, m, d_keys_dst,
+            (uint64_t *)d_vals_dst);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
 // type-erased front end (elem_bytes 4 or 8)
 int select_flagged(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_bytes, void *d_pos_out,
                    const void *d_pay_in, void *d_pay_out, const void *d_pay2_in, void *d_pay2_out,
@@ -331,6 +588,23 @@ int key_flags_device(const uint64_t *d_keys, uint64_t n, int class_bit, uint8_t 
     return GK_OK;
 }
 
+// head/ambiguous flags of keys sorted on bits [lo_bits, 64) only, repairing short prefix runs in place;
+// *d_descent (zeroed by the caller) becomes 1 when a kFlagLong run is out of order
+int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t n, int lo_bits,
+                         int class_bit, uint8_t *d_flags, unsigned int *d_descent, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kTieTile - 1) / kTieTile;
+    if (val_bytes == 4)
+        tie_fix_flags_kernel<uint32_t><<<(unsigned)tiles, kTieThreads, 0, st>>>(
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+    else
+        tie_fix_flags_kernel<uint64_t><<<(unsigned)tiles, kTieThreads, 0, st>>>(
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
 int sba_flags_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
                      uint64_t n, uint32_t kmer_len, const void *d_dst, uint8_t extra,
                      uint8_t *d_flags, cudaStream_t st)
@@ -364,7 +638,13 @@ int scatter_device(const void *d_src, const void *d_pos, uint64_t n, int idx_byt
     return GK_OK;
 }
 
-// hist (host, max_bin+1 int64, may be NULL) and totals[0] = sum of sizes, totals[1] = groups counted.
+// largest histogram bin the last group_hist call on this thread wrote (the host table is only written
+// up to it: callers hand in a zeroed table)
+static thread_local uint64_t g_last_top_bin = 0;
+uint64_t last_hist_top_bin() { return g_last_top_bin; }
+void set_last_hist_top_bin(uint64_t v) { g_last_top_bin = v; }
+
+// hist (host, max_bin+1 int64, ALREADY ZERO, may be NULL) and totals[0] = sum of sizes, totals[1] = groups counted.
 // Groups whose first slot has (flags & skip_mask) != 0 are left out (skip_mask 0: none).
 static int group_hist_impl(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
                            const uint8_t *d_flags, uint8_t skip_mask, uint64_t min_group,
@@ -405,8 +685,8 @@ static int group_hist_impl(const void *d_offsets, int pos_bytes, uint64_t n_grou
     unsigned long long totals[3] = {0, 0, 0};
     GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
-    if (h_hist) {
-        memset(h_hist, 0, hist_bytes);
+    g_last_top_bin = totals[2];
+    if (h_hist) {  // the caller's table is already zero: only the occupied head crosses PCIe
         GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));
     }
@@ -511,6 +791,7 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
     if (threadIdx.x < 3) s_total[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long total = 0, counted = 0, top_bin = 0;
+    uint32_t ones = 0, twos = 0;  // groups of size 1 and 2 (a random genome has little else): no atomics
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
     auto close_group = [&](uint64_t head, uint64_t size) {
@@ -520,7 +801,9 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
             ++counted;
             const uint64_t bin = size < max_bin ? size : max_bin;
             if (bin > top_bin) top_bin = bin;
-            if (bin < kHistSmallBins) atomicAdd(&s_small[bin], 1u);
+            if (bin == 1) ++ones;
+            else if (bin == 2) ++twos;
+            else if (bin < kHistSmallBins) atomicAdd(&s_small[bin], 1u);
             else atomicAdd(&hist[bin], 1ull);
         }
     };
@@ -556,12 +839,16 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
 
     total = warp_sum(total);
     counted = warp_sum(counted);
+    ones = warp_sum(ones);
+    twos = warp_sum(twos);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, top_bin, o);
         top_bin = other > top_bin ? other : top_bin;
     }
     if (lane == 0) {
+        if (ones) atomicAdd(&s_small[1], ones);
+        if (twos) atomicAdd(&s_small[2], twos);
         atomicAdd(&s_total[0], total);
         atomicAdd(&s_total[1], counted);
         atomicMax(&s_total[2], top_bin);
@@ -593,7 +880,7 @@ int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask
         return GK_ERR_ARG;
     }
     const size_t hist_bytes = (size_t)(max_bin + 1) * 8;
-    if (h_hist) memset(h_hist, 0, hist_bytes);
+    g_last_top_bin = 0;
     if (h_total) *h_total = 0;
     if (h_counted) *h_counted = 0;
     if (n == 0) return GK_OK;
@@ -619,8 +906,10 @@ int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask
     unsigned long long totals[3] = {0, 0, 0};
     GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    g_last_top_bin = totals[2];
     if (h_hist) {
-        // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB)
+        // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB);
+        // the caller's table is already zero
         GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));
     }
@@ -760,6 +1049,7 @@ int gk_group_size_hist(const uint64_t *d_offsets, uint64_t n_groups, uint64_t n,
                        uint64_t max_group, uint64_t max_bin, int64_t *h_hist_out,
                        int64_t *h_total_out, void *stream)
 {
+    if (h_hist_out) memset(h_hist_out, 0, (size_t)(max_bin + 1) * 8);
     return group_hist_device(d_offsets, 8, n_groups, n, min_group, max_group, max_bin, h_hist_out,
                              h_total_out, nullptr, as_stream(stream));
 }

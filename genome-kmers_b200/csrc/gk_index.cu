@@ -3,6 +3,8 @@
 //   gk_index_sort          <- Kmers.sort()                    kmers.py:1624-1652
 //   gk_index_group_counts  <- get_kmer_group_size_hist()       kmers.py:454-520 (:1072, :1166)
 // Host-side orchestration only; the kernels live in gk_pack.cu / gk_sort.cu / gk_group.cu.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "gk_common.cuh"
@@ -16,10 +18,26 @@ int pack_keys_device(const uint8_t *, uint64_t, const uint64_t *, uint32_t, uint
                      uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *,
                      cudaStream_t);
 int pack4_gather_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, uint32_t,
-                        uint64_t *, cudaStream_t);
+                        const uint64_t *, uint64_t *, cudaStream_t);
+int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
+                            cudaStream_t);
+int gather2_u64_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, cudaStream_t);
+int iota_device(void *, uint64_t, int, cudaStream_t);
+int block_offsets_device(const void *, uint64_t, uint64_t, const void *, int, unsigned long long *, cudaStream_t);
+int subset_expand_device(const void *, const void *, const uint64_t *, const uint64_t *, const uint64_t *,
+                         const void *, const void *, const unsigned long long *, uint64_t, uint64_t, int, int,
+                         void *, uint8_t *, cudaStream_t);
 int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, int *,
                             cudaStream_t, SortTiming *);
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
+int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *, cudaStream_t);
+int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
+int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &, int, void *, const uint64_t *,
+                       uint64_t *, const void *, void *, cudaStream_t);
+int pack4_words_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const uint64_t *,
+                       uint64_t *, uint64_t *, cudaStream_t);
+int scatter_pairs_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, void *,
+                         cudaStream_t);
 int sba_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const void *,
                      uint8_t, uint8_t *, cudaStream_t);
 int scatter_device(const void *, const void *, uint64_t, int, void *, cudaStream_t);
@@ -27,6 +45,8 @@ int group_hist_device(const void *, int, uint64_t, uint64_t, uint64_t, uint64_t,
                       int64_t *, int64_t *, cudaStream_t);
 int group_hist_masked_device(const void *, int, uint64_t, uint64_t, const uint8_t *, uint8_t, uint64_t,
                              uint64_t, uint64_t, int64_t *, int64_t *, cudaStream_t);
+uint64_t last_hist_top_bin();
+void set_last_hist_top_bin(uint64_t);
 int flag_group_hist_device(const uint8_t *, uint64_t, uint8_t, uint64_t, uint64_t, uint64_t, int64_t *,
                            int64_t *, int64_t *, cudaStream_t);
 int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, const gk_filter &,
@@ -42,10 +62,6 @@ int pair_keys_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_
 int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint8_t *,
                         cudaStream_t);
 
-constexpr uint8_t kFlagHead = 1;
-constexpr uint8_t kFlagAmb = 2;
-constexpr uint8_t kFlagPass = 4;
-constexpr uint8_t kFlagMulti = 8;
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
 // destroying an index per query does not pay a device-wide synchronising cudaFree
@@ -154,44 +170,120 @@ struct StageMarks {
     int levels = 1;
 };
 
-// After the main radix sort: head flags from the sorted keys, then the ambiguous windows (which
-// already sit in the right slots as a set) are ordered among themselves by their full 4-bit keys,
-// 16 symbols per word, least significant word first, stable; their head flags come from the
-// byte comparator.  d_idx holds the sorted starts and is updated in place.
-static int finish_sorted(gk_index *ix, const uint64_t *keys_sorted, void *d_idx, uint8_t *d_flags,
-                         uint64_t n, int class_bit, uint32_t key_len, uint64_t n_amb, cudaStream_t st)
+// First key bit the LSD passes of the main sort cover.  0 = plain LSD over the whole key.  Otherwise only
+// the top 8*ceil((log2(n)+4)/8) bits are sorted -- 16 times more prefix buckets than k-mers, so about one
+// k-mer in twenty shares its bucket -- and tie_fix_flags orders each bucket by the remaining low bits while
+// it computes the head flags.  GK_SORT_HYBRID=0 switches this off; GK_SORT_PREFIX_BITS=b
+// forces a prefix width (tests use it to drive tiny inputs through the tie-repair and long-run paths).
+static int prefix_begin_bit(uint64_t n, int key_bits)
+{
+    const char *off = getenv("GK_SORT_HYBRID");
+    if (off && off[0] == '0') return 0;
+    const int total_passes = (key_bits + 7) / 8;
+    int prefix_passes;
+    const char *force = getenv("GK_SORT_PREFIX_BITS");
+    if (force && *force) {
+        prefix_passes = (atoi(force) + 7) / 8;
+        if (prefix_passes < 1) prefix_passes = 1;
+    } else {
+        if (n < (1ull << 16)) return 0;
+        int need = 4;
+        while ((1ull << (need - 4)) < n && need < 68) ++need;  // 2^need >= 16 n
+        prefix_passes = (need + 7) / 8;
+    }
+    if (prefix_passes >= total_passes) return 0;
+    return key_bits - 8 * prefix_passes;
+}
+
+// Stable sort of the (key, start) pairs by key bits [0, key_bits), up to the slots that refine_subset
+// repairs afterwards, and head/ambiguous flags of that order.  The pair buffers ping-pong; *in_alt tells
+// where the result is.  *d_descent (device word, zeroed here) becomes non-zero when a long prefix run is
+// out of order; the caller reads it back together with whatever else it needs (no synchronise here).
+static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, void *idx_b, int ib,
+                               uint64_t n, int key_bits, int class_bit, uint8_t *d_flags, int *in_alt,
+                               unsigned int *d_descent, SortTiming *timing, cudaStream_t st)
+{
+    const int begin = prefix_begin_bit(n, key_bits);
+    GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
+    GK_TRY(radix_sort_pairs_device(keys_a, keys_b, idx_a, idx_b, ib, n, begin, key_bits, in_alt, st, timing));
+    uint64_t *ks = *in_alt ? keys_b : keys_a;
+    void *is = *in_alt ? idx_b : idx_a;
+    if (begin == 0) return key_flags_device(ks, n, class_bit, d_flags, st);
+    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, st);
+}
+
+// After the main sort and its flags pass, two kinds of slots may still hold the wrong element:
+//   * ambiguous windows: in the right slots as a set, ordered by `value` only -> order them by their
+//     terminator-aware 4-bit rank words (16 symbols per word);
+//   * members of long prefix runs (kFlagLong), when the flags pass saw one of them out of order.
+// Both sets are mostly huge blocks of identical elements (N runs, exact repeats), so they are sorted in
+// run-length compressed form (gk_refine.cu): cost follows the number of blocks, not of elements.
+// d_idx holds the sorted starts and is updated in place, and so are the flags of the repaired slots.
+static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx, uint8_t *d_flags, uint64_t n,
+                         int class_bit, uint32_t key_len, int key_bits, uint64_t n_amb, bool descent,
+                         cudaStream_t st)
 {
     const int ib = ix->idx_bytes;
-    GK_TRY(key_flags_device(keys_sorted, n, class_bit, d_flags, st));
-    if (n_amb == 0) return GK_OK;
-    DeviceBuffer slot_pos, amb_a, amb_b, akeys_a, akeys_b;
-    GK_TRY(slot_pos.alloc((size_t)n_amb * ib, st));
-    GK_TRY(amb_a.alloc((size_t)n_amb * ib, st));
-    GK_TRY(amb_b.alloc((size_t)n_amb * ib, st));
-    GK_TRY(akeys_a.alloc((size_t)n_amb * 8, st));
-    GK_TRY(akeys_b.alloc((size_t)n_amb * 8, st));
-    uint64_t found = 0;
-    GK_TRY(select_flagged(d_flags, n, kFlagAmb, ib, slot_pos.ptr, d_idx, amb_a.ptr, nullptr, nullptr,
-                          &found, st));
-    if (found != n_amb) {
-        set_error("ambiguous window count mismatch: packed %llu, selected %llu",
-                  (unsigned long long)n_amb, (unsigned long long)found);
+    const uint8_t mask = (uint8_t)((n_amb ? kFlagAmb : 0) | (descent ? kFlagLong : 0));
+    if (!mask || n == 0) return GK_OK;
+    uint64_t m = 0;
+    DeviceBuffer sel_temp;
+    GK_TRY(select_pairs_count(d_flags, n, mask, sel_temp, &m, st));
+    if (m < n_amb) {
+        set_error("ambiguous window count mismatch: packed %llu, selected %llu", (unsigned long long)n_amb,
+                  (unsigned long long)m);
         return GK_ERR_INTERNAL;
     }
-    void *cur = amb_a.ptr, *alt = amb_b.ptr;
-    const int words = ((int)key_len + 15) / 16;
-    for (int w = words - 1; w >= 0; --w) {
-        const int syms = ((int)key_len - 16 * w < 16) ? (int)key_len - 16 * w : 16;
-        GK_TRY(pack4_gather_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, (uint32_t)w, key_len,
-                                   akeys_a.as<uint64_t>(), st));
-        int alt_has = 0;
-        GK_TRY(radix_sort_pairs_device(akeys_a.as<uint64_t>(), akeys_b.as<uint64_t>(), cur, alt, ib, n_amb,
-                                       64 - 4 * syms, 64, &alt_has, st, nullptr));
-        if (alt_has) { void *t = cur; cur = alt; alt = t; }
+    if (m == 0) return GK_OK;
+    DeviceBuffer pos, key, idx, w0, w1, rh, rep_start;
+    GK_TRY(pos.alloc((size_t)m * ib, st));
+    GK_TRY(key.alloc((size_t)m * 8, st));
+    GK_TRY(idx.alloc((size_t)m * ib, st));
+    GK_TRY(select_pairs_write(d_flags, n, mask, sel_temp, ib, pos.ptr, keys_sorted, key.as<uint64_t>(), d_idx,
+                              idx.ptr, st));
+    const int words = n_amb ? ((int)key_len + 15) / 16 : 0;
+    const uint64_t *w0p = nullptr, *w1p = nullptr;
+    if (words >= 1) {
+        GK_TRY(w0.alloc((size_t)m * 8, st));
+        if (words >= 2) GK_TRY(w1.alloc((size_t)m * 8, st));
+        GK_TRY(pack4_words_device(ix->d_sba, ix->sba_len, idx.ptr, ib, m, key_len, key.as<uint64_t>(),
+                                  w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
+        w0p = w0.as<uint64_t>();
+        if (words >= 2) w1p = w1.as<uint64_t>();
     }
-    GK_TRY(scatter_device(cur, slot_pos.ptr, n_amb, ib, d_idx, st));
-    GK_TRY(sba_flags_device(ix->d_sba, ix->sba_len, cur, ib, n_amb, key_len, slot_pos.ptr, kFlagAmb,
-                            d_flags, st));
+    GK_TRY(rh.alloc((size_t)((m + 15) & ~15ull), st));
+    GK_TRY(subset_rep_flags_device(key.as<uint64_t>(), w0p, w1p, m, rh.as<uint8_t>(), st));
+    GK_TRY(rep_start.alloc((size_t)m * ib, st));
+    uint64_t R = 0;
+    GK_TRY(select_flagged(rh.as<uint8_t>(), m, kFlagHead, ib, rep_start.ptr, nullptr, nullptr, nullptr, nullptr,
+                          &R, st));
+
+    // stable LSD over the words of the block representatives, least significant word first
+    DeviceBuffer perm_a, perm_b, rk_a, rk_b, out_off;
+    GK_TRY(perm_a.alloc((size_t)R * ib, st));
+    GK_TRY(perm_b.alloc((size_t)R * ib, st));
+    GK_TRY(rk_a.alloc((size_t)(R + 1) * 8, st));
+    GK_TRY(rk_b.alloc((size_t)(R + 1) * 8, st));
+    GK_TRY(iota_device(perm_a.ptr, R, ib, st));
+    void *cur = perm_a.ptr, *alt = perm_b.ptr;
+    auto sort_word = [&](const uint64_t *word, int begin_bit, int end_bit) -> int {
+        GK_TRY(gather2_u64_device(word, rep_start.ptr, cur, R, ib, rk_a.as<uint64_t>(), st));
+        int alt_has = 0;
+        GK_TRY(radix_sort_pairs_device(rk_a.as<uint64_t>(), rk_b.as<uint64_t>(), cur, alt, ib, R, begin_bit,
+                                       end_bit, &alt_has, st, nullptr));
+        if (alt_has) { void *t = cur; cur = alt; alt = t; }
+        return GK_OK;
+    };
+    if (R > 1) {
+        if (words >= 2) GK_TRY(sort_word(w1p, 64 - 4 * ((int)key_len - 16), 64));
+        if (words >= 1) GK_TRY(sort_word(w0p, 64 - 4 * ((int)key_len < 16 ? (int)key_len : 16), 64));
+        GK_TRY(sort_word(key.as<uint64_t>(), 0, key_bits));
+    }
+    GK_TRY(out_off.alloc((size_t)R * 8, st));
+    GK_TRY(block_offsets_device(rep_start.ptr, R, m, cur, ib, out_off.as<unsigned long long>(), st));
+    GK_TRY(subset_expand_device(pos.ptr, idx.ptr, key.as<uint64_t>(), w0p, w1p, rep_start.ptr, cur,
+                                out_off.as<unsigned long long>(), R, m, class_bit, ib, d_idx, d_flags, st));
+    GK_CUDA(cudaStreamSynchronize(st));  // the scratch above is released in stream order after this
     return GK_OK;
 }
 
@@ -213,8 +305,8 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
     GK_TRY(idx_b.alloc((size_t)n * ib, st));
     GK_TRY(out_idx.alloc((size_t)n * ib, st));
-    GK_TRY(n_amb_dev.alloc(8, st));
-    GK_CUDA(cudaMemsetAsync(n_amb_dev.ptr, 0, 8, st));
+    GK_TRY(n_amb_dev.alloc(16, st));
+    GK_CUDA(cudaMemsetAsync(n_amb_dev.ptr, 0, 16, st));
 
     marks.pack0 = tm.mark();
     GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
@@ -222,21 +314,24 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
                             keys_a.as<uint64_t>(), ib, out_idx.ptr, n_amb_dev.as<unsigned long long>(), st));
     marks.pack1 = tm.mark();
     int in_alt = 0;
-    GK_TRY(radix_sort_pairs_device(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib,
-                                   n, 0, key_bits, &in_alt, st, &marks.main_sort));
+    GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
+    unsigned long long *d_counters = n_amb_dev.as<unsigned long long>();  // [0] ambiguous windows, [1] descent
+    GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
+                               key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt,
+                               reinterpret_cast<unsigned int *>(d_counters + 1), &marks.main_sort, st));
     const uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
     if (in_alt) out_idx.swap(idx_b);
     idx_b.reset();
 
-    uint64_t n_amb = 0;
-    GK_CUDA(cudaMemcpyAsync(&n_amb, n_amb_dev.ptr, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_counters[2] = {0, 0};
+    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_amb = h_counters[0];
     marks.n_amb = n_amb;
 
     marks.fix0 = tm.mark();
-    GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
-    GK_TRY(finish_sorted(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len,
-                         n_amb, st));
+    GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
+                         n_amb, (h_counters[1] & 0xffffffffull) != 0, st));
     marks.fix1 = tm.mark();
     return GK_OK;
 }
@@ -471,26 +566,27 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     const int key_bits = 2 * (int)k + (class_bit ? 2 : 0);
     SortTiming timing = {0.f, 0.f, 0};
     int in_alt = 0;
-    GK_TRY(radix_sort_pairs_device(d_keys, d_keys_alt, d_idx, d_idx_alt, ib, n_local, 0, key_bits, &in_alt, st,
-                                   &timing));
-    const uint64_t *keys_sorted = in_alt ? d_keys_alt : d_keys;
-    const void *idx_sorted = in_alt ? d_idx_alt : d_idx;
     ix->n = n_local;
     GK_TRY(ix->d_idx.alloc((size_t)n_local * ib, st));
     GK_TRY(ix->d_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
+    DeviceBuffer descent;
+    GK_TRY(descent.alloc(4, st));
+    GK_TRY(sort_pairs_and_flag(d_keys, d_keys_alt, d_idx, d_idx_alt, ib, n_local, key_bits, class_bit,
+                               (uint8_t *)ix->d_flags.ptr, &in_alt, descent.as<unsigned int>(), &timing, st));
+    const uint64_t *keys_sorted = in_alt ? d_keys_alt : d_keys;
+    const void *idx_sorted = in_alt ? d_idx_alt : d_idx;
     if (n_local)
         GK_CUDA(cudaMemcpyAsync(ix->d_idx.ptr, idx_sorted, (size_t)n_local * ib, cudaMemcpyDeviceToDevice, st));
     const int f0 = tm.mark();
+    unsigned int h_descent = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_descent, descent.ptr, 4, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
     uint64_t n_amb = 0;
-    if (class_bit && n_local) {
-        // count the slots whose class bit is 0 (the flags pass marks them)
-        GK_TRY(key_flags_device(keys_sorted, n_local, class_bit, (uint8_t *)ix->d_flags.ptr, st));
+    if (class_bit && n_local)  // the slots whose key has class bit 0 (the flags pass marked them)
         GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n_local, kFlagAmb, ib, nullptr, nullptr, nullptr,
                               nullptr, nullptr, &n_amb, st));
-    }
-    if (n_local)
-        GK_TRY(finish_sorted(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
-                             n_amb, st));
+    GK_TRY(refine_subset(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
+                         key_bits, n_amb, h_descent != 0, st));
     const int f1 = tm.mark();
     ix->idx_ready = true;
     ix->flags_mark_amb = true;
@@ -548,16 +644,17 @@ static int flags_for(gk_index *ix, uint32_t kmer_len, const uint8_t **d_flags, D
     return GK_OK;
 }
 
-int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t min_group,
-                          uint64_t max_group, uint64_t max_bin, int64_t *h_hist_out,
-                          int64_t *h_total_out, void *stream)
+// shared body: h_hist_out must already be zero; only bins [0, last_hist_top_bin()] are written
+static int index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t min_group,
+                              uint64_t max_group, uint64_t max_bin, int64_t *h_hist_out, int64_t *h_total_out,
+                              void *stream)
 {
     if (!ix) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
     gk_filter keep_all = {GK_FILTER_KEEP_ALL, 0, 0, 0};
     const gk_filter f = filter ? *filter : keep_all;
-    if (h_hist_out) memset(h_hist_out, 0, (size_t)(max_bin + 1) * 8);
     if (h_total_out) *h_total_out = 0;
+    set_last_hist_top_bin(0);
     if (ix->n == 0) return GK_OK;
     GK_TRY(ensure_indices(ix, st));
     const int ib = ix->idx_bytes;
@@ -591,18 +688,35 @@ int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filt
         if (min_group > 1) return GK_OK;
         if (h_hist_out) h_hist_out[1 < max_bin ? 1 : max_bin] = (int64_t)m;
         if (h_total_out) *h_total_out = (int64_t)m;
+        set_last_hist_top_bin(1 < max_bin ? 1 : max_bin);
         return GK_OK;
     }
-    DeviceBuffer flags, offsets;
+    DeviceBuffer flags;
     GK_TRY(flags.alloc((size_t)((m + 15) & ~15ull), st));
     GK_TRY(sba_flags_device(ix->d_sba, ix->sba_len, d_list, ib, m, kmer_len, nullptr, 0,
                             flags.as<uint8_t>(), st));
-    GK_TRY(offsets.alloc((size_t)m * ib, st));
-    uint64_t n_groups = 0;
-    GK_TRY(select_flagged(flags.as<uint8_t>(), m, kFlagHead, ib, offsets.ptr, nullptr, nullptr, nullptr,
-                          nullptr, &n_groups, st));
-    return group_hist_device(offsets.ptr, ib, n_groups, m, min_group, max_group, max_bin, h_hist_out,
-                             h_total_out, nullptr, st);
+    return flag_group_hist_device(flags.as<uint8_t>(), m, 0, min_group, max_group, max_bin, h_hist_out,
+                                  h_total_out, nullptr, st);
+}
+
+int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t min_group,
+                          uint64_t max_group, uint64_t max_bin, int64_t *h_hist_out, int64_t *h_total_out,
+                          void *stream)
+{
+    if (h_hist_out) memset(h_hist_out, 0, (size_t)(max_bin + 1) * 8);
+    return index_group_counts(ix, kmer_len, filter, min_group, max_group, max_bin, h_hist_out, h_total_out,
+                              stream);
+}
+
+int gk_index_group_counts_zeroed(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t min_group,
+                                 uint64_t max_group, uint64_t max_bin, int64_t *h_hist_zeroed,
+                                 int64_t *h_total_out, uint64_t *h_top_bin_out, void *stream)
+{
+    if (h_top_bin_out) *h_top_bin_out = 0;
+    const int rc = index_group_counts(ix, kmer_len, filter, min_group, max_group, max_bin, h_hist_zeroed,
+                                      h_total_out, stream);
+    if (rc == GK_OK && h_top_bin_out) *h_top_bin_out = last_hist_top_bin();
+    return rc;
 }
 
 int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups, uint64_t *h_offsets_out,

@@ -166,10 +166,14 @@ template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pack4_gather_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                     const IdxT *__restrict__ idx, uint64_t n, uint32_t word, uint32_t max_len,
-                    uint64_t *__restrict__ keys_out)
+                    const uint64_t *__restrict__ class_keys, uint64_t *__restrict__ keys_out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        if (class_keys && (class_keys[r] & 1ull)) {  // pure window: its radix key already says everything
+            keys_out[r] = 0;
+            continue;
+        }
         const uint64_t s = (uint64_t)idx[r];
         const uint32_t lo = 16u * word;
         const uint32_t hi = (lo + 16u < max_len) ? lo + 16u : max_len;
@@ -183,6 +187,54 @@ pack4_gather_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
         }
         keys_out[r] = key;
     }
+}
+
+// Both 4-bit rank words of a window of max_len <= 32 symbols in one read of its bytes.  Pure windows
+// (class bit set in class_keys) get zeros: their radix key already says everything.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pack4_words_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const IdxT *__restrict__ idx, uint64_t n,
+                   uint32_t max_len, const uint64_t *__restrict__ class_keys, uint64_t *__restrict__ w0_out,
+                   uint64_t *__restrict__ w1_out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        uint64_t w0 = 0, w1 = 0;
+        if (!(class_keys && (class_keys[r] & 1ull))) {
+            const uint64_t s = (uint64_t)idx[r];
+            for (uint32_t j = 0; j < max_len; ++j) {
+                const uint64_t p = s + j;
+                const uint64_t code = (p < sba_len) ? rank4(sba[p]) : 0u;
+                if (code == 0) break;  // '$' / end of array: the k-mer ends here and sorts first
+                if (j < 16) w0 |= code << (4u * (15u - j));
+                else w1 |= code << (4u * (31u - j));
+            }
+        }
+        w0_out[r] = w0;
+        if (w1_out) w1_out[r] = w1;
+    }
+}
+
+int pack4_words_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes, uint64_t n,
+                       uint32_t max_len, const uint64_t *d_class_keys, uint64_t *d_w0, uint64_t *d_w1,
+                       cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    if (max_len > 32) {
+        set_error("pack4_words: at most 32 symbols");
+        return GK_ERR_ARG;
+    }
+    uint64_t blocks = (n + 255) / 256;
+    uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (idx_bytes == 4)
+        pack4_words_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_sba, sba_len, (const uint32_t *)d_idx, n, max_len, d_class_keys, d_w0, d_w1);
+    else
+        pack4_words_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
+            d_sba, sba_len, (const uint64_t *)d_idx, n, max_len, d_class_keys, d_w0, d_w1);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
 }
 
 int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_seg_starts,
@@ -218,8 +270,8 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
 }
 
 int pack4_gather_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
-                        uint64_t n, uint32_t word, uint32_t max_len, uint64_t *d_keys_out,
-                        cudaStream_t st)
+                        uint64_t n, uint32_t word, uint32_t max_len, const uint64_t *d_class_keys,
+                        uint64_t *d_keys_out, cudaStream_t st)
 {
     if (n == 0) return GK_OK;
     uint64_t blocks = (n + 255) / 256;
@@ -227,10 +279,10 @@ int pack4_gather_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_id
     if (blocks > cap) blocks = cap;
     if (idx_bytes == 4)
         pack4_gather_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_sba, sba_len, (const uint32_t *)d_idx, n, word, max_len, d_keys_out);
+            d_sba, sba_len, (const uint32_t *)d_idx, n, word, max_len, d_class_keys, d_keys_out);
     else
         pack4_gather_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_sba, sba_len, (const uint64_t *)d_idx, n, word, max_len, d_keys_out);
+            d_sba, sba_len, (const uint64_t *)d_idx, n, word, max_len, d_class_keys, d_keys_out);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -18,9 +18,6 @@
 
 namespace gk {
 
-constexpr uint8_t kFlagHead = 1;
-constexpr uint8_t kFlagPass = 4;
-constexpr uint8_t kFlagMulti = 8;  // member of a group with more than one element
 
 constexpr int kHpThreads = 256;
 constexpr int kHpPerThread = 16;
@@ -176,6 +173,180 @@ key2_scatter_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__
     }
 }
 
+// ---- run-length compressed stable sort of a selected subset ---------------------------------------------
+// After the main sort, two kinds of slots may still hold the wrong element: members of long prefix runs
+// that are out of order, and ambiguous windows (ordered by `value` only, not yet by their real symbols).
+// Both sets are dominated by huge blocks of identical elements (every window inside an N run, every copy
+// of an exact repeat), so the subset is sorted in compressed form:
+//   subset_rep_flags   r starts a block iff its (key, w0, w1) differs from element r-1 of the subset
+//   (select)           block representatives: first subset position of every block
+//   (LSD sorts)        the representatives only, stable, least significant word first
+//   block offsets      exclusive scan of the block lengths in sorted order
+//   subset_expand      every output position finds its block by binary search and copies the start index
+//                      into the slot; the head flag is set at the first element of a block whose words
+//                      differ from the previous block's
+// Cost is proportional to the number of blocks, not to the number of elements.
+
+__global__ void __launch_bounds__(256)
+subset_rep_flags_kernel(const uint64_t *__restrict__ key, const uint64_t *__restrict__ w0,
+                        const uint64_t *__restrict__ w1, uint64_t m, uint8_t *__restrict__ rh)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        bool head = (r == 0) || key[r] != key[r - 1];
+        if (!head && w0) head = w0[r] != w0[r - 1];
+        if (!head && w1) head = w1[r] != w1[r - 1];
+        rh[r] = head ? kFlagHead : 0;
+    }
+}
+
+// out[q] = src[at[perm ? perm[q] : q]]
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather2_u64_kernel(const uint64_t *__restrict__ src, const T *__restrict__ at, const T *__restrict__ perm,
+                   uint64_t count, uint64_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
+        const uint64_t j = perm ? (uint64_t)perm[q] : q;
+        out[q] = src[(uint64_t)at[j]];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+iota_kernel(T *__restrict__ out, uint64_t count)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) out[q] = (T)q;
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+template <typename T>
+__device__ __forceinline__ unsigned long long block_len(const T *__restrict__ rep_start, uint64_t R, uint64_t m,
+                                                        const T *__restrict__ perm, uint64_t q)
+{
+    const uint64_t j = (uint64_t)perm[q];
+    const uint64_t a = (uint64_t)rep_start[j];
+    const uint64_t b = (j + 1 < R) ? (uint64_t)rep_start[j + 1] : m;
+    return b - a;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads)
+block_len_tile_sums_kernel(const T *__restrict__ rep_start, uint64_t R, uint64_t m, const T *__restrict__ perm,
+                           unsigned long long *__restrict__ tile_sums)
+{
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    unsigned long long sum = 0;
+    for (int i = 0; i < kScanPerThread; ++i)
+        if (q0 + i < R) sum += block_len(rep_start, R, m, perm, q0 + i);
+    sum = warp_sum(sum);
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += s_warp[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// one CTA: exclusive scan of 64-bit tile sums in place
+__global__ void __launch_bounds__(1024)
+scan_u64_kernel(unsigned long long *__restrict__ data, uint64_t count)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < count; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long c = (i < count) ? data[i] : 0;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+        if (i < count) data[i] = pre + inc - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads)
+block_offsets_kernel(const T *__restrict__ rep_start, uint64_t R, uint64_t m, const T *__restrict__ perm,
+                     const unsigned long long *__restrict__ tile_offsets,
+                     unsigned long long *__restrict__ out_off)
+{
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    const uint64_t q0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    unsigned long long len[kScanPerThread];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        len[i] = (q0 + i < R) ? block_len(rep_start, R, m, perm, q0 + i) : 0;
+        sum += len[i];
+    }
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long run = tile_offsets[blockIdx.x] + inc - sum;
+    for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        if (q0 + i < R) out_off[q0 + i] = run;
+        run += len[i];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+subset_expand_kernel(const T *__restrict__ pos, const T *__restrict__ idx_sel, const uint64_t *__restrict__ key,
+                     const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1,
+                     const T *__restrict__ rep_start, const T *__restrict__ perm,
+                     const unsigned long long *__restrict__ out_off, uint64_t R, uint64_t m, int class_bit,
+                     T *__restrict__ d_idx, uint8_t *__restrict__ d_flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += stride) {
+        uint64_t lo = 0, hi = R;  // last block whose offset is <= o
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (o < out_off[mid]) hi = mid; else lo = mid + 1;
+        }
+        const uint64_t q = lo - 1;
+        const uint64_t src0 = (uint64_t)rep_start[(uint64_t)perm[q]];
+        const uint64_t src = src0 + (o - out_off[q]);
+        const uint64_t slot = (uint64_t)pos[o];
+        bool head = (o == 0) || ((uint64_t)pos[o - 1] + 1 != slot);  // the slot before is not in the subset
+        if (!head && o == out_off[q]) {
+            const uint64_t prv = (uint64_t)rep_start[(uint64_t)perm[q - 1]];
+            head = key[src0] != key[prv] || (w0 && w0[src0] != w0[prv]) || (w1 && w1[src0] != w1[prv]);
+        }
+        const bool amb = class_bit && !(key[src] & 1ull);
+        d_idx[slot] = idx_sel[src];
+        d_flags[slot] = (amb ? kFlagAmb : 0) | (head ? kFlagHead : 0);
+    }
+}
+
 static int grid_for(uint64_t items)
 {
     uint64_t blocks = (items + 255) / 256;
@@ -237,6 +408,86 @@ int key2_scatter_device(const uint64_t *d_keys_sorted, const uint32_t *d_sub_idx
     if (m == 0) return GK_OK;
     key2_scatter_kernel<<<grid_for(m), 256, 0, st>>>(d_keys_sorted, d_sub_idx_sorted, d_slots, m, d_idx,
                                                      d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int subset_rep_flags_device(const uint64_t *d_key, const uint64_t *d_w0, const uint64_t *d_w1, uint64_t m,
+                            uint8_t *d_rh, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    subset_rep_flags_kernel<<<grid_for(m), 256, 0, st>>>(d_key, d_w0, d_w1, m, d_rh);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int gather2_u64_device(const uint64_t *d_src, const void *d_at, const void *d_perm, uint64_t count, int t_bytes,
+                       uint64_t *d_out, cudaStream_t st)
+{
+    if (count == 0) return GK_OK;
+    if (t_bytes == 4)
+        gather2_u64_kernel<uint32_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint32_t *)d_at,
+                                                                      (const uint32_t *)d_perm, count, d_out);
+    else
+        gather2_u64_kernel<uint64_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint64_t *)d_at,
+                                                                      (const uint64_t *)d_perm, count, d_out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int iota_device(void *d_out, uint64_t count, int t_bytes, cudaStream_t st)
+{
+    if (count == 0) return GK_OK;
+    if (t_bytes == 4) iota_kernel<uint32_t><<<grid_for(count), 256, 0, st>>>((uint32_t *)d_out, count);
+    else iota_kernel<uint64_t><<<grid_for(count), 256, 0, st>>>((uint64_t *)d_out, count);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// d_out_off[q] = sum of the lengths of the blocks perm[0..q)
+template <typename T>
+static int block_offsets_impl(const T *d_rep_start, uint64_t R, uint64_t m, const T *d_perm,
+                              unsigned long long *d_out_off, cudaStream_t st)
+{
+    const uint64_t tiles = (R + kScanTile - 1) / kScanTile;
+    DeviceBuffer sums;
+    GK_TRY(sums.alloc((size_t)tiles * 8, st));
+    block_len_tile_sums_kernel<T><<<(unsigned)tiles, kScanThreads, 0, st>>>(d_rep_start, R, m, d_perm,
+                                                                            sums.as<unsigned long long>());
+    GK_LAUNCH_CHECK();
+    scan_u64_kernel<<<1, 1024, 0, st>>>(sums.as<unsigned long long>(), tiles);
+    GK_LAUNCH_CHECK();
+    block_offsets_kernel<T><<<(unsigned)tiles, kScanThreads, 0, st>>>(d_rep_start, R, m, d_perm,
+                                                                      sums.as<unsigned long long>(), d_out_off);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int block_offsets_device(const void *d_rep_start, uint64_t R, uint64_t m, const void *d_perm, int t_bytes,
+                         unsigned long long *d_out_off, cudaStream_t st)
+{
+    if (R == 0) return GK_OK;
+    if (t_bytes == 4)
+        return block_offsets_impl<uint32_t>((const uint32_t *)d_rep_start, R, m, (const uint32_t *)d_perm,
+                                            d_out_off, st);
+    return block_offsets_impl<uint64_t>((const uint64_t *)d_rep_start, R, m, (const uint64_t *)d_perm, d_out_off,
+                                        st);
+}
+
+int subset_expand_device(const void *d_pos, const void *d_idx_sel, const uint64_t *d_key, const uint64_t *d_w0,
+                         const uint64_t *d_w1, const void *d_rep_start, const void *d_perm,
+                         const unsigned long long *d_out_off, uint64_t R, uint64_t m, int class_bit, int t_bytes,
+                         void *d_idx, uint8_t *d_flags, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    if (t_bytes == 4)
+        subset_expand_kernel<uint32_t><<<grid_for(m), 256, 0, st>>>(
+            (const uint32_t *)d_pos, (const uint32_t *)d_idx_sel, d_key, d_w0, d_w1, (const uint32_t *)d_rep_start,
+            (const uint32_t *)d_perm, d_out_off, R, m, class_bit, (uint32_t *)d_idx, d_flags);
+    else
+        subset_expand_kernel<uint64_t><<<grid_for(m), 256, 0, st>>>(
+            (const uint64_t *)d_pos, (const uint64_t *)d_idx_sel, d_key, d_w0, d_w1, (const uint64_t *)d_rep_start,
+            (const uint64_t *)d_perm, d_out_off, R, m, class_bit, (uint64_t *)d_idx, d_flags);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

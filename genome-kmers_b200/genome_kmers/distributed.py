@@ -128,11 +128,11 @@ class NativeEngine:
 
     def shard_counts(self, shard, k, filt, min_group, max_group, max_bin):
         hist = np.zeros(max_bin + 1, dtype=np.int64)
-        total = ctypes.c_int64(0)
+        total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
         flt = filt if filt is not None else _native.GkFilter(0, 0, 0, 0)
-        _native.check(self.lib.gk_index_group_counts(shard["handle"], k, ctypes.byref(flt), min_group,
-                                                     max_group or 0, max_bin, _native.host_ptr(hist),
-                                                     ctypes.byref(total), self.stream()))
+        _native.check(self.lib.gk_index_group_counts_zeroed(shard["handle"], k, ctypes.byref(flt), min_group,
+                                                            max_group or 0, max_bin, _native.host_ptr(hist),
+                                                            ctypes.byref(total), ctypes.byref(top), self.stream()))
         return hist, int(total.value)
 
     def shard_indices_host(self, shard):

@@ -405,12 +405,13 @@ class Kmers:
         flt = self._native_filter(kmer_filter_func)
         self._ensure_device()
         self._push_host_indices()
+        # np.zeros hands out untouched zero pages: the library writes the occupied bins only
         hist = np.zeros(max_counts_bin + 1, dtype=np.int64) if want_hist else None
-        total = ctypes.c_int64(0)
-        _native.check(_native.lib().gk_index_group_counts(
+        total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
+        _native.check(_native.lib().gk_index_group_counts_zeroed(
             self._ix, kmer_len or 0, ctypes.byref(flt), min_group_size, max_group_size or 0,
             max_counts_bin, None if hist is None else _native.host_ptr(hist), ctypes.byref(total),
-            self._stream()))
+            ctypes.byref(top), self._stream()))
         return hist, int(total.value)
 
     def get_kmer_count(self, kmer_len: Union[int, None], kmer_filter_func: Callable = kmer_filter_keep_all,

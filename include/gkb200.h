@@ -171,6 +171,13 @@ int gk_index_copy_indices(gk_index *ix, void *h_dst, void *stream);
 int gk_index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *filter,
                           uint64_t min_group, uint64_t max_group, uint64_t max_bin,
                           int64_t *h_hist_out, int64_t *h_total_out, void *stream);
+/* Same query for a caller whose table is ALREADY all zero (fresh calloc / numpy.zeros pages): only bins
+ * [0, *h_top_bin_out] are written, so the reference's default 8 MB table (max_counts_bin = 1000000,
+ * kmers.py:1091) is never touched beyond the occupied bins. */
+int gk_index_group_counts_zeroed(gk_index *ix, uint32_t kmer_len, const gk_filter *filter,
+                                 uint64_t min_group, uint64_t max_group, uint64_t max_bin,
+                                 int64_t *h_hist_zeroed, int64_t *h_total_out, uint64_t *h_top_bin_out,
+                                 void *stream);
 /* Group table of the sorted index for kmer_len: number of groups, and (optionally, host
  * buffers of n_groups entries obtained by a first call with NULLs) offsets into the sorted
  * order and sizes.  This is the unique-k-mer set: one entry per distinct k-mer. */

@@ -57,6 +57,52 @@ def test_golden_init_sort_and_counts(name):
                                  qu["max_group"]) == ans["total"]
 
 
+HYBRID_CASES = [n for n in FIXED if n.split("_k")[0] in
+                ("rand5k", "iupac4k", "lowcomplex", "edgeT", "repeat", "repeatN", "iupac4k_both", "rand120k",
+                 "rand120kN_both", "lowcomplex_both", "repeat_both")]
+
+
+@pytest.mark.parametrize("prefix_bits", [8, 16, 24])
+@pytest.mark.parametrize("name", HYBRID_CASES)
+def test_golden_with_forced_prefix_sort(name, prefix_bits, monkeypatch):
+    """The hybrid sort (LSD passes over the top bits + in-place tie repair + long-run fallback) must give
+    the same order as plain LSD whatever the prefix width; tiny prefixes force the long-run path."""
+    monkeypatch.setenv("GK_SORT_PREFIX_BITS", str(prefix_bits))
+    case = golden_case(name)
+    sc, km = _kmers_for(case)
+    km.sort()
+    got = km.kmer_sba_start_indices
+    bad = np.flatnonzero(got != case["sorted"])
+    assert len(bad) == 0, f"{name}: first mismatches at {bad[:8]}"
+    for qu, ans in zip(case["queries"], case["answers"]):
+        hist, total = km.get_kmer_group_counts(
+            qu["kmer_len"], kmer_filter_func=_filter(qu["filter"]), min_group_size=qu["min_group"],
+            max_group_size=qu["max_group"], max_counts_bin=qu["max_bin"])
+        assert total == ans["total"], (name, qu)
+        assert np.array_equal(hist, dense_hist(ans, qu["max_bin"])), (name, qu)
+
+
+@pytest.mark.parametrize("mode", ["0", "auto", "16", "32"])
+def test_hybrid_and_plain_sort_agree_on_skewed_input(mode, monkeypatch):
+    """Low-complexity + repeats + N runs: long prefix runs, some out of order, some uniform."""
+    if mode == "0":
+        monkeypatch.setenv("GK_SORT_HYBRID", "0")
+    elif mode != "auto":
+        monkeypatch.setenv("GK_SORT_PREFIX_BITS", mode)
+    rng = np.random.default_rng(7)
+    unit = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 700)]
+    parts = []
+    for i in range(60):                       # 60 diverged copies of one 700-mer + poly-A + N runs
+        copy = unit.copy()
+        copy[rng.integers(0, 700, 3)] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 3)]
+        parts += [copy, np.full(int(rng.integers(5, 80)), ord("A"), dtype=np.uint8)]
+        if i % 7 == 0:
+            parts.append(np.full(int(rng.integers(40, 400)), ord("N"), dtype=np.uint8))
+    parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 120_000)])
+    seq = np.concatenate(parts)
+    _oracle_compare([("chr0", seq[:len(seq) // 2]), ("chr1", seq[len(seq) // 2:])], 31, "both")
+
+
 @pytest.mark.parametrize("name", VARIABLE)
 def test_golden_variable_length_modes(name):
     """sort() with min_kmer_len != max_kmer_len."""
