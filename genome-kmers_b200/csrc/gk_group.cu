@@ -78,21 +78,24 @@ constexpr int kTieTile = kTieThreads * kTiePerThread;  // slots per CTA
 constexpr int kTieHalo = kTieMaxRun;                   // keys staged either side of the tile
 
 // A CTA stages its tile of keys (plus a halo) in shared memory, so that every neighbour look-up is a
-// shared-memory read.  Pass 1 classifies every slot (alone / member of a short run / member of a long
-// run), writes the flags nobody else will write and queues the first slot of every short run; pass 2
-// hands the queued runs to consecutive threads, so the ranking code runs on full warps instead of on
-// the one or two lanes per warp that happen to hold a run head.
+// shared-memory read.  Nineteen slots in twenty are alone in their prefix bucket, so the work is split
+// into three dense passes instead of one divergent one (a warp pays for every path one of its lanes takes):
+//   1  every slot: compare prefixes with both neighbours; alone -> write the flag, else queue the slot
+//   2  queued slots: bounded search for the run's ends; long run -> own flag (+ descent report),
+//      first slot of a short run -> queue the run
+//   3  queued runs: rank the run by the full key in registers, write keys, values and flags in place
 template <typename ValT>
 __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent)
 {
     __shared__ uint64_t s_key[kTieTile + 2 * kTieHalo];
-    __shared__ uint16_t s_queue[kTieTile / 2];
-    __shared__ uint32_t s_count;
-    const uint32_t t = threadIdx.x;
+    __shared__ uint16_t s_member[kTieTile];
+    __shared__ uint16_t s_run[kTieTile / 2];
+    __shared__ uint32_t s_n_member, s_n_run;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint64_t tile0 = (uint64_t)blockIdx.x * kTieTile;
-    if (t == 0) s_count = 0;
+    if (t == 0) { s_n_member = 0; s_n_run = 0; }
     // slot p lives at s_key[p - tile0 + kTieHalo]; slots outside [0, n) are never looked at
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
@@ -107,58 +110,77 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     }
     __syncthreads();
 
-    auto pre_at = [&](int64_t i) -> uint64_t { return s_key[i + kTieHalo] >> lo_bits; };  // i = p - tile0
-    auto valid = [&](int64_t i) -> bool { return (int64_t)tile0 + i >= 0 && tile0 + (uint64_t)i < n; };
+    auto pre_at = [&](int i) -> uint64_t { return s_key[i + kTieHalo] >> lo_bits; };  // i = p - tile0
+    auto valid = [&](int i) -> bool { return (i >= 0 || tile0 >= (uint64_t)(-i)) && tile0 + (int64_t)i < n; };
 
+    // ---- 1 ---------------------------------------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
-        const int64_t i = (int64_t)j * kTieThreads + t;
+        const int i = j * kTieThreads + (int)t;
         const uint64_t p = tile0 + (uint64_t)i;
-        if (p >= n) continue;
+        bool tied = false;
+        if (p < n) {
+            const uint64_t k = s_key[i + kTieHalo];
+            const uint64_t pre = k >> lo_bits;
+            const bool ph = (p == 0) || pre_at(i - 1) != pre;
+            const bool nh = (p + 1 == n) || pre_at(i + 1) != pre;
+            tied = !(ph && nh);
+            if (!tied) flags[p] = (class_bit && !(k & 1ull)) ? kFlagAmb : kFlagHead;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, tied);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_n_member, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (tied) s_member[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+
+    // ---- 2 ---------------------------------------------------------------------------------------------
+    const uint32_t n_member = s_n_member;
+    for (uint32_t r = t; r < n_member; r += kTieThreads) {
+        const int i = s_member[r];
+        const uint64_t p = tile0 + (uint64_t)i;
         const uint64_t k = s_key[i + kTieHalo];
         const uint64_t pre = k >> lo_bits;
-        const bool ph = !valid(i - 1) || pre_at(i - 1) != pre;
-        const bool nh = !valid(i + 1) || pre_at(i + 1) != pre;
-        const bool amb = class_bit && !(k & 1ull);
-        if (ph && nh) {
-            flags[p] = amb ? kFlagAmb : kFlagHead;
-            continue;
-        }
-        // bounded search for the run's first and last slot (all inside the staged window)
-        int64_t h = i, e = i;
+        const bool ph = (p == 0) || pre_at(i - 1) != pre;
+        const bool nh = (p + 1 == n) || pre_at(i + 1) != pre;
+        int h = i;
         bool is_long = false;
         if (!ph) {
             int back = 1;
             for (; back < kTieMaxRun; ++back) {
-                const int64_t q = i - back;
+                const int q = i - back;
                 if (!valid(q - 1) || pre_at(q - 1) != pre) break;
             }
             if (back == kTieMaxRun) is_long = true; else h = i - back;
         }
         if (!is_long && !nh) {
-            const int64_t limit = h + kTieMaxRun;  // first slot that must NOT belong to the run
-            int64_t q = i + 1;
+            const int limit = h + kTieMaxRun;  // first slot that must NOT belong to the run
+            int q = i + 1;
             for (;; ++q) {
                 if (!valid(q + 1) || pre_at(q + 1) != pre) break;
                 if (q + 1 >= limit) { is_long = true; break; }
             }
-            e = q;
-            if (e >= limit) is_long = true;
+            if (q >= limit) is_long = true;
         }
         if (is_long) {
             const uint64_t kp = ph ? 0 : s_key[i - 1 + kTieHalo];
             const bool head = ph || kp != k;
+            const bool amb = class_bit && !(k & 1ull);
             if (!ph && k < kp) atomicOr(descent, 1u);
             flags[p] = (amb ? kFlagAmb : (head ? kFlagHead : 0)) | kFlagLong;
-            continue;
+        } else if (ph) {
+            s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)i;  // a short run that starts in this tile
         }
-        if (i == h) s_queue[atomicAdd(&s_count, 1u)] = (uint16_t)i;  // runs that start in this tile
     }
     __syncthreads();
 
-    const uint32_t n_runs = s_count;
+    // ---- 3 ---------------------------------------------------------------------------------------------
+    const uint32_t n_runs = s_n_run;
     for (uint32_t r = t; r < n_runs; r += kTieThreads) {
-        const int64_t h = s_queue[r];
+        const int h = s_run[r];
         const uint64_t pre = pre_at(h);
         int len = 1;
         while (len < kTieMaxRun && valid(h + len) && pre_at(h + len) == pre) ++len;
@@ -719,8 +741,35 @@ int group_hist_masked_device(const void *d_offsets, int pos_bytes, uint64_t n_gr
 // the tiles, then the histogram pass.  Reads the flags twice (2 B per k-mer) and writes nothing per
 // k-mer, instead of materialising 4-8 B per distinct k-mer and reading them back.
 constexpr int kGfThreads = 256;
-constexpr int kGfPerThread = 16;
+constexpr int kGfPerThread = 64;
 constexpr int kGfTile = kGfThreads * kGfPerThread;
+
+// bit i of the result = (flags[p0+i] & (1 << bit)) != 0 for i < 64; positions >= n read as 0
+__device__ __forceinline__ uint64_t load_flag_bits64(const uint8_t *__restrict__ flags, uint64_t n, uint64_t p0,
+                                                     int bit)
+{
+    uint64_t out = 0;
+    if (p0 + 64 <= n) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(flags + p0);
+        uint4 q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // four flag bytes -> four bits: the products land on bits 24..27 without carries
+                const uint32_t nib = ((((w[j] >> bit) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+                out |= (uint64_t)nib << (16 * i + 4 * j);
+            }
+        }
+    } else {
+        for (int i = 0; i < 64; ++i)
+            if (p0 + i < n && ((flags[p0 + i] >> bit) & 1u)) out |= 1ull << i;
+    }
+    return out;
+}
 
 // last head position + 1 inside each tile (0 = none)
 __global__ void __launch_bounds__(kGfThreads)
@@ -729,8 +778,8 @@ flag_tile_last_head_kernel(const uint8_t *__restrict__ flags, uint64_t n,
 {
     __shared__ unsigned long long s_max[kGfThreads / 32];
     const uint64_t p0 = (uint64_t)blockIdx.x * kGfTile + (uint64_t)threadIdx.x * kGfPerThread;
-    const uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, kFlagHead) : 0u;
-    unsigned long long last = bits ? p0 + (31 - __clz(bits)) + 1 : 0ull;
+    const uint64_t bits = (p0 < n) ? load_flag_bits64(flags, n, p0, 0) : 0ull;
+    unsigned long long last = bits ? p0 + (63 - __clzll((long long)bits)) + 1 : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long v = __shfl_xor_sync(0xffffffffu, last, o);
@@ -793,6 +842,7 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
     unsigned long long total = 0, counted = 0, top_bin = 0;
     uint32_t ones = 0, twos = 0;  // groups of size 1 and 2 (a random genome has little else): no atomics
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const int skip_bit = skip_mask ? (__ffs((int)skip_mask) - 1) : 0;
 
     auto close_group = [&](uint64_t head, uint64_t size) {
         if (skip_mask && (flags[head] & skip_mask)) return;  // e.g. groups of ambiguous k-mers
@@ -810,8 +860,8 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t p0 = tile * kGfTile + (uint64_t)threadIdx.x * kGfPerThread;
-        uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, kFlagHead) : 0u;
-        const unsigned long long last = bits ? p0 + (31 - __clz(bits)) + 1 : 0ull;
+        const uint64_t bits = (p0 < n) ? load_flag_bits64(flags, n, p0, 0) : 0ull;
+        const unsigned long long last = bits ? p0 + (63 - __clzll((long long)bits)) + 1 : 0ull;
         unsigned long long inc = last;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -822,18 +872,33 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
         __syncthreads();
         unsigned long long pre = carry[tile];
         for (uint32_t w = 0; w < warp; ++w) pre = s_warp[w] > pre ? s_warp[w] : pre;
-        unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) prev = 0;
-        prev = prev > pre ? prev : pre;  // position + 1 of the latest head before this thread's flags
-        while (bits) {
-            const uint32_t i = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint64_t p = p0 + i;
-            if (prev) close_group(prev - 1, p - (prev - 1));
-            prev = p + 1;
+        unsigned long long incoming = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) incoming = 0;
+        incoming = incoming > pre ? incoming : pre;  // position + 1 of the latest head before this thread
+        // groups of one k-mer whose head and successor head are both in this thread's flags: bit tricks
+        const uint64_t pairs = bits & (bits << 1);    // bit i: heads at i-1 and at i
+        uint64_t fast = pairs;
+        if (skip_mask) fast &= ~(load_flag_bits64(flags, n, p0, skip_bit) << 1);  // skipped groups: dropped
+        if (min_group <= 1) {
+            const uint32_t c = (uint32_t)__popcll(fast);
+            ones += c;
+            total += c;
+            counted += c;
+            if (c && top_bin < 1) top_bin = 1;
+        }
+        uint64_t slow = bits & ~pairs;                // heads that close a longer or a cross-thread group
+        while (slow) {
+            const int i = __ffsll((long long)slow) - 1;
+            slow &= slow - 1;
+            const uint64_t lower = bits & ((1ull << i) - 1ull);
+            const unsigned long long prev = lower ? p0 + (63 - __clzll((long long)lower)) + 1 : incoming;
+            if (prev) close_group(prev - 1, (p0 + i) - (prev - 1));
         }
         // the thread that owns the last position also closes the last group
-        if (p0 < n && n - 1 < p0 + kGfPerThread && prev) close_group(prev - 1, n - (prev - 1));
+        if (p0 < n && n - 1 < p0 + kGfPerThread) {
+            const unsigned long long prev = bits ? last : incoming;
+            if (prev) close_group(prev - 1, n - (prev - 1));
+        }
         __syncthreads();
     }
 
