@@ -13,6 +13,8 @@
 //                min_group <= size <= max_group (kmers.py:514-518, :612-614); small sizes are
 //                privatised in shared memory because a random genome puts almost every group in
 //                bin 1.
+#include <vector>
+
 #include "gk_common.cuh"
 
 namespace gk {
@@ -660,11 +662,86 @@ int scatter_device(const void *d_src, const void *d_pos, uint64_t n, int idx_byt
     return GK_OK;
 }
 
-// largest histogram bin the last group_hist call on this thread wrote (the host table is only written
-// up to it: callers hand in a zeroed table)
+// The device histogram is a dense table of max_bin + 1 counters (8 MB at the reference's default
+// max_counts_bin), but only a handful of bins are ever occupied, and one giant group (an N run) puts
+// a count into the LAST bin.  So the table never crosses PCIe: a compaction kernel lists the non-empty
+// bins as (bin, count) pairs, and the host scatters them into the caller's zeroed table.
+static thread_local std::vector<unsigned long long> g_last_pairs;  // (bin, count) of the last call
 static thread_local uint64_t g_last_top_bin = 0;
 uint64_t last_hist_top_bin() { return g_last_top_bin; }
 void set_last_hist_top_bin(uint64_t v) { g_last_top_bin = v; }
+const std::vector<unsigned long long> &last_hist_pairs() { return g_last_pairs; }
+void set_last_hist_single(uint64_t bin, uint64_t count)
+{
+    g_last_pairs.clear();
+    if (count) { g_last_pairs.push_back(bin); g_last_pairs.push_back(count); }
+    g_last_top_bin = count ? bin : 0;
+}
+
+constexpr uint64_t kPairsInline = 250;    // pairs that come back with the totals in one copy
+constexpr uint64_t kPairsCapacity = 65536;
+
+__global__ void __launch_bounds__(256)
+hist_compact_kernel(const unsigned long long *__restrict__ hist, uint64_t n_bins,
+                    unsigned long long *__restrict__ n_pairs, unsigned long long *__restrict__ pairs,
+                    uint64_t capacity)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bins; i += stride) {
+        const unsigned long long c = hist[i];
+        if (c) {
+            const unsigned long long slot = atomicAdd(n_pairs, 1ull);
+            if (slot < capacity) {
+                pairs[2 * slot] = i;
+                pairs[2 * slot + 1] = c;
+            }
+        }
+    }
+}
+
+// device layout used by both histogram drivers: [hist (max_bin+1)][totals x3][n_pairs][pairs 2*capacity]
+static size_t hist_buffer_bytes(uint64_t max_bin) { return (size_t)(max_bin + 1) * 8 + 32 + kPairsCapacity * 16; }
+
+// After the histogram kernel: compact, fetch totals + pairs, scatter into h_hist (already zero, may be NULL).
+static int collect_hist(unsigned long long *d_hist, uint64_t max_bin, int64_t *h_hist, int64_t *h_total,
+                        int64_t *h_counted, cudaStream_t st)
+{
+    unsigned long long *d_totals = d_hist + (max_bin + 1);
+    unsigned long long *d_n_pairs = d_totals + 3;
+    unsigned long long *d_pairs = d_n_pairs + 1;
+    const uint64_t n_bins = max_bin + 1;
+    uint64_t blocks = (n_bins + 255) / 256;
+    const uint64_t cap_blocks = (uint64_t)sm_count() * 8;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    hist_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_hist, n_bins, d_n_pairs, d_pairs, kPairsCapacity);
+    GK_LAUNCH_CHECK();
+    unsigned long long head[4 + 2 * kPairsInline];
+    GK_CUDA(cudaMemcpyAsync(head, d_totals, sizeof(head), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_pairs = head[3];
+    g_last_pairs.assign(head + 4, head + 4 + 2 * (n_pairs < kPairsInline ? n_pairs : kPairsInline));
+    if (n_pairs > kPairsInline) {
+        DeviceBuffer big;
+        const unsigned long long *src = d_pairs;
+        if (n_pairs > kPairsCapacity) {  // more distinct group sizes than the list holds: redo with room
+            GK_TRY(big.alloc((size_t)(n_pairs + 1) * 16, st));
+            GK_CUDA(cudaMemsetAsync(big.ptr, 0, 8, st));
+            hist_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_hist, n_bins, big.as<unsigned long long>(),
+                                                                   big.as<unsigned long long>() + 2, n_pairs);
+            GK_LAUNCH_CHECK();
+            src = big.as<unsigned long long>() + 2;
+        }
+        g_last_pairs.resize((size_t)2 * n_pairs);
+        GK_CUDA(cudaMemcpyAsync(g_last_pairs.data(), src, (size_t)n_pairs * 16, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+    }
+    g_last_top_bin = head[2];
+    if (h_hist)
+        for (size_t i = 0; i + 1 < g_last_pairs.size(); i += 2) h_hist[g_last_pairs[i]] = (int64_t)g_last_pairs[i + 1];
+    if (h_total) *h_total = (int64_t)head[0];
+    if (h_counted) *h_counted = (int64_t)head[1];
+    return GK_OK;
+}
 
 // hist (host, max_bin+1 int64, ALREADY ZERO, may be NULL) and totals[0] = sum of sizes, totals[1] = groups counted.
 // Groups whose first slot has (flags & skip_mask) != 0 are left out (skip_mask 0: none).
@@ -687,8 +764,8 @@ static int group_hist_impl(const void *d_offsets, int pos_bytes, uint64_t n_grou
     }
     DeviceBuffer buf;
     const size_t hist_bytes = (size_t)(max_bin + 1) * 8;
-    GK_TRY(buf.alloc(hist_bytes + 24, st));
-    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 24, st));
+    GK_TRY(buf.alloc(hist_buffer_bytes(max_bin), st));
+    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 32, st));
     unsigned long long *d_hist = buf.as<unsigned long long>();
     unsigned long long *d_totals = d_hist + (max_bin + 1);
     if (n_groups) {
@@ -703,18 +780,7 @@ static int group_hist_impl(const void *d_offsets, int pos_bytes, uint64_t n_grou
                                                               max_group, max_bin, d_hist, d_totals);
         GK_LAUNCH_CHECK();
     }
-    // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB)
-    unsigned long long totals[3] = {0, 0, 0};
-    GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaStreamSynchronize(st));
-    g_last_top_bin = totals[2];
-    if (h_hist) {  // the caller's table is already zero: only the occupied head crosses PCIe
-        GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-    }
-    if (h_total) *h_total = (int64_t)totals[0];
-    if (h_counted) *h_counted = (int64_t)totals[1];
-    return GK_OK;
+    return collect_hist(d_hist, max_bin, h_hist, h_total, h_counted, st);
 }
 
 int group_hist_device(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
@@ -945,18 +1011,18 @@ int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask
         return GK_ERR_ARG;
     }
     const size_t hist_bytes = (size_t)(max_bin + 1) * 8;
-    g_last_top_bin = 0;
+    set_last_hist_single(0, 0);
     if (h_total) *h_total = 0;
     if (h_counted) *h_counted = 0;
     if (n == 0) return GK_OK;
     const uint64_t tiles = (n + kGfTile - 1) / kGfTile;
-    DeviceBuffer buf;
-    // [hist][totals x3][tile_last][carry]
-    GK_TRY(buf.alloc(hist_bytes + 24 + (size_t)tiles * 16, st));
-    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 24, st));
+    DeviceBuffer buf, scan;
+    GK_TRY(buf.alloc(hist_buffer_bytes(max_bin), st));
+    GK_TRY(scan.alloc((size_t)tiles * 16, st));
+    GK_CUDA(cudaMemsetAsync(buf.ptr, 0, hist_bytes + 32, st));
     unsigned long long *d_hist = buf.as<unsigned long long>();
     unsigned long long *d_totals = d_hist + (max_bin + 1);
-    unsigned long long *d_last = d_totals + 3;
+    unsigned long long *d_last = scan.as<unsigned long long>();
     unsigned long long *d_carry = d_last + tiles;
     flag_tile_last_head_kernel<<<(unsigned)tiles, kGfThreads, 0, st>>>(d_flags, n, d_last);
     GK_LAUNCH_CHECK();
@@ -968,19 +1034,7 @@ int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask
                                                                    min_group, max_group, max_bin, d_hist,
                                                                    d_totals);
     GK_LAUNCH_CHECK();
-    unsigned long long totals[3] = {0, 0, 0};
-    GK_CUDA(cudaMemcpyAsync(totals, d_totals, 24, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaStreamSynchronize(st));
-    g_last_top_bin = totals[2];
-    if (h_hist) {
-        // totals[2] = largest bin touched: only hist[0..top] crosses PCIe (the default table is 8 MB);
-        // the caller's table is already zero
-        GK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)(totals[2] + 1) * 8, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-    }
-    if (h_total) *h_total = (int64_t)totals[0];
-    if (h_counted) *h_counted = (int64_t)totals[1];
-    return GK_OK;
+    return collect_hist(d_hist, max_bin, h_hist, h_total, h_counted, st);
 }
 
 // ---- k-mer filters as device predicates (kmers.py:14-259) ------------------------------------------

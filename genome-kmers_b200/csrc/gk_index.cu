@@ -5,6 +5,8 @@
 // Host-side orchestration only; the kernels live in gk_pack.cu / gk_sort.cu / gk_group.cu.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "gk_common.cuh"
@@ -46,7 +48,8 @@ int group_hist_device(const void *, int, uint64_t, uint64_t, uint64_t, uint64_t,
 int group_hist_masked_device(const void *, int, uint64_t, uint64_t, const uint8_t *, uint8_t, uint64_t,
                              uint64_t, uint64_t, int64_t *, int64_t *, cudaStream_t);
 uint64_t last_hist_top_bin();
-void set_last_hist_top_bin(uint64_t);
+const std::vector<unsigned long long> &last_hist_pairs();
+void set_last_hist_single(uint64_t, uint64_t);
 int flag_group_hist_device(const uint8_t *, uint64_t, uint8_t, uint64_t, uint64_t, uint64_t, int64_t *,
                            int64_t *, int64_t *, cudaStream_t);
 int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, const gk_filter &,
@@ -654,7 +657,7 @@ static int index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *
     gk_filter keep_all = {GK_FILTER_KEEP_ALL, 0, 0, 0};
     const gk_filter f = filter ? *filter : keep_all;
     if (h_total_out) *h_total_out = 0;
-    set_last_hist_top_bin(0);
+    set_last_hist_single(0, 0);
     if (ix->n == 0) return GK_OK;
     GK_TRY(ensure_indices(ix, st));
     const int ib = ix->idx_bytes;
@@ -688,7 +691,7 @@ static int index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *
         if (min_group > 1) return GK_OK;
         if (h_hist_out) h_hist_out[1 < max_bin ? 1 : max_bin] = (int64_t)m;
         if (h_total_out) *h_total_out = (int64_t)m;
-        set_last_hist_top_bin(1 < max_bin ? 1 : max_bin);
+        set_last_hist_single(1 < max_bin ? 1 : max_bin, m);
         return GK_OK;
     }
     DeviceBuffer flags;
@@ -717,6 +720,31 @@ int gk_index_group_counts_zeroed(gk_index *ix, uint32_t kmer_len, const gk_filte
                                       h_total_out, stream);
     if (rc == GK_OK && h_top_bin_out) *h_top_bin_out = last_hist_top_bin();
     return rc;
+}
+
+int gk_index_group_counts_sparse(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t min_group,
+                                 uint64_t max_group, uint64_t max_bin, uint64_t *h_bins_out,
+                                 int64_t *h_counts_out, uint64_t capacity, uint64_t *h_n_pairs_out,
+                                 int64_t *h_total_out, void *stream)
+{
+    if (!h_n_pairs_out) return GK_ERR_ARG;
+    *h_n_pairs_out = 0;
+    GK_TRY(index_group_counts(ix, kmer_len, filter, min_group, max_group, max_bin, nullptr, h_total_out, stream));
+    std::vector<std::pair<unsigned long long, unsigned long long>> pairs;
+    const std::vector<unsigned long long> &flat = last_hist_pairs();
+    for (size_t i = 0; i + 1 < flat.size(); i += 2) pairs.emplace_back(flat[i], flat[i + 1]);
+    std::sort(pairs.begin(), pairs.end());
+    *h_n_pairs_out = pairs.size();
+    if (pairs.size() > capacity || (pairs.size() && (!h_bins_out || !h_counts_out))) {
+        set_error("gk_index_group_counts_sparse: %llu occupied bins do not fit the capacity %llu",
+                  (unsigned long long)pairs.size(), (unsigned long long)capacity);
+        return GK_ERR_ARG;
+    }
+    for (size_t i = 0; i < pairs.size(); ++i) {
+        h_bins_out[i] = pairs[i].first;
+        h_counts_out[i] = (int64_t)pairs[i].second;
+    }
+    return GK_OK;
 }
 
 int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups, uint64_t *h_offsets_out,

@@ -52,6 +52,11 @@ class NativeEngine:
     def stream(self):
         return int(self.torch.cuda.current_stream().cuda_stream)
 
+    def mark(self):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.torch.cuda.current_stream())
+        return ev
+
     def to_device(self, host_u8: np.ndarray):
         return self.torch.from_numpy(np.ascontiguousarray(host_u8)).to(self.device, non_blocking=True)
 
@@ -135,11 +140,31 @@ class NativeEngine:
                                                             ctypes.byref(total), ctypes.byref(top), self.stream()))
         return hist, int(total.value)
 
+    def shard_counts_sparse(self, shard, k, filt, min_group, max_group, max_bin):
+        """(bins uint64, counts int64, total): the occupied histogram bins only."""
+        flt = filt if filt is not None else _native.GkFilter(0, 0, 0, 0)
+        cap = 1 << 12
+        while True:
+            bins = np.empty(cap, dtype=np.uint64)
+            counts = np.empty(cap, dtype=np.int64)
+            n_pairs, total = ctypes.c_uint64(0), ctypes.c_int64(0)
+            rc = self.lib.gk_index_group_counts_sparse(
+                shard["handle"], k, ctypes.byref(flt), min_group, max_group or 0, max_bin, _native.host_ptr(bins),
+                _native.host_ptr(counts), cap, ctypes.byref(n_pairs), ctypes.byref(total), self.stream())
+            if rc == _native.GK_ERR_ARG and n_pairs.value > cap:
+                cap = int(n_pairs.value)
+                continue
+            _native.check(rc)
+            return bins[:n_pairs.value], counts[:n_pairs.value], int(total.value)
+
     def shard_indices_host(self, shard):
-        out = np.empty(shard["n"], dtype=np.uint32 if shard["idx_bytes"] == 4 else np.uint64)
+        torch = self.torch
+        wide = shard["idx_bytes"] == 8
+        # pinned staging (torch caches pinned blocks) so that the D2H copy runs at PCIe speed
+        buf = torch.empty(shard["n"], dtype=torch.int64 if wide else torch.int32, pin_memory=True)
         if shard["n"]:
-            _native.check(self.lib.gk_index_copy_indices(shard["handle"], _native.host_ptr(out), self.stream()))
-        return out
+            _native.check(self.lib.gk_index_copy_indices(shard["handle"], buf.data_ptr(), self.stream()))
+        return buf.numpy().view(np.uint64 if wide else np.uint32)
 
     def shard_free(self, shard):
         if shard and shard.get("handle") is not None:
@@ -205,12 +230,28 @@ class ShardedKmers:
         self.idx_bytes = 8 if self.total_len > 0xFFFFFFFF else 4
         self.shard = None
         self.stats = {}
+        self._marks = []
         self._is_sorted = False
 
     # -------------------------------------------------------------------------------------------
+    def _mark(self, name):
+        """Phase boundary: a CUDA event on the current stream (no synchronise); see phase_ms()."""
+        mk = getattr(self.engine, "mark", None)
+        if mk is not None:
+            self._marks.append((name, mk()))
+
+    def phase_ms(self):
+        """Device time between consecutive phase marks of the last sort() (call after a synchronise)."""
+        out = {}
+        for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
     def sort(self):
         eng, dist = self.engine, self.dist
         k, world, rank = self.k, self.world, self.rank
+        self._marks = []
+        self._mark("start")
         if k > 31:
             raise NotImplementedError("the multi-GPU path handles single-word k-mers (k <= 31)")
         counts = eng.alphabet(self.d_sba)
@@ -219,8 +260,10 @@ class ShardedKmers:
             raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
         class_bit = 1 if (counts[2] > 0 or counts[0] > 0) else 0
         first, end = slice_bounds(self.total_len, world, rank)
+        self._mark("alphabet")
         keys, idx = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
         n_local_in = int(keys.numel())
+        self._mark("pack")
 
         # ---- splitters from evenly spaced samples --------------------------------------------------
         if world > 1:
@@ -240,10 +283,12 @@ class ShardedKmers:
         else:
             splitters_host, splitters = np.zeros(0, dtype=np.uint64), None
         self.splitters = splitters_host
+        self._mark("splitters")
 
         # ---- partition by destination, exchange -----------------------------------------------------
         keys_p, idx_p, send_counts = eng.partition(keys, idx, splitters, world)
         del keys, idx
+        self._mark("partition")
         if world > 1:
             send_t = eng.from_host_i64(send_counts)
             recv_t = eng.empty_like_n(send_t, world)
@@ -263,6 +308,7 @@ class ShardedKmers:
             keys_r, idx_r = keys_p, idx_p
             self.exchange_bytes_sent = 0
         del keys_p, idx_p
+        self._mark("exchange")
 
         # ---- local sort + refinement + flags ------------------------------------------------------------
         if self.shard is not None:
@@ -270,6 +316,7 @@ class ShardedKmers:
         self.shard = eng.shard_index(self.d_sba, self.seg_starts, k, keys_r, idx_r, class_bit)
         self.stats = dict(self.shard["stats"])
         self.stats.update(n_packed=n_local_in, n_shard=int(self.shard["n"]), class_bit=class_bit)
+        self._mark("local_sort")
         self._is_sorted = True
 
     # -------------------------------------------------------------------------------------------
@@ -281,18 +328,37 @@ class ShardedKmers:
         kmer_len = self.k if kmer_len is None else kmer_len
         if kmer_len != self.k:
             raise NotImplementedError("the multi-GPU path counts groups for the sort length only")
-        hist, total = self.engine.shard_counts(self.shard, kmer_len, filt, min_group_size, max_group_size,
-                                               max_counts_bin)
-        if self.world > 1:
-            top = int(np.flatnonzero(hist).max()) + 1 if hist.any() else 1
-            head = self.engine.from_host_i64(np.array([top, total], dtype=np.int64))
-            self.dist.all_reduce(head[:1], op=self.dist.ReduceOp.MAX, group=self.group)
-            self.dist.all_reduce(head[1:], op=self.dist.ReduceOp.SUM, group=self.group)
-            top, total = (int(v) for v in self._to_host_i64(head))
-            part = self.engine.from_host_i64(hist[:top])
-            self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group)
-            hist = np.zeros_like(hist)
-            hist[:top] = self._to_host_i64(part)
+        sparse = getattr(self.engine, "shard_counts_sparse", None)
+        if sparse is not None:
+            bins, counts, total = sparse(self.shard, kmer_len, filt, min_group_size, max_group_size,
+                                         max_counts_bin)
+        else:
+            dense, total = self.engine.shard_counts(self.shard, kmer_len, filt, min_group_size, max_group_size,
+                                                    max_counts_bin)
+            bins = np.flatnonzero(dense).astype(np.uint64)
+            counts = dense[bins.astype(np.int64)]
+        hist = np.zeros(max_counts_bin + 1, dtype=np.int64)
+        if self.world == 1:
+            hist[bins.astype(np.int64)] = counts
+            return hist, total
+        # the occupied bins of every rank are all-gathered as (bin, count) pairs: a few hundred bytes,
+        # instead of all-reducing the 8 MB table the reference's default max_counts_bin implies
+        head = self.engine.from_host_i64(np.array([len(bins), total], dtype=np.int64))
+        heads = [self.engine.empty_like_n(head, 2) for _ in range(self.world)]
+        self.dist.all_gather(heads, head, group=self.group)
+        heads = np.stack([self._to_host_i64(h) for h in heads])
+        width = int(heads[:, 0].max())
+        total = int(heads[:, 1].sum())
+        if width:
+            mine = np.zeros(2 * width, dtype=np.int64)
+            mine[:len(bins)] = bins.astype(np.int64)
+            mine[width:width + len(bins)] = counts
+            mine_t = self.engine.from_host_i64(mine)
+            parts = [self.engine.empty_like_n(mine_t, 2 * width) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine_t, group=self.group)
+            for r, part in enumerate(parts):
+                arr, m = self._to_host_i64(part), int(heads[r, 0])
+                np.add.at(hist, arr[:m], arr[width:width + m])
         return hist, total
 
     def local_start_indices(self) -> np.ndarray:
@@ -372,12 +438,18 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
     hist = None
 
     def step(d_forward):
+        m0 = eng.mark()
         sk = ShardedKmers(d_forward, all_starts, k, "both", engine=eng)
+        m1 = eng.mark()
         sk.sort()
+        m2 = eng.mark()
         h, total = sk.get_kmer_group_counts(k, max_counts_bin=max_bin)
         assert total == n_total, (total, n_total)
-        stats, sent = sk.stats, sk.exchange_bytes_sent
+        stats, sent = dict(sk.stats), sk.exchange_bytes_sent
         sk.close()
+        m3 = eng.mark()
+        stats["_sk_marks"] = [("begin", m0), ("both_strands", m1)] + sk._marks[1:] + [("count_allreduce", m3)]
+        del m2
         return h, stats, sent
 
     for _ in range(args.warmup):
@@ -411,17 +483,24 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         shard_bytes = 0
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+
+        def e2e_step():
             d_in = load_inputs()
             sk = ShardedKmers(d_in, all_starts, k, "both", engine=eng)
             sk.sort()
             h, total = sk.get_kmer_group_counts(k, max_counts_bin=max_bin)
-            local = sk.local_start_indices()
-            shard_bytes = int(local.nbytes)
+            local = sk.local_start_indices()     # D2H of this rank's shard of the sorted starts (pinned)
             sk.close()
+            assert total == n_total
+            return int(local.nbytes)
+
+        for _ in range(2):                       # warm the pinned-buffer cache and the NCCL channels
+            e2e_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            shard_bytes = e2e_step()
         torch.cuda.synchronize()
         dist.barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
@@ -433,6 +512,11 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
 
     sent_all = torch.tensor([float(np.mean([s for _, s in per_step]))], dtype=torch.float64, device="cuda")
     dist.all_reduce(sent_all, op=dist.ReduceOp.SUM)
+    phase_ms = {}
+    for stats, _ in per_step:
+        marks = stats.pop("_sk_marks", [])
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b) / len(per_step)
     if rank == 0:
         passes = per_step[-1][0]["sort_passes"]
         pass_ms = float(np.mean([s["sort_ms"] for s, _ in per_step])) / max(passes, 1)
@@ -451,6 +535,8 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
             "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()),
                          "note": "one all-to-all of (u64 key, u32 start) pairs; (G-1)/G of all pairs cross NVLink"},
             "cpu_baseline": None, "clocks": clock_info,
+            "phase_ms_rank0": {k_: round(v, 3) for k_, v in phase_ms.items()},
+            "local_sort_stats_rank0": {k_: v for k_, v in per_step[-1][0].items()},
             "result": {"kmers": int(n_total), "distinct_kmers": int(hist.sum())},
         }
         print(json.dumps(line), flush=True)

@@ -178,6 +178,13 @@ int gk_index_group_counts_zeroed(gk_index *ix, uint32_t kmer_len, const gk_filte
                                  uint64_t min_group, uint64_t max_group, uint64_t max_bin,
                                  int64_t *h_hist_zeroed, int64_t *h_total_out, uint64_t *h_top_bin_out,
                                  void *stream);
+/* Same query, sparse: the occupied bins as (bin, count) pairs in ascending bin order.  This is what
+ * the multi-GPU driver exchanges between ranks.  GK_ERR_ARG (with *h_n_pairs_out set) when the
+ * pairs do not fit `capacity`. */
+int gk_index_group_counts_sparse(gk_index *ix, uint32_t kmer_len, const gk_filter *filter,
+                                 uint64_t min_group, uint64_t max_group, uint64_t max_bin,
+                                 uint64_t *h_bins_out, int64_t *h_counts_out, uint64_t capacity,
+                                 uint64_t *h_n_pairs_out, int64_t *h_total_out, void *stream);
 /* Group table of the sorted index for kmer_len: number of groups, and (optionally, host
  * buffers of n_groups entries obtained by a first call with NULLs) offsets into the sorted
  * order and sizes.  This is the unique-k-mer set: one entry per distinct k-mer. */
