@@ -282,22 +282,30 @@ def run_single_gpu(args):
     per_step_stats = []
     last_hist = [None]
 
+    host_phase_ms = []
+
     def device_step():
         """inputs (forward byte array) resident in HBM; outputs stay on the device except the histogram"""
+        t = [time.perf_counter()]
         _native.check(lib.gk_sba_both_strands(d_fwd.data_ptr(), total_len, d_both.data_ptr(), sp))
         handle = ctypes.c_void_p()
         _native.check(lib.gk_index_create(d_both.data_ptr(), both_len, _native.host_ptr(both_starts),
                                           len(both_starts), K, K, ctypes.byref(handle)))
+        t.append(time.perf_counter())
         try:
             _native.check(lib.gk_index_sort(handle, ctypes.byref(stats), sp))
+            t.append(time.perf_counter())
             hist = np.zeros(MAX_BIN + 1, dtype=np.int64)   # fresh zero pages, as Kmers.get_kmer_group_counts does
             total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
             _native.check(lib.gk_index_group_counts_zeroed(handle, K, None, 1, 0, MAX_BIN, _native.host_ptr(hist),
                                                            ctypes.byref(total), ctypes.byref(top), sp))
             assert total.value == n, (total.value, n)
             last_hist[0] = hist
+            t.append(time.perf_counter())
         finally:
             lib.gk_index_destroy(handle)
+        t.append(time.perf_counter())
+        host_phase_ms.append([round(1e3 * (b - a), 3) for a, b in zip(t[:-1], t[1:])])
         return stats.as_dict()
 
     for _ in range(args.warmup):
@@ -404,6 +412,7 @@ def run_single_gpu(args):
                    "ambiguous_windows": int(per_step_stats[-1]["n_ambiguous"]),
                    "key_bits": per_step_stats[-1]["key_bits"]},
         "step_wall_ms": [round(v, 3) for v in step_wall_ms],
+        "host_phase_ms_create_sort_count_destroy": host_phase_ms[-min(3, len(host_phase_ms)):],
     }
     if args.bases != BASES_PER_GPU:
         line["config"]["workload"] += f" [REDUCED to {args.bases} bp: not a valid bench number]"

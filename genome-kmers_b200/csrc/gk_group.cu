@@ -79,62 +79,81 @@ constexpr int kTiePerThread = 8;
 constexpr int kTieTile = kTieThreads * kTiePerThread;  // slots per CTA
 constexpr int kTieHalo = kTieMaxRun;                   // keys staged either side of the tile
 
-// A CTA stages its tile of keys (plus a halo) in shared memory, so that every neighbour look-up is a
-// shared-memory read.  Nineteen slots in twenty are alone in their prefix bucket, so the work is split
-// into three dense passes instead of one divergent one (a warp pays for every path one of its lanes takes):
+// A CTA stages the PREFIXES of its tile of keys (plus a halo) in shared memory, so that every neighbour
+// look-up is a shared-memory read of 4 bytes (PreT = uint32_t whenever the prefix fits).  Nineteen slots
+// in twenty are alone in their prefix bucket, so the work is split into three dense passes instead of one
+// divergent one (a warp pays for every path one of its lanes takes):
 //   1  every slot: compare prefixes with both neighbours; alone -> write the flag, else queue the slot
 //   2  queued slots: bounded search for the run's ends; long run -> own flag (+ descent report),
 //      first slot of a short run -> queue the run
 //   3  queued runs: rank the run by the full key in registers, write keys, values and flags in place
-template <typename ValT>
+template <typename ValT, typename PreT>
 __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent)
 {
-    __shared__ uint64_t s_key[kTieTile + 2 * kTieHalo];
+    __shared__ PreT s_pre[kTieTile + 2 * kTieHalo];
     __shared__ uint16_t s_member[kTieTile];
     __shared__ uint16_t s_run[kTieTile / 2];
     __shared__ uint32_t s_n_member, s_n_run;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint64_t tile0 = (uint64_t)blockIdx.x * kTieTile;
     if (t == 0) { s_n_member = 0; s_n_run = 0; }
-    // slot p lives at s_key[p - tile0 + kTieHalo]; slots outside [0, n) are never looked at
+    // slot p lives at s_pre[p - tile0 + kTieHalo]; slots outside [0, n) are never looked at
+    PreT my_pre[kTiePerThread];
+    uint32_t my_amb = 0;
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
         const uint64_t p = tile0 + (uint64_t)j * kTieThreads + t;
-        if (p < n) s_key[kTieHalo + j * kTieThreads + t] = keys[p];
+        const uint64_t k = (p < n) ? keys[p] : 0ull;
+        my_pre[j] = (PreT)(k >> lo_bits);
+        my_amb |= ((class_bit && !(k & 1ull)) ? 1u : 0u) << j;
+        s_pre[kTieHalo + j * kTieThreads + t] = my_pre[j];
     }
     if (t < 2 * kTieHalo) {
         const bool before = t < kTieHalo;
         const uint64_t p = before ? tile0 - kTieHalo + t : tile0 + kTieTile + (t - kTieHalo);
         const bool ok = before ? (tile0 >= (uint64_t)kTieHalo - t) : (p < n);
-        if (ok) s_key[before ? t : kTieHalo + kTieTile + (t - kTieHalo)] = keys[p];
+        if (ok) s_pre[before ? t : kTieHalo + kTieTile + (t - kTieHalo)] = (PreT)(keys[p] >> lo_bits);
     }
     __syncthreads();
 
-    auto pre_at = [&](int i) -> uint64_t { return s_key[i + kTieHalo] >> lo_bits; };  // i = p - tile0
+    auto pre_at = [&](int i) -> PreT { return s_pre[i + kTieHalo]; };  // i = p - tile0
     auto valid = [&](int i) -> bool { return (i >= 0 || tile0 >= (uint64_t)(-i)) && tile0 + (int64_t)i < n; };
 
     // ---- 1 ---------------------------------------------------------------------------------------------
+    // tile-relative 32-bit indices; the two array ends are the only places without a neighbour
+    const int n_in_tile = (n - tile0 < (uint64_t)kTieTile) ? (int)(n - tile0) : kTieTile;
+    const int first_i = (tile0 == 0) ? 0 : -1;                                  // slot without predecessor
+    const int last_i = (n - tile0 <= (uint64_t)kTieTile) ? n_in_tile - 1 : -1;  // slot without successor
+    uint8_t *tile_flags = flags + tile0;
+    uint32_t tied_mask = 0;
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
         const int i = j * kTieThreads + (int)t;
-        const uint64_t p = tile0 + (uint64_t)i;
-        bool tied = false;
-        if (p < n) {
-            const uint64_t k = s_key[i + kTieHalo];
-            const uint64_t pre = k >> lo_bits;
-            const bool ph = (p == 0) || pre_at(i - 1) != pre;
-            const bool nh = (p + 1 == n) || pre_at(i + 1) != pre;
-            tied = !(ph && nh);
-            if (!tied) flags[p] = (class_bit && !(k & 1ull)) ? kFlagAmb : kFlagHead;
+        if (i < n_in_tile) {
+            const PreT pre = my_pre[j];
+            const bool ph = (i == first_i) | (s_pre[i - 1 + kTieHalo] != pre);
+            const bool nh = (i == last_i) | (s_pre[i + 1 + kTieHalo] != pre);
+            if (ph & nh) tile_flags[i] = ((my_amb >> j) & 1u) ? kFlagAmb : kFlagHead;
+            else tied_mask |= 1u << j;
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, tied);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_n_member, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (tied) s_member[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
+    {   // one queue reservation per warp for all eight rounds
+        const uint32_t cnt = __popc(tied_mask);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        uint32_t base = 0;
+        if (lane == 31 && inc) base = atomicAdd(&s_n_member, inc);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+        while (tied_mask) {
+            const int j = __ffs(tied_mask) - 1;
+            tied_mask &= tied_mask - 1;
+            s_member[base++] = (uint16_t)(j * kTieThreads + (int)t);
         }
     }
     __syncthreads();
@@ -144,8 +163,7 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     for (uint32_t r = t; r < n_member; r += kTieThreads) {
         const int i = s_member[r];
         const uint64_t p = tile0 + (uint64_t)i;
-        const uint64_t k = s_key[i + kTieHalo];
-        const uint64_t pre = k >> lo_bits;
+        const PreT pre = pre_at(i);
         const bool ph = (p == 0) || pre_at(i - 1) != pre;
         const bool nh = (p + 1 == n) || pre_at(i + 1) != pre;
         int h = i;
@@ -167,8 +185,9 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             }
             if (q >= limit) is_long = true;
         }
-        if (is_long) {
-            const uint64_t kp = ph ? 0 : s_key[i - 1 + kTieHalo];
+        if (is_long) {  // nobody rewrites the keys of a long run: read them where they are
+            const uint64_t k = keys[p];
+            const uint64_t kp = ph ? 0 : keys[p - 1];
             const bool head = ph || kp != k;
             const bool amb = class_bit && !(k & 1ull);
             if (!ph && k < kp) atomicOr(descent, 1u);
@@ -183,16 +202,16 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     const uint32_t n_runs = s_n_run;
     for (uint32_t r = t; r < n_runs; r += kTieThreads) {
         const int h = s_run[r];
-        const uint64_t pre = pre_at(h);
+        const PreT pre = pre_at(h);
         int len = 1;
         while (len < kTieMaxRun && valid(h + len) && pre_at(h + len) == pre) ++len;
+        const uint64_t g = tile0 + (uint64_t)h;
         uint64_t kk[kTieMaxRun];
 #pragma unroll
-        for (int i = 0; i < kTieMaxRun; ++i) kk[i] = (i < len) ? s_key[h + i + kTieHalo] : ~0ull;
+        for (int i = 0; i < kTieMaxRun; ++i) kk[i] = (i < len) ? keys[g + i] : ~0ull;
         bool sorted = true;
 #pragma unroll
         for (int i = 1; i < kTieMaxRun; ++i) sorted = sorted && (i >= len || kk[i - 1] <= kk[i]);
-        const uint64_t g = tile0 + (uint64_t)h;
         if (sorted) {  // about half of the two-element runs: only the flags are missing
 #pragma unroll
             for (int i = 0; i < kTieMaxRun; ++i) {
@@ -619,11 +638,19 @@ int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t
 {
     if (n == 0) return GK_OK;
     const uint64_t tiles = (n + kTieTile - 1) / kTieTile;
-    if (val_bytes == 4)
-        tie_fix_flags_kernel<uint32_t><<<(unsigned)tiles, kTieThreads, 0, st>>>(
+    const bool narrow = (64 - lo_bits) <= 32;  // the prefix fits 32 bits
+    const unsigned grid = (unsigned)tiles;
+    if (val_bytes == 4 && narrow)
+        tie_fix_flags_kernel<uint32_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
             d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+    else if (val_bytes == 4)
+        tie_fix_flags_kernel<uint32_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+    else if (narrow)
+        tie_fix_flags_kernel<uint64_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
     else
-        tie_fix_flags_kernel<uint64_t><<<(unsigned)tiles, kTieThreads, 0, st>>>(
+        tie_fix_flags_kernel<uint64_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
             d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
     GK_LAUNCH_CHECK();
     return GK_OK;

@@ -17,8 +17,8 @@ namespace gk {
 int kmer_count_host(const uint64_t *, uint32_t, uint64_t, uint32_t, uint64_t *);
 int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, void *, cudaStream_t);
 int pack_keys_device(const uint8_t *, uint64_t, const uint64_t *, uint32_t, uint32_t, uint32_t, int,
-                     uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *,
-                     cudaStream_t);
+                     uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *, int, int,
+                     unsigned long long *, cudaStream_t);
 int pack4_gather_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, uint32_t,
                         const uint64_t *, uint64_t *, cudaStream_t);
 int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
@@ -30,7 +30,7 @@ int subset_expand_device(const void *, const void *, const uint64_t *, const uin
                          const void *, const void *, const unsigned long long *, uint64_t, uint64_t, int, int,
                          void *, uint8_t *, cudaStream_t);
 int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, int *,
-                            cudaStream_t, SortTiming *);
+                            cudaStream_t, SortTiming *, const unsigned long long *d_pre_hist = nullptr);
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
 int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *, cudaStream_t);
 int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
@@ -204,11 +204,14 @@ static int prefix_begin_bit(uint64_t n, int key_bits)
 // out of order; the caller reads it back together with whatever else it needs (no synchronise here).
 static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, void *idx_b, int ib,
                                uint64_t n, int key_bits, int class_bit, uint8_t *d_flags, int *in_alt,
-                               unsigned int *d_descent, SortTiming *timing, cudaStream_t st)
+                               unsigned int *d_descent, SortTiming *timing, cudaStream_t st,
+                               const unsigned long long *d_pre_hist = nullptr)
 {
+    // d_pre_hist: digit histograms of bits [prefix_begin_bit(n, key_bits), key_bits) counted by the producer
     const int begin = prefix_begin_bit(n, key_bits);
     GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
-    GK_TRY(radix_sort_pairs_device(keys_a, keys_b, idx_a, idx_b, ib, n, begin, key_bits, in_alt, st, timing));
+    GK_TRY(radix_sort_pairs_device(keys_a, keys_b, idx_a, idx_b, ib, n, begin, key_bits, in_alt, st, timing,
+                                   d_pre_hist));
     uint64_t *ks = *in_alt ? keys_b : keys_a;
     void *is = *in_alt ? idx_b : idx_a;
     if (begin == 0) return key_flags_device(ks, n, class_bit, d_flags, st);
@@ -302,7 +305,7 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
     const int key_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
     marks.key_bits = key_bits;
 
-    DeviceBuffer keys_a, keys_b, n_amb_dev;
+    DeviceBuffer keys_a, keys_b, n_amb_dev, pre_hist;
     Owned idx_b;
     GK_TRY(keys_a.alloc((size_t)n * 8, st));
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
@@ -310,18 +313,24 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
     GK_TRY(out_idx.alloc((size_t)n * ib, st));
     GK_TRY(n_amb_dev.alloc(16, st));
     GK_CUDA(cudaMemsetAsync(n_amb_dev.ptr, 0, 16, st));
+    // the pack kernel counts the digits of the radix passes while it writes the keys
+    const int begin_bit = prefix_begin_bit(n, key_bits);
+    GK_TRY(pre_hist.alloc(8 * 256 * sizeof(unsigned long long), st));
+    GK_CUDA(cudaMemsetAsync(pre_hist.ptr, 0, pre_hist.bytes, st));
 
     marks.pack0 = tm.mark();
     GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
                             (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
-                            keys_a.as<uint64_t>(), ib, out_idx.ptr, n_amb_dev.as<unsigned long long>(), st));
+                            keys_a.as<uint64_t>(), ib, out_idx.ptr, n_amb_dev.as<unsigned long long>(),
+                            begin_bit, key_bits, pre_hist.as<unsigned long long>(), st));
     marks.pack1 = tm.mark();
     int in_alt = 0;
     GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
     unsigned long long *d_counters = n_amb_dev.as<unsigned long long>();  // [0] ambiguous windows, [1] descent
     GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
                                key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt,
-                               reinterpret_cast<unsigned int *>(d_counters + 1), &marks.main_sort, st));
+                               reinterpret_cast<unsigned int *>(d_counters + 1), &marks.main_sort, st,
+                               pre_hist.as<unsigned long long>()));
     const uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
     if (in_alt) out_idx.swap(idx_b);
     idx_b.reset();

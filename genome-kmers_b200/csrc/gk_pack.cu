@@ -29,6 +29,7 @@ constexpr int kPackThreads = 256;
 constexpr int kPackPerThread = 16;
 constexpr int kPackTile = kPackThreads * kPackPerThread;  // window starts per CTA
 constexpr int kPackChunks = kPackTile / 16 + 2;           // 16-byte chunks staged (tile + 32 B halo)
+constexpr int kPackHistPasses = 8;                        // digit positions counted on the fly
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kPackThreads)
@@ -36,7 +37,8 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                  const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint32_t valid_len,
                  uint32_t key_len, int class_bit, uint64_t first_start, uint64_t end_start,
                  uint64_t out_base, uint64_t *__restrict__ keys_out, IdxT *__restrict__ idx_out,
-                 unsigned long long *__restrict__ n_amb_out)
+                 unsigned long long *__restrict__ n_amb_out, uint64_t n_tiles, int hist_begin_bit,
+                 int hist_end_bit, unsigned long long *__restrict__ g_hist /* [passes][256] or null */)
 {
     __shared__ __align__(16) uint8_t s_bytes[kPackChunks * 16];
     __shared__ uint32_t s_codes[kPackChunks];
@@ -44,10 +46,18 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     __shared__ __align__(4) uint16_t s_sep[kPackChunks + 2];
     __shared__ uint32_t s_sep_pre[kPackChunks / 2 + 2];
     __shared__ uint32_t s_seg0;
+    // digit histograms of the keys this CTA emits, for the radix passes that follow (the sort would
+    // otherwise read all keys once more just to count digits); flushed once per CTA
+    __shared__ uint32_t s_hist[kPackHistPasses][256];
 
     const uint32_t t = threadIdx.x;
+    const int hist_passes = g_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
+    if (g_hist)
+        for (int i = t; i < kPackHistPasses * 256; i += kPackThreads) (&s_hist[0][0])[i] = 0;
+    uint32_t n_amb = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // tiles are aligned to the byte array, not to first_start, so 128-bit loads stay aligned
-    const uint64_t tile0 = (first_start / kPackTile + blockIdx.x) * (uint64_t)kPackTile;
+    const uint64_t tile0 = (first_start / kPackTile + tile) * (uint64_t)kPackTile;
 
     // ---- stage bytes, convert to streams ----------------------------------------------------
     const bool aligned = (reinterpret_cast<uintptr_t>(sba) & 15u) == 0;
@@ -119,7 +129,6 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     // ---- cut windows ---------------------------------------------------------------------------
     const uint32_t seg0 = s_seg0;
     const uint64_t key_mask = (key_len >= 32) ? 0xFFFFFFFFull : ((1ull << key_len) - 1ull);
-    uint32_t n_amb = 0;
 #pragma unroll 4
     for (int j = 0; j < kPackPerThread; ++j) {
         const uint32_t q = t + j * kPackThreads;
@@ -152,6 +161,23 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
         const uint64_t pos = i - (uint64_t)valid_len * seg - out_base;
         keys_out[pos] = key;
         idx_out[pos] = (IdxT)i;
+#pragma unroll
+        for (int p = 0; p < kPackHistPasses; ++p) {
+            if (p < hist_passes) {
+                const int lo = hist_begin_bit + 8 * p;
+                const int bits = (hist_end_bit - lo < 8) ? hist_end_bit - lo : 8;
+                atomicAdd(&s_hist[p][(uint32_t)(key >> lo) & ((1u << bits) - 1u)], 1u);
+            }
+        }
+    }
+    __syncthreads();  // the staged streams are rewritten by the next tile
+    }
+    if (g_hist) {
+        __syncthreads();
+        for (int i = t; i < hist_passes * 256; i += kPackThreads) {
+            const uint32_t c = (&s_hist[0][0])[i];
+            if (c) atomicAdd(&g_hist[i], (unsigned long long)c);
+        }
     }
     if (n_amb_out) {
         n_amb = warp_sum(n_amb);
@@ -241,7 +267,8 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
                      uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
                      uint64_t first_start, uint64_t end_start, uint64_t out_base,
                      uint64_t *d_keys_out, int idx_bytes, void *d_idx_out,
-                     unsigned long long *d_n_amb, cudaStream_t st)
+                     unsigned long long *d_n_amb, int hist_begin_bit, int hist_end_bit,
+                     unsigned long long *d_hist, cudaStream_t st)
 {
     if (key_len < 1 || key_len > 32 || valid_len < key_len || (class_bit && key_len > 31)) {
         set_error("pack_keys: key_len %u / valid_len %u / class_bit %d out of range", key_len,
@@ -252,19 +279,24 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
     if (first_start >= end_start) return GK_OK;
     const uint64_t tile_first = first_start / kPackTile;
     const uint64_t tile_last = (end_start - 1) / kPackTile;
-    const uint64_t grid = tile_last - tile_first + 1;
-    if (grid > 0x7FFFFFFFull) {
-        set_error("pack_keys: range too large for one launch");
+    const uint64_t n_tiles = tile_last - tile_first + 1;
+    if (d_hist && (hist_end_bit - hist_begin_bit + 7) / 8 > kPackHistPasses) {
+        set_error("pack_keys: at most %d digit positions can be counted", kPackHistPasses);
         return GK_ERR_ARG;
     }
+    // persistent CTAs (8 fit an SM) so that the shared histograms are flushed ~1000 times, not per tile
+    uint64_t grid = (uint64_t)sm_count() * 8;
+    if (grid > n_tiles) grid = n_tiles;
     if (idx_bytes == 4)
         pack_keys_kernel<uint32_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
             d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
-            end_start, out_base, d_keys_out, (uint32_t *)d_idx_out, d_n_amb);
+            end_start, out_base, d_keys_out, (uint32_t *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit,
+            hist_end_bit, d_hist);
     else
         pack_keys_kernel<uint64_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
             d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
-            end_start, out_base, d_keys_out, (uint64_t *)d_idx_out, d_n_amb);
+            end_start, out_base, d_keys_out, (uint64_t *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit,
+            hist_end_bit, d_hist);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -335,7 +367,7 @@ extern "C" int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64
     GK_CUDA(cudaMemsetAsync(amb.ptr, 0, 8, st));
     GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, valid_len, key_len,
                             class_bit, first_start, end_start, base, d_keys_out, idx_bytes,
-                            d_idx_out, amb.as<unsigned long long>(), st));
+                            d_idx_out, amb.as<unsigned long long>(), 0, 0, nullptr, st));
     uint64_t n_amb = 0;
     GK_CUDA(cudaMemcpyAsync(&n_amb, amb.ptr, 8, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));

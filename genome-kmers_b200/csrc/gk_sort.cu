@@ -395,7 +395,7 @@ constexpr SortConfig kSortConfigs[] = {
     {512, 16, 1},  // 5: 8192-pair tiles
 };
 constexpr int kNumSortConfigs = (int)(sizeof(kSortConfigs) / sizeof(kSortConfigs[0]));
-constexpr int kDefaultSortConfig = 0;
+constexpr int kDefaultSortConfig = 3;
 
 static int sort_config_id()
 {
@@ -430,7 +430,8 @@ static int dispatch_pass(int cfg, const PassArgs &a, cudaStream_t st)
 static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                         int val_bytes, uint64_t n, int begin_bit, int end_bit,
                         const uint64_t *d_splitters, uint32_t n_split, int *result_in_alt,
-                        unsigned long long *h_bin_counts, cudaStream_t st, SortTiming *timing)
+                        unsigned long long *h_bin_counts, cudaStream_t st, SortTiming *timing,
+                        const unsigned long long *d_pre_hist = nullptr)
 {
     if (timing) { timing->hist_ms = 0.f; timing->passes_ms = 0.f; timing->passes = 0; }
     if (val_bytes != 4 && val_bytes != 8) {
@@ -478,10 +479,12 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         if (need < 1) need = 1;
         if ((uint64_t)hist_grid > need) hist_grid = (int)need;
     }
-    digit_histogram_kernel<<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, d_splitters,
-                                                              n_split, d_hist);
-    GK_LAUNCH_CHECK();
-    scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_hist, d_base);
+    if (!d_pre_hist) {  // the producer of the keys may have counted the digits already (gk_pack.cu)
+        digit_histogram_kernel<<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, d_splitters,
+                                                                  n_split, d_hist);
+        GK_LAUNCH_CHECK();
+    }
+    scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_pre_hist ? d_pre_hist : d_hist, d_base);
     GK_LAUNCH_CHECK();
     if (timing) GK_CUDA(cudaEventRecord(ev[1], st));
 
@@ -526,10 +529,11 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
 
 int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                             int val_bytes, uint64_t n, int begin_bit, int end_bit,
-                            int *result_in_alt, cudaStream_t st, SortTiming *timing)
+                            int *result_in_alt, cudaStream_t st, SortTiming *timing,
+                            const unsigned long long *d_pre_hist)
 {
     return run_onesweep(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit, end_bit, nullptr,
-                        0, result_in_alt, nullptr, st, timing);
+                        0, result_in_alt, nullptr, st, timing, d_pre_hist);
 }
 
 // Stable partition of the pairs by destination = number of splitters <= key.  Output always lands
@@ -563,7 +567,7 @@ extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void 
         return GK_ERR_ARG;
     }
     return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
-                                   end_bit, result_in_alt, as_stream(stream), nullptr);
+                                   end_bit, result_in_alt, as_stream(stream), nullptr, nullptr);
 }
 
 extern "C" int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,
