@@ -76,6 +76,47 @@ uint64_t gk_launch_count(int reset)
     return v;
 }
 
+// ---- peer-visible device memory (multi-GPU exchange buffers) -----------------------------------------
+// cudaMalloc memory (pool memory cannot be exported) + CUDA IPC handles; one process per GPU on one box.
+int gk_peer_alloc(uint64_t bytes, void **d_ptr_out)
+{
+    if (!d_ptr_out) return GK_ERR_ARG;
+    *d_ptr_out = nullptr;
+    GK_CUDA(cudaMalloc(d_ptr_out, bytes ? bytes : 16));
+    return GK_OK;
+}
+
+int gk_peer_free(void *d_ptr)
+{
+    if (d_ptr) GK_CUDA(cudaFree(d_ptr));
+    return GK_OK;
+}
+
+int gk_peer_export(void *d_ptr, uint8_t *handle64_out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_ptr || !handle64_out) return GK_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    GK_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64_out, &h, 64);
+    return GK_OK;
+}
+
+int gk_peer_open(const uint8_t *handle64, void **d_ptr_out)
+{
+    if (!handle64 || !d_ptr_out) return GK_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GK_CUDA(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GK_OK;
+}
+
+int gk_peer_close(void *d_ptr)
+{
+    if (d_ptr) GK_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return GK_OK;
+}
+
 int gk_device_info(int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem_bytes)
 {
     int dev = 0;

@@ -127,6 +127,14 @@ struct StatusTraits<uint64_t> {
 constexpr uint32_t kLookbackSpinLimit = 1u << 24;  // then flag an error instead of hanging the GPU
 constexpr int kLookbackBatch = 4;                  // predecessor status words loaded per round trip
 
+// Multi-GPU partition straight into the destination ranks' receive buffers (peer memory over NVLink):
+// digit d's pairs go to keys[d] / vals[d]; bin_base[d] holds the offset of this rank's segment there.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    uint64_t *keys[kMaxPeers];
+    void *vals[kMaxPeers];
+};
+
 template <typename ValT, int THREADS, int IPT>
 struct OnesweepSmem {
     static constexpr int kTile = THREADS * IPT;
@@ -137,6 +145,8 @@ struct OnesweepSmem {
     unsigned long long global_off[kRadix];  // bin's global start minus its start inside the tile
     uint32_t global_off32[kRadix];          // the same modulo 2^32 (enough when n < 2^32)
     uint64_t splitters[kRadix];
+    uint64_t *peer_keys[kMaxPeers];
+    ValT *peer_vals[kMaxPeers];
     uint32_t bin_excl[kRadix];
     uint32_t warp_sums[kRadix / 32];
     uint32_t tile;
@@ -188,7 +198,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
                 const ValT *__restrict__ vals_in, ValT *__restrict__ vals_out, uint64_t n,
                 int shift, uint32_t digit_mask, const uint64_t *__restrict__ splitters, uint32_t n_split,
                 const unsigned long long *__restrict__ bin_base, uint32_t *__restrict__ tile_counter,
-                StatusT *__restrict__ status, int *__restrict__ err)
+                StatusT *__restrict__ status, int *__restrict__ err, const PeerTable *__restrict__ peer)
 {
     using Smem = OnesweepSmem<ValT, THREADS, IPT>;
     using ST = StatusTraits<StatusT>;
@@ -205,6 +215,10 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
     for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;
     if (PARTITION && t < n_split) s.splitters[t] = splitters[t];
+    if (PARTITION && peer && t < kMaxPeers) {
+        s.peer_keys[t] = peer->keys[t];
+        s.peer_vals[t] = reinterpret_cast<ValT *>(peer->vals[t]);
+    }
     __syncthreads();
     auto digit_of = [&](uint64_t k) -> uint32_t {
         if (PARTITION) return splitter_digit(s.splitters, n_split, k);
@@ -328,6 +342,21 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     // ---- E ------------------------------------------------------------------------------------------
     // 32-bit offsets when every destination index fits (StatusT is 32-bit exactly when n < 2^30)
     constexpr bool kNarrow = sizeof(StatusT) == 4;
+    if (PARTITION && peer) {
+        // every pair goes to its destination rank's buffer: long contiguous runs per destination
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = t + j * THREADS;
+            if (p < tile_valid) {
+                const uint64_t k = s.keys[p];
+                const uint32_t d = digit_of(k);
+                const uint64_t dst = (uint64_t)(s.global_off[d] + p);
+                s.peer_keys[d][dst] = k;
+                s.peer_vals[d][dst] = s.vals[p];
+            }
+        }
+        return;
+    }
     if (full_tile) {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -358,6 +387,7 @@ struct PassArgs {
     const uint64_t *kin; uint64_t *kout; const void *vin; void *vout; uint64_t n;
     int shift, bits; const uint64_t *splitters; uint32_t n_split;
     const unsigned long long *bin_base; uint32_t *tile_counter; void *status; int *err;
+    const PeerTable *peer;
 };
 
 template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
@@ -371,7 +401,7 @@ static int launch_pass_impl(const PassArgs &a, cudaStream_t st)
     const uint64_t tiles = (a.n + Smem::kTile - 1) / Smem::kTile;
     kernel<<<(unsigned)tiles, THREADS, sizeof(Smem), st>>>(
         a.kin, a.kout, (const ValT *)a.vin, (ValT *)a.vout, a.n, a.shift, (1u << a.bits) - 1u, a.splitters,
-        a.n_split, a.bin_base, a.tile_counter, (StatusT *)a.status, a.err);
+        a.n_split, a.bin_base, a.tile_counter, (StatusT *)a.status, a.err, a.peer);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -495,7 +525,7 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         const int bits = d_splitters ? kRadixBits : ((end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits);
         GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
         PassArgs pa = {kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, d_base + p * kRadix,
-                       d_ctr + p, d_status, d_err};
+                       d_ctr + p, d_status, d_err, nullptr};
         int rc;
         if (val_bytes == 4)
             rc = wide ? dispatch_pass<uint32_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint32_t, uint32_t>(cfg, pa, st);
@@ -554,6 +584,96 @@ int partition_pairs_device(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals,
     return GK_OK;
 }
 
+// Destination counts only (one read of the keys): the ranks exchange them to size and place the segments
+// before any pair moves.
+int partition_count_device(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                           uint64_t *h_counts, cudaStream_t st)
+{
+    if (n_parts < 1 || n_parts > (uint32_t)kRadix) {
+        set_error("partition_count: n_parts must be in [1, 256]");
+        return GK_ERR_ARG;
+    }
+    for (uint32_t d = 0; d < n_parts; ++d) h_counts[d] = 0;
+    if (n == 0) return GK_OK;
+    DeviceBuffer hist;
+    GK_TRY(hist.alloc(kRadix * sizeof(unsigned long long), st));
+    GK_CUDA(cudaMemsetAsync(hist.ptr, 0, hist.bytes, st));
+    int grid = sm_count() * 2;
+    uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
+    if (need < 1) need = 1;
+    if ((uint64_t)grid > need) grid = (int)need;
+    digit_histogram_kernel<<<grid, kHistThreads, 0, st>>>(d_keys, n, 0, 8, d_splitters, n_parts - 1,
+                                                          hist.as<unsigned long long>());
+    GK_LAUNCH_CHECK();
+    unsigned long long bins[kRadix];
+    GK_CUDA(cudaMemcpyAsync(bins, hist.ptr, sizeof(bins), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t d = 0; d < n_parts; ++d) h_counts[d] = bins[d];
+    return GK_OK;
+}
+
+// One stable partition pass whose output lands in the destination ranks' buffers.  h_dst_keys / h_dst_vals:
+// n_parts device pointers (local or peer-mapped); h_dst_offsets[d]: first element of this rank's segment
+// in destination d.  No synchronise: the caller orders the consumers behind the launch.
+int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
+                                const uint64_t *d_splitters, uint32_t n_parts, uint64_t *const *h_dst_keys,
+                                void *const *h_dst_vals, const uint64_t *h_dst_offsets, cudaStream_t st)
+{
+    if (n_parts < 1 || n_parts > (uint32_t)kMaxPeers) {
+        set_error("partition_pairs_peer: n_parts must be in [1, %d]", kMaxPeers);
+        return GK_ERR_ARG;
+    }
+    if (val_bytes != 4 && val_bytes != 8) {
+        set_error("partition_pairs_peer: val_bytes must be 4 or 8");
+        return GK_ERR_ARG;
+    }
+    if (n == 0) return GK_OK;
+    const int cfg = sort_config_id();
+    const int tile = kSortConfigs[cfg].threads * kSortConfigs[cfg].ipt;
+    const uint64_t tiles = (n + tile - 1) / tile;
+    const bool wide = n >= (1ull << 30);
+    const size_t status_bytes = (size_t)tiles * kRadix * (wide ? 8 : 4);
+    // temp layout: [bin_base 256 x u64][counter + err, 64 B][peer table][status]
+    const size_t head_bytes = kRadix * 8 + 64 + sizeof(PeerTable);
+    DeviceBuffer temp;
+    GK_TRY(temp.alloc(head_bytes + status_bytes, st));
+    unsigned char *base = temp.as<unsigned char>();
+    unsigned long long h_base[kRadix];
+    memset(h_base, 0, sizeof(h_base));
+    for (uint32_t d = 0; d < n_parts; ++d) h_base[d] = h_dst_offsets[d];
+    PeerTable h_peer;
+    memset(&h_peer, 0, sizeof(h_peer));
+    for (uint32_t d = 0; d < n_parts; ++d) {
+        h_peer.keys[d] = h_dst_keys[d];
+        h_peer.vals[d] = h_dst_vals[d];
+    }
+    GK_CUDA(cudaMemsetAsync(base + kRadix * 8, 0, 64 + status_bytes + sizeof(PeerTable), st));
+    GK_CUDA(cudaMemcpyAsync(base, h_base, sizeof(h_base), cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(base + kRadix * 8 + 64, &h_peer, sizeof(h_peer), cudaMemcpyHostToDevice, st));
+    // the two small uploads read pageable host memory: they have completed when the calls return
+    uint32_t *d_ctr = reinterpret_cast<uint32_t *>(base + kRadix * 8);
+    int *d_err = reinterpret_cast<int *>(d_ctr + 8);
+    PassArgs pa = {d_keys, nullptr, d_vals, nullptr, n, 0, kRadixBits, d_splitters ? d_splitters : d_keys,
+                   n_parts - 1, reinterpret_cast<const unsigned long long *>(base), d_ctr,
+                   base + head_bytes, d_err, reinterpret_cast<const PeerTable *>(base + kRadix * 8 + 64)};
+    int rc;
+    if (val_bytes == 4)
+        rc = wide ? dispatch_pass<uint32_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint32_t, uint32_t>(cfg, pa, st);
+    else
+        rc = wide ? dispatch_pass<uint64_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint64_t, uint32_t>(cfg, pa, st);
+    GK_TRY(rc);
+    // the scratch is released in stream order (after the kernel); look-back failures surface as a hang
+    // guard only: report them on the next synchronising call of the caller
+    int h_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("partition_pairs_peer: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
+    return GK_OK;
+}
+
 }  // namespace gk
 
 using namespace gk;
@@ -583,4 +703,29 @@ extern "C" int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *
     return partition_pairs_device(d_keys, d_keys_out, d_vals, d_vals_out, val_bytes, n,
                                   d_splitters ? d_splitters : d_keys, n_parts, h_counts_out,
                                   as_stream(stream));
+}
+
+extern "C" int gk_partition_count(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                                  uint64_t *h_counts_out, void *stream)
+{
+    if (!h_counts_out || (n && !d_keys) || (n_parts > 1 && !d_splitters)) {
+        set_error("gk_partition_count: null buffer");
+        return GK_ERR_ARG;
+    }
+    return partition_count_device(d_keys, n, d_splitters ? d_splitters : d_keys, n_parts, h_counts_out,
+                                  as_stream(stream));
+}
+
+extern "C" int gk_partition_pairs_peer(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
+                                       const uint64_t *d_splitters, uint32_t n_parts,
+                                       uint64_t *const *h_dst_keys, void *const *h_dst_vals,
+                                       const uint64_t *h_dst_offsets, void *stream)
+{
+    if (!h_dst_keys || !h_dst_vals || !h_dst_offsets || (n && (!d_keys || !d_vals)) ||
+        (n_parts > 1 && !d_splitters)) {
+        set_error("gk_partition_pairs_peer: null buffer");
+        return GK_ERR_ARG;
+    }
+    return partition_pairs_peer_device(d_keys, d_vals, val_bytes, n, d_splitters, n_parts, h_dst_keys,
+                                       h_dst_vals, h_dst_offsets, as_stream(stream));
 }

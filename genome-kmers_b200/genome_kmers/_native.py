@@ -70,6 +70,13 @@ SIGNATURES = {
                             _u64, _p(_u64), _p(_u64), _vp]),
     "gk_radix_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _int, _int, _p(_int), _vp]),
     "gk_partition_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _vp, _u32, _vp, _vp]),
+    "gk_partition_count": (_int, [_vp, _u64, _vp, _u32, _vp, _vp]),
+    "gk_partition_pairs_peer": (_int, [_vp, _vp, _int, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gk_peer_alloc": (_int, [_u64, _p(_vp)]),
+    "gk_peer_free": (_int, [_vp]),
+    "gk_peer_export": (_int, [_vp, _vp]),
+    "gk_peer_open": (_int, [_vp, _p(_vp)]),
+    "gk_peer_close": (_int, [_vp]),
     "gk_rle_keys": (_int, [_vp, _u64, _vp, _p(_u64), _vp]),
     "gk_group_size_hist": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp, _p(ctypes.c_int64), _vp]),
     "gk_index_create": (_int, [_vp, _u64, _vp, _u32, _u32, _u32, _p(_vp)]),

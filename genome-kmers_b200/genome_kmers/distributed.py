@@ -23,6 +23,7 @@ The compute steps go through an `engine` object.  The default engine calls the C
 a GPU; tests on CPU (gloo, world_size 2) inject a NumPy engine to exercise the orchestration only.
 """
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -113,6 +114,42 @@ class NativeEngine:
     def empty_like_n(self, ref, n):
         return self.torch.empty(n, dtype=ref.dtype, device=self.device)
 
+    # ---- fused partition + exchange over peer memory ------------------------------------------------
+    def peer_exchange(self, dist, group, capacity, idx_bytes):
+        return PeerExchange.get(self, dist, group, capacity, idx_bytes)
+
+    def partition_count(self, keys, splitters, n_parts):
+        counts = np.zeros(n_parts, dtype=np.uint64)
+        sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
+        _native.check(self.lib.gk_partition_count(keys.data_ptr(), keys.numel(), sp, n_parts,
+                                                  _native.host_ptr(counts), self.stream()))
+        return counts.astype(np.int64)
+
+    def partition_peer(self, keys, idx, splitters, n_parts, px, offsets):
+        sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _native.check(self.lib.gk_partition_pairs_peer(
+            keys.data_ptr(), idx.data_ptr(), idx.element_size(), keys.numel(), sp, n_parts,
+            _native.host_ptr(px.key_ptrs), _native.host_ptr(px.idx_ptrs), _native.host_ptr(off), self.stream()))
+
+    def shard_index_ptr(self, d_sba, seg_starts, k, keys_ptr, idx_ptr, n, idx_bytes, class_bit):
+        """Sort pairs that already sit in library-owned buffers (the peer receive buffers)."""
+        torch = self.torch
+        handle = ctypes.c_void_p()
+        _native.check(self.lib.gk_index_create(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
+                                               len(seg_starts), k, k, ctypes.byref(handle)))
+        stats = _native.GkSortStats()
+        k_alt = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        i_alt = torch.empty(max(n, 1), dtype=torch.int32 if idx_bytes == 4 else torch.int64, device=self.device)
+        try:
+            _native.check(self.lib.gk_index_sort_pairs(handle, keys_ptr, k_alt.data_ptr(), idx_ptr,
+                                                       i_alt.data_ptr(), n, class_bit, ctypes.byref(stats),
+                                                       self.stream()))
+        except Exception:
+            self.lib.gk_index_destroy(handle)
+            raise
+        return {"handle": handle, "n": n, "stats": stats.as_dict(), "idx_bytes": idx_bytes}
+
     def shard_index(self, d_sba, seg_starts, k, keys, idx, class_bit):
         """Sort the received pairs and return an opaque shard handle."""
         torch = self.torch
@@ -176,6 +213,69 @@ class NativeEngine:
 
     def from_host_i64(self, arr):
         return self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
+
+
+class PeerExchange:
+    """Receive buffers of every rank, mapped into every rank (CUDA IPC over NVLink peer memory).
+
+    The fused partition kernel (gk_partition_pairs_peer) writes each (key, start) pair directly into the
+    buffer of the rank that owns its key range.  Buffers are allocated once per (group, capacity) and
+    reused by later sorts; `capacity` counts pairs."""
+
+    _cache = {}
+
+    def __init__(self, engine, dist, group, capacity: int, idx_bytes: int):
+        torch, lib = engine.torch, engine.lib
+        self.lib, self.capacity, self.idx_bytes = lib, int(capacity), idx_bytes
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.my_keys, self.my_idx = ctypes.c_void_p(), ctypes.c_void_p()
+        _native.check(lib.gk_peer_alloc(self.capacity * 8, ctypes.byref(self.my_keys)))
+        _native.check(lib.gk_peer_alloc(self.capacity * idx_bytes, ctypes.byref(self.my_idx)))
+        handles = np.zeros(128, dtype=np.uint8)
+        _native.check(lib.gk_peer_export(self.my_keys, _native.host_ptr(handles)))
+        _native.check(lib.gk_peer_export(self.my_idx, _native.host_ptr(handles[64:])))
+        mine = torch.from_numpy(handles).to(engine.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        self.key_ptrs = np.zeros(self.world, dtype=np.uint64)
+        self.idx_ptrs = np.zeros(self.world, dtype=np.uint64)
+        self._opened = []
+        for r, g in enumerate(gathered):
+            if r == self.rank:
+                self.key_ptrs[r], self.idx_ptrs[r] = self.my_keys.value, self.my_idx.value
+                continue
+            h = np.ascontiguousarray(g.cpu().numpy())
+            pk, pi = ctypes.c_void_p(), ctypes.c_void_p()
+            _native.check(lib.gk_peer_open(_native.host_ptr(h), ctypes.byref(pk)))
+            _native.check(lib.gk_peer_open(_native.host_ptr(h[64:]), ctypes.byref(pi)))
+            self._opened += [pk, pi]
+            self.key_ptrs[r], self.idx_ptrs[r] = pk.value, pi.value
+
+    @classmethod
+    def get(cls, engine, dist, group, capacity: int, idx_bytes: int):
+        key = (id(group), dist.get_world_size(group), idx_bytes)
+        px = cls._cache.get(key)
+        if px is None or px.capacity < capacity:   # every rank computes the same capacity: collective-safe
+            if px is not None:
+                px.close()
+            px = cls(engine, dist, group, capacity, idx_bytes)
+            cls._cache[key] = px
+        return px
+
+    def close(self):
+        for p in self._opened:
+            self.lib.gk_peer_close(p)
+        self._opened = []
+        if self.my_keys:
+            self.lib.gk_peer_free(self.my_keys)
+            self.lib.gk_peer_free(self.my_idx)
+            self.my_keys = self.my_idx = None
+
+    @classmethod
+    def close_all(cls):
+        for px in cls._cache.values():
+            px.close()
+        cls._cache.clear()
 
 
 def choose_splitters(sorted_samples: np.ndarray, n_parts: int) -> np.ndarray:
@@ -286,34 +386,67 @@ class ShardedKmers:
         self._mark("splitters")
 
         # ---- partition by destination, exchange -----------------------------------------------------
-        keys_p, idx_p, send_counts = eng.partition(keys, idx, splitters, world)
-        del keys, idx
-        self._mark("partition")
-        if world > 1:
-            send_t = eng.from_host_i64(send_counts)
-            recv_t = eng.empty_like_n(send_t, world)
-            dist.all_to_all_single(recv_t, send_t, group=self.group)
-            recv_counts = self._to_host_i64(recv_t)
-            n_recv = int(recv_counts.sum())
-            keys_r = eng.empty_like_n(keys_p, n_recv)
-            idx_r = eng.empty_like_n(idx_p, n_recv)
-            in_splits, out_splits = [int(c) for c in send_counts], [int(c) for c in recv_counts]
-            dist.all_to_all_single(keys_r, keys_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
-                                   group=self.group)
-            dist.all_to_all_single(idx_r, idx_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
-                                   group=self.group)
-            self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank])
-                                           * (8 + idx_p.element_size()))
-        else:
-            keys_r, idx_r = keys_p, idx_p
-            self.exchange_bytes_sent = 0
-        del keys_p, idx_p
-        self._mark("exchange")
+        use_peer = (world > 1 and hasattr(eng, "peer_exchange")
+                    and os.environ.get("GK_PEER_EXCHANGE", "1") != "0")
+        recv_ptrs = None
+        if use_peer:
+            # fused: counts first (placement), then ONE kernel partitions and writes every pair straight
+            # into its destination rank's receive buffer over NVLink peer memory
+            send_counts = eng.partition_count(keys, splitters, world)
+            mine = eng.from_host_i64(send_counts)
+            rows = [eng.empty_like_n(mine, world) for _ in range(world)]
+            dist.all_gather(rows, mine, group=self.group)
+            matrix = np.stack([self._to_host_i64(r) for r in rows])          # [source, destination]
+            recv_total = matrix.sum(axis=0)
+            n_windows_all = int(matrix.sum())
+            capacity = int(1.25 * n_windows_all / world) + (1 << 20)
+            self._mark("partition")
+            if int(recv_total.max()) <= capacity:
+                px = eng.peer_exchange(dist, self.group, capacity, self.idx_bytes)
+                offsets = matrix[:rank, :].sum(axis=0)
+                eng.partition_peer(keys, idx, splitters, world, px, offsets)
+                token = eng.from_host_i64(np.zeros(1, dtype=np.int64))
+                dist.all_reduce(token, group=self.group)     # every rank's writes have landed behind this
+                recv_ptrs = (px.my_keys, px.my_idx, int(recv_total[rank]))
+                self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank]) * (8 + self.idx_bytes))
+                del keys, idx
+                self._mark("exchange")
+            else:
+                use_peer = False                             # skew beyond the buffers: NCCL path below
+        if not use_peer:
+            keys_p, idx_p, send_counts = eng.partition(keys, idx, splitters, world)
+            del keys, idx
+            self._mark("partition")
+            if world > 1:
+                send_t = eng.from_host_i64(send_counts)
+                recv_t = eng.empty_like_n(send_t, world)
+                dist.all_to_all_single(recv_t, send_t, group=self.group)
+                recv_counts = self._to_host_i64(recv_t)
+                n_recv = int(recv_counts.sum())
+                keys_r = eng.empty_like_n(keys_p, n_recv)
+                idx_r = eng.empty_like_n(idx_p, n_recv)
+                in_splits, out_splits = [int(c) for c in send_counts], [int(c) for c in recv_counts]
+                dist.all_to_all_single(keys_r, keys_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                       group=self.group)
+                dist.all_to_all_single(idx_r, idx_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                       group=self.group)
+                self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank])
+                                               * (8 + idx_p.element_size()))
+            else:
+                keys_r, idx_r = keys_p, idx_p
+                self.exchange_bytes_sent = 0
+            del keys_p, idx_p
+            self._mark("exchange")
 
         # ---- local sort + refinement + flags ------------------------------------------------------------
         if self.shard is not None:
             eng.shard_free(self.shard)
-        self.shard = eng.shard_index(self.d_sba, self.seg_starts, k, keys_r, idx_r, class_bit)
+        if recv_ptrs is not None:
+            self.shard = eng.shard_index_ptr(self.d_sba, self.seg_starts, k, recv_ptrs[0], recv_ptrs[1],
+                                             recv_ptrs[2], self.idx_bytes, class_bit)
+        else:
+            self.shard = eng.shard_index(self.d_sba, self.seg_starts, k, keys_r, idx_r, class_bit)
+        self.exchange_mode = "peer" if recv_ptrs is not None else "nccl"
         self.stats = dict(self.shard["stats"])
         self.stats.update(n_packed=n_local_in, n_shard=int(self.shard["n"]), class_bit=class_bit)
         self._mark("local_sort")
@@ -446,6 +579,7 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
         h, total = sk.get_kmer_group_counts(k, max_counts_bin=max_bin)
         assert total == n_total, (total, n_total)
         stats, sent = dict(sk.stats), sk.exchange_bytes_sent
+        stats["_mode"] = sk.exchange_mode
         sk.close()
         m3 = eng.mark()
         stats["_sk_marks"] = [("begin", m0), ("both_strands", m1)] + sk._marks[1:] + [("count_allreduce", m3)]
@@ -513,7 +647,9 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
     sent_all = torch.tensor([float(np.mean([s for _, s in per_step]))], dtype=torch.float64, device="cuda")
     dist.all_reduce(sent_all, op=dist.ReduceOp.SUM)
     phase_ms = {}
+    exchange_mode = per_step[-1][0].pop("_mode", "nccl")
     for stats, _ in per_step:
+        stats.pop("_mode", None)
         marks = stats.pop("_sk_marks", [])
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
             phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b) / len(per_step)
@@ -532,8 +668,9 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "avg_launch_ms": pass_ms,
                          "launches_per_step": passes, "pairs_on_rank0": int(n_shard)},
-            "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()),
-                         "note": "one all-to-all of (u64 key, u32 start) pairs; (G-1)/G of all pairs cross NVLink"},
+            "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()), "mode": exchange_mode,
+                         "note": "(G-1)/G of all (u64 key, u32 start) pairs cross NVLink once: written by the "
+                                 "partition kernel into peer memory (mode peer) or one NCCL all-to-all (mode nccl)"},
             "cpu_baseline": None, "clocks": clock_info,
             "phase_ms_rank0": {k_: round(v, 3) for k_, v in phase_ms.items()},
             "local_sort_stats_rank0": {k_: v for k_, v in per_step[-1][0].items()},
@@ -541,4 +678,5 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
+    PeerExchange.close_all()
     dist.destroy_process_group()

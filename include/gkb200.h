@@ -128,6 +128,26 @@ int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
 int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,
                        int val_bytes, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
                        uint64_t *h_counts_out, void *stream);
+/* Fused partition + exchange (multi-GPU): the same stable partition pass, but every pair
+ * is written straight into its destination rank's receive buffer over NVLink peer memory, so the
+ * exchange overlaps the partition tile by tile and no separate all-to-all of the pairs is needed.
+ *   gk_partition_count       destination counts only (the ranks exchange them to place the segments)
+ *   gk_partition_pairs_peer  h_dst_keys / h_dst_vals: n_parts <= 16 device pointers, local or opened with
+ *                            gk_peer_open; h_dst_offsets[d]: first element of this rank's segment in
+ *                            destination d.  Consumers on other ranks must be ordered behind this call
+ *                            by the caller (a stream-ordered collective). */
+int gk_partition_count(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                       uint64_t *h_counts_out, void *stream);
+int gk_partition_pairs_peer(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
+                            const uint64_t *d_splitters, uint32_t n_parts, uint64_t *const *h_dst_keys,
+                            void *const *h_dst_vals, const uint64_t *h_dst_offsets, void *stream);
+/* Peer-visible device memory for those buffers: cudaMalloc + CUDA IPC handles (64 bytes), one process
+ * per GPU on one box. */
+int gk_peer_alloc(uint64_t bytes, void **d_ptr_out);
+int gk_peer_free(void *d_ptr);
+int gk_peer_export(void *d_ptr, uint8_t *handle64_out);
+int gk_peer_open(const uint8_t *handle64, void **d_ptr_out);
+int gk_peer_close(void *d_ptr);
 /* Run-length pass over sorted keys (north_star subsystem 3): group offsets (positions where a
  * new key starts; d_offsets_out has room for n entries), number of groups. */
 int gk_rle_keys(const uint64_t *d_keys_sorted, uint64_t n, uint64_t *d_offsets_out,

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""
+Multi-GPU parity check (run under torchrun, one rank per GPU; not collected by pytest directly --
+tests/test_gpu_multi.py launches it when the box has at least two GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_check.py
+
+Every rank builds the same seeded genome, the ranks sort + count it as ONE key-range sharded index
+(both exchange modes), and rank 0 compares the concatenated shards and the histogram with the CPU oracle.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "genome-kmers_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import gpu_utils as gu
+    import oracle
+    from genome_kmers import distributed as gkd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    world = dist.get_world_size()
+    failures = []
+    cases = [(31, 600_000, 6, 8), (21, 400_000, 3, 0), (12, 300_000, 2, 3)]
+    for k, n_bases, n_rec, runs in cases:
+        rng = np.random.default_rng(1000 + k)
+        recs = gu.random_genome(rng, n_bases, n_rec, n_runs=runs, run_lo=50, run_hi=5000,
+                                n_scatter=20 if runs else 0)
+        sba = np.concatenate([np.concatenate([seq, np.array([36], dtype=np.uint8)]) for _, seq in recs])[:-1]
+        starts = np.cumsum([0] + [len(seq) + 1 for _, seq in recs[:-1]]).astype(np.uint64)
+        both, both_starts = oracle.both_strands(sba, starts)
+        want = hist_want = total_want = None
+        if rank == 0:
+            want = oracle.sort_indices(both, oracle.init_indices(both_starts, len(both), k), k, k,
+                                       threads=min(8, oracle.max_threads()))
+            hist_want, total_want = oracle.group_hist(both, want, k, max_bin=1000)
+        for mode in ("1", "0"):
+            os.environ["GK_PEER_EXCHANGE"] = mode
+            sk = gkd.ShardedKmers(sba, starts, k, "both")
+            sk.sort()
+            hist, total = sk.get_kmer_group_counts(k, max_counts_bin=1000)
+            got = sk.gather_start_indices(0)
+            used = sk.exchange_mode
+            sk.close()
+            if rank == 0:
+                ok = (len(got) == len(want) and np.array_equal(got.astype(np.uint64), want)
+                      and total == total_want and np.array_equal(hist, hist_want))
+                print(f"k={k} world={world} exchange={used}: {'ok' if ok else 'MISMATCH'} "
+                      f"({len(got)} k-mers, {int(hist.sum())} distinct)", flush=True)
+                if not ok:
+                    failures.append((k, used))
+                if mode == "1" and used != "peer":
+                    failures.append((k, "peer exchange was not used"))
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.broadcast(flag, 0)
+    gkd.PeerExchange.close_all()
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(flag.item()):
+        print("FAILED", failures, flush=True)
+        sys.exit(1)
+    if rank == 0:
+        print("multi-GPU parity ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()
