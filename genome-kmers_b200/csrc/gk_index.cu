@@ -38,6 +38,9 @@ int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &,
                        uint64_t *, const void *, void *, cudaStream_t);
 int pack4_words_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const uint64_t *,
                        uint64_t *, uint64_t *, cudaStream_t);
+int rank4_stream_device(const uint8_t *, uint64_t, uint64_t *, cudaStream_t);
+int pack4_words_stream_device(const uint64_t *, const void *, int, uint64_t, uint32_t, const uint64_t *, uint64_t *,
+                              uint64_t *, cudaStream_t);
 int scatter_pairs_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, void *,
                          cudaStream_t);
 int sba_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const void *,
@@ -252,8 +255,12 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     if (words >= 1) {
         GK_TRY(w0.alloc((size_t)m * 8, st));
         if (words >= 2) GK_TRY(w1.alloc((size_t)m * 8, st));
-        GK_TRY(pack4_words_device(ix->d_sba, ix->sba_len, idx.ptr, ib, m, key_len, key.as<uint64_t>(),
-                                  w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
+        // 4-bit rank stream of the byte array (half a byte per position), then two funnel shifts per window
+        DeviceBuffer stream;
+        GK_TRY(stream.alloc((size_t)(ix->sba_len / 16 + 3) * 8, st));
+        GK_TRY(rank4_stream_device(ix->d_sba, ix->sba_len, stream.as<uint64_t>(), st));
+        GK_TRY(pack4_words_stream_device(stream.as<uint64_t>(), idx.ptr, ib, m, key_len, key.as<uint64_t>(),
+                                         w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
         w0p = w0.as<uint64_t>();
         if (words >= 2) w1p = w1.as<uint64_t>();
     }

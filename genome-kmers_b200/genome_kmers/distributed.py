@@ -644,6 +644,11 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
                "d2h_bytes_per_step": shard_bytes * world,
                "api": "ShardedKmers(...).sort(); get_kmer_group_counts(); local_start_indices() on every rank"}
 
+    last = per_step[-1][0]
+    mine = [last.get("total_ms", 0.0), last.get("fixup_ms", 0.0), float(last.get("n_shard", 0)),
+            float(last.get("n_ambiguous", 0))]
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine)
     sent_all = torch.tensor([float(np.mean([s for _, s in per_step]))], dtype=torch.float64, device="cuda")
     dist.all_reduce(sent_all, op=dist.ReduceOp.SUM)
     phase_ms = {}
@@ -673,6 +678,10 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
                                  "partition kernel into peer memory (mode peer) or one NCCL all-to-all (mode nccl)"},
             "cpu_baseline": None, "clocks": clock_info,
             "phase_ms_rank0": {k_: round(v, 3) for k_, v in phase_ms.items()},
+            "per_rank_local_sort": {"total_ms": [round(r[0], 3) for r in per_rank],
+                                    "refine_ms": [round(r[1], 3) for r in per_rank],
+                                    "pairs": [int(r[2]) for r in per_rank],
+                                    "ambiguous": [int(r[3]) for r in per_rank]},
             "local_sort_stats_rank0": {k_: v for k_, v in per_step[-1][0].items()},
             "result": {"kmers": int(n_total), "distinct_kmers": int(hist.sum())},
         }
