@@ -67,6 +67,8 @@ int pair_keys_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_
                      cudaStream_t);
 int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint8_t *,
                         cudaStream_t);
+int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, const uint64_t *,
+                         uint32_t, uint64_t, uint64_t *, cudaStream_t);
 
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
@@ -230,7 +232,7 @@ static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, 
 // d_idx holds the sorted starts and is updated in place, and so are the flags of the repaired slots.
 static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx, uint8_t *d_flags, uint64_t n,
                          int class_bit, uint32_t key_len, int key_bits, uint64_t n_amb, bool descent,
-                         cudaStream_t st)
+                         bool terminated, cudaStream_t st)
 {
     const int ib = ix->idx_bytes;
     const uint8_t mask = (uint8_t)((n_amb ? kFlagAmb : 0) | (descent ? kFlagLong : 0));
@@ -255,12 +257,20 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     if (words >= 1) {
         GK_TRY(w0.alloc((size_t)m * 8, st));
         if (words >= 2) GK_TRY(w1.alloc((size_t)m * 8, st));
-        // 4-bit rank stream of the byte array (half a byte per position), then two funnel shifts per window
-        DeviceBuffer stream;
-        GK_TRY(stream.alloc((size_t)(ix->sba_len / 16 + 3) * 8, st));
-        GK_TRY(rank4_stream_device(ix->d_sba, ix->sba_len, stream.as<uint64_t>(), st));
-        GK_TRY(pack4_words_stream_device(stream.as<uint64_t>(), idx.ptr, ib, m, key_len, key.as<uint64_t>(),
-                                         w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
+        if (m >= ix->sba_len / 64 && !terminated) {
+            // many windows: 4-bit rank stream of the whole byte array (half a byte per position), then
+            // two funnel shifts per window
+            DeviceBuffer stream;
+            GK_TRY(stream.alloc((size_t)(ix->sba_len / 16 + 3) * 8, st));
+            GK_TRY(rank4_stream_device(ix->d_sba, ix->sba_len, stream.as<uint64_t>(), st));
+            GK_TRY(pack4_words_stream_device(stream.as<uint64_t>(), idx.ptr, ib, m, key_len, key.as<uint64_t>(),
+                                             w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
+        } else {
+            // few windows, or windows that may end at a '$' (variable-length mode): read their bytes
+            // directly; this kernel stops at the terminator (kmers.py:360-378)
+            GK_TRY(pack4_words_device(ix->d_sba, ix->sba_len, idx.ptr, ib, m, key_len, key.as<uint64_t>(),
+                                      w0.as<uint64_t>(), words >= 2 ? w1.as<uint64_t>() : nullptr, st));
+        }
         w0p = w0.as<uint64_t>();
         if (words >= 2) w1p = w1.as<uint64_t>();
     }
@@ -350,15 +360,18 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
 
     marks.fix0 = tm.mark();
     GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
-                         n_amb, (h_counters[1] & 0xffffffffull) != 0, st));
+                         n_amb, (h_counters[1] & 0xffffffffull) != 0, valid_len < key_len, st));
     marks.fix1 = tm.mark();
     return GK_OK;
 }
 
 // One prefix-doubling round: cur (sorted by the first h symbols, flags = h-groups) -> windows of
 // h2 <= 2h symbols.  See gk_refine.cu.  32-bit indices only.
-static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, Owned &cur_idx, Owned &cur_flags,
-                        uint64_t &n_cur, uint32_t *d_rank, cudaStream_t st)
+// keep_len: windows that do not fit their record at this length are dropped (fixed k: h2; variable-length
+// mode: 1, nothing is dropped and a window that ends early sorts first).  *m_out: members of groups with
+// more than one element that were re-sorted (0 = the order has converged).
+static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, uint32_t keep_len, bool var_mode, Owned &cur_idx,
+                        Owned &cur_flags, uint64_t &n_cur, uint32_t *d_rank, uint64_t *m_out, cudaStream_t st)
 {
     const uint32_t delta = h2 - h;
     DeviceBuffer gid, vflags;
@@ -368,7 +381,7 @@ static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, Owned &cur_idx, O
     // keep the windows that still fit their record at length h2 (order preserved)
     GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
     GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
-                              (uint32_t)ix->h_segs.size(), ix->sba_len, h2, vflags.as<uint8_t>(), st));
+                              (uint32_t)ix->h_segs.size(), ix->sba_len, keep_len, vflags.as<uint8_t>(), st));
     Owned new_idx, new_flags;
     DeviceBuffer new_gid;
     GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
@@ -390,8 +403,13 @@ static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, Owned &cur_idx, O
         GK_TRY(sub_idx_alt.alloc((size_t)m * 4, st));
         GK_TRY(keys.alloc((size_t)m * 8, st));
         GK_TRY(keys_alt.alloc((size_t)m * 8, st));
-        GK_TRY(pair_keys_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
-                                keys.as<uint64_t>(), st));
+        if (var_mode)
+            GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
+                                        (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
+                                        ix->sba_len, keys.as<uint64_t>(), st));
+        else
+            GK_TRY(pair_keys_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
+                                    keys.as<uint64_t>(), st));
         int in_alt = 0;
         GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr,
                                        sub_idx_alt.ptr, 4, m, 0, 64, &in_alt, st, nullptr));
@@ -401,6 +419,34 @@ static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, Owned &cur_idx, O
                                    (uint8_t *)new_flags.ptr, st));
     }
     GK_CUDA(cudaStreamSynchronize(st));  // scratch above is released in stream order after this
+    cur_idx.swap(new_idx);
+    cur_flags.swap(new_flags);
+    n_cur = n_new;
+    if (m_out) *m_out = m;
+    return GK_OK;
+}
+
+// Drop the windows shorter than min_len from a sorted order (variable-length mode sorts every start of
+// every record so that all ranks exist).  Equal windows have equal lengths, so groups go or stay whole.
+static int drop_short_windows(gk_index *ix, uint32_t min_len, Owned &cur_idx, Owned &cur_flags, uint64_t &n_cur,
+                              cudaStream_t st)
+{
+    DeviceBuffer gid, vflags, new_gid;
+    GK_TRY(gid.alloc((size_t)n_cur * 4, st));
+    GK_TRY(head_positions_device((const uint8_t *)cur_flags.ptr, (const uint32_t *)cur_idx.ptr, n_cur,
+                                 gid.as<uint32_t>(), nullptr, st));
+    GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
+    GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
+                              (uint32_t)ix->h_segs.size(), ix->sba_len, min_len, vflags.as<uint8_t>(), st));
+    Owned new_idx, new_flags;
+    GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
+    GK_TRY(new_gid.alloc((size_t)n_cur * 4, st));
+    uint64_t n_new = 0;
+    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, nullptr, cur_idx.ptr, new_idx.ptr, gid.ptr,
+                          new_gid.ptr, &n_new, st));
+    GK_TRY(new_flags.alloc((size_t)((n_new + 15) & ~15ull), st));
+    GK_TRY(gid_flags_device(new_gid.as<uint32_t>(), n_new, (uint8_t *)new_flags.ptr, st));
+    GK_CUDA(cudaStreamSynchronize(st));
     cur_idx.swap(new_idx);
     cur_flags.swap(new_flags);
     n_cur = n_new;
@@ -495,17 +541,61 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         return GK_ERR_INVALID_KMERS;
     }
     const bool fixed = ix->max_len != 0 && ix->max_len == ix->min_len;
-    if (!fixed) {
-        set_error("sort() with min_kmer_len != max_kmer_len (variable-length / suffix order) is not "
-                  "available on the GPU path yet");
-        return GK_ERR_UNSUPPORTED;
-    }
     const bool has_amb = ix->n_amb_letters > 0 || ix->n_bad > 0;
     const uint32_t k = ix->min_len;
     stats.n_windows = ix->n;
     int t_ref0 = -1, t_ref1 = -1;
     if (ix->n == 0) {
         ix->sorted = true;
+    } else if (!fixed) {
+        // Variable-length mode (min_kmer_len < max_kmer_len, or max_kmer_len None = suffix order inside each
+        // record): compare up to max_kmer_len symbols, a window that reaches its record's '$' first sorts
+        // first (kmers.py:360-378).  '$' is one more non-ACGT symbol for the two-class keys.
+        if (ix->idx_bytes != 4) {
+            set_error("variable-length k-mers on a byte array of 2^32 or more positions are not available yet");
+            return GK_ERR_UNSUPPORTED;
+        }
+        ix->flags_mark_amb = false;
+        const uint32_t max_len = ix->max_len;  // 0 = None
+        if (max_len != 0 && max_len <= 31) {
+            GK_TRY(sort_level1(ix, ix->min_len, max_len, true, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
+        } else {
+            // longer than one key word: sort EVERY start of every record by its first 31 symbols (so that
+            // every position has a rank), double the compared length until max_kmer_len (or the longest
+            // record) is covered or nothing is tied any more, then drop the windows shorter than min_kmer_len
+            uint64_t longest = 0;
+            for (size_t r = 0; r < ix->h_segs.size(); ++r) {
+                const uint64_t e = (r + 1 < ix->h_segs.size()) ? ix->h_segs[r + 1] - 1 : ix->sba_len;
+                if (e - ix->h_segs[r] > longest) longest = e - ix->h_segs[r];
+            }
+            const uint64_t target = (max_len != 0 && max_len < longest) ? max_len : longest;
+            uint64_t n_cur = 0;
+            GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, 1, &n_cur));
+            Owned cur_idx, cur_flags;
+            GK_TRY(sort_level1(ix, 1, 31, true, n_cur, cur_idx, cur_flags, marks, tm, st));
+            DeviceBuffer rank;
+            GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
+            t_ref0 = tm.mark();
+            uint64_t h = 31;
+            while (h < target) {
+                const uint64_t h2 = (2 * h < target) ? 2 * h : target;
+                uint64_t moved = 0;
+                GK_TRY(refine_level(ix, (uint32_t)h, (uint32_t)h2, 1, true, cur_idx, cur_flags, n_cur,
+                                    rank.as<uint32_t>(), &moved, st));
+                h = h2;
+                ++marks.levels;
+                if (moved == 0) break;
+            }
+            if (ix->min_len > 1) GK_TRY(drop_short_windows(ix, ix->min_len, cur_idx, cur_flags, n_cur, st));
+            t_ref1 = tm.mark();
+            if (n_cur != ix->n) {
+                set_error("variable-length sort kept %llu windows, expected %llu", (unsigned long long)n_cur,
+                          (unsigned long long)ix->n);
+                return GK_ERR_INTERNAL;
+            }
+            ix->d_idx.swap(cur_idx);
+            ix->d_flags.swap(cur_flags);
+        }
     } else if (k <= 31 || (k == 32 && !has_amb)) {
         GK_TRY(sort_level1(ix, k, k, has_amb, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
         ix->flags_mark_amb = true;
@@ -527,7 +617,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         uint32_t h = k1;
         while (h < k) {
             const uint32_t h2 = (2 * h < k) ? 2 * h : k;
-            GK_TRY(refine_level(ix, h, h2, cur_idx, cur_flags, n_cur, rank.as<uint32_t>(), st));
+            GK_TRY(refine_level(ix, h, h2, h2, false, cur_idx, cur_flags, n_cur, rank.as<uint32_t>(), nullptr, st));
             h = h2;
             ++marks.levels;
         }
@@ -542,7 +632,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     }
     ix->idx_ready = true;
     ix->flags_valid = ix->n > 0;
-    ix->flags_kmer_len = k;
+    ix->flags_kmer_len = fixed ? k : ix->max_len;  // (None -> 0: such queries take the comparator path)
     ix->sorted = true;
     const int t1 = tm.mark();
     GK_CUDA(cudaStreamSynchronize(st));
@@ -605,7 +695,7 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n_local, kFlagAmb, ib, nullptr, nullptr, nullptr,
                               nullptr, nullptr, &n_amb, st));
     GK_TRY(refine_subset(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
-                         key_bits, n_amb, h_descent != 0, st));
+                         key_bits, n_amb, h_descent != 0, false, st));
     const int f1 = tm.mark();
     ix->idx_ready = true;
     ix->flags_mark_amb = true;

@@ -355,7 +355,10 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
                      unsigned long long *d_n_amb, int hist_begin_bit, int hist_end_bit,
                      unsigned long long *d_hist, cudaStream_t st)
 {
-    if (key_len < 1 || key_len > 32 || valid_len < key_len || (class_bit && key_len > 31)) {
+    // valid_len < key_len is the variable-length mode: windows shorter than the key end at their record's
+    // '$', which the key treats like any other non-ACGT symbol (it sorts below A); needs the class bit
+    if (key_len < 1 || key_len > 32 || valid_len < 1 || (valid_len < key_len && !class_bit) ||
+        (class_bit && key_len > 31)) {
         set_error("pack_keys: key_len %u / valid_len %u / class_bit %d out of range", key_len,
                   valid_len, class_bit);
         return GK_ERR_ARG;

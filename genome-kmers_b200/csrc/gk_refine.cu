@@ -158,6 +158,25 @@ pair_keys_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__restric
         keys[r] = ((uint64_t)sub_gid[r] << 32) | rank_of_start[(uint64_t)sub_idx[r] + delta];
 }
 
+// Variable-length mode (kmers.py:360-378): a window ends at its record's '$'.  When start + delta is at or
+// past that '$' the second half is empty and sorts first (0); real ranks are shifted up by one.
+__global__ void __launch_bounds__(256)
+pair_keys_var_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__restrict__ sub_gid, uint64_t m,
+                     const uint32_t *__restrict__ rank_of_start, uint32_t delta,
+                     const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint64_t sba_len,
+                     uint64_t *__restrict__ keys)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const uint64_t s = sub_idx[r];
+        const uint32_t seg = upper_seg(seg_starts, n_seg, s);
+        const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;  // position of '$'
+        const uint64_t q = s + delta;
+        const uint32_t second = (q < seg_end) ? rank_of_start[q] + 1u : 0u;
+        keys[r] = ((uint64_t)sub_gid[r] << 32) | second;
+    }
+}
+
 // the re-sorted subset goes back to its slots with fresh head flags
 __global__ void __launch_bounds__(256)
 key2_scatter_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ sub_idx_sorted,
@@ -397,6 +416,17 @@ int pair_keys_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, uint6
 {
     if (m == 0) return GK_OK;
     pair_keys_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_rank_of_start, delta, d_keys);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int pair_keys_var_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, uint64_t m,
+                         const uint32_t *d_rank_of_start, uint32_t delta, const uint64_t *d_seg_starts,
+                         uint32_t n_seg, uint64_t sba_len, uint64_t *d_keys, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    pair_keys_var_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_rank_of_start, delta,
+                                                      d_seg_starts, n_seg, sba_len, d_keys);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -223,6 +223,7 @@ class PeerExchange:
     reused by later sorts; `capacity` counts pairs."""
 
     _cache = {}
+    MAX_BYTES = 64 << 30   # per rank; beyond this the NCCL all-to-all path is used
 
     def __init__(self, engine, dist, group, capacity: int, idx_bytes: int):
         torch, lib = engine.torch, engine.lib
@@ -354,12 +355,19 @@ class ShardedKmers:
         self._mark("start")
         if k > 31:
             raise NotImplementedError("the multi-GPU path handles single-word k-mers (k <= 31)")
-        counts = eng.alphabet(self.d_sba)
+        first, end = slice_bounds(self.total_len, world, rank)
+        # (16-byte aligned cut points, so that the scan keeps its 128-bit loads)
+        a16 = (first // 16) * 16 if rank > 0 else 0
+        b16 = (end // 16) * 16 if rank < world - 1 else self.total_len
+        counts = eng.alphabet(self.d_sba[a16:b16] if world > 1 else self.d_sba)
+        if world > 1:   # every rank scans its own slice of the byte array; the three counters are summed
+            tot = eng.from_host_i64(counts.astype(np.int64))
+            dist.all_reduce(tot, group=self.group)
+            counts = self._to_host_i64(tot).astype(np.uint64)
         n_sep_expected = len(self.seg_starts) - 1
         if int(counts[1]) != n_sep_expected:
             raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
         class_bit = 1 if (counts[2] > 0 or counts[0] > 0) else 0
-        first, end = slice_bounds(self.total_len, world, rank)
         self._mark("alphabet")
         keys, idx = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
         n_local_in = int(keys.numel())
@@ -398,10 +406,11 @@ class ShardedKmers:
             dist.all_gather(rows, mine, group=self.group)
             matrix = np.stack([self._to_host_i64(r) for r in rows])          # [source, destination]
             recv_total = matrix.sum(axis=0)
-            n_windows_all = int(matrix.sum())
-            capacity = int(1.25 * n_windows_all / world) + (1 << 20)
+            # every rank sees the same matrix, so every rank computes the same capacity: the largest
+            # receive count plus 10 % head-room (the buffers are cached and only ever grow)
+            capacity = int(1.1 * int(recv_total.max())) + (1 << 20)
             self._mark("partition")
-            if int(recv_total.max()) <= capacity:
+            if capacity * (8 + self.idx_bytes) <= PeerExchange.MAX_BYTES:
                 px = eng.peer_exchange(dist, self.group, capacity, self.idx_bytes)
                 offsets = matrix[:rank, :].sum(axis=0)
                 eng.partition_peer(keys, idx, splitters, world, px, offsets)
