@@ -53,6 +53,9 @@ void count_launch(int n = 1);
 // All scratch comes from the device's default mempool (cudaMallocAsync); the release threshold
 // is raised once so repeated sorts reuse the same pages instead of going back to the driver.
 int ensure_pool_configured();
+void trace_alloc(double ms, size_t bytes);  // GK_TRACE=1: allocation time accounting (gk_core.cu)
+
+double trace_now_ms();
 
 struct DeviceBuffer {
     void *ptr = nullptr;
@@ -69,7 +72,9 @@ struct DeviceBuffer {
         bytes = n;
         if (n == 0) return GK_OK;
         GK_TRY(ensure_pool_configured());
+        const double t0 = trace_now_ms();
         GK_CUDA(cudaMallocAsync(&ptr, n, s));
+        trace_alloc(trace_now_ms() - t0, n);
         return GK_OK;
     }
     void release()

@@ -1,6 +1,8 @@
 // gk_core.cu -- library plumbing: status strings, thread-local error text, launch counter,
 // memory pool configuration, device info.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include "gk_common.cuh"
 
@@ -31,6 +33,38 @@ int ensure_pool_configured()
     GK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     configured_device = dev;
     return GK_OK;
+}
+
+// ---- GK_TRACE=1: where does host time go? ----------------------------------------------------------------
+static thread_local double g_alloc_ms = 0.0;
+static thread_local uint64_t g_alloc_calls = 0, g_alloc_bytes = 0;
+static int trace_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("GK_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on;
+}
+double trace_now_ms()
+{
+    if (!trace_enabled()) return 0.0;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+void trace_alloc(double ms, size_t bytes)
+{
+    if (!trace_enabled()) return;
+    g_alloc_ms += ms;
+    g_alloc_calls += 1;
+    g_alloc_bytes += bytes;
+}
+void trace_report(const char *what)
+{
+    if (!trace_enabled()) return;
+    fprintf(stderr, "[gk trace] %s: %llu pool allocations, %.1f MB, %.3f ms in cudaMallocAsync\n", what,
+            (unsigned long long)g_alloc_calls, (double)g_alloc_bytes / 1e6, g_alloc_ms);
+    g_alloc_ms = 0.0;
+    g_alloc_calls = g_alloc_bytes = 0;
 }
 
 int sm_count()

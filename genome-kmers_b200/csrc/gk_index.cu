@@ -13,6 +13,7 @@
 
 namespace gk {
 
+void trace_report(const char *what);
 // kernels / device drivers from the other translation units
 int kmer_count_host(const uint64_t *, uint32_t, uint64_t, uint32_t, uint64_t *);
 int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, void *, cudaStream_t);
@@ -69,6 +70,9 @@ int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, ui
                         cudaStream_t);
 int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, const uint64_t *,
                          uint32_t, uint64_t, uint64_t *, cudaStream_t);
+int subset_rank_update_device(const uint32_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *,
+                              cudaStream_t);
+int gather_u32_device(const uint32_t *, const uint32_t *, uint64_t, uint32_t *, cudaStream_t);
 
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
@@ -90,7 +94,9 @@ struct Owned {
         stream = st;
         if (n == 0) return GK_OK;
         GK_TRY(ensure_pool_configured());
+        const double t0 = trace_now_ms();
         GK_CUDA(cudaMallocAsync(&ptr, n, st));
+        trace_alloc(trace_now_ms() - t0, n);
         bytes = n;
         return GK_OK;
     }
@@ -365,64 +371,90 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool 
     return GK_OK;
 }
 
-// One prefix-doubling round: cur (sorted by the first h symbols, flags = h-groups) -> windows of
-// h2 <= 2h symbols.  See gk_refine.cu.  32-bit indices only.
-// keep_len: windows that do not fit their record at this length are dropped (fixed k: h2; variable-length
-// mode: 1, nothing is dropped and a window that ends early sorts first).  *m_out: members of groups with
-// more than one element that were re-sorted (0 = the order has converged).
-static int refine_level(gk_index *ix, uint32_t h, uint32_t h2, uint32_t keep_len, bool var_mode, Owned &cur_idx,
-                        Owned &cur_flags, uint64_t &n_cur, uint32_t *d_rank, uint64_t *m_out, cudaStream_t st)
+// Prefix doubling (gk_refine.cu) for k-mers longer than one key word and for the variable-length mode.
+// In: every start of every record, sorted by its first h0 symbols with a window that reaches its record's
+// '$' first sorting first; flags = groups of equal h0-prefixes.  A round h -> h2 <= 2h orders the members
+// of every group with more than one element by the pair (group, rank_h[start + h2 - h]); an empty second
+// half (the window ended) sorts first.  Only the O(n) set-up touches every k-mer: rank_h of every start
+// (= sorted position of the first member of its group) and the list of members of multi-element groups.
+// The rounds then work on that shrinking list only and scatter their results into the global order.
+static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint64_t n_cur, uint64_t h0,
+                           uint64_t target, int *levels, cudaStream_t st)
 {
-    const uint32_t delta = h2 - h;
-    DeviceBuffer gid, vflags;
+    if (h0 >= target || n_cur < 2) return GK_OK;
+    uint32_t *d_idx = (uint32_t *)cur_idx.ptr;
+    uint8_t *d_flags = (uint8_t *)cur_flags.ptr;
+    DeviceBuffer rank, gid, mflags;
+    GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
     GK_TRY(gid.alloc((size_t)n_cur * 4, st));
-    GK_TRY(head_positions_device((const uint8_t *)cur_flags.ptr, (const uint32_t *)cur_idx.ptr, n_cur,
-                                 gid.as<uint32_t>(), d_rank, st));
-    // keep the windows that still fit their record at length h2 (order preserved)
-    GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
-    GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
-                              (uint32_t)ix->h_segs.size(), ix->sba_len, keep_len, vflags.as<uint8_t>(), st));
-    Owned new_idx, new_flags;
-    DeviceBuffer new_gid;
-    GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
-    GK_TRY(new_gid.alloc((size_t)n_cur * 4, st));
-    uint64_t n_new = 0;
-    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, nullptr, cur_idx.ptr, new_idx.ptr,
-                          gid.ptr, new_gid.ptr, &n_new, st));
-    GK_TRY(new_flags.alloc((size_t)((n_new + 15) & ~15ull), st));
-    GK_TRY(gid_flags_device(new_gid.as<uint32_t>(), n_new, (uint8_t *)new_flags.ptr, st));
-    // members of groups with more than one element are the only ones that can move
-    DeviceBuffer slots, sub_idx, sub_idx_alt, sub_gid, keys, keys_alt;
-    GK_TRY(slots.alloc((size_t)n_new * 4, st));
-    GK_TRY(sub_idx.alloc((size_t)n_new * 4, st));
-    GK_TRY(sub_gid.alloc((size_t)n_new * 4, st));
+    GK_TRY(head_positions_device(d_flags, d_idx, n_cur, gid.as<uint32_t>(), rank.as<uint32_t>(), st));
+    GK_TRY(mflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
+    GK_TRY(gid_flags_device(gid.as<uint32_t>(), n_cur, mflags.as<uint8_t>(), st));
     uint64_t m = 0;
-    GK_TRY(select_flagged((const uint8_t *)new_flags.ptr, n_new, kFlagMulti, 4, slots.ptr, new_idx.ptr,
-                          sub_idx.ptr, new_gid.ptr, sub_gid.ptr, &m, st));
-    if (m > 0) {
-        GK_TRY(sub_idx_alt.alloc((size_t)m * 4, st));
+    GK_TRY(select_flagged(mflags.as<uint8_t>(), n_cur, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          &m, st));
+    DeviceBuffer slots, sub_idx, sub_gid;
+    if (m) {
+        GK_TRY(slots.alloc((size_t)m * 4, st));
+        GK_TRY(sub_idx.alloc((size_t)m * 4, st));
+        GK_TRY(sub_gid.alloc((size_t)m * 4, st));
+        GK_TRY(select_flagged(mflags.as<uint8_t>(), n_cur, kFlagMulti, 4, slots.ptr, d_idx, sub_idx.ptr, gid.ptr,
+                              sub_gid.ptr, nullptr, st));
+    }
+    gid.release();
+    mflags.release();
+    uint64_t h = h0;
+    while (h < target && m > 0) {
+        const uint64_t h2 = (2 * h < target) ? 2 * h : target;
+        const uint32_t delta = (uint32_t)(h2 - h);
+        DeviceBuffer keys, keys_alt, idx_alt, hf, gsub, gslot, mf;
         GK_TRY(keys.alloc((size_t)m * 8, st));
         GK_TRY(keys_alt.alloc((size_t)m * 8, st));
-        if (var_mode)
-            GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
-                                        (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
-                                        ix->sba_len, keys.as<uint64_t>(), st));
-        else
-            GK_TRY(pair_keys_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, d_rank, delta,
+        GK_TRY(idx_alt.alloc((size_t)m * 4, st));
+        GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, rank.as<uint32_t>(), delta,
+                                    (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->sba_len,
                                     keys.as<uint64_t>(), st));
         int in_alt = 0;
-        GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr,
-                                       sub_idx_alt.ptr, 4, m, 0, 64, &in_alt, st, nullptr));
-        GK_TRY(key2_scatter_device(in_alt ? keys_alt.as<uint64_t>() : keys.as<uint64_t>(),
-                                   in_alt ? sub_idx_alt.as<uint32_t>() : sub_idx.as<uint32_t>(),
-                                   slots.as<uint32_t>(), m, (uint32_t *)new_idx.ptr,
-                                   (uint8_t *)new_flags.ptr, st));
+        GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr, idx_alt.ptr, 4, m,
+                                       0, 64, &in_alt, st, nullptr));
+        const uint64_t *K = in_alt ? keys_alt.as<uint64_t>() : keys.as<uint64_t>();
+        const uint32_t *I = in_alt ? idx_alt.as<uint32_t>() : sub_idx.as<uint32_t>();
+        GK_TRY(key2_scatter_device(K, I, slots.as<uint32_t>(), m, d_idx, d_flags, st));
+        // the groups inside the list after this round, the new ranks, the members that are still tied
+        GK_TRY(hf.alloc((size_t)((m + 15) & ~15ull), st));
+        GK_TRY(key_flags_device(K, m, 0, hf.as<uint8_t>(), st));
+        GK_TRY(gsub.alloc((size_t)m * 4, st));
+        GK_TRY(head_positions_device(hf.as<uint8_t>(), I, m, gsub.as<uint32_t>(), nullptr, st));
+        GK_TRY(gslot.alloc((size_t)m * 4, st));
+        GK_TRY(subset_rank_update_device(slots.as<uint32_t>(), gsub.as<uint32_t>(), I, m, gslot.as<uint32_t>(),
+                                         rank.as<uint32_t>(), st));
+        GK_TRY(mf.alloc((size_t)((m + 15) & ~15ull), st));
+        GK_TRY(gid_flags_device(gsub.as<uint32_t>(), m, mf.as<uint8_t>(), st));
+        uint64_t m2 = 0;
+        GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr, &m2,
+                              st));
+        DeviceBuffer pos, new_slots, new_idx, new_gid;
+        if (m2) {
+            GK_TRY(pos.alloc((size_t)m2 * 4, st));
+            GK_TRY(new_slots.alloc((size_t)m2 * 4, st));
+            GK_TRY(new_idx.alloc((size_t)m2 * 4, st));
+            GK_TRY(new_gid.alloc((size_t)m2 * 4, st));
+            GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, 4, pos.ptr, I, new_idx.ptr, gslot.ptr, new_gid.ptr,
+                                  nullptr, st));
+            GK_TRY(gather_u32_device(slots.as<uint32_t>(), pos.as<uint32_t>(), m2, new_slots.as<uint32_t>(), st));
+        }
+        GK_CUDA(cudaStreamSynchronize(st));  // the round's scratch is released in stream order after this
+        slots.release(); sub_idx.release(); sub_gid.release();
+        if (m2) {
+            // adopt the new lists (move the pointers: DeviceBuffer has no move assignment)
+            slots.ptr = new_slots.ptr; slots.bytes = new_slots.bytes; slots.stream = st; new_slots.ptr = nullptr;
+            sub_idx.ptr = new_idx.ptr; sub_idx.bytes = new_idx.bytes; sub_idx.stream = st; new_idx.ptr = nullptr;
+            sub_gid.ptr = new_gid.ptr; sub_gid.bytes = new_gid.bytes; sub_gid.stream = st; new_gid.ptr = nullptr;
+        }
+        m = m2;
+        h = h2;
+        if (levels) ++*levels;
     }
-    GK_CUDA(cudaStreamSynchronize(st));  // scratch above is released in stream order after this
-    cur_idx.swap(new_idx);
-    cur_flags.swap(new_flags);
-    n_cur = n_new;
-    if (m_out) *m_out = m;
     return GK_OK;
 }
 
@@ -545,85 +577,45 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     const uint32_t k = ix->min_len;
     stats.n_windows = ix->n;
     int t_ref0 = -1, t_ref1 = -1;
+    const uint32_t max_len = ix->max_len;  // 0 = None
     if (ix->n == 0) {
         ix->sorted = true;
-    } else if (!fixed) {
-        // Variable-length mode (min_kmer_len < max_kmer_len, or max_kmer_len None = suffix order inside each
-        // record): compare up to max_kmer_len symbols, a window that reaches its record's '$' first sorts
-        // first (kmers.py:360-378).  '$' is one more non-ACGT symbol for the two-class keys.
-        if (ix->idx_bytes != 4) {
-            set_error("variable-length k-mers on a byte array of 2^32 or more positions are not available yet");
-            return GK_ERR_UNSUPPORTED;
-        }
-        ix->flags_mark_amb = false;
-        const uint32_t max_len = ix->max_len;  // 0 = None
-        if (max_len != 0 && max_len <= 31) {
-            GK_TRY(sort_level1(ix, ix->min_len, max_len, true, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
-        } else {
-            // longer than one key word: sort EVERY start of every record by its first 31 symbols (so that
-            // every position has a rank), double the compared length until max_kmer_len (or the longest
-            // record) is covered or nothing is tied any more, then drop the windows shorter than min_kmer_len
-            uint64_t longest = 0;
-            for (size_t r = 0; r < ix->h_segs.size(); ++r) {
-                const uint64_t e = (r + 1 < ix->h_segs.size()) ? ix->h_segs[r + 1] - 1 : ix->sba_len;
-                if (e - ix->h_segs[r] > longest) longest = e - ix->h_segs[r];
-            }
-            const uint64_t target = (max_len != 0 && max_len < longest) ? max_len : longest;
-            uint64_t n_cur = 0;
-            GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, 1, &n_cur));
-            Owned cur_idx, cur_flags;
-            GK_TRY(sort_level1(ix, 1, 31, true, n_cur, cur_idx, cur_flags, marks, tm, st));
-            DeviceBuffer rank;
-            GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
-            t_ref0 = tm.mark();
-            uint64_t h = 31;
-            while (h < target) {
-                const uint64_t h2 = (2 * h < target) ? 2 * h : target;
-                uint64_t moved = 0;
-                GK_TRY(refine_level(ix, (uint32_t)h, (uint32_t)h2, 1, true, cur_idx, cur_flags, n_cur,
-                                    rank.as<uint32_t>(), &moved, st));
-                h = h2;
-                ++marks.levels;
-                if (moved == 0) break;
-            }
-            if (ix->min_len > 1) GK_TRY(drop_short_windows(ix, ix->min_len, cur_idx, cur_flags, n_cur, st));
-            t_ref1 = tm.mark();
-            if (n_cur != ix->n) {
-                set_error("variable-length sort kept %llu windows, expected %llu", (unsigned long long)n_cur,
-                          (unsigned long long)ix->n);
-                return GK_ERR_INTERNAL;
-            }
-            ix->d_idx.swap(cur_idx);
-            ix->d_flags.swap(cur_flags);
-        }
-    } else if (k <= 31 || (k == 32 && !has_amb)) {
+    } else if (fixed && (k <= 31 || (k == 32 && !has_amb))) {
         GK_TRY(sort_level1(ix, k, k, has_amb, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
         ix->flags_mark_amb = true;
-    } else {
+    } else if (!fixed && max_len != 0 && max_len <= 31) {
+        // Variable-length mode inside one key word: compare up to max_kmer_len symbols, a window that reaches
+        // its record's '$' first sorts first (kmers.py:360-378).  '$' is one more non-ACGT symbol for the
+        // two-class keys.
         ix->flags_mark_amb = false;
-        // multi-word k-mers: exact order of the first k1 symbols, then prefix doubling on ranks
+        GK_TRY(sort_level1(ix, ix->min_len, max_len, true, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
+    } else {
+        // Longer than one key word -- fixed k > 32, max_kmer_len > 31, or None (suffix order inside each
+        // record).  Sort EVERY start of every record by its first 31 symbols, terminator-aware, so that
+        // every position has a rank; double the compared length until the target is covered or nothing is
+        // tied any more; finally drop the windows shorter than min_kmer_len.
         if (ix->idx_bytes != 4) {
-            set_error("kmer_len %u on a byte array of 2^32 or more positions is not available yet", k);
+            set_error("k-mers longer than one key word on a byte array of 2^32 or more positions are not "
+                      "available yet");
             return GK_ERR_UNSUPPORTED;
         }
-        const uint32_t k1 = has_amb ? 31 : 32;
-        uint64_t n_cur = 0;
-        GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, k1, &n_cur));
-        Owned cur_idx, cur_flags;
-        GK_TRY(sort_level1(ix, k1, k1, has_amb, n_cur, cur_idx, cur_flags, marks, tm, st));
-        DeviceBuffer rank;
-        GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
-        t_ref0 = tm.mark();
-        uint32_t h = k1;
-        while (h < k) {
-            const uint32_t h2 = (2 * h < k) ? 2 * h : k;
-            GK_TRY(refine_level(ix, h, h2, h2, false, cur_idx, cur_flags, n_cur, rank.as<uint32_t>(), nullptr, st));
-            h = h2;
-            ++marks.levels;
+        ix->flags_mark_amb = false;
+        uint64_t longest = 0;
+        for (size_t r = 0; r < ix->h_segs.size(); ++r) {
+            const uint64_t e = (r + 1 < ix->h_segs.size()) ? ix->h_segs[r + 1] - 1 : ix->sba_len;
+            if (e - ix->h_segs[r] > longest) longest = e - ix->h_segs[r];
         }
+        const uint64_t target = (max_len != 0 && max_len < longest) ? max_len : longest;
+        uint64_t n_cur = 0;
+        GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, 1, &n_cur));
+        Owned cur_idx, cur_flags;
+        GK_TRY(sort_level1(ix, 1, 31, true, n_cur, cur_idx, cur_flags, marks, tm, st));
+        t_ref0 = tm.mark();
+        GK_TRY(doubling_rounds(ix, cur_idx, cur_flags, n_cur, 31, target, &marks.levels, st));
+        if (ix->min_len > 1) GK_TRY(drop_short_windows(ix, ix->min_len, cur_idx, cur_flags, n_cur, st));
         t_ref1 = tm.mark();
         if (n_cur != ix->n) {
-            set_error("refinement kept %llu windows, expected %llu", (unsigned long long)n_cur,
+            set_error("doubling kept %llu windows, expected %llu", (unsigned long long)n_cur,
                       (unsigned long long)ix->n);
             return GK_ERR_INTERNAL;
         }
@@ -647,6 +639,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;
+    trace_report("gk_index_sort");
     return GK_OK;
 }
 

@@ -366,6 +366,29 @@ subset_expand_kernel(const T *__restrict__ pos, const T *__restrict__ idx_sel, c
     }
 }
 
+// subset bookkeeping of the doubling rounds: global slot of every member's group head, and the new rank of
+// every member's start (rank = sorted position of the first member of its group)
+__global__ void __launch_bounds__(256)
+subset_rank_update_kernel(const uint32_t *__restrict__ slots, const uint32_t *__restrict__ gid_sub,
+                          const uint32_t *__restrict__ idx_sorted, uint64_t m, uint32_t *__restrict__ gid_slot,
+                          uint32_t *__restrict__ rank_of_start)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const uint32_t g = slots[gid_sub[r]];
+        gid_slot[r] = g;
+        rank_of_start[idx_sorted[r]] = g;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ at, uint64_t count,
+                  uint32_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += stride) out[r] = src[at[r]];
+}
+
 static int grid_for(uint64_t items)
 {
     uint64_t blocks = (items + 255) / 256;
@@ -427,6 +450,24 @@ int pair_keys_var_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, u
     if (m == 0) return GK_OK;
     pair_keys_var_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_rank_of_start, delta,
                                                       d_seg_starts, n_seg, sba_len, d_keys);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int subset_rank_update_device(const uint32_t *d_slots, const uint32_t *d_gid_sub, const uint32_t *d_idx_sorted,
+                              uint64_t m, uint32_t *d_gid_slot, uint32_t *d_rank_of_start, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    subset_rank_update_kernel<<<grid_for(m), 256, 0, st>>>(d_slots, d_gid_sub, d_idx_sorted, m, d_gid_slot,
+                                                           d_rank_of_start);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int gather_u32_device(const uint32_t *d_src, const uint32_t *d_at, uint64_t count, uint32_t *d_out, cudaStream_t st)
+{
+    if (count == 0) return GK_OK;
+    gather_u32_kernel<<<grid_for(count), 256, 0, st>>>(d_src, d_at, count, d_out);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -187,6 +187,40 @@ def test_seeded_random_vs_oracle(k, strands, n_bases, n_rec, runs):
     _oracle_compare(recs, k, strands)
 
 
+@pytest.mark.parametrize("min_len,max_len,strands,n_bases,n_rec,runs", [
+    (5, None, "forward", 60_000, 4, 3),       # suffix order inside each record
+    (1, None, "forward", 30_000, 7, 0),
+    (3, 20, "forward", 200_000, 5, 4),        # one key word, windows shorter than the key near record ends
+    (1, 31, "both", 150_000, 3, 2),
+    (10, 40, "forward", 200_000, 5, 4),       # two doubling rounds, short windows dropped at the end
+    (20, 100, "both", 120_000, 6, 3),
+])
+def test_variable_length_modes_vs_oracle(min_len, max_len, strands, n_bases, n_rec, runs):
+    """sort() with min_kmer_len < max_kmer_len / max_kmer_len None (kmers.py:360-378), SURVEY.md 8f N5."""
+    rng = np.random.default_rng(7 * min_len + (max_len or 0) + n_bases)
+    recs = gu.random_genome(rng, n_bases, n_rec, n_runs=runs, run_lo=20, run_hi=400, n_scatter=10 if runs else 0)
+    # plant repeats so that many windows stay tied for hundreds of symbols
+    recs = [(nm, seq.copy()) for nm, seq in recs]
+    unit = recs[0][1][100:700].copy()
+    for nm, seq in recs[1:]:
+        seq[50:650] = unit
+        seq[-300:] = unit[:300]               # identical record tails: suffixes equal up to the terminator
+    sc = SequenceCollection.from_arrays(recs, strands_to_load=strands)
+    km = Kmers(sc, min_len, max_len, source_strand=strands)
+    km.sort()
+    got = km.kmer_sba_start_indices.astype(np.uint64)
+    sba, starts = sc.forward_sba, sc._forward_sba_seg_starts.astype(np.uint64)
+    if strands == "both":
+        sba, starts = oracle.both_strands(sba, starts)
+    want = oracle.sort_indices(sba, oracle.init_indices(starts, len(sba), min_len), min_len, max_len, threads=8)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, f"first mismatches at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
+    for kmer_len in (max_len, min_len):
+        hist, total = km.get_kmer_group_counts(kmer_len, max_counts_bin=500)
+        o_hist, o_total = oracle.group_hist(sba, want, kmer_len or 0, max_bin=500)
+        assert total == o_total and np.array_equal(hist, o_hist), kmer_len
+
+
 def test_config1_shape_vs_oracle():
     """BASELINE.json configs[0]: 4.6 Mbp, one record, forward, k=21 (the reference's CPU case)."""
     rng = np.random.default_rng(42)
