@@ -279,12 +279,25 @@ class PeerExchange:
         cls._cache.clear()
 
 
-def choose_splitters(sorted_samples: np.ndarray, n_parts: int) -> np.ndarray:
-    """n_parts-1 splitters at the even quantiles of the pooled, sorted samples (uint64)."""
+AMBIGUOUS_COST = 2.5   # local-sort cost of an ambiguous window relative to a pure one (refinement), measured
+
+
+def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 0) -> np.ndarray:
+    """n_parts-1 splitters at the even quantiles of the pooled, sorted samples (uint64).
+
+    With class_bit the quantiles are taken over COST, not count: a key with class bit 0 is an ambiguous
+    window, which also goes through the refinement.  One N run makes millions of them with ONE key, which no
+    key splitter can cut, so the rank that gets that group is given correspondingly fewer other keys."""
     m = len(sorted_samples)
     if n_parts <= 1 or m == 0:
         return np.zeros(0, dtype=np.uint64)
-    pos = (np.arange(1, n_parts, dtype=np.int64) * m) // n_parts
+    if class_bit:
+        weight = np.where((sorted_samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
+        cum = np.cumsum(weight)
+        targets = cum[-1] * np.arange(1, n_parts, dtype=np.float64) / n_parts
+        pos = np.minimum(np.searchsorted(cum, targets, side="left"), m - 1)
+    else:
+        pos = (np.arange(1, n_parts, dtype=np.int64) * m) // n_parts
     return np.ascontiguousarray(sorted_samples[pos], dtype=np.uint64)
 
 
@@ -386,7 +399,7 @@ class ShardedKmers:
             dist.all_gather(gathered, padded, group=self.group)
             pooled = [g[1:1 + int(g[0].item())] for g in gathered]
             pooled = eng.sort_keys(self._cat(pooled))
-            splitters_host = choose_splitters(self._to_host_u64(pooled), world)
+            splitters_host = choose_splitters(self._to_host_u64(pooled), world, class_bit)
             splitters = eng.from_host_i64(splitters_host.view(np.int64))
         else:
             splitters_host, splitters = np.zeros(0, dtype=np.uint64), None
