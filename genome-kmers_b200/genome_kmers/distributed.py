@@ -292,10 +292,47 @@ def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 
     if n_parts <= 1 or m == 0:
         return np.zeros(0, dtype=np.uint64)
     if class_bit:
+        # blocks of equal keys (a part can only begin where a key begins) and their costs
         weight = np.where((sorted_samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
-        cum = np.cumsum(weight)
-        targets = cum[-1] * np.arange(1, n_parts, dtype=np.float64) / n_parts
-        pos = np.minimum(np.searchsorted(cum, targets, side="left"), m - 1)
+        first = np.flatnonzero(np.concatenate([[True], sorted_samples[1:] != sorted_samples[:-1]]))
+        cost = np.add.reduceat(weight, first)
+        cum = np.concatenate([[0.0], np.cumsum(cost)])        # cum[b] = cost of blocks [0, b)
+
+        def pack(limit):
+            """Greedy: fill every part up to `limit`; returns the first block of parts 1, 2, ..."""
+            cuts, b = [], 0
+            while b < len(cost) and len(cuts) < n_parts:
+                e = int(np.searchsorted(cum, cum[b] + limit, side="right")) - 1   # blocks [b, e) fit
+                e = max(e, b + 1)
+                if e >= len(cost):
+                    return cuts, True
+                cuts.append(e)
+                b = e
+            return cuts, False
+
+        lo, hi = max(float(cost.max()), cum[-1] / n_parts), float(cum[-1])
+        for _ in range(48):                                   # smallest bottleneck that needs <= n_parts parts
+            mid = 0.5 * (lo + hi)
+            cuts, ok = pack(mid)
+            if ok and len(cuts) <= n_parts - 1:
+                hi = mid
+            else:
+                lo = mid
+        cuts, _ = pack(hi)
+        # a block heavier than an even share sets the bottleneck and leaves parts unused: split the heaviest
+        # parts that still hold more than one block, nearest to their middle, until every rank has work
+        bounds = [0] + cuts + [len(cost)]
+        while len(bounds) - 1 < n_parts:
+            spans = [(cum[bounds[i + 1]] - cum[bounds[i]], i) for i in range(len(bounds) - 1)
+                     if bounds[i + 1] - bounds[i] > 1]
+            if not spans:
+                break
+            _, i = max(spans)
+            a, b = bounds[i], bounds[i + 1]
+            half = int(np.searchsorted(cum, 0.5 * (cum[a] + cum[b]), side="left"))
+            bounds.insert(i + 1, min(max(half, a + 1), b - 1))
+        cuts = (bounds[1:-1] + [len(cost) - 1] * n_parts)[:n_parts - 1]
+        pos = first[np.asarray(cuts, dtype=np.int64)]
     else:
         pos = (np.arange(1, n_parts, dtype=np.int64) * m) // n_parts
     return np.ascontiguousarray(sorted_samples[pos], dtype=np.uint64)
