@@ -513,6 +513,10 @@ int gk_index_create(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_se
     ix->n = n;
     // the reference refuses more than 2^32-1 k-mers (kmers.py:805-808); here the index widens
     ix->idx_bytes = (sba_len > 0xFFFFFFFFull) ? 8 : 4;
+    {   // GK_FORCE_IDX64=1 (tests): exercise the 64-bit start-index path on small inputs
+        const char *f = getenv("GK_FORCE_IDX64");
+        if (f && *f && *f != '0') ix->idx_bytes = 8;
+    }
     int rc = ix->d_segs.alloc((size_t)n_seg * 8);
     if (rc == GK_OK) {
         cudaError_t e = cudaMemcpy(ix->d_segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice);

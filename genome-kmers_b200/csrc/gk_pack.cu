@@ -45,6 +45,7 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     __shared__ __align__(4) uint16_t s_amb[kPackChunks + 2];
     __shared__ __align__(4) uint16_t s_sep[kPackChunks + 2];
     __shared__ uint32_t s_sep_pre[kPackChunks / 2 + 2];
+    __shared__ uint32_t s_valid[kPackTile / 32];  // bit b of word w: a window may start at 32w + b
     __shared__ uint32_t s_seg0;
     // digit histograms of the keys this CTA emits, for the radix passes that follow (the sort would
     // otherwise read all keys once more just to count digits); flushed once per CTA
@@ -100,6 +101,19 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     // exclusive prefix of '$' counts per 32-position word (one warp, kPackChunks/2 words)
     const uint32_t *amb32 = reinterpret_cast<const uint32_t *>(s_amb);
     const uint32_t *sep32 = reinterpret_cast<const uint32_t *>(s_sep);
+    // a window of valid_len <= 32 symbols may start at position b iff no '$' (or array end, staged as '$')
+    // lies in [b, b + valid_len): smear the '$' bits to the right by valid_len - 1 with doubling shifts
+    const bool fast_valid = valid_len <= 32;
+    if (fast_valid && t >= 32 && t < 32 + kPackTile / 32) {
+        const uint32_t w = t - 32;
+        uint64_t y = ((uint64_t)sep32[w + 1] << 32) | sep32[w];
+        for (uint32_t done = 1; done < valid_len;) {
+            const uint32_t d = (done < valid_len - done) ? done : valid_len - done;
+            y |= y >> d;
+            done += d;
+        }
+        s_valid[w] = ~(uint32_t)y;
+    }
     if (t < 32) {
         constexpr int n_words = kPackChunks / 2;          // 129
         constexpr int per_lane = (n_words + 31) / 32;     // 5
@@ -129,16 +143,27 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     // ---- cut windows ---------------------------------------------------------------------------
     const uint32_t seg0 = s_seg0;
     const uint64_t key_mask = (key_len >= 32) ? 0xFFFFFFFFull : ((1ull << key_len) - 1ull);
+    // tile-relative bounds of the requested range of starts, and the output slot of tile position 0
+    const uint32_t q_lo = first_start > tile0 ? (uint32_t)((first_start - tile0 < (uint64_t)kPackTile)
+                                                               ? first_start - tile0 : kPackTile) : 0u;
+    const uint32_t q_hi = end_start > tile0 ? (uint32_t)((end_start - tile0 < (uint64_t)kPackTile)
+                                                             ? end_start - tile0 : kPackTile) : 0u;
+    const uint64_t tile_pos0 = tile0 - (uint64_t)valid_len * seg0 - out_base;  // (modular arithmetic)
 #pragma unroll 4
     for (int j = 0; j < kPackPerThread; ++j) {
         const uint32_t q = t + j * kPackThreads;
+        if (q < q_lo || q >= q_hi) continue;
         const uint64_t i = tile0 + q;
-        if (i < first_start || i >= end_start) continue;
         const uint32_t mw = q >> 5, mo = q & 31u;
-        const uint32_t seg = seg0 + s_sep_pre[mw] + __popc(sep32[mw] & ((1u << mo) - 1u));
-        if (seg >= n_seg) continue;
-        const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;
-        if (i + valid_len > seg_end) continue;  // also rejects '$' positions themselves
+        const uint32_t seg_rel = s_sep_pre[mw] + __popc(sep32[mw] & ((1u << mo) - 1u));
+        if (fast_valid) {
+            if (!((s_valid[mw] >> mo) & 1u)) continue;
+        } else {
+            const uint32_t seg = seg0 + seg_rel;
+            if (seg >= n_seg) continue;
+            const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;
+            if (i + valid_len > seg_end) continue;  // also rejects '$' positions themselves
+        }
 
         const uint32_t cw = q >> 4, co = 2u * (q & 15u);
         const uint32_t c0 = s_codes[cw], c1 = s_codes[cw + 1], c2 = s_codes[cw + 2];
@@ -158,7 +183,7 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
             value = ((rem >= 64) ? 0ull : (prefix << rem)) + ((uint64_t)below << (rem - 2));
         }
         const uint64_t key = class_bit ? ((value << 1) | (pure ? 1ull : 0ull)) : value;
-        const uint64_t pos = i - (uint64_t)valid_len * seg - out_base;
+        const uint64_t pos = tile_pos0 + q - (uint64_t)valid_len * seg_rel;
         keys_out[pos] = key;
         idx_out[pos] = (IdxT)i;
 #pragma unroll

@@ -379,6 +379,8 @@ class ShardedKmers:
             self.d_sba = d_fwd
             self.total_len = n
         self.idx_bytes = 8 if self.total_len > 0xFFFFFFFF else 4
+        if os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0"):   # tests: 64-bit starts on small inputs
+            self.idx_bytes = 8
         self.shard = None
         self.stats = {}
         self._marks = []
@@ -703,6 +705,8 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
                "d2h_bytes_per_step": shard_bytes * world,
                "api": "ShardedKmers(...).sort(); get_kmer_group_counts(); local_start_indices() on every rank"}
 
+    eng_idx_bytes = 8 if (2 * (world * chunk_len - 1) + 1 > 0xFFFFFFFF
+                          or os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0")) else 4
     last = per_step[-1][0]
     mine = [last.get("total_ms", 0.0), last.get("fixup_ms", 0.0), float(last.get("n_shard", 0)),
             float(last.get("n_ambiguous", 0))]
@@ -722,16 +726,23 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
         pass_ms = float(np.mean([s["sort_ms"] for s, _ in per_step])) / max(passes, 1)
         n_shard = per_step[-1][0]["n_shard"]
         peak, peak_src = measured_hbm_peak()
-        achieved = 2 * 12 * n_shard / (pass_ms * 1e-3) / 1e9
+        pair_bytes = 8 + eng_idx_bytes
+        achieved = 2 * pair_bytes * n_shard / (pass_ms * 1e-3) / 1e9
         line = {
             "metric": metric, "value": n_total / (ms_per_step * 1e-3) / 1e9, "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches - 0),
+            "config": dict(workload_config(world), **({} if n_bases == 100_000_000 else {
+                "workload": f"NOT the bench workload: {n_bases} bp per GPU x {world} GPUs = "
+                            f"{n_bases * world / 1e9:.2f} Gbp, {n_records} records per GPU, N runs, both strands, "
+                            f"k={k} (BASELINE.json configs[2] size when bases x GPUs = 3.1e9)",
+                "bases_per_gpu": n_bases, "kmers_total": int(n_total)})),
+            "e2e": e2e, "gpu_launches": int(launches - 0),
             "roofline": {"bound": "hbm", "kernel": "gk::onesweep_kernel on rank 0's key range",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "avg_launch_ms": pass_ms,
-                         "launches_per_step": passes, "pairs_on_rank0": int(n_shard)},
+                         "launches_per_step": passes, "pairs_on_rank0": int(n_shard),
+                         "pair_bytes": pair_bytes},
             "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()), "mode": exchange_mode,
                          "note": "(G-1)/G of all (u64 key, u32 start) pairs cross NVLink once: written by the "
                                  "partition kernel into peer memory (mode peer) or one NCCL all-to-all (mode nccl)"},

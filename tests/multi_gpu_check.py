@@ -34,8 +34,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     world = dist.get_world_size()
     failures = []
-    cases = [(31, 600_000, 6, 8), (21, 400_000, 3, 0), (12, 300_000, 2, 3)]
-    for k, n_bases, n_rec, runs in cases:
+    cases = [(31, 600_000, 6, 8, False), (21, 400_000, 3, 0, False), (12, 300_000, 2, 3, False),
+             (31, 500_000, 5, 6, True)]                      # last: 64-bit start indices (GK_FORCE_IDX64)
+    for k, n_bases, n_rec, runs, wide in cases:
+        os.environ["GK_FORCE_IDX64"] = "1" if wide else "0"
         rng = np.random.default_rng(1000 + k)
         recs = gu.random_genome(rng, n_bases, n_rec, n_runs=runs, run_lo=50, run_hi=5000,
                                 n_scatter=20 if runs else 0)
@@ -58,7 +60,7 @@ def main():
             if rank == 0:
                 ok = (len(got) == len(want) and np.array_equal(got.astype(np.uint64), want)
                       and total == total_want and np.array_equal(hist, hist_want))
-                print(f"k={k} world={world} exchange={used}: {'ok' if ok else 'MISMATCH'} "
+                print(f"k={k} world={world} exchange={used} idx64={wide}: {'ok' if ok else 'MISMATCH'} "
                       f"({len(got)} k-mers, {int(hist.sum())} distinct)", flush=True)
                 if not ok:
                     failures.append((k, used))

@@ -38,7 +38,7 @@ def test_golden_init_sort_and_counts(name):
     sc, km = _kmers_for(case)
     assert len(km) == case["n_kmers"]
     assert np.array_equal(km.kmer_sba_start_indices, case["init"])          # A3
-    assert km.kmer_sba_start_indices.dtype == np.uint32
+    assert km.kmer_sba_start_indices.dtype == (np.uint64 if os.environ.get("GK_FORCE_IDX64") else np.uint32)
     try:
         km.sort()                                                             # A4 + A5
     except NotImplementedError as exc:
@@ -101,6 +101,31 @@ def test_hybrid_and_plain_sort_agree_on_skewed_input(mode, monkeypatch):
     parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 120_000)])
     seq = np.concatenate(parts)
     _oracle_compare([("chr0", seq[:len(seq) // 2]), ("chr1", seq[len(seq) // 2:])], 31, "both")
+
+
+@pytest.mark.parametrize("name", ["rand5k_k21", "iupac4k_both_k31", "lowcomplex_k31", "rand120kN_both_k31", "sl2_k3"])
+def test_golden_with_64bit_start_indices(name, monkeypatch):
+    """Byte arrays of 2^32 or more positions switch the start indices to uint64 (the reference refuses,
+    kmers.py:805-808); GK_FORCE_IDX64 drives small inputs through that path."""
+    monkeypatch.setenv("GK_FORCE_IDX64", "1")
+    case = golden_case(name)
+    sc, km = _kmers_for(case)
+    km.sort()
+    got = km.kmer_sba_start_indices
+    assert got.dtype == np.uint64
+    assert np.array_equal(got, case["sorted"].astype(np.uint64))
+    for qu, ans in zip(case["queries"], case["answers"]):
+        hist, total = km.get_kmer_group_counts(
+            qu["kmer_len"], kmer_filter_func=_filter(qu["filter"]), min_group_size=qu["min_group"],
+            max_group_size=qu["max_group"], max_counts_bin=qu["max_bin"])
+        assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"])), (name, qu)
+
+
+def test_seeded_random_with_64bit_start_indices(monkeypatch):
+    monkeypatch.setenv("GK_FORCE_IDX64", "1")
+    rng = np.random.default_rng(64)
+    recs = gu.random_genome(rng, 700_000, 4, n_runs=5, run_lo=50, run_hi=3000, n_scatter=20)
+    _oracle_compare(recs, 31, "both")
 
 
 @pytest.mark.parametrize("name", VARIABLE)
