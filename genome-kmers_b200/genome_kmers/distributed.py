@@ -311,7 +311,9 @@ def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 
             return cuts, False
 
         lo, hi = max(float(cost.max()), cum[-1] / n_parts), float(cum[-1])
-        for _ in range(48):                                   # smallest bottleneck that needs <= n_parts parts
+        if float(cost.max()) * 50 < cum[-1] / n_parts:        # no heavy block: even shares, nothing to search
+            lo = hi = 1.02 * cum[-1] / n_parts
+        for _ in range(14 if hi > lo else 0):                 # smallest bottleneck that needs <= n_parts parts
             mid = 0.5 * (lo + hi)
             cuts, ok = pack(mid)
             if ok and len(cuts) <= n_parts - 1:
@@ -436,9 +438,11 @@ class ShardedKmers:
                 padded[1 + sample.numel():] = 0
             gathered = [eng.empty_like_n(keys, SAMPLES_PER_RANK + 1) for _ in range(world)]
             dist.all_gather(gathered, padded, group=self.group)
-            pooled = [g[1:1 + int(g[0].item())] for g in gathered]
-            pooled = eng.sort_keys(self._cat(pooled))
-            splitters_host = choose_splitters(self._to_host_u64(pooled), world, class_bit)
+            # one device-to-host copy of all samples; 32 k keys are sorted faster on the host than through
+            # eight tiny radix passes and their synchronisations
+            table = self._to_host_u64(self._cat(gathered)).reshape(world, SAMPLES_PER_RANK + 1)
+            pooled = np.sort(np.concatenate([row[1:1 + int(row[0])] for row in table]))
+            splitters_host = choose_splitters(pooled, world, class_bit)
             splitters = eng.from_host_i64(splitters_host.view(np.int64))
         else:
             splitters_host, splitters = np.zeros(0, dtype=np.uint64), None
