@@ -880,6 +880,63 @@ int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups, uint6
     return GK_OK;
 }
 
+// Group table of the k-mers that pass `filter`, in the current order (kmers.py:523-648: a k-mer that fails
+// is skipped and the next passing one is compared with the previous PASSING one).  Two-call protocol: with
+// NULL outputs only the counts are returned.  h_kept_pos_out[j] = position in the (sorted) index of the
+// j-th passing k-mer; offsets index that list.  On an unsorted index every passing k-mer is its own group.
+int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t *h_n_kept,
+                             uint64_t *h_n_groups, uint64_t *h_kept_pos_out, uint64_t *h_offsets_out,
+                             uint64_t *h_sizes_out, void *stream)
+{
+    if (!ix || !filter || !h_n_kept || !h_n_groups) return GK_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    *h_n_kept = *h_n_groups = 0;
+    if (ix->n == 0) return GK_OK;
+    GK_TRY(ensure_indices(ix, st));
+    const int ib = ix->idx_bytes;
+    const uint64_t n = ix->n;
+    DeviceBuffer pass_flags, kept, kept_pos, flags, offsets;
+    GK_TRY(pass_flags.alloc((size_t)((n + 15) & ~15ull), st));
+    GK_TRY(filter_flags_device(ix->d_sba, ix->sba_len, ix->d_idx.ptr, ib, n, *filter, pass_flags.as<uint8_t>(), st));
+    GK_TRY(kept.alloc((size_t)n * ib, st));
+    GK_TRY(kept_pos.alloc((size_t)n * ib, st));
+    uint64_t m = 0;
+    GK_TRY(select_flagged(pass_flags.as<uint8_t>(), n, kFlagPass, ib, kept_pos.ptr, ix->d_idx.ptr, kept.ptr, nullptr,
+                          nullptr, &m, st));
+    *h_n_kept = m;
+    if (m == 0) return GK_OK;
+    uint64_t n_groups = m;
+    if (ix->sorted) {
+        GK_TRY(flags.alloc((size_t)((m + 15) & ~15ull), st));
+        GK_TRY(sba_flags_device(ix->d_sba, ix->sba_len, kept.ptr, ib, m, kmer_len, nullptr, 0, flags.as<uint8_t>(),
+                                st));
+        GK_TRY(offsets.alloc((size_t)m * 8, st));
+        GK_TRY(select_flagged(flags.as<uint8_t>(), m, kFlagHead, 8, offsets.ptr, nullptr, nullptr, nullptr, nullptr,
+                              &n_groups, st));
+    }
+    *h_n_groups = n_groups;
+    if (h_kept_pos_out) {
+        std::vector<unsigned char> tmp((size_t)m * ib);
+        GK_CUDA(cudaMemcpyAsync(tmp.data(), kept_pos.ptr, (size_t)m * ib, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        for (uint64_t j = 0; j < m; ++j)
+            h_kept_pos_out[j] = ib == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(tmp.data())[j]
+                                        : reinterpret_cast<const uint64_t *>(tmp.data())[j];
+    }
+    if (h_offsets_out) {
+        if (ix->sorted) {
+            GK_CUDA(cudaMemcpyAsync(h_offsets_out, offsets.ptr, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaStreamSynchronize(st));
+        } else {
+            for (uint64_t g = 0; g < n_groups; ++g) h_offsets_out[g] = g;
+        }
+        if (h_sizes_out)
+            for (uint64_t g = 0; g < n_groups; ++g)
+                h_sizes_out[g] = ((g + 1 < n_groups) ? h_offsets_out[g + 1] : m) - h_offsets_out[g];
+    }
+    return GK_OK;
+}
+
 int gk_sort_count_host(const uint8_t *h_sba, uint64_t sba_len, const uint64_t *h_seg_starts,
                        uint32_t n_seg, uint32_t kmer_len, int strands, int idx_bytes, void *h_idx_out,
                        uint64_t max_bin, int64_t *h_hist_out, int64_t *h_total_out,

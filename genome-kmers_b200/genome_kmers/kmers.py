@@ -472,10 +472,11 @@ class Kmers:
         flt = kmer_filter_func
         if not isinstance(flt, KmerFilter):
             self._native_filter(flt)
-        if flt.filter_id != _native.FILTER_KEEP_ALL:
-            raise NotImplementedError("get_kmers with a filter is not available on the GPU path yet")
         idx = self.kmer_sba_start_indices
-        if self._is_sorted:
+        kept_pos = None                      # positions (kmer_num) of the k-mers that pass the filter
+        if flt.filter_id != _native.FILTER_KEEP_ALL:
+            kept_pos, offsets, sizes = self._filtered_groups(kmer_len, flt)
+        elif self._is_sorted:
             offsets, sizes = self.get_kmer_groups(kmer_len)
         else:
             offsets = np.arange(len(idx), dtype=np.uint64)
@@ -487,7 +488,8 @@ class Kmers:
             if size < min_group_size or (max_group_size is not None and size > max_group_size):
                 continue
             n_yield = size if yield_first_n is None else min(size, yield_first_n)
-            for kmer_num in range(off, off + n_yield):
+            for member in range(off, off + n_yield):
+                kmer_num = member if kept_pos is None else int(kept_pos[member])
                 if locate is None:
                     yield kmer_num, n_yield, size
                 else:
@@ -500,6 +502,24 @@ class Kmers:
                             raise ValueError(
                                 f"kmer_len ({kmer_len}) for kmer_num ({kmer_num}) extends beyond the end of the segment")
                     yield kmer_num, strand, chrom, seq_idx, this_len, n_yield, size
+
+    def _filtered_groups(self, kmer_len, flt: KmerFilter):
+        """(kept_pos, offsets, sizes): group table over the k-mers that pass the filter (device-side)."""
+        self._ensure_device()
+        self._push_host_indices()
+        lib = _native.lib()
+        nat = flt.native()
+        n_kept, n_groups = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _native.check(lib.gk_index_groups_filtered(self._ix, kmer_len or 0, ctypes.byref(nat), ctypes.byref(n_kept),
+                                                   ctypes.byref(n_groups), None, None, None, self._stream()))
+        kept_pos = np.zeros(n_kept.value, dtype=np.uint64)
+        offsets = np.zeros(n_groups.value, dtype=np.uint64)
+        sizes = np.zeros(n_groups.value, dtype=np.uint64)
+        if n_kept.value:
+            _native.check(lib.gk_index_groups_filtered(
+                self._ix, kmer_len or 0, ctypes.byref(nat), ctypes.byref(n_kept), ctypes.byref(n_groups),
+                _native.host_ptr(kept_pos), _native.host_ptr(offsets), _native.host_ptr(sizes), self._stream()))
+        return kept_pos, offsets, sizes
 
     def _locate_all(self, idx, one_based):
         """kmer_num -> (strand symbol, record name, forward sequence index, segment end)."""

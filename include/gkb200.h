@@ -211,6 +211,14 @@ int gk_index_group_counts_sparse(gk_index *ix, uint32_t kmer_len, const gk_filte
 int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups,
                     uint64_t *h_offsets_out, uint64_t *h_sizes_out, void *stream);
 
+/* Group table of the k-mers that pass `filter` (kmers.py:586-601: failing k-mers are skipped, a passing
+ * k-mer is compared with the previous PASSING one).  Two-call protocol as above.  h_kept_pos_out[j] =
+ * position in the index of the j-th passing k-mer; offsets and sizes refer to that list.  On an unsorted
+ * index every passing k-mer is its own group (kmers.py:1061-1064).  Behind Kmers.get_kmers(filter). */
+int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t *h_n_kept,
+                             uint64_t *h_n_groups, uint64_t *h_kept_pos_out, uint64_t *h_offsets_out,
+                             uint64_t *h_sizes_out, void *stream);
+
 /* ---- one-shot host entry point (host buffers in, host buffers out) ------------------------ */
 /* sba (forward strand, records joined by '$') -> sorted start indices + histogram.  strands:
  * 0 forward, 2 both (index space of forward || '$' || revcomp).  h_idx_out may be NULL.

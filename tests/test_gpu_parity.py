@@ -11,7 +11,8 @@ import pytest
 
 import oracle
 from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
-from genome_kmers.kmers import Kmers, gen_no_ambiguous_bases_filter, kmer_filter_keep_all
+from genome_kmers.kmers import (Kmers, gen_kmer_gc_content_filter_func, gen_kmer_homopolymer_filter_func,
+                                gen_no_ambiguous_bases_filter, kmer_filter_keep_all)
 from genome_kmers.sequence_collection import SequenceCollection
 import gpu_utils as gu
 
@@ -146,6 +147,38 @@ def test_golden_variable_length_modes(name):
         assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"]))
 
 
+@pytest.mark.parametrize("name", ["sl2_k3", "rand5k_k21", "iupac4k_both_k31", "rand120kN_both_k31"])
+def test_one_shot_host_entry_point(name):
+    """gk_sort_count_host: host buffers in, host buffers out -- what a non-Python host binds."""
+    import ctypes
+
+    from genome_kmers import _native
+
+    case = golden_case(name)
+    lib = _native.lib()
+    sc = SequenceCollection(sequence_list=[tuple(r) for r in case["seq_list"]], strands_to_load="forward")
+    sba = np.ascontiguousarray(sc.forward_sba)
+    starts = np.ascontiguousarray(sc._forward_sba_seg_starts, dtype=np.uint64)
+    k = case["min_len"]
+    n = case["n_kmers"]
+    idx = np.zeros(n, dtype=np.uint32)
+    max_bin = 64
+    hist = np.zeros(max_bin + 1, dtype=np.int64)
+    total, n_out = ctypes.c_int64(0), ctypes.c_uint64(0)
+    stats = _native.GkSortStats()
+    _native.check(lib.gk_sort_count_host(
+        _native.host_ptr(sba), len(sba), _native.host_ptr(starts), len(starts), k,
+        2 if case["strands"] == "both" else 0, 4, _native.host_ptr(idx), max_bin, _native.host_ptr(hist),
+        ctypes.byref(total), ctypes.byref(n_out), ctypes.byref(stats)))
+    assert n_out.value == n and total.value == n
+    assert np.array_equal(idx, case["sorted"])
+    qu = next((q, a) for q, a in zip(case["queries"], case["answers"])
+              if q["kmer_len"] == k and q["filter"] is None and q["min_group"] == 1 and q["max_group"] is None)
+    want = dense_hist(qu[1], qu[0]["max_bin"])
+    m = min(len(want), len(hist)) - 1
+    assert np.array_equal(hist[:m], want[:m])
+
+
 def test_counts_with_other_kmer_len_and_unsorted():
     case = golden_case("rand5k_k21_count11")
     sc, km = _kmers_for(case)
@@ -173,6 +206,45 @@ def test_group_table_is_the_unique_kmer_set():
     assert [kmers.count(u) for u in uniq] == sizes.tolist()
     minimal = list(km.get_kmers(3, min_group_size=2, yield_first_n=1))
     assert [kmers[num] for num, _, _ in minimal] == [u for u, s in zip(uniq, sizes) if s >= 2]
+
+
+@pytest.mark.parametrize("name,make_filter", [
+    ("iupac4k_k21", lambda k: gen_no_ambiguous_bases_filter(k)),
+    ("rand5k_k21", lambda k: gen_kmer_gc_content_filter_func(0.4, 0.6, k)),
+    ("lowcomplex_k8", lambda k: gen_kmer_homopolymer_filter_func(3, k)),
+    ("rand5k_k3", lambda k: gen_kmer_gc_content_filter_func(0.3, 0.7, k)),
+])
+def test_get_kmers_with_device_filters(name, make_filter):
+    """get_kmers(filter): a failing k-mer is skipped and the next passing one is compared with the previous
+    PASSING one (kmers.py:586-601); checked against a host walk of the sorted order."""
+    case = golden_case(name)
+    sc, km = _kmers_for(case)
+    k = case["min_len"]
+    filt = make_filter(k)
+    sba = sc.forward_sba
+    # unsorted: every passing k-mer is its own group
+    want = [(num, 1, 1) for num, s in enumerate(km.kmer_sba_start_indices) if filt(sba, "forward", int(s))]
+    assert list(km.get_kmers(k, kmer_filter_func=filt)) == want
+    km.sort()
+    groups, prev = [], None
+    for num, s in enumerate(km.kmer_sba_start_indices):
+        if not filt(sba, "forward", int(s)):
+            continue
+        kmer = sba[int(s):int(s) + k].tobytes()
+        if prev is not None and kmer == prev:
+            groups[-1].append(num)
+        else:
+            groups.append([num])
+            prev = kmer
+    assert len(groups) > 0
+    for min_g, max_g, first_n in [(1, None, None), (2, None, 1), (1, 3, 2), (1, 1, None)]:
+        want = [(num, min(len(g), first_n or len(g)), len(g)) for g in groups
+                if len(g) >= min_g and (max_g is None or len(g) <= max_g) for num in g[:first_n or len(g)]]
+        got = list(km.get_kmers(k, kmer_filter_func=filt, min_group_size=min_g, max_group_size=max_g,
+                                yield_first_n=first_n))
+        assert got == want, (min_g, max_g, first_n)
+    # and the counts agree with the same walk
+    assert km.get_kmer_count(k, filt) == sum(len(g) for g in groups)
 
 
 def _oracle_compare(records, k, strands, threads=8, filt_k=None):
