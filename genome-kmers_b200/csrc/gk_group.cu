@@ -92,23 +92,27 @@ __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent)
 {
+    // bit (i + 32) of s_cont: slot i (tile-relative, -8 <= i < kTieTile + 8) has the same prefix as slot i - 1
+    constexpr int kContWords = kTieTile / 32 + 2;
     __shared__ PreT s_pre[kTieTile + 2 * kTieHalo];
+    __shared__ uint32_t s_cont[kContWords + 1];
     __shared__ uint16_t s_member[kTieTile];
     __shared__ uint16_t s_run[kTieTile / 2];
     __shared__ uint32_t s_n_member, s_n_run;
-    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint64_t tile0 = (uint64_t)blockIdx.x * kTieTile;
-    if (t == 0) { s_n_member = 0; s_n_run = 0; }
-    // slot p lives at s_pre[p - tile0 + kTieHalo]; slots outside [0, n) are never looked at
+    const int n_in_tile = (n - tile0 < (uint64_t)kTieTile) ? (int)(n - tile0) : kTieTile;
+    if (t == 0) { s_n_member = 0; s_n_run = 0; s_cont[kContWords] = 0; }
+    // slot i lives at s_pre[i + kTieHalo]; slots outside [0, n) are never looked at
     PreT my_pre[kTiePerThread];
     uint32_t my_amb = 0;
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
-        const uint64_t p = tile0 + (uint64_t)j * kTieThreads + t;
-        const uint64_t k = (p < n) ? keys[p] : 0ull;
+        const int i = j * kTieThreads + (int)t;
+        const uint64_t k = (i < n_in_tile) ? keys[tile0 + i] : 0ull;
         my_pre[j] = (PreT)(k >> lo_bits);
         my_amb |= ((class_bit && !(k & 1ull)) ? 1u : 0u) << j;
-        s_pre[kTieHalo + j * kTieThreads + t] = my_pre[j];
+        s_pre[kTieHalo + i] = my_pre[j];
     }
     if (t < 2 * kTieHalo) {
         const bool before = t < kTieHalo;
@@ -118,12 +122,16 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     }
     __syncthreads();
 
-    auto pre_at = [&](int i) -> PreT { return s_pre[i + kTieHalo]; };  // i = p - tile0
     auto valid = [&](int i) -> bool { return (i >= 0 || tile0 >= (uint64_t)(-i)) && tile0 + (int64_t)i < n; };
+    // count bits [first, first + count) of the continuation mask, count <= 8, first >= -32
+    auto cont_bits = [&](int first, int count) -> uint32_t {
+        const uint32_t u = (uint32_t)(first + 32);
+        const uint64_t w = ((uint64_t)s_cont[(u >> 5) + 1] << 32) | s_cont[u >> 5];
+        return (uint32_t)(w >> (u & 31u)) & ((1u << count) - 1u);
+    };
 
     // ---- 1 ---------------------------------------------------------------------------------------------
-    // tile-relative 32-bit indices; the two array ends are the only places without a neighbour
-    const int n_in_tile = (n - tile0 < (uint64_t)kTieTile) ? (int)(n - tile0) : kTieTile;
+    // the two array ends are the only places without a neighbour
     const int first_i = (tile0 == 0) ? 0 : -1;                                  // slot without predecessor
     const int last_i = (n - tile0 <= (uint64_t)kTieTile) ? n_in_tile - 1 : -1;  // slot without successor
     uint8_t *tile_flags = flags + tile0;
@@ -131,13 +139,25 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
 #pragma unroll
     for (int j = 0; j < kTiePerThread; ++j) {
         const int i = j * kTieThreads + (int)t;
+        bool cont = false;
         if (i < n_in_tile) {
             const PreT pre = my_pre[j];
             const bool ph = (i == first_i) | (s_pre[i - 1 + kTieHalo] != pre);
             const bool nh = (i == last_i) | (s_pre[i + 1 + kTieHalo] != pre);
+            cont = !ph;
             if (ph & nh) tile_flags[i] = ((my_amb >> j) & 1u) ? kFlagAmb : kFlagHead;
             else tied_mask |= 1u << j;
         }
+        const uint32_t word = __ballot_sync(0xffffffffu, cont);
+        if (lane == 0) s_cont[j * (kTieThreads / 32) + warp + 1] = word;
+    }
+    if (warp == 0) {  // the halo words: eight slots before the tile, eight after it
+        const int ib = -32 + (int)lane, ia = kTieTile + (int)lane;
+        const bool cb = ib >= -(kTieHalo - 1) && valid(ib - 1) && valid(ib) &&
+                        s_pre[ib - 1 + kTieHalo] == s_pre[ib + kTieHalo];
+        const bool ca = lane < (uint32_t)kTieHalo && valid(ia) && s_pre[ia - 1 + kTieHalo] == s_pre[ia + kTieHalo];
+        const uint32_t wb = __ballot_sync(0xffffffffu, cb), wa = __ballot_sync(0xffffffffu, ca);
+        if (lane == 0) { s_cont[0] = wb; s_cont[kContWords - 1] = wa; }
     }
     {   // one queue reservation per warp for all eight rounds
         const uint32_t cnt = __popc(tied_mask);
@@ -159,41 +179,31 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     __syncthreads();
 
     // ---- 2 ---------------------------------------------------------------------------------------------
+    // run geometry from the continuation bits: d slots back to the run's first slot, f slots on to its last
     const uint32_t n_member = s_n_member;
     for (uint32_t r = t; r < n_member; r += kTieThreads) {
         const int i = s_member[r];
-        const uint64_t p = tile0 + (uint64_t)i;
-        const PreT pre = pre_at(i);
-        const bool ph = (p == 0) || pre_at(i - 1) != pre;
-        const bool nh = (p + 1 == n) || pre_at(i + 1) != pre;
-        int h = i;
+        const bool ph = !cont_bits(i, 1);
         bool is_long = false;
+        int d = 0;
         if (!ph) {
-            int back = 1;
-            for (; back < kTieMaxRun; ++back) {
-                const int q = i - back;
-                if (!valid(q - 1) || pre_at(q - 1) != pre) break;
-            }
-            if (back == kTieMaxRun) is_long = true; else h = i - back;
+            const uint32_t back = cont_bits(i - (kTieMaxRun - 1), kTieMaxRun - 1);  // slots i-7 .. i-1
+            const int ones = __clz((int)~(back << (32 - (kTieMaxRun - 1))));      // leading ones from slot i-1
+            if (ones >= kTieMaxRun - 1) is_long = true; else d = ones + 1;
         }
-        if (!is_long && !nh) {
-            const int limit = h + kTieMaxRun;  // first slot that must NOT belong to the run
-            int q = i + 1;
-            for (;; ++q) {
-                if (!valid(q + 1) || pre_at(q + 1) != pre) break;
-                if (q + 1 >= limit) { is_long = true; break; }
-            }
-            if (q >= limit) is_long = true;
-        }
+        const uint32_t fwd = cont_bits(i + 1, kTieMaxRun);                         // slots i+1 .. i+8
+        const int f = __ffs((int)~fwd) - 1;                                        // trailing ones
+        if (d + f + 1 > kTieMaxRun) is_long = true;
         if (is_long) {  // nobody rewrites the keys of a long run: read them where they are
+            const uint64_t p = tile0 + (uint64_t)i;
             const uint64_t k = keys[p];
             const uint64_t kp = ph ? 0 : keys[p - 1];
             const bool head = ph || kp != k;
             const bool amb = class_bit && !(k & 1ull);
             if (!ph && k < kp) atomicOr(descent, 1u);
             flags[p] = (amb ? kFlagAmb : (head ? kFlagHead : 0)) | kFlagLong;
-        } else if (ph) {
-            s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)i;  // a short run that starts in this tile
+        } else if (ph) {  // a short run that starts in this tile: slot and length - 1
+            s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)(i | (f << 11));
         }
     }
     __syncthreads();
@@ -201,18 +211,31 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     // ---- 3 ---------------------------------------------------------------------------------------------
     const uint32_t n_runs = s_n_run;
     for (uint32_t r = t; r < n_runs; r += kTieThreads) {
-        const int h = s_run[r];
-        const PreT pre = pre_at(h);
-        int len = 1;
-        while (len < kTieMaxRun && valid(h + len) && pre_at(h + len) == pre) ++len;
+        const int h = s_run[r] & 2047;
+        const int len = (s_run[r] >> 11) + 1;
         const uint64_t g = tile0 + (uint64_t)h;
+        if (len == 2) {  // nearly every run: one compare, at most one swap
+            const uint64_t k0 = keys[g], k1 = keys[g + 1];
+            const bool a0 = class_bit && !(k0 & 1ull), a1 = class_bit && !(k1 & 1ull);
+            if (k1 < k0) {
+                const ValT v0 = vals[g], v1 = vals[g + 1];
+                keys[g] = k1; keys[g + 1] = k0;
+                vals[g] = v1; vals[g + 1] = v0;
+                flags[g] = a1 ? kFlagAmb : kFlagHead;
+                flags[g + 1] = a0 ? kFlagAmb : kFlagHead;
+            } else {
+                flags[g] = a0 ? kFlagAmb : kFlagHead;
+                flags[g + 1] = a1 ? kFlagAmb : (k1 != k0 ? kFlagHead : 0);
+            }
+            continue;
+        }
         uint64_t kk[kTieMaxRun];
 #pragma unroll
         for (int i = 0; i < kTieMaxRun; ++i) kk[i] = (i < len) ? keys[g + i] : ~0ull;
         bool sorted = true;
 #pragma unroll
         for (int i = 1; i < kTieMaxRun; ++i) sorted = sorted && (i >= len || kk[i - 1] <= kk[i]);
-        if (sorted) {  // about half of the two-element runs: only the flags are missing
+        if (sorted) {  // only the flags are missing
 #pragma unroll
             for (int i = 0; i < kTieMaxRun; ++i) {
                 if (i < len) {
