@@ -423,11 +423,13 @@ constexpr SortConfig kSortConfigs[] = {
     {256, 24, 2},  // 3: 6144-pair tiles
     {512, 12, 1},  // 4: 6144-pair tiles
     {512, 16, 1},  // 5: 8192-pair tiles
+    {256, 28, 2},  // 6: 7168-pair tiles
+    {256, 32, 2},  // 7: 8192-pair tiles, 112 KB smem, 128 regs: the largest tile two CTAs per SM allow
 };
 constexpr int kNumSortConfigs = (int)(sizeof(kSortConfigs) / sizeof(kSortConfigs[0]));
-constexpr int kDefaultSortConfig = 3;
+constexpr int kDefaultSortConfig = 7;
 
-static int sort_config_id()
+static int sort_config_id_raw()
 {
     static int id = -1;
     if (id < 0) {
@@ -441,6 +443,13 @@ static int sort_config_id()
     return id;
 }
 
+// 64-bit values make a pair 16 bytes: the two largest tiles would no longer fit two CTAs per SM
+static int sort_config_id(int val_bytes)
+{
+    const int id = sort_config_id_raw();
+    return (val_bytes == 8 && (id == 6 || id == 7)) ? 3 : id;
+}
+
 template <typename ValT, typename StatusT>
 static int dispatch_pass(int cfg, const PassArgs &a, cudaStream_t st)
 {
@@ -450,6 +459,8 @@ static int dispatch_pass(int cfg, const PassArgs &a, cudaStream_t st)
     case 3: return launch_pass<ValT, StatusT, 256, 24, 2>(a, st);
     case 4: return launch_pass<ValT, StatusT, 512, 12, 1>(a, st);
     case 5: return launch_pass<ValT, StatusT, 512, 16, 1>(a, st);
+    case 6: return launch_pass<ValT, StatusT, 256, 28, 2>(a, st);
+    case 7: return launch_pass<ValT, StatusT, 256, 32, 2>(a, st);
     default: return launch_pass<ValT, StatusT, 256, 16, 3>(a, st);
     }
 }
@@ -482,7 +493,7 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         return GK_ERR_ARG;
     }
 
-    const int cfg = sort_config_id();
+    const int cfg = sort_config_id(val_bytes);
     const int tile = kSortConfigs[cfg].threads * kSortConfigs[cfg].ipt;
     const uint64_t tiles = (n + tile - 1) / tile;
     const bool wide = n >= (1ull << 30);
@@ -628,7 +639,7 @@ int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int 
         return GK_ERR_ARG;
     }
     if (n == 0) return GK_OK;
-    const int cfg = sort_config_id();
+    const int cfg = sort_config_id(val_bytes);
     const int tile = kSortConfigs[cfg].threads * kSortConfigs[cfg].ipt;
     const uint64_t tiles = (n + tile - 1) / tile;
     const bool wide = n >= (1ull << 30);
