@@ -14,6 +14,7 @@
 namespace gk {
 
 void trace_report(const char *what);
+void set_deferred_sort_error_word(int *d_err);
 // kernels / device drivers from the other translation units
 int kmer_count_host(const uint64_t *, uint32_t, uint64_t, uint32_t, uint64_t *);
 int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, void *, cudaStream_t);
@@ -312,8 +313,7 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     GK_TRY(block_offsets_device(rep_start.ptr, R, m, cur, ib, out_off.as<unsigned long long>(), st));
     GK_TRY(subset_expand_device(pos.ptr, idx.ptr, key.as<uint64_t>(), w0p, w1p, rep_start.ptr, cur,
                                 out_off.as<unsigned long long>(), R, m, class_bit, ib, d_idx, d_flags, st));
-    GK_CUDA(cudaStreamSynchronize(st));  // the scratch above is released in stream order after this
-    return GK_OK;
+    return GK_OK;  // the scratch above is released in stream order (cudaFreeAsync): no synchronise needed
 }
 
 // Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
@@ -568,6 +568,14 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     EventTimer tm(st);
     StageMarks marks;
     const int t0 = tm.mark();
+    // one device error word for every small sort of this call, checked once at the end
+    DeviceBuffer sort_err;
+    GK_TRY(sort_err.alloc(4, st));
+    GK_CUDA(cudaMemsetAsync(sort_err.ptr, 0, 4, st));
+    struct ErrWordGuard {
+        explicit ErrWordGuard(int *p) { set_deferred_sort_error_word(p); }
+        ~ErrWordGuard() { set_deferred_sort_error_word(nullptr); }
+    } err_guard(sort_err.as<int>());
 
     GK_TRY(ensure_alphabet(ix, st));
     if (ix->n_sep != ix->h_segs.size() - 1) {
@@ -631,7 +639,13 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     ix->flags_kmer_len = fixed ? k : ix->max_len;  // (None -> 0: such queries take the comparator path)
     ix->sorted = true;
     const int t1 = tm.mark();
+    int h_sort_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    if (h_sort_err) {
+        set_error("radix sort: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
     stats.pack_ms = tm.ms(marks.pack0, marks.pack1);
     stats.hist_ms = marks.main_sort.hist_ms;
     stats.sort_ms = marks.main_sort.passes_ms;

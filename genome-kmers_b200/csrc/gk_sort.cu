@@ -465,6 +465,12 @@ static int dispatch_pass(int cfg, const PassArgs &a, cudaStream_t st)
     }
 }
 
+// A caller that runs many small sorts back to back (gk_index_sort: refinement, doubling rounds) lends a
+// device error word for the look-back guard; such sorts return without synchronising the stream and the
+// caller checks the word once at its own final synchronise.
+static thread_local int *g_deferred_err = nullptr;
+void set_deferred_sort_error_word(int *d_err) { g_deferred_err = d_err; }
+
 // Shared driver: histogram(s) + scan + `passes` onesweep launches.  splitters != nullptr selects
 // the single partition pass (digit = destination rank); h_bin_counts (256 entries, optional)
 // receives the first pass's histogram.
@@ -506,7 +512,8 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     unsigned long long *d_hist = temp.as<unsigned long long>();
     unsigned long long *d_base = d_hist + kMaxPasses * kRadix;
     uint32_t *d_ctr = reinterpret_cast<uint32_t *>(d_base + kMaxPasses * kRadix);
-    int *d_err = reinterpret_cast<int *>(d_ctr + kMaxPasses);
+    const bool deferred = g_deferred_err && !timing && !h_bin_counts;
+    int *d_err = deferred ? g_deferred_err : reinterpret_cast<int *>(d_ctr + kMaxPasses);
     void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
     GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
 
@@ -548,6 +555,7 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     }
     if (result_in_alt) *result_in_alt = passes & 1;
     if (timing) GK_CUDA(cudaEventRecord(ev[2], st));
+    if (deferred) return GK_OK;  // scratch is released in stream order; the caller checks the error word
 
     int h_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -82,3 +82,30 @@ def test_splitters_and_slices():
     bounds = [slice_bounds(1001, 4, r) for r in range(4)]
     assert bounds[0][0] == 0 and bounds[-1][1] == 1001
     assert all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
+
+
+def test_cost_balanced_splitters_around_a_giant_group():
+    """One N run = millions of ambiguous windows with ONE key (class bit 0).  A key splitter cannot cut that
+    group; the cost-weighted, bottleneck-optimal cuts give its owner fewer other keys instead."""
+    sys.path[:0] = [os.path.join(ROOT, "genome-kmers_b200")]
+    from genome_kmers.distributed import AMBIGUOUS_COST, choose_splitters
+
+    rng = np.random.default_rng(3)
+    m, parts = 8 * 4096, 8
+    pure = (np.sort(rng.integers(0, 1 << 62, m, dtype=np.uint64)) << np.uint64(1)) | np.uint64(1)
+    giant = np.full(int(0.044 * m), np.uint64(3) << np.uint64(61), dtype=np.uint64)   # 4.4 % of the samples
+    samples = np.sort(np.concatenate([pure, giant]))
+    sp = choose_splitters(samples, parts, class_bit=1)
+    assert len(sp) == parts - 1 and bool((sp[1:] >= sp[:-1]).all())
+    dest = np.searchsorted(sp, samples, side="right")
+    weight = np.where((samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
+    share = np.array([weight[dest == r].sum() for r in range(parts)]) / weight.sum() * parts
+    assert share.max() < 1.08, share                       # even quantiles by count give the owner 1.3+
+    assert len(set(dest[samples == giant[0]].tolist())) == 1    # the group stays on one rank
+    # without heavy keys no part is more than 3 % above an even share
+    sp0 = choose_splitters(pure, parts, class_bit=1)
+    d0 = np.searchsorted(sp0, pure, side="right")
+    assert np.bincount(d0, minlength=parts).max() < 1.03 * m / parts
+    # degenerate inputs
+    assert choose_splitters(np.full(16, 5, dtype=np.uint64), 4, class_bit=1).size == 3
+    assert choose_splitters(np.zeros(0, dtype=np.uint64), 4, class_bit=1).size == 0
