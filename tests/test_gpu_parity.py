@@ -318,6 +318,47 @@ def test_variable_length_modes_vs_oracle(min_len, max_len, strands, n_bases, n_r
         assert total == o_total and np.array_equal(hist, o_hist), kmer_len
 
 
+def _rec(text):
+    return np.frombuffer(text.encode(), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("label,records,k,strands", [
+    ("one k-mer", [("a", _rec("ACGTACGTAC"))], 10, "forward"),
+    ("record of exactly k next to a long one", [("a", _rec("ACGTTGCA")), ("b", _rec("ACGTTGCAACGTTGCATT"))], 8, "both"),
+    ("poly-A: one pure giant group", [("a", np.full(150_000, ord("A"), dtype=np.uint8))], 31, "forward"),
+    ("only N: one ambiguous giant group", [("a", np.full(90_000, ord("N"), dtype=np.uint8))], 21, "both"),
+    ("two-letter low complexity", [("a", np.frombuffer(b"AT" * 60_000, dtype=np.uint8).copy()),
+                                   ("b", np.frombuffer(b"ATT" * 30_000, dtype=np.uint8).copy())], 31, "both"),
+    ("k=32 without ambiguous symbols (no class bit)", [("a", np.frombuffer(b"ACGT", dtype=np.uint8)[
+        np.random.default_rng(5).integers(0, 4, 120_000)].copy())], 32, "both"),
+    ("k=1", [("a", _rec("ACGTNNRYACGT" * 2000)), ("b", _rec("TTTTGGGG" * 500))], 1, "both"),
+    ("every IUPAC letter", [("a", np.frombuffer(b"ACGTRYSWKMBDHVN", dtype=np.uint8)[
+        np.random.default_rng(6).integers(0, 15, 80_000)].copy())], 12, "both"),
+])
+def test_edge_inputs_vs_oracle(label, records, k, strands):
+    _oracle_compare(records, k, strands)
+
+
+def test_small_max_counts_bin_and_group_limits():
+    """counts_by_group_size[min(size, max_counts_bin)] with a giant group and tiny tables (kmers.py:514-518)."""
+    seq = np.concatenate([np.full(5000, ord("N"), dtype=np.uint8),
+                          np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(9).integers(0, 4, 20_000)],
+                          np.full(300, ord("A"), dtype=np.uint8)])
+    sc = SequenceCollection.from_arrays([("a", seq)], strands_to_load="forward")
+    km = Kmers(sc, 8, 8)
+    km.sort()
+    sba, starts = sc.forward_sba, sc._forward_sba_seg_starts.astype(np.uint64)
+    want = oracle.sort_indices(sba, oracle.init_indices(starts, len(sba), 8), 8, 8)
+    assert np.array_equal(km.kmer_sba_start_indices.astype(np.uint64), want)
+    for max_bin in (1, 2, 7, 5000):
+        for min_g, max_g in ((1, None), (2, None), (1, 3), (290, 5000), (3, 3)):
+            hist, total = km.get_kmer_group_counts(8, min_group_size=min_g, max_group_size=max_g,
+                                                   max_counts_bin=max_bin)
+            o_hist, o_total = oracle.group_hist(sba, want, 8, min_group=min_g, max_group=max_g, max_bin=max_bin)
+            assert total == o_total and np.array_equal(hist, o_hist), (max_bin, min_g, max_g)
+            assert km.get_kmer_count(8, min_group_size=min_g, max_group_size=max_g) == o_total
+
+
 def test_config1_shape_vs_oracle():
     """BASELINE.json configs[0]: 4.6 Mbp, one record, forward, k=21 (the reference's CPU case)."""
     rng = np.random.default_rng(42)
