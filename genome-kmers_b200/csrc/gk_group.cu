@@ -104,24 +104,6 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     const int n_in_tile = (n - tile0 < (uint64_t)kTieTile) ? (int)(n - tile0) : kTieTile;
     if (t == 0) { s_n_member = 0; s_n_run = 0; s_cont[kContWords] = 0; }
     // slot i lives at s_pre[i + kTieHalo]; slots outside [0, n) are never looked at
-    PreT my_pre[kTiePerThread];
-    uint32_t my_amb = 0;
-#pragma unroll
-    for (int j = 0; j < kTiePerThread; ++j) {
-        const int i = j * kTieThreads + (int)t;
-        const uint64_t k = (i < n_in_tile) ? keys[tile0 + i] : 0ull;
-        my_pre[j] = (PreT)(k >> lo_bits);
-        my_amb |= ((class_bit && !(k & 1ull)) ? 1u : 0u) << j;
-        s_pre[kTieHalo + i] = my_pre[j];
-    }
-    if (t < 2 * kTieHalo) {
-        const bool before = t < kTieHalo;
-        const uint64_t p = before ? tile0 - kTieHalo + t : tile0 + kTieTile + (t - kTieHalo);
-        const bool ok = before ? (tile0 >= (uint64_t)kTieHalo - t) : (p < n);
-        if (ok) s_pre[before ? t : kTieHalo + kTieTile + (t - kTieHalo)] = (PreT)(keys[p] >> lo_bits);
-    }
-    __syncthreads();
-
     auto valid = [&](int i) -> bool { return (i >= 0 || tile0 >= (uint64_t)(-i)) && tile0 + (int64_t)i < n; };
     // count bits [first, first + count) of the continuation mask, count <= 8, first >= -32
     auto cont_bits = [&](int first, int count) -> uint32_t {
@@ -129,35 +111,91 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
         const uint64_t w = ((uint64_t)s_cont[(u >> 5) + 1] << 32) | s_cont[u >> 5];
         return (uint32_t)(w >> (u & 31u)) & ((1u << count) - 1u);
     };
-
-    // ---- 1 ---------------------------------------------------------------------------------------------
-    // the two array ends are the only places without a neighbour
-    const int first_i = (tile0 == 0) ? 0 : -1;                                  // slot without predecessor
-    const int last_i = (n - tile0 <= (uint64_t)kTieTile) ? n_in_tile - 1 : -1;  // slot without successor
     uint8_t *tile_flags = flags + tile0;
     uint32_t tied_mask = 0;
+    // nearly every tile lies inside the array with both halos: no bounds logic at all there
+    const bool interior = tile0 >= (uint64_t)kTieHalo && tile0 + kTieTile + kTieHalo <= n;
+    if (interior) {
+        const uint64_t *tile_keys = keys + tile0;
+        PreT my_pre[kTiePerThread];
+        uint32_t my_amb = 0;
 #pragma unroll
-    for (int j = 0; j < kTiePerThread; ++j) {
-        const int i = j * kTieThreads + (int)t;
-        bool cont = false;
-        if (i < n_in_tile) {
+        for (int j = 0; j < kTiePerThread; ++j) {
+            const uint64_t k = tile_keys[j * kTieThreads + (int)t];
+            my_pre[j] = (PreT)(k >> lo_bits);
+            my_amb |= (uint32_t)(~k & 1ull) << j;
+            s_pre[kTieHalo + j * kTieThreads + (int)t] = my_pre[j];
+        }
+        if (!class_bit) my_amb = 0;
+        if (t < 2 * kTieHalo) {
+            const int i = t < (uint32_t)kTieHalo ? (int)t - kTieHalo : kTieTile + (int)t - kTieHalo;
+            s_pre[i + kTieHalo] = (PreT)(tile_keys[i] >> lo_bits);
+        }
+        __syncthreads();
+        // ---- 1 (interior) ---------------------------------------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < kTiePerThread; ++j) {
+            const int i = j * kTieThreads + (int)t;
             const PreT pre = my_pre[j];
-            const bool ph = (i == first_i) | (s_pre[i - 1 + kTieHalo] != pre);
-            const bool nh = (i == last_i) | (s_pre[i + 1 + kTieHalo] != pre);
-            cont = !ph;
+            const bool ph = s_pre[i - 1 + kTieHalo] != pre;
+            const bool nh = s_pre[i + 1 + kTieHalo] != pre;
             if (ph & nh) tile_flags[i] = ((my_amb >> j) & 1u) ? kFlagAmb : kFlagHead;
             else tied_mask |= 1u << j;
+            const uint32_t word = __ballot_sync(0xffffffffu, !ph);
+            if (lane == 0) s_cont[j * (kTieThreads / 32) + warp + 1] = word;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, cont);
-        if (lane == 0) s_cont[j * (kTieThreads / 32) + warp + 1] = word;
-    }
-    if (warp == 0) {  // the halo words: eight slots before the tile, eight after it
-        const int ib = -32 + (int)lane, ia = kTieTile + (int)lane;
-        const bool cb = ib >= -(kTieHalo - 1) && valid(ib - 1) && valid(ib) &&
-                        s_pre[ib - 1 + kTieHalo] == s_pre[ib + kTieHalo];
-        const bool ca = lane < (uint32_t)kTieHalo && valid(ia) && s_pre[ia - 1 + kTieHalo] == s_pre[ia + kTieHalo];
-        const uint32_t wb = __ballot_sync(0xffffffffu, cb), wa = __ballot_sync(0xffffffffu, ca);
-        if (lane == 0) { s_cont[0] = wb; s_cont[kContWords - 1] = wa; }
+        if (warp == 0) {  // the halo words: eight slots before the tile, eight after it
+            const int ib = -32 + (int)lane, ia = kTieTile + (int)lane;
+            const bool cb = ib >= -(kTieHalo - 1) && s_pre[ib - 1 + kTieHalo] == s_pre[ib + kTieHalo];
+            const bool ca = lane < (uint32_t)kTieHalo && s_pre[ia - 1 + kTieHalo] == s_pre[ia + kTieHalo];
+            const uint32_t wb = __ballot_sync(0xffffffffu, cb), wa = __ballot_sync(0xffffffffu, ca);
+            if (lane == 0) { s_cont[0] = wb; s_cont[kContWords - 1] = wa; }
+        }
+    } else {
+        PreT my_pre[kTiePerThread];
+        uint32_t my_amb = 0;
+#pragma unroll
+        for (int j = 0; j < kTiePerThread; ++j) {
+            const int i = j * kTieThreads + (int)t;
+            const uint64_t k = (i < n_in_tile) ? keys[tile0 + i] : 0ull;
+            my_pre[j] = (PreT)(k >> lo_bits);
+            my_amb |= ((class_bit && !(k & 1ull)) ? 1u : 0u) << j;
+            s_pre[kTieHalo + i] = my_pre[j];
+        }
+        if (t < 2 * kTieHalo) {
+            const bool before = t < kTieHalo;
+            const uint64_t p = before ? tile0 - kTieHalo + t : tile0 + kTieTile + (t - kTieHalo);
+            const bool ok = before ? (tile0 >= (uint64_t)kTieHalo - t) : (p < n);
+            if (ok) s_pre[before ? t : kTieHalo + kTieTile + (t - kTieHalo)] = (PreT)(keys[p] >> lo_bits);
+        }
+        __syncthreads();
+        // ---- 1 (array ends) -------------------------------------------------------------------------------
+        const int first_i = (tile0 == 0) ? 0 : -1;                                  // slot without predecessor
+        const int last_i = (n - tile0 <= (uint64_t)kTieTile) ? n_in_tile - 1 : -1;  // slot without successor
+#pragma unroll
+        for (int j = 0; j < kTiePerThread; ++j) {
+            const int i = j * kTieThreads + (int)t;
+            bool cont = false;
+            if (i < n_in_tile) {
+                const PreT pre = my_pre[j];
+                const bool ph = (i == first_i) | (s_pre[i - 1 + kTieHalo] != pre);
+                const bool nh = (i == last_i) | (s_pre[i + 1 + kTieHalo] != pre);
+                cont = !ph;
+                if (ph & nh) tile_flags[i] = ((my_amb >> j) & 1u) ? kFlagAmb : kFlagHead;
+                else tied_mask |= 1u << j;
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, cont);
+            if (lane == 0) s_cont[j * (kTieThreads / 32) + warp + 1] = word;
+        }
+        if (warp == 0) {
+            const int ib = -32 + (int)lane, ia = kTieTile + (int)lane;
+            const bool cb = ib >= -(kTieHalo - 1) && valid(ib - 1) && valid(ib) &&
+                            s_pre[ib - 1 + kTieHalo] == s_pre[ib + kTieHalo];
+            const bool ca = lane < (uint32_t)kTieHalo && valid(ia) &&
+                            s_pre[ia - 1 + kTieHalo] == s_pre[ia + kTieHalo];
+            const uint32_t wb = __ballot_sync(0xffffffffu, cb), wa = __ballot_sync(0xffffffffu, ca);
+            if (lane == 0) { s_cont[0] = wb; s_cont[kContWords - 1] = wa; }
+        }
     }
     {   // one queue reservation per warp for all eight rounds
         const uint32_t cnt = __popc(tied_mask);

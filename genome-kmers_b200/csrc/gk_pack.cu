@@ -31,7 +31,7 @@ constexpr int kPackTile = kPackThreads * kPackPerThread;  // window starts per C
 constexpr int kPackChunks = kPackTile / 16 + 2;           // 16-byte chunks staged (tile + 32 B halo)
 constexpr int kPackHistPasses = 8;                        // digit positions counted on the fly
 
-template <typename IdxT>
+template <typename IdxT, int HP>
 __global__ void __launch_bounds__(kPackThreads)
 pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                  const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint32_t valid_len,
@@ -186,9 +186,10 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
         const uint64_t pos = tile_pos0 + q - (uint64_t)valid_len * seg_rel;
         keys_out[pos] = key;
         idx_out[pos] = (IdxT)i;
+        // HP >= 0: the number of counted digit positions is a compile-time constant (no branches)
 #pragma unroll
         for (int p = 0; p < kPackHistPasses; ++p) {
-            if (p < hist_passes) {
+            if (p < (HP >= 0 ? HP : hist_passes)) {
                 const int lo = hist_begin_bit + 8 * p;
                 const int bits = (hist_end_bit - lo < 8) ? hist_end_bit - lo : 8;
                 atomicAdd(&s_hist[p][(uint32_t)(key >> lo) & ((1u << bits) - 1u)], 1u);
@@ -400,16 +401,23 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
     // persistent CTAs (8 fit an SM) so that the shared histograms are flushed ~1000 times, not per tile
     uint64_t grid = (uint64_t)sm_count() * 8;
     if (grid > n_tiles) grid = n_tiles;
-    if (idx_bytes == 4)
-        pack_keys_kernel<uint32_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
-            d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
-            end_start, out_base, d_keys_out, (uint32_t *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit,
-            hist_end_bit, d_hist);
-    else
-        pack_keys_kernel<uint64_t><<<(unsigned)grid, kPackThreads, 0, st>>>(
-            d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,
-            end_start, out_base, d_keys_out, (uint64_t *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit,
-            hist_end_bit, d_hist);
+    const int hp = d_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
+#define GK_PACK_LAUNCH(IDX, HPV)                                                                       \
+    pack_keys_kernel<IDX, HPV><<<(unsigned)grid, kPackThreads, 0, st>>>(                               \
+        d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start, end_start,   \
+        out_base, d_keys_out, (IDX *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit, hist_end_bit, d_hist)
+    if (idx_bytes == 4) {
+        if (hp == 0) GK_PACK_LAUNCH(uint32_t, 0);
+        else if (hp == 4) GK_PACK_LAUNCH(uint32_t, 4);
+        else if (hp == 5) GK_PACK_LAUNCH(uint32_t, 5);
+        else GK_PACK_LAUNCH(uint32_t, -1);
+    } else {
+        if (hp == 0) GK_PACK_LAUNCH(uint64_t, 0);
+        else if (hp == 4) GK_PACK_LAUNCH(uint64_t, 4);
+        else if (hp == 5) GK_PACK_LAUNCH(uint64_t, 5);
+        else GK_PACK_LAUNCH(uint64_t, -1);
+    }
+#undef GK_PACK_LAUNCH
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
