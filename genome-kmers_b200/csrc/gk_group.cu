@@ -520,20 +520,6 @@ select_pairs_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-scatter_pairs_kernel(const uint64_t *__restrict__ keys_src, const T *__restrict__ vals_src,
-                     const T *__restrict__ pos, uint64_t m, uint64_t *__restrict__ keys_dst,
-                     T *__restrict__ vals_dst)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
-        const uint64_t d = (uint64_t)pos[r];
-        keys_dst[d] = keys_src[r];
-        vals_dst[d] = vals_src[r];
-    }
-}
-
 // Two-step ordered selection of (key, value) pairs: select_pairs_count leaves the tile offsets in
 // `temp` and returns the number of flagged positions (synchronises), so that the caller can size the
 // outputs; select_pairs_write then fills them.
@@ -578,25 +564,6 @@ int select_pairs_write(const uint8_t *d_flags, uint64_t n, uint8_t mask, const D
     return GK_OK;
 }
 
-int scatter_pairs_device(const uint64_t *d_keys_src, const void *d_vals_src, const void *d_pos, uint64_t m,
-                         int val_bytes, uint64_t *d_keys_dst, void *d_vals_dst, cudaStream_t st)
-{
-    if (m == 0) return GK_OK;
-    uint64_t blocks = (m + 255) / 256;
-    const uint64_t cap = (uint64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    if (val_bytes == 4)
-        scatter_pairs_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_keys_src, (const uint32_t *)d_vals_src, (const uint32_t *)d_pos, m, d_keys_dst,
-            (uint32_t *)d_vals_dst);
-    else
-        scatter_pairs_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_keys_src, (const uint64_t *)d_vals_src, (const uint64_t *)d_pos, m, d_keys_dst,
-            (uint64_t *)d_vals_dst);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
-}
-
 // type-erased front end (elem_bytes 4 or 8)
 int select_flagged(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_bytes, void *d_pos_out,
                    const void *d_pay_in, void *d_pay_out, const void *d_pay2_in, void *d_pay2_out,
@@ -609,17 +576,6 @@ int select_flagged(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_by
     return select_flagged_device<uint64_t>(d_flags, n, mask, (uint64_t *)d_pos_out,
                                            (const uint64_t *)d_pay_in, (uint64_t *)d_pay_out,
                                            (const uint64_t *)d_pay2_in, (uint64_t *)d_pay2_out, h_count, st);
-}
-
-// scatter: dst_array[pos[r]] = src[r]
-template <typename IdxT>
-__global__ void __launch_bounds__(256)
-scatter_kernel(const IdxT *__restrict__ src, const IdxT *__restrict__ pos, uint64_t n,
-               IdxT *__restrict__ dst_array)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride)
-        dst_array[(uint64_t)pos[r]] = src[r];
 }
 
 // ---- group-size histogram -----------------------------------------------------------------------------
@@ -735,21 +691,6 @@ int sba_flags_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, 
     return GK_OK;
 }
 
-int scatter_device(const void *d_src, const void *d_pos, uint64_t n, int idx_bytes, void *d_dst,
-                   cudaStream_t st)
-{
-    if (n == 0) return GK_OK;
-    const int grid = launch_grid(n, 256);
-    if (idx_bytes == 4)
-        scatter_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_src,
-                                                       (const uint32_t *)d_pos, n, (uint32_t *)d_dst);
-    else
-        scatter_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)d_src,
-                                                       (const uint64_t *)d_pos, n, (uint64_t *)d_dst);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
-}
-
 // The device histogram is a dense table of max_bin + 1 counters (8 MB at the reference's default
 // max_counts_bin), but only a handful of bins are ever occupied, and one giant group (an N run) puts
 // a count into the LAST bin.  So the table never crosses PCIe: a compaction kernel lists the non-empty
@@ -757,7 +698,6 @@ int scatter_device(const void *d_src, const void *d_pos, uint64_t n, int idx_byt
 static thread_local std::vector<unsigned long long> g_last_pairs;  // (bin, count) of the last call
 static thread_local uint64_t g_last_top_bin = 0;
 uint64_t last_hist_top_bin() { return g_last_top_bin; }
-void set_last_hist_top_bin(uint64_t v) { g_last_top_bin = v; }
 const std::vector<unsigned long long> &last_hist_pairs() { return g_last_pairs; }
 void set_last_hist_single(uint64_t bin, uint64_t count)
 {
@@ -877,15 +817,6 @@ int group_hist_device(const void *d_offsets, int pos_bytes, uint64_t n_groups, u
 {
     return group_hist_impl(d_offsets, pos_bytes, n_groups, n, nullptr, 0, min_group, max_group, max_bin,
                            h_hist, h_total, h_counted, st);
-}
-
-int group_hist_masked_device(const void *d_offsets, int pos_bytes, uint64_t n_groups, uint64_t n,
-                             const uint8_t *d_flags, uint8_t skip_mask, uint64_t min_group,
-                             uint64_t max_group, uint64_t max_bin, int64_t *h_hist, int64_t *h_total,
-                             cudaStream_t st)
-{
-    return group_hist_impl(d_offsets, pos_bytes, n_groups, n, d_flags, skip_mask, min_group, max_group,
-                           max_bin, h_hist, h_total, nullptr, st);
 }
 
 // ---- group-size histogram straight from the head flags (no offsets array) ---------------------------

@@ -21,8 +21,6 @@ int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, voi
 int pack_keys_device(const uint8_t *, uint64_t, const uint64_t *, uint32_t, uint32_t, uint32_t, int,
                      uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *, int, int,
                      unsigned long long *, cudaStream_t);
-int pack4_gather_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, uint32_t,
-                        const uint64_t *, uint64_t *, cudaStream_t);
 int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
                             cudaStream_t);
 int gather2_u64_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, cudaStream_t);
@@ -43,15 +41,10 @@ int pack4_words_device(const uint8_t *, uint64_t, const void *, int, uint64_t, u
 int rank4_stream_device(const uint8_t *, uint64_t, uint64_t *, cudaStream_t);
 int pack4_words_stream_device(const uint64_t *, const void *, int, uint64_t, uint32_t, const uint64_t *, uint64_t *,
                               uint64_t *, cudaStream_t);
-int scatter_pairs_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, void *,
-                         cudaStream_t);
 int sba_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const void *,
                      uint8_t, uint8_t *, cudaStream_t);
-int scatter_device(const void *, const void *, uint64_t, int, void *, cudaStream_t);
 int group_hist_device(const void *, int, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, int64_t *,
                       int64_t *, int64_t *, cudaStream_t);
-int group_hist_masked_device(const void *, int, uint64_t, uint64_t, const uint8_t *, uint8_t, uint64_t,
-                             uint64_t, uint64_t, int64_t *, int64_t *, cudaStream_t);
 uint64_t last_hist_top_bin();
 const std::vector<unsigned long long> &last_hist_pairs();
 void set_last_hist_single(uint64_t, uint64_t);
@@ -65,8 +58,6 @@ int head_positions_device(const uint8_t *, const uint32_t *, uint64_t, uint32_t 
 int valid_flags_device(const uint32_t *, uint64_t, const uint64_t *, uint32_t, uint64_t, uint32_t, uint8_t *,
                        cudaStream_t);
 int gid_flags_device(const uint32_t *, uint64_t, uint8_t *, cudaStream_t);
-int pair_keys_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, uint64_t *,
-                     cudaStream_t);
 int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint8_t *,
                         cudaStream_t);
 int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, const uint64_t *,

@@ -19,8 +19,8 @@
 // stable integer sort places every window correctly relative to all pure windows; only runs
 // of non-pure windows with equal value need the 4-bit refinement in gk_index.cu.
 //
-// pack4_gather_kernel: terminator-aware 4-bit rank words for an arbitrary list of starts (the
-// refinement keys).
+// pack4_words_kernel / rank4_stream_kernel: terminator-aware 4-bit rank words for an arbitrary list of
+// starts (the refinement keys).
 #include "gk_common.cuh"
 
 namespace gk {
@@ -211,38 +211,10 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     }
 }
 
-// Terminator-aware 4-bit rank word `word` (symbols [16*word, 16*word+16) of the window, most
-// significant first) for each start in idx; symbols at or after a '$'/end of array are 0, so
-// a shorter k-mer sorts first (kmers.py:360-378).
-template <typename IdxT>
-__global__ void __launch_bounds__(256)
-pack4_gather_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
-                    const IdxT *__restrict__ idx, uint64_t n, uint32_t word, uint32_t max_len,
-                    const uint64_t *__restrict__ class_keys, uint64_t *__restrict__ keys_out)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-        if (class_keys && (class_keys[r] & 1ull)) {  // pure window: its radix key already says everything
-            keys_out[r] = 0;
-            continue;
-        }
-        const uint64_t s = (uint64_t)idx[r];
-        const uint32_t lo = 16u * word;
-        const uint32_t hi = (lo + 16u < max_len) ? lo + 16u : max_len;
-        uint64_t key = 0;
-        bool alive = true;
-        for (uint32_t j = 0; j < hi && alive; ++j) {
-            const uint64_t p = s + j;
-            const uint32_t code = (p < sba_len) ? rank4(sba[p]) : 0u;
-            if (code == 0) { alive = false; break; }
-            if (j >= lo) key |= (uint64_t)code << (4u * (15u - (j - lo)));
-        }
-        keys_out[r] = key;
-    }
-}
-
-// Both 4-bit rank words of a window of max_len <= 32 symbols in one read of its bytes.  Pure windows
-// (class bit set in class_keys) get zeros: their radix key already says everything.
+// Both 4-bit rank words (16 symbols per word, most significant first) of a window of max_len <= 32 symbols
+// in one read of its bytes; symbols at or after a '$' / the end of the array are 0, so a shorter k-mer sorts
+// first (kmers.py:360-378).  Pure windows (class bit set in class_keys) get zeros: their radix key already
+// says everything.
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pack4_words_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const IdxT *__restrict__ idx, uint64_t n,
@@ -418,24 +390,6 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
         else GK_PACK_LAUNCH(uint64_t, -1);
     }
 #undef GK_PACK_LAUNCH
-    GK_LAUNCH_CHECK();
-    return GK_OK;
-}
-
-int pack4_gather_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,
-                        uint64_t n, uint32_t word, uint32_t max_len, const uint64_t *d_class_keys,
-                        uint64_t *d_keys_out, cudaStream_t st)
-{
-    if (n == 0) return GK_OK;
-    uint64_t blocks = (n + 255) / 256;
-    uint64_t cap = (uint64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    if (idx_bytes == 4)
-        pack4_gather_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_sba, sba_len, (const uint32_t *)d_idx, n, word, max_len, d_class_keys, d_keys_out);
-    else
-        pack4_gather_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
-            d_sba, sba_len, (const uint64_t *)d_idx, n, word, max_len, d_class_keys, d_keys_out);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

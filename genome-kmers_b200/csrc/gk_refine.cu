@@ -1,19 +1,22 @@
-// gk_refine.cu -- prefix-doubling refinement for k-mers longer than one key word (SURVEY.md 8a A4,
-// north_star subsystem 2 "extended with prefix-doubling refinement").
+// gk_refine.cu -- kernels of the two refinement stages that follow the main sort (SURVEY.md 8a A4,
+// north_star subsystem 2 "extended with prefix-doubling refinement"); orchestration in gk_index.cu.
 //
-// After the windows are sorted by their first h symbols (head flags mark the h-groups), the rank
-// of a start is the sorted position of its group's first member.  A window of h2 <= 2h symbols is
-// then ordered by the pair (rank_h[start], rank_h[start + h2 - h]): both halves are h-windows that
-// lie inside the same record.  Only members of groups with more than one element can move, so the
-// pair sort runs on that subset and the rest keeps its slot.
-//
-//   head_positions   group id (= position of the group's head) for every sorted position, and
-//                    rank_of_start[idx[p]] = that id.  Tile max-scan, 3 kernels.
-//   valid_flags      which windows still fit their record at the next length
-//   gid_flags        head flags after compaction (group id changes) + "group has >1 member" marks
-//   pair_keys        key2 = (gid << 32) | rank_of_start[start + delta]
-//   key2_flags       head flags inside the re-sorted subset, scattered to their slots
-// Indices are 32-bit here: the multi-level path is limited to byte arrays below 2^32.
+// 1. Prefix doubling (k-mers longer than one key word, variable-length mode).  After the windows are
+//    sorted by their first h symbols (head flags mark the h-groups), the rank of a start is the sorted
+//    position of its group's first member.  A window of h2 <= 2h symbols is then ordered by the pair
+//    (rank_h[start], rank_h[start + h2 - h]); a window that ends at its record's '$' before start + h2 - h
+//    has an empty second half, which sorts first.  Only members of groups with more than one element can
+//    move, so the rounds run on that shrinking list and the rest keeps its slot.
+//      head_positions     group id (= position of the group's head) for every sorted position, and
+//                         rank_of_start[idx[p]] = that id.  Tile max-scan, 3 kernels.
+//      valid_flags        which windows fit their record at a given length (final drop of short windows)
+//      gid_flags          head flags from group ids + "group has more than one member" marks
+//      pair_keys_var      key2 = (group << 32) | (rank_of_start[start + delta] + 1, or 0 when empty)
+//      key2_scatter       re-sorted list -> slots, with fresh head flags
+//      subset_rank_update ranks of the list members after a round
+// 2. Run-length compressed stable sort of a selected subset (ambiguous windows, out-of-order long prefix
+//    runs): subset_rep_flags, block offsets (scan), subset_expand -- see below.
+// Indices are 32-bit in stage 1: the multi-level path is limited to byte arrays below 2^32 positions.
 #include "gk_common.cuh"
 
 namespace gk {
@@ -147,15 +150,6 @@ gid_flags_kernel(const uint32_t *__restrict__ gid, uint64_t n, uint8_t *__restri
         const bool next_head = (p + 1 == n) || gid[p + 1] != g;
         flags[p] = (head ? kFlagHead : 0) | ((head && next_head) ? 0 : kFlagMulti);
     }
-}
-
-__global__ void __launch_bounds__(256)
-pair_keys_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__restrict__ sub_gid, uint64_t m,
-                 const uint32_t *__restrict__ rank_of_start, uint32_t delta, uint64_t *__restrict__ keys)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride)
-        keys[r] = ((uint64_t)sub_gid[r] << 32) | rank_of_start[(uint64_t)sub_idx[r] + delta];
 }
 
 // Variable-length mode (kmers.py:360-378): a window ends at its record's '$'.  When start + delta is at or
@@ -430,15 +424,6 @@ int gid_flags_device(const uint32_t *d_gid, uint64_t n, uint8_t *d_flags, cudaSt
 {
     if (n == 0) return GK_OK;
     gid_flags_kernel<<<grid_for(n), 256, 0, st>>>(d_gid, n, d_flags);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
-}
-
-int pair_keys_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, uint64_t m,
-                     const uint32_t *d_rank_of_start, uint32_t delta, uint64_t *d_keys, cudaStream_t st)
-{
-    if (m == 0) return GK_OK;
-    pair_keys_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_rank_of_start, delta, d_keys);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
