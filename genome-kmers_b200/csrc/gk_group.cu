@@ -90,7 +90,8 @@ constexpr int kTieHalo = kTieMaxRun;                   // keys staged either sid
 template <typename ValT, typename PreT>
 __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
-                     int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent)
+                     int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent,
+                     unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */)
 {
     // bit (i + 32) of s_cont: slot i (tile-relative, -8 <= i < kTieTile + 8) has the same prefix as slot i - 1
     constexpr int kContWords = kTieTile / 32 + 2;
@@ -127,6 +128,10 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             s_pre[kTieHalo + j * kTieThreads + (int)t] = my_pre[j];
         }
         if (!class_bit) my_amb = 0;
+        if (n_amb_out && class_bit) {
+            const uint32_t c = warp_sum((uint32_t)__popc(my_amb));
+            if (lane == 0 && c) atomicAdd(n_amb_out, (unsigned long long)c);
+        }
         if (t < 2 * kTieHalo) {
             const int i = t < (uint32_t)kTieHalo ? (int)t - kTieHalo : kTieTile + (int)t - kTieHalo;
             s_pre[i + kTieHalo] = (PreT)(tile_keys[i] >> lo_bits);
@@ -159,8 +164,12 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             const int i = j * kTieThreads + (int)t;
             const uint64_t k = (i < n_in_tile) ? keys[tile0 + i] : 0ull;
             my_pre[j] = (PreT)(k >> lo_bits);
-            my_amb |= ((class_bit && !(k & 1ull)) ? 1u : 0u) << j;
+            my_amb |= ((i < n_in_tile && class_bit && !(k & 1ull)) ? 1u : 0u) << j;
             s_pre[kTieHalo + i] = my_pre[j];
+        }
+        if (n_amb_out && class_bit) {
+            const uint32_t c = warp_sum((uint32_t)__popc(my_amb));
+            if (lane == 0 && c) atomicAdd(n_amb_out, (unsigned long long)c);
         }
         if (t < 2 * kTieHalo) {
             const bool before = t < kTieHalo;
@@ -651,7 +660,8 @@ int key_flags_device(const uint64_t *d_keys, uint64_t n, int class_bit, uint8_t 
 // head/ambiguous flags of keys sorted on bits [lo_bits, 64) only, repairing short prefix runs in place;
 // *d_descent (zeroed by the caller) becomes 1 when a kFlagLong run is out of order
 int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t n, int lo_bits,
-                         int class_bit, uint8_t *d_flags, unsigned int *d_descent, cudaStream_t st)
+                         int class_bit, uint8_t *d_flags, unsigned int *d_descent,
+                         unsigned long long *d_n_amb, cudaStream_t st)
 {
     if (n == 0) return GK_OK;
     const uint64_t tiles = (n + kTieTile - 1) / kTieTile;
@@ -659,16 +669,16 @@ int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t
     const unsigned grid = (unsigned)tiles;
     if (val_bytes == 4 && narrow)
         tie_fix_flags_kernel<uint32_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
     else if (val_bytes == 4)
         tie_fix_flags_kernel<uint32_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
     else if (narrow)
         tie_fix_flags_kernel<uint64_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
     else
         tie_fix_flags_kernel<uint64_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent);
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

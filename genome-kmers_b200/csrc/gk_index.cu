@@ -32,7 +32,8 @@ int subset_expand_device(const void *, const void *, const uint64_t *, const uin
 int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, int *,
                             cudaStream_t, SortTiming *, const unsigned long long *d_pre_hist = nullptr);
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
-int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *, cudaStream_t);
+int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *,
+                         unsigned long long *, cudaStream_t);
 int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
 int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &, int, void *, const uint64_t *,
                        uint64_t *, const void *, void *, cudaStream_t);
@@ -208,8 +209,12 @@ static int prefix_begin_bit(uint64_t n, int key_bits)
 static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, void *idx_b, int ib,
                                uint64_t n, int key_bits, int class_bit, uint8_t *d_flags, int *in_alt,
                                unsigned int *d_descent, SortTiming *timing, cudaStream_t st,
-                               const unsigned long long *d_pre_hist = nullptr)
+                               const unsigned long long *d_pre_hist = nullptr,
+                               unsigned long long *d_n_amb = nullptr, bool *n_amb_counted = nullptr)
 {
+    // d_n_amb (zeroed by the caller): the tie-repair pass also counts the ambiguous slots on request, for
+    // callers that did not pack the keys themselves (*n_amb_counted tells whether it ran)
+    if (n_amb_counted) *n_amb_counted = false;
     // d_pre_hist: digit histograms of bits [prefix_begin_bit(n, key_bits), key_bits) counted by the producer
     const int begin = prefix_begin_bit(n, key_bits);
     GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
@@ -218,7 +223,8 @@ static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, 
     uint64_t *ks = *in_alt ? keys_b : keys_a;
     void *is = *in_alt ? idx_b : idx_a;
     if (begin == 0) return key_flags_device(ks, n, class_bit, d_flags, st);
-    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, st);
+    if (n_amb_counted) *n_amb_counted = d_n_amb != nullptr;
+    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, d_n_amb, st);
 }
 
 // After the main sort and its flags pass, two kinds of slots may still hold the wrong element:
@@ -680,20 +686,24 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     ix->n = n_local;
     GK_TRY(ix->d_idx.alloc((size_t)n_local * ib, st));
     GK_TRY(ix->d_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
-    DeviceBuffer descent;
-    GK_TRY(descent.alloc(4, st));
+    DeviceBuffer descent;  // [0..3] descent word, [8..15] count of ambiguous slots
+    GK_TRY(descent.alloc(16, st));
+    GK_CUDA(cudaMemsetAsync(descent.ptr, 0, 16, st));
+    bool amb_counted = false;
     GK_TRY(sort_pairs_and_flag(d_keys, d_keys_alt, d_idx, d_idx_alt, ib, n_local, key_bits, class_bit,
-                               (uint8_t *)ix->d_flags.ptr, &in_alt, descent.as<unsigned int>(), &timing, st));
+                               (uint8_t *)ix->d_flags.ptr, &in_alt, descent.as<unsigned int>(), &timing, st,
+                               nullptr, descent.as<unsigned long long>() + 1, &amb_counted));
     const uint64_t *keys_sorted = in_alt ? d_keys_alt : d_keys;
     const void *idx_sorted = in_alt ? d_idx_alt : d_idx;
     if (n_local)
         GK_CUDA(cudaMemcpyAsync(ix->d_idx.ptr, idx_sorted, (size_t)n_local * ib, cudaMemcpyDeviceToDevice, st));
     const int f0 = tm.mark();
-    unsigned int h_descent = 0;
-    GK_CUDA(cudaMemcpyAsync(&h_descent, descent.ptr, 4, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_words[2] = {0, 0};
+    GK_CUDA(cudaMemcpyAsync(h_words, descent.ptr, 16, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
-    uint64_t n_amb = 0;
-    if (class_bit && n_local)  // the slots whose key has class bit 0 (the flags pass marked them)
+    const unsigned int h_descent = (unsigned int)(h_words[0] & 0xffffffffull);
+    uint64_t n_amb = h_words[1];
+    if (class_bit && n_local && !amb_counted)  // plain LSD path: count the slots the flags pass marked
         GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n_local, kFlagAmb, ib, nullptr, nullptr, nullptr,
                               nullptr, nullptr, &n_amb, st));
     GK_TRY(refine_subset(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
