@@ -66,6 +66,10 @@ int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uin
 int subset_rank_update_device(const uint32_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *,
                               cudaStream_t);
 int gather_u32_device(const uint32_t *, const uint32_t *, uint64_t, uint32_t *, cudaStream_t);
+int multi_flags_device(const uint8_t *, uint64_t, uint8_t *, cudaStream_t);
+int clear_finished_multi_device(const uint32_t *, uint64_t, const uint64_t *, uint32_t, uint64_t, uint64_t, uint8_t *,
+                                cudaStream_t);
+int gather_u8_device(const uint8_t *, const void *, int, uint64_t, uint8_t, uint8_t *, cudaStream_t);
 
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
@@ -381,15 +385,20 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
     if (h0 >= target || n_cur < 2) return GK_OK;
     uint32_t *d_idx = (uint32_t *)cur_idx.ptr;
     uint8_t *d_flags = (uint8_t *)cur_flags.ptr;
+    // members of groups with more than one element, straight from the head flags: when there are none
+    // (every k-mer already differs within the first h0 symbols) no rank is ever looked up
     DeviceBuffer rank, gid, mflags;
-    GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
-    GK_TRY(gid.alloc((size_t)n_cur * 4, st));
-    GK_TRY(head_positions_device(d_flags, d_idx, n_cur, gid.as<uint32_t>(), rank.as<uint32_t>(), st));
     GK_TRY(mflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
-    GK_TRY(gid_flags_device(gid.as<uint32_t>(), n_cur, mflags.as<uint8_t>(), st));
+    GK_TRY(multi_flags_device(d_flags, n_cur, mflags.as<uint8_t>(), st));
+    GK_TRY(clear_finished_multi_device(d_idx, n_cur, (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
+                                       ix->sba_len, h0, mflags.as<uint8_t>(), st));
     uint64_t m = 0;
     GK_TRY(select_flagged(mflags.as<uint8_t>(), n_cur, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr,
                           &m, st));
+    if (m == 0) return GK_OK;
+    GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
+    GK_TRY(gid.alloc((size_t)n_cur * 4, st));
+    GK_TRY(head_positions_device(d_flags, d_idx, n_cur, gid.as<uint32_t>(), rank.as<uint32_t>(), st));
     DeviceBuffer slots, sub_idx, sub_gid;
     if (m) {
         GK_TRY(slots.alloc((size_t)m * 4, st));
@@ -427,6 +436,8 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
                                          rank.as<uint32_t>(), st));
         GK_TRY(mf.alloc((size_t)((m + 15) & ~15ull), st));
         GK_TRY(gid_flags_device(gsub.as<uint32_t>(), m, mf.as<uint8_t>(), st));
+        GK_TRY(clear_finished_multi_device(I, m, (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
+                                           ix->sba_len, h2, mf.as<uint8_t>(), st));
         uint64_t m2 = 0;
         GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr, &m2,
                               st));
@@ -460,22 +471,20 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
 static int drop_short_windows(gk_index *ix, uint32_t min_len, Owned &cur_idx, Owned &cur_flags, uint64_t &n_cur,
                               cudaStream_t st)
 {
-    DeviceBuffer gid, vflags, new_gid;
-    GK_TRY(gid.alloc((size_t)n_cur * 4, st));
-    GK_TRY(head_positions_device((const uint8_t *)cur_flags.ptr, (const uint32_t *)cur_idx.ptr, n_cur,
-                                 gid.as<uint32_t>(), nullptr, st));
+    DeviceBuffer vflags, pos;
     GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
     GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
                               (uint32_t)ix->h_segs.size(), ix->sba_len, min_len, vflags.as<uint8_t>(), st));
     Owned new_idx, new_flags;
     GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
-    GK_TRY(new_gid.alloc((size_t)n_cur * 4, st));
+    GK_TRY(pos.alloc((size_t)n_cur * 4, st));
     uint64_t n_new = 0;
-    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, nullptr, cur_idx.ptr, new_idx.ptr, gid.ptr,
-                          new_gid.ptr, &n_new, st));
+    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, pos.ptr, cur_idx.ptr, new_idx.ptr, nullptr,
+                          nullptr, &n_new, st));
+    // groups go or stay whole, so the head flag of a kept window is still right
     GK_TRY(new_flags.alloc((size_t)((n_new + 15) & ~15ull), st));
-    GK_TRY(gid_flags_device(new_gid.as<uint32_t>(), n_new, (uint8_t *)new_flags.ptr, st));
-    GK_CUDA(cudaStreamSynchronize(st));
+    GK_TRY(gather_u8_device((const uint8_t *)cur_flags.ptr, pos.ptr, 4, n_new, kFlagHead, (uint8_t *)new_flags.ptr,
+                            st));
     cur_idx.swap(new_idx);
     cur_flags.swap(new_flags);
     n_cur = n_new;

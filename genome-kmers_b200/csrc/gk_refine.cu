@@ -375,6 +375,46 @@ subset_rank_update_kernel(const uint32_t *__restrict__ slots, const uint32_t *__
     }
 }
 
+// kFlagMulti on every member of a group with more than one element, straight from the head flags
+__global__ void __launch_bounds__(256)
+multi_flags_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const bool head = flags[p] & kFlagHead;
+        const bool next_head = (p + 1 == n) || (flags[p + 1] & kFlagHead);
+        out[p] = (head ? kFlagHead : 0) | ((head && next_head) ? 0 : kFlagMulti);
+    }
+}
+
+// A window that reaches its record's '$' within the first h symbols is fully compared: its group holds
+// identical k-mers and can never split again.  Clear kFlagMulti on those members (few windows are marked,
+// so the segment search runs rarely).
+__global__ void __launch_bounds__(256)
+clear_finished_multi_kernel(const uint32_t *__restrict__ idx, uint64_t n, const uint64_t *__restrict__ seg_starts,
+                            uint32_t n_seg, uint64_t sba_len, uint64_t h, uint8_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const uint8_t f = flags[p];
+        if (!(f & kFlagMulti)) continue;
+        const uint64_t s = idx[p];
+        const uint32_t seg = upper_seg(seg_starts, n_seg, s);
+        const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;  // position of '$'
+        if (s + h > seg_end) flags[p] = f & (uint8_t)~kFlagMulti;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_u8_kernel(const uint8_t *__restrict__ src, const T *__restrict__ at, uint64_t count, uint8_t keep_mask,
+                 uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += stride)
+        out[r] = src[(uint64_t)at[r]] & keep_mask;
+}
+
 __global__ void __launch_bounds__(256)
 gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ at, uint64_t count,
                   uint32_t *__restrict__ out)
@@ -445,6 +485,37 @@ int subset_rank_update_device(const uint32_t *d_slots, const uint32_t *d_gid_sub
     if (m == 0) return GK_OK;
     subset_rank_update_kernel<<<grid_for(m), 256, 0, st>>>(d_slots, d_gid_sub, d_idx_sorted, m, d_gid_slot,
                                                            d_rank_of_start);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int multi_flags_device(const uint8_t *d_flags, uint64_t n, uint8_t *d_out, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    multi_flags_kernel<<<grid_for(n), 256, 0, st>>>(d_flags, n, d_out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int clear_finished_multi_device(const uint32_t *d_idx, uint64_t n, const uint64_t *d_seg_starts, uint32_t n_seg,
+                                uint64_t sba_len, uint64_t h, uint8_t *d_flags, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    clear_finished_multi_kernel<<<grid_for(n), 256, 0, st>>>(d_idx, n, d_seg_starts, n_seg, sba_len, h, d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int gather_u8_device(const uint8_t *d_src, const void *d_at, int at_bytes, uint64_t count, uint8_t keep_mask,
+                     uint8_t *d_out, cudaStream_t st)
+{
+    if (count == 0) return GK_OK;
+    if (at_bytes == 4)
+        gather_u8_kernel<uint32_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint32_t *)d_at, count, keep_mask,
+                                                                    d_out);
+    else
+        gather_u8_kernel<uint64_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint64_t *)d_at, count, keep_mask,
+                                                                    d_out);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
