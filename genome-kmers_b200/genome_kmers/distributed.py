@@ -30,7 +30,7 @@ import numpy as np
 
 from genome_kmers import _native
 
-SAMPLES_PER_RANK = 4096
+SAMPLES_PER_RANK = 2048
 
 
 def _torch():
@@ -295,16 +295,20 @@ def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 
         # blocks of equal keys (a part can only begin where a key begins) and their costs
         weight = np.where((sorted_samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
         first = np.flatnonzero(np.concatenate([[True], sorted_samples[1:] != sorted_samples[:-1]]))
-        cost = np.add.reduceat(weight, first)
-        cum = np.concatenate([[0.0], np.cumsum(cost)])        # cum[b] = cost of blocks [0, b)
+        run = np.concatenate([[0.0], np.cumsum(weight)])      # run[i] = cost of samples [0, i)
+        cum = np.concatenate([run[first], run[-1:]])          # cum[b] = cost of blocks [0, b)
+        cost = np.diff(cum)
+        n_blocks = len(cost)
+        find = cum.searchsorted
 
         def pack(limit):
             """Greedy: fill every part up to `limit`; returns the first block of parts 1, 2, ..."""
             cuts, b = [], 0
-            while b < len(cost) and len(cuts) < n_parts:
-                e = int(np.searchsorted(cum, cum[b] + limit, side="right")) - 1   # blocks [b, e) fit
-                e = max(e, b + 1)
-                if e >= len(cost):
+            while b < n_blocks and len(cuts) < n_parts:
+                e = int(find(cum[b] + limit, "right")) - 1    # blocks [b, e) fit
+                if e <= b:
+                    e = b + 1
+                if e >= n_blocks:
                     return cuts, True
                 cuts.append(e)
                 b = e
