@@ -526,7 +526,7 @@ class Kmers:
         sc = self.seq_coll
         strand = self.kmer_source_strand
         if strand == "both":
-            raise NotImplementedError("kmer_info_to_yield='full' is not available for source_strand='both'")
+            return self._locate_all_both(idx, one_based)
         seg, seq_idx = sc.locate_sba_indices(idx, strand, one_based)
         sba, starts, names = sc._strand_arrays(strand)
         ends = np.concatenate([starts[1:].astype(np.int64) - 2, [len(sba) - 1]])
@@ -535,6 +535,32 @@ class Kmers:
         def locate(kmer_num):
             s = int(seg[kmer_num])
             return symbol, names[s], int(seq_idx[kmer_num]), int(ends[s])
+
+        return locate
+
+    def _locate_all_both(self, idx, one_based):
+        """source_strand='both': start i < L is forward_sba[i] ('+'), i > L is revcomp_sba[i - L - 1] ('-'),
+        each located exactly as the reference locates an index of that strand
+        (sequence_collection.py:930-978).  The segment end is in the coordinates of the indexed array."""
+        sc = self.seq_coll
+        n_fwd = len(sc.forward_sba)
+        idx = np.asarray(idx, dtype=np.int64)
+        is_rc = idx > n_fwd
+        seg = np.empty(len(idx), dtype=np.int64)
+        seq_idx = np.empty(len(idx), dtype=np.int64)
+        seg[~is_rc], seq_idx[~is_rc] = sc.locate_sba_indices(idx[~is_rc], "forward", one_based)
+        seg[is_rc], seq_idx[is_rc] = sc.locate_sba_indices(idx[is_rc] - (n_fwd + 1), "reverse_complement",
+                                                         one_based)
+        ends, names = {}, {}
+        for rc, strand in ((False, "forward"), (True, "reverse_complement")):
+            sba, starts, names[rc] = sc._strand_arrays(strand)
+            ends[rc] = (np.concatenate([starts[1:].astype(np.int64) - 2, [len(sba) - 1]])
+                        + (n_fwd + 1 if rc else 0))
+
+        def locate(kmer_num):
+            rc = bool(is_rc[kmer_num])
+            s = int(seg[kmer_num])
+            return "-" if rc else "+", names[rc][s], int(seq_idx[kmer_num]), int(ends[rc][s])
 
         return locate
 

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
+from conftest import (dense_hist, expected_get_kmers_tuples, filter_from_spec, get_kmers_entries,
+                      get_kmers_entry_id, golden_case, golden_case_names, is_fixed_k)
 from genome_kmers.kmers import (Kmers, gen_kmer_gc_content_filter_func, gen_kmer_homopolymer_filter_func,
                                 gen_no_ambiguous_bases_filter, kmer_filter_keep_all)
 from genome_kmers.sequence_collection import SequenceCollection
@@ -245,6 +246,25 @@ def test_get_kmers_with_device_filters(name, make_filter):
         assert got == want, (min_g, max_g, first_n)
     # and the counts agree with the same walk
     assert km.get_kmer_count(k, filt) == sum(len(g) for g in groups)
+
+
+@pytest.mark.parametrize("entry", get_kmers_entries(), ids=get_kmers_entry_id)
+def test_golden_get_kmers(entry):
+    """Row N2: Kmers.get_kmers against tuples the real reference yielded (tests/golden/make_golden_get_kmers.py)
+    -- minimum and full info, 0/1-based, filters, group limits, yield_first_n, sorted and unsorted.
+    source_strand='both': the reference ran its forward path over forward + '<name>_rc' records; a k-mer of a
+    reverse-complemented record is ('-', name, forward sequence index) here, the reference's own convention for
+    its reverse-complement strand (sequence_collection.py:101-153)."""
+    case, qu = golden_case(entry["case"]), entry["query"]
+    sc, km = _kmers_for(case)
+    if qu["sorted"]:
+        km.sort()
+        assert np.array_equal(km.kmer_sba_start_indices, case["sorted"])
+    got = list(km.get_kmers(qu["kmer_len"], one_based_seq_index=qu["one_based"],
+                            kmer_filter_func=filter_from_spec(qu["filter"]), kmer_info_to_yield=qu["info"],
+                            min_group_size=qu["min_group"], max_group_size=qu["max_group"],
+                            yield_first_n=qu["first_n"]))
+    assert got == expected_get_kmers_tuples(entry, case)
 
 
 def _oracle_compare(records, k, strands, threads=8, filt_k=None):

@@ -9,6 +9,8 @@ import re
 import numpy as np
 import pytest
 
+from conftest import (expected_get_kmers_tuples, filter_from_spec, get_kmers_entries, get_kmers_entry_id,
+                      golden_case)
 from genome_kmers import _native
 from genome_kmers.kmers import (Kmers, KmerFilter, compare_sba_kmers_lexicographically,
                                 crispr_ngg_pam_filter, gen_kmer_gc_content_filter_func,
@@ -174,3 +176,51 @@ def test_scalar_comparator_matches_reference_docstring_example():
     assert compare_sba_kmers_lexicographically(sba, sba, 15, 36, None) == (-1, 0)
     assert compare_sba_kmers_lexicographically(sba, sba, 16, 37, None) == (0, 0)   # both terminate
     assert compare_sba_kmers_lexicographically(sba, sba, 16, 18, None) == (-1, 0)  # 'A$' < 'AAT..'
+
+
+# ---------------------------------------------------------------------------------------------------
+# get_kmers host logic (tuple construction, record lookup, group limits) against tuples the REAL
+# reference yielded (tests/golden/golden_get_kmers.json).  The group table normally comes from the GPU
+# (gk_index_groups / gk_index_groups_filtered); here a TEST DOUBLE derives it on the host with the
+# scalar comparator and the host evaluation of the filters, so the rest of get_kmers runs without a GPU.
+# tests/test_gpu_parity.py::test_golden_get_kmers runs the same entries through the device path.
+# ---------------------------------------------------------------------------------------------------
+class _HostGroupTableKmers(Kmers):
+    def _host_groups(self, kmer_len, flt):
+        sba = self._indexed_bytes()
+        idx = self.kmer_sba_start_indices
+        strand = "forward"
+        kept = [p for p, s in enumerate(idx) if flt(sba, strand, int(s))]
+        offsets, sizes = [], []
+        for j, p in enumerate(kept):
+            same = (self._is_sorted and j > 0 and compare_sba_kmers_lexicographically(
+                sba, sba, int(idx[kept[j - 1]]), int(idx[p]), kmer_len)[0] == 0)
+            if same:
+                sizes[-1] += 1
+            else:
+                offsets.append(j)
+                sizes.append(1)
+        return (np.array(kept, dtype=np.uint64), np.array(offsets, dtype=np.uint64),
+                np.array(sizes, dtype=np.uint64))
+
+    def get_kmer_groups(self, kmer_len):
+        _, offsets, sizes = self._host_groups(kmer_len, kmer_filter_keep_all)
+        return offsets, sizes
+
+    def _filtered_groups(self, kmer_len, flt):
+        return self._host_groups(kmer_len, flt)
+
+
+@pytest.mark.parametrize("entry", get_kmers_entries(), ids=get_kmers_entry_id)
+def test_get_kmers_host_logic_against_reference_tuples(entry):
+    case, qu = golden_case(entry["case"]), entry["query"]
+    sc = SequenceCollection(sequence_list=[tuple(r) for r in case["seq_list"]], strands_to_load=case["strands"])
+    km = _HostGroupTableKmers(sc, min_kmer_len=case["min_len"], max_kmer_len=case["max_len"],
+                              source_strand=case["strands"])
+    km.kmer_sba_start_indices = (case["sorted"] if qu["sorted"] else case["init"]).astype(np.uint32)
+    km._is_sorted = bool(qu["sorted"])
+    got = list(km.get_kmers(qu["kmer_len"], one_based_seq_index=qu["one_based"],
+                            kmer_filter_func=filter_from_spec(qu["filter"]), kmer_info_to_yield=qu["info"],
+                            min_group_size=qu["min_group"], max_group_size=qu["max_group"],
+                            yield_first_n=qu["first_n"]))
+    assert got == expected_get_kmers_tuples(entry, case)
