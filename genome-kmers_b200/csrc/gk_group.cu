@@ -428,9 +428,26 @@ __global__ void __launch_bounds__(kSelThreads)
 select_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
                     const unsigned long long *__restrict__ tile_offsets, T *__restrict__ pos_out,
                     const T *__restrict__ pay_in, T *__restrict__ pay_out,
-                    const T *__restrict__ pay2_in, T *__restrict__ pay2_out)
+                    const T *__restrict__ pay2_in, T *__restrict__ pay2_out,
+                    const uint8_t *__restrict__ pay8_in, uint8_t *__restrict__ pay8_out, uint8_t pay8_mask)
 {
     __shared__ uint32_t s_warp[kSelThreads / 32];
+    {   // a tile that keeps all of its elements (dropping a handful of windows from a whole index): a shifted,
+        // fully coalesced copy
+        const uint64_t tile0 = (uint64_t)blockIdx.x * kSelTile;
+        const uint64_t t_off = tile_offsets[blockIdx.x];
+        const uint64_t t_cnt = tile_offsets[blockIdx.x + 1] - t_off;
+        const uint64_t t_len = (n - tile0 < (uint64_t)kSelTile) ? n - tile0 : (uint64_t)kSelTile;
+        if (t_cnt == t_len) {
+            for (uint32_t i = threadIdx.x; i < (uint32_t)t_len; i += kSelThreads) {
+                if (pos_out) pos_out[t_off + i] = (T)(tile0 + i);
+                if (pay_out) pay_out[t_off + i] = pay_in[tile0 + i];
+                if (pay2_out) pay2_out[t_off + i] = pay2_in[tile0 + i];
+                if (pay8_out) pay8_out[t_off + i] = pay8_in[tile0 + i] & pay8_mask;
+            }
+            return;
+        }
+    }
     const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * kSelPerThread;
     const uint32_t bits = (p0 < n) ? load_flag_bits(flags, n, p0, mask) : 0;
     const uint32_t c = __popc(bits);
@@ -453,16 +470,18 @@ select_write_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t mask,
         if (pos_out) pos_out[out] = (T)(p0 + i);
         if (pay_out) pay_out[out] = pay_in[p0 + i];
         if (pay2_out) pay2_out[out] = pay2_in[p0 + i];
+        if (pay8_out) pay8_out[out] = pay8_in[p0 + i] & pay8_mask;
         ++out;
     }
 }
 
 // Ordered selection of the positions p with (flags[p] & mask) != 0: optionally the positions
-// themselves and up to two payload arrays gathered at those positions.
+// themselves, up to two payload arrays and one byte array (masked with pay8_mask) gathered at those positions.
 template <typename T>
 int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, T *d_pos_out,
                           const T *d_pay_in, T *d_pay_out, const T *d_pay2_in, T *d_pay2_out,
-                          uint64_t *h_count, cudaStream_t st)
+                          uint64_t *h_count, cudaStream_t st, const uint8_t *d_pay8_in = nullptr,
+                          uint8_t *d_pay8_out = nullptr, uint8_t pay8_mask = 0xff)
 {
     if (h_count) *h_count = 0;
     if (n == 0) return GK_OK;
@@ -478,7 +497,8 @@ int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, T *d
     select_scan_kernel<<<1, 1024, 0, st>>>(d_counts, tiles, d_offsets);
     GK_LAUNCH_CHECK();
     select_write_kernel<T><<<(unsigned)tiles, kSelThreads, 0, st>>>(
-        d_flags, n, mask, d_offsets, d_pos_out, d_pay_in, d_pay_out, d_pay2_in, d_pay2_out);
+        d_flags, n, mask, d_offsets, d_pos_out, d_pay_in, d_pay_out, d_pay2_in, d_pay2_out, d_pay8_in, d_pay8_out,
+        pay8_mask);
     GK_LAUNCH_CHECK();
     if (h_count) {
         GK_CUDA(cudaMemcpyAsync(h_count, d_offsets + tiles, 8, cudaMemcpyDeviceToHost, st));
@@ -489,10 +509,10 @@ int select_flagged_device(const uint8_t *d_flags, uint64_t n, uint8_t mask, T *d
 
 template int select_flagged_device<uint32_t>(const uint8_t *, uint64_t, uint8_t, uint32_t *, const uint32_t *,
                                              uint32_t *, const uint32_t *, uint32_t *, uint64_t *,
-                                             cudaStream_t);
+                                             cudaStream_t, const uint8_t *, uint8_t *, uint8_t);
 template int select_flagged_device<uint64_t>(const uint8_t *, uint64_t, uint8_t, uint64_t *, const uint64_t *,
                                              uint64_t *, const uint64_t *, uint64_t *, uint64_t *,
-                                             cudaStream_t);
+                                             cudaStream_t, const uint8_t *, uint8_t *, uint8_t);
 
 // ordered selection of (key, value) pairs at flagged positions, with the positions themselves
 template <typename T>
@@ -585,6 +605,21 @@ int select_flagged(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_by
     return select_flagged_device<uint64_t>(d_flags, n, mask, (uint64_t *)d_pos_out,
                                            (const uint64_t *)d_pay_in, (uint64_t *)d_pay_out,
                                            (const uint64_t *)d_pay2_in, (uint64_t *)d_pay2_out, h_count, st);
+}
+
+// ordered selection of one payload array plus the (masked) bytes of a byte array, e.g. start indices and
+// their head flags; no position list
+int select_flagged_with_bytes(const uint8_t *d_flags, uint64_t n, uint8_t mask, int elem_bytes,
+                              const void *d_pay_in, void *d_pay_out, const uint8_t *d_bytes_in,
+                              uint8_t *d_bytes_out, uint8_t bytes_mask, uint64_t *h_count, cudaStream_t st)
+{
+    if (elem_bytes == 4)
+        return select_flagged_device<uint32_t>(d_flags, n, mask, nullptr, (const uint32_t *)d_pay_in,
+                                               (uint32_t *)d_pay_out, nullptr, nullptr, h_count, st, d_bytes_in,
+                                               d_bytes_out, bytes_mask);
+    return select_flagged_device<uint64_t>(d_flags, n, mask, nullptr, (const uint64_t *)d_pay_in,
+                                           (uint64_t *)d_pay_out, nullptr, nullptr, h_count, st, d_bytes_in,
+                                           d_bytes_out, bytes_mask);
 }
 
 // ---- group-size histogram -----------------------------------------------------------------------------

@@ -55,6 +55,8 @@ int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, 
                         uint8_t *, cudaStream_t);
 int select_flagged(const uint8_t *, uint64_t, uint8_t, int, void *, const void *, void *, const void *,
                    void *, uint64_t *, cudaStream_t);
+int select_flagged_with_bytes(const uint8_t *, uint64_t, uint8_t, int, const void *, void *, const uint8_t *,
+                              uint8_t *, uint8_t, uint64_t *, cudaStream_t);
 int head_positions_device(const uint8_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
 int valid_flags_device(const uint32_t *, uint64_t, const uint64_t *, uint32_t, uint64_t, uint32_t, uint8_t *,
                        cudaStream_t);
@@ -69,7 +71,6 @@ int gather_u32_device(const uint32_t *, const uint32_t *, uint64_t, uint32_t *, 
 int multi_flags_device(const uint8_t *, uint64_t, uint8_t *, cudaStream_t);
 int clear_finished_multi_device(const uint32_t *, uint64_t, const uint64_t *, uint32_t, uint64_t, uint64_t, uint8_t *,
                                 cudaStream_t);
-int gather_u8_device(const uint8_t *, const void *, int, uint64_t, uint8_t, uint8_t *, cudaStream_t);
 
 
 // index-lifetime device allocation; stream-ordered like the scratch buffers so that creating and
@@ -471,20 +472,19 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
 static int drop_short_windows(gk_index *ix, uint32_t min_len, Owned &cur_idx, Owned &cur_flags, uint64_t &n_cur,
                               cudaStream_t st)
 {
-    DeviceBuffer vflags, pos;
+    DeviceBuffer vflags;
     GK_TRY(vflags.alloc((size_t)((n_cur + 15) & ~15ull), st));
     GK_TRY(valid_flags_device((const uint32_t *)cur_idx.ptr, n_cur, (const uint64_t *)ix->d_segs.ptr,
                               (uint32_t)ix->h_segs.size(), ix->sba_len, min_len, vflags.as<uint8_t>(), st));
     Owned new_idx, new_flags;
     GK_TRY(new_idx.alloc((size_t)n_cur * 4, st));
-    GK_TRY(pos.alloc((size_t)n_cur * 4, st));
+    GK_TRY(new_flags.alloc((size_t)((n_cur + 15) & ~15ull), st));
     uint64_t n_new = 0;
-    GK_TRY(select_flagged(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, pos.ptr, cur_idx.ptr, new_idx.ptr, nullptr,
-                          nullptr, &n_new, st));
-    // groups go or stay whole, so the head flag of a kept window is still right
-    GK_TRY(new_flags.alloc((size_t)((n_new + 15) & ~15ull), st));
-    GK_TRY(gather_u8_device((const uint8_t *)cur_flags.ptr, pos.ptr, 4, n_new, kFlagHead, (uint8_t *)new_flags.ptr,
-                            st));
+    // groups go or stay whole, so the head flag of a kept window is still right: starts and head flags move
+    // together in one ordered select (tiles that keep every window are copied straight through)
+    GK_TRY(select_flagged_with_bytes(vflags.as<uint8_t>(), n_cur, kFlagPass, 4, cur_idx.ptr, new_idx.ptr,
+                                     (const uint8_t *)cur_flags.ptr, (uint8_t *)new_flags.ptr, kFlagHead, &n_new,
+                                     st));
     cur_idx.swap(new_idx);
     cur_flags.swap(new_flags);
     n_cur = n_new;

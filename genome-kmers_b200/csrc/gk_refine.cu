@@ -125,17 +125,55 @@ head_positions_kernel(const uint8_t *__restrict__ flags, const uint32_t *__restr
     }
 }
 
-// flags[p] = kFlagPass iff the window of `len` symbols at idx[p] stays inside its record
+// Segment tables up to this size are staged in shared memory by the per-element kernels below (a binary
+// search per element through global memory is what made them slow); larger tables are searched in place.
+constexpr uint32_t kSegSmem = 1024;
+
+__device__ __forceinline__ const uint64_t *stage_segments(const uint64_t *__restrict__ seg_starts, uint32_t n_seg,
+                                                          uint64_t *s_seg)
+{
+    if (n_seg > kSegSmem) return seg_starts;
+    for (uint32_t i = threadIdx.x; i < n_seg; i += blockDim.x) s_seg[i] = seg_starts[i];
+    __syncthreads();
+    return s_seg;
+}
+
+// flags[p] = kFlagPass iff the window of `len` symbols at idx[p] stays inside its record.
+// Elements [first, n), one per thread (the tail of the vector kernel, or everything).
 __global__ void __launch_bounds__(256)
-valid_flags_kernel(const uint32_t *__restrict__ idx, uint64_t n, const uint64_t *__restrict__ seg_starts,
-                   uint32_t n_seg, uint64_t sba_len, uint32_t len, uint8_t *__restrict__ flags)
+valid_flags_kernel(const uint32_t *__restrict__ idx, uint64_t first, uint64_t n,
+                   const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint64_t sba_len, uint32_t len,
+                   uint8_t *__restrict__ flags)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    for (uint64_t p = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
         const uint64_t s = idx[p];
         const uint32_t seg = upper_seg(seg_starts, n_seg, s);
         const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;
         flags[p] = (s + len <= seg_end) ? kFlagPass : 0;
+    }
+}
+
+// the same for groups of four starts: one 16-byte load, one 4-byte store per thread and group
+__global__ void __launch_bounds__(256)
+valid_flags_vec_kernel(const uint32_t *__restrict__ idx, uint64_t groups, const uint64_t *__restrict__ seg_starts,
+                       uint32_t n_seg, uint64_t sba_len, uint32_t len, uint8_t *__restrict__ flags)
+{
+    __shared__ uint64_t s_seg[kSegSmem];
+    const uint64_t *segs = stage_segments(seg_starts, n_seg, s_seg);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const uint4 q = reinterpret_cast<const uint4 *>(idx)[g];
+        const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint64_t s = v[i];
+            const uint32_t seg = upper_seg(segs, n_seg, s);
+            const uint64_t seg_end = (seg + 1 < n_seg) ? segs[seg + 1] - 1 : sba_len;
+            out |= ((s + len <= seg_end) ? (uint32_t)kFlagPass : 0u) << (8 * i);
+        }
+        reinterpret_cast<uint32_t *>(flags)[g] = out;
     }
 }
 
@@ -375,27 +413,53 @@ subset_rank_update_kernel(const uint32_t *__restrict__ slots, const uint32_t *__
     }
 }
 
-// kFlagMulti on every member of a group with more than one element, straight from the head flags
+// kFlagMulti on every member of a group with more than one element, straight from the head flags.
+// Elements [first, n), one per thread (the tail of the vector kernel, or everything).
 __global__ void __launch_bounds__(256)
-multi_flags_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint8_t *__restrict__ out)
+multi_flags_kernel(const uint8_t *__restrict__ flags, uint64_t first, uint64_t n, uint8_t *__restrict__ out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    for (uint64_t p = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
         const bool head = flags[p] & kFlagHead;
         const bool next_head = (p + 1 == n) || (flags[p + 1] & kFlagHead);
         out[p] = (head ? kFlagHead : 0) | ((head && next_head) ? 0 : kFlagMulti);
     }
 }
 
-// A window that reaches its record's '$' within the first h symbols is fully compared: its group holds
-// identical k-mers and can never split again.  Clear kFlagMulti on those members (few windows are marked,
-// so the segment search runs rarely).
+// the same for groups of sixteen flags: one 16-byte load (+ the next group's first flag), one 16-byte store
 __global__ void __launch_bounds__(256)
-clear_finished_multi_kernel(const uint32_t *__restrict__ idx, uint64_t n, const uint64_t *__restrict__ seg_starts,
-                            uint32_t n_seg, uint64_t sba_len, uint64_t h, uint8_t *__restrict__ flags)
+multi_flags_vec_kernel(const uint8_t *__restrict__ flags, uint64_t groups, uint64_t n, uint8_t *__restrict__ out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const uint4 q = reinterpret_cast<const uint4 *>(flags)[g];
+        const uint64_t p0 = g * 16;
+        const uint32_t next = (p0 + 16 < n) ? flags[p0 + 16] : (uint32_t)kFlagHead;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t heads = (next & kFlagHead) << 16;  // bit i: flag i of the group (bit 16: the next group's first)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) heads |= ((w[i >> 2] >> (8 * (i & 3))) & (uint32_t)kFlagHead) << i;
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const bool head = (heads >> i) & 1u, next_head = (heads >> (i + 1)) & 1u;
+            const uint32_t f = (head ? (uint32_t)kFlagHead : 0u) | ((head && next_head) ? 0u : (uint32_t)kFlagMulti);
+            o[i >> 2] |= f << (8 * (i & 3));
+        }
+        reinterpret_cast<uint4 *>(out)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// A window that reaches its record's '$' within the first h symbols is fully compared: its group holds
+// identical k-mers and can never split again.  Clear kFlagMulti on those members.
+// Elements [first, n), one per thread (the tail of the vector kernel, or everything).
+__global__ void __launch_bounds__(256)
+clear_finished_multi_kernel(const uint32_t *__restrict__ idx, uint64_t first, uint64_t n,
+                            const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint64_t sba_len, uint64_t h,
+                            uint8_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
         const uint8_t f = flags[p];
         if (!(f & kFlagMulti)) continue;
         const uint64_t s = idx[p];
@@ -405,14 +469,31 @@ clear_finished_multi_kernel(const uint32_t *__restrict__ idx, uint64_t n, const 
     }
 }
 
-template <typename T>
+// the same for groups of sixteen flags: a group without a marked member costs one 16-byte load
 __global__ void __launch_bounds__(256)
-gather_u8_kernel(const uint8_t *__restrict__ src, const T *__restrict__ at, uint64_t count, uint8_t keep_mask,
-                 uint8_t *__restrict__ out)
+clear_finished_multi_vec_kernel(const uint32_t *__restrict__ idx, uint64_t groups,
+                                const uint64_t *__restrict__ seg_starts, uint32_t n_seg, uint64_t sba_len,
+                                uint64_t h, uint8_t *__restrict__ flags)
 {
+    __shared__ uint64_t s_seg[kSegSmem];
+    const uint64_t *segs = stage_segments(seg_starts, n_seg, s_seg);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += stride)
-        out[r] = src[(uint64_t)at[r]] & keep_mask;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const uint4 q = reinterpret_cast<const uint4 *>(flags)[g];
+        const uint32_t multi = (uint32_t)kFlagMulti * 0x01010101u;
+        if (((q.x | q.y | q.z | q.w) & multi) == 0) continue;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint64_t p0 = g * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint8_t f = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+            if (!(f & kFlagMulti)) continue;
+            const uint64_t s = idx[p0 + i];
+            const uint32_t seg = upper_seg(segs, n_seg, s);
+            const uint64_t seg_end = (seg + 1 < n_seg) ? segs[seg + 1] - 1 : sba_len;
+            if (s + h > seg_end) flags[p0 + i] = f & (uint8_t)~kFlagMulti;  // only this thread touches the group
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -455,8 +536,19 @@ int valid_flags_device(const uint32_t *d_idx, uint64_t n, const uint64_t *d_seg_
                        uint64_t sba_len, uint32_t len, uint8_t *d_flags, cudaStream_t st)
 {
     if (n == 0) return GK_OK;
-    valid_flags_kernel<<<grid_for(n), 256, 0, st>>>(d_idx, n, d_seg_starts, n_seg, sba_len, len, d_flags);
-    GK_LAUNCH_CHECK();
+    // vector kernel over the 16-byte aligned bulk, scalar kernel over the tail (or over everything)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_idx) & 15u) | (reinterpret_cast<uintptr_t>(d_flags) & 3u)) == 0;
+    const uint64_t groups = aligned ? n / 4 : 0;
+    if (groups) {
+        valid_flags_vec_kernel<<<grid_for(groups), 256, 0, st>>>(d_idx, groups, d_seg_starts, n_seg, sba_len, len,
+                                                                  d_flags);
+        GK_LAUNCH_CHECK();
+    }
+    if (groups * 4 < n) {
+        valid_flags_kernel<<<grid_for(n - groups * 4), 256, 0, st>>>(d_idx, groups * 4, n, d_seg_starts, n_seg,
+                                                                     sba_len, len, d_flags);
+        GK_LAUNCH_CHECK();
+    }
     return GK_OK;
 }
 
@@ -492,8 +584,16 @@ int subset_rank_update_device(const uint32_t *d_slots, const uint32_t *d_gid_sub
 int multi_flags_device(const uint8_t *d_flags, uint64_t n, uint8_t *d_out, cudaStream_t st)
 {
     if (n == 0) return GK_OK;
-    multi_flags_kernel<<<grid_for(n), 256, 0, st>>>(d_flags, n, d_out);
-    GK_LAUNCH_CHECK();
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_flags) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
+    const uint64_t groups = aligned ? n / 16 : 0;
+    if (groups) {
+        multi_flags_vec_kernel<<<grid_for(groups), 256, 0, st>>>(d_flags, groups, n, d_out);
+        GK_LAUNCH_CHECK();
+    }
+    if (groups * 16 < n) {
+        multi_flags_kernel<<<grid_for(n - groups * 16), 256, 0, st>>>(d_flags, groups * 16, n, d_out);
+        GK_LAUNCH_CHECK();
+    }
     return GK_OK;
 }
 
@@ -501,22 +601,18 @@ int clear_finished_multi_device(const uint32_t *d_idx, uint64_t n, const uint64_
                                 uint64_t sba_len, uint64_t h, uint8_t *d_flags, cudaStream_t st)
 {
     if (n == 0) return GK_OK;
-    clear_finished_multi_kernel<<<grid_for(n), 256, 0, st>>>(d_idx, n, d_seg_starts, n_seg, sba_len, h, d_flags);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
-}
-
-int gather_u8_device(const uint8_t *d_src, const void *d_at, int at_bytes, uint64_t count, uint8_t keep_mask,
-                     uint8_t *d_out, cudaStream_t st)
-{
-    if (count == 0) return GK_OK;
-    if (at_bytes == 4)
-        gather_u8_kernel<uint32_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint32_t *)d_at, count, keep_mask,
-                                                                    d_out);
-    else
-        gather_u8_kernel<uint64_t><<<grid_for(count), 256, 0, st>>>(d_src, (const uint64_t *)d_at, count, keep_mask,
-                                                                    d_out);
-    GK_LAUNCH_CHECK();
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_flags) & 15u) == 0;
+    const uint64_t groups = aligned ? n / 16 : 0;
+    if (groups) {
+        clear_finished_multi_vec_kernel<<<grid_for(groups), 256, 0, st>>>(d_idx, groups, d_seg_starts, n_seg, sba_len,
+                                                                           h, d_flags);
+        GK_LAUNCH_CHECK();
+    }
+    if (groups * 16 < n) {
+        clear_finished_multi_kernel<<<grid_for(n - groups * 16), 256, 0, st>>>(d_idx, groups * 16, n, d_seg_starts,
+                                                                               n_seg, sba_len, h, d_flags);
+        GK_LAUNCH_CHECK();
+    }
     return GK_OK;
 }
 

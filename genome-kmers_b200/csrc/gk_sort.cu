@@ -414,7 +414,7 @@ static int launch_pass(const PassArgs &a, cudaStream_t st)
 }
 
 // Tile shapes (threads, pairs per thread, CTAs per SM the register budget is compiled for).
-// Selected once per process; GK_SORT_CFG overrides the default for tuning runs.
+// GK_SORT_CFG overrides the default for tuning runs.
 struct SortConfig { int threads, ipt, minb; };
 constexpr SortConfig kSortConfigs[] = {
     {256, 16, 3},  // 0: 4096-pair tiles, 61 KB smem, <=80 regs
@@ -431,16 +431,14 @@ constexpr int kDefaultSortConfig = 7;
 
 static int sort_config_id_raw()
 {
-    static int id = -1;
-    if (id < 0) {
-        id = kDefaultSortConfig;
-        const char *e = getenv("GK_SORT_CFG");
-        if (e && *e) {
-            const int v = atoi(e);
-            if (v >= 0 && v < kNumSortConfigs) id = v;
-        }
+    // read on every call (a getenv per sort is nothing next to the launches): one tuning process can compare
+    // tile shapes, tools/bench_sort.py --env GK_SORT_CFG
+    const char *e = getenv("GK_SORT_CFG");
+    if (e && *e) {
+        const int v = atoi(e);
+        if (v >= 0 && v < kNumSortConfigs) return v;
     }
-    return id;
+    return kDefaultSortConfig;
 }
 
 // 64-bit values make a pair 16 bytes: the two largest tiles would no longer fit two CTAs per SM

@@ -3,7 +3,7 @@
 Side measurements for the other BASELINE.json configs (not the bench line): sort + count through the
 public API on one GPU, device-resident timing (CUDA events around sort() + get_kmer_group_counts()).
 
-    python tools/bench_configs.py [c1] [c4] [c5] [c5big]
+    python tools/bench_configs.py [c1] [c4] [c4k64] [c5] [c5big]
 """
 import json
 import os
@@ -61,6 +61,8 @@ def main():
     if "c4" in which:
         for k in (64, 100):
             run(f"C4 100 Mbp both k={k}", 100_000_000, 10, 0, "both", k)
+    if "c4k64" in which:            # one configuration, two repetitions: launch lists under ncu
+        run("C4 100 Mbp both k=64", 100_000_000, 10, 0, "both", 64, reps=2)
     if "c5" in which:
         for k in (15, 21, 27, 31, 32, 33, 47, 63):
             run(f"k-sweep 100 Mbp both k={k}", 100_000_000, 10, 0, "both", k)
