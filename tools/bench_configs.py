@@ -3,7 +3,7 @@
 Side measurements for the other BASELINE.json configs (not the bench line): sort + count through the
 public API on one GPU, device-resident timing (CUDA events around sort() + get_kmer_group_counts()).
 
-    python tools/bench_configs.py [c1] [c4] [c4k64] [c5] [c5big]
+    python tools/bench_configs.py [c1] [c4] [c4k64] [c5] [c5k63] [c5big]
 """
 import json
 import os
@@ -66,6 +66,8 @@ def main():
     if "c5" in which:
         for k in (15, 21, 27, 31, 32, 33, 47, 63):
             run(f"k-sweep 100 Mbp both k={k}", 100_000_000, 10, 0, "both", k)
+    if "c5k63" in which:
+        run("C5 1 Gbp both k=63", 1_000_000_000, 10, 0, "both", 63, reps=2)
     if "c5big" in which:
         for k in (15, 31, 63):
             run(f"C5 1 Gbp both k={k}", 1_000_000_000, 10, 0, "both", k, reps=2)
