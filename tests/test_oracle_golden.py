@@ -117,3 +117,52 @@ def test_sorted_3mers_match_reference_docs():
     assert kmers == sorted(kmers)
     assert kmers[:5] == ["AAT", "ACC", "AGG", "ATC", "ATC"] or kmers[0] == "AAT"
     assert len(kmers) == 29
+
+
+# ---------------------------------------------------------------------------------------------------
+# the oracle's group walk and all six filters against the tuples the real reference's get_kmers yielded
+# (tests/golden/golden_get_kmers.json, tests/golden/make_golden_get_kmers.py)
+# ---------------------------------------------------------------------------------------------------
+def _oracle_filter(spec):
+    if spec is None:
+        return (oracle.FILTER_KEEP_ALL, 0, 0, 0)
+    kind, args = spec[0], spec[1:]
+    if kind == "no_ambiguous":
+        return (oracle.FILTER_NO_AMBIGUOUS, args[0], 0, 0)
+    if kind == "min_length":
+        return (oracle.FILTER_MIN_LENGTH, args[0], 0, 0)
+    if kind == "homopolymer":
+        return (oracle.FILTER_HOMOPOLYMER, args[0], args[1], 0)
+    if kind == "gc":  # the reference converts the fractions to counts once (kmers.py:143-144)
+        lo, hi, k = args
+        return (oracle.FILTER_GC_COUNT, int(np.ceil(k * lo)), int(np.floor(k * hi)), k)
+    if kind == "ngg_pam":
+        return (oracle.FILTER_NGG_PAM, 0, 0, 0)
+    raise ValueError(spec)
+
+
+from conftest import get_kmers_entries, get_kmers_entry_id  # noqa: E402
+
+
+@pytest.mark.parametrize("entry", get_kmers_entries(), ids=get_kmers_entry_id)
+def test_oracle_group_walk_matches_reference_get_kmers(entry):
+    """A6 + N1: groups (first member, size) of kmer_info_by_group_generator (kmers.py:523-648) with every
+    built-in filter (kmers.py:14-259), group limits and the unsorted mode."""
+    case, qu = golden_case(entry["case"]), entry["query"]
+    sba, _ = _build(case)
+    idx = case["sorted"] if qu["sorted"] else case["init"]
+    _, total, first, size = oracle.group_hist(
+        sba, idx, qu["kmer_len"], sorted_=qu["sorted"], filt=_oracle_filter(qu["filter"]),
+        min_group=qu["min_group"], max_group=qu["max_group"], max_bin=8, want_groups=True)
+    # the reference's tuples end with (group_size_yielded, group_size_total); a group's first tuple carries
+    # the kmer_num of its first passing member
+    want_first, want_size, left = [], [], 0
+    for t in entry["tuples"]:
+        if left == 0:
+            want_first.append(t[0])
+            want_size.append(t[-1])
+            left = t[-2]
+        left -= 1
+    assert first.tolist() == want_first
+    assert size.tolist() == want_size
+    assert total == sum(want_size)
