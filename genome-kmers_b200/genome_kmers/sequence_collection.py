@@ -329,10 +329,13 @@ class SequenceCollection:
                   "_revcomp_sba_seg_starts", "revcomp_record_names", "_strands_loaded")
 
     def save(self, save_file_path: Path, mode: str = "w", format: str = "hdf5") -> None:
+        """Same on-disk layout as the reference (sequence_collection.py:1331-1365 HDF5, :1407-1426 shelve),
+        so that either implementation loads what the other one saved."""
         if format == "shelve":
             with shelve.open(str(save_file_path)) as db:
                 for attr in self._PERSISTED:
-                    db[attr] = getattr(self, attr)
+                    db["seq_coll." + attr] = getattr(self, attr)
+                db["seq_coll._fasta_file_path"] = self._fasta_file_path
         elif format == "hdf5":
             h5py = _require_h5py()
             with h5py.File(save_file_path, mode) as file:
@@ -347,14 +350,17 @@ class SequenceCollection:
                     empty_u32 if self._revcomp_sba_seg_starts is None else self._revcomp_sba_seg_starts)
                 grp["revcomp_record_names"] = self.revcomp_record_names or []
                 grp["_strands_loaded"] = self._strands_loaded or ""
+                grp["_fasta_file_path"] = str(self._fasta_file_path or "")
         else:
             raise ValueError(f"format ({format}) not recognized")
 
     def load(self, load_file_path: Path, format: str = "hdf5") -> None:
+        """Reads the reference's layout (sequence_collection.py:1367-1405 HDF5, :1428-1446 shelve)."""
         if format == "shelve":
             with shelve.open(str(load_file_path)) as db:
                 for attr in self._PERSISTED:
-                    setattr(self, attr, db[attr])
+                    setattr(self, attr, db["seq_coll." + attr])
+                self._fasta_file_path = db["seq_coll._fasta_file_path"]
         elif format == "hdf5":
             h5py = _require_h5py()
             with h5py.File(load_file_path, "r") as file:
@@ -375,6 +381,8 @@ class SequenceCollection:
                 self._revcomp_sba_seg_starts = arr("_revcomp_sba_seg_starts")
                 self.revcomp_record_names = names("revcomp_record_names")
                 self._strands_loaded = grp["_strands_loaded"][()].decode("utf-8") or None
+                fasta = grp["_fasta_file_path"][()].decode("utf-8")
+                self._fasta_file_path = Path(fasta) if fasta else None
         else:
             raise ValueError(f"format ({format}) not recognized")
 

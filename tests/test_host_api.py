@@ -224,3 +224,99 @@ def test_get_kmers_host_logic_against_reference_tuples(entry):
                             min_group_size=qu["min_group"], max_group_size=qu["max_group"],
                             yield_first_n=qu["first_n"]))
     assert got == expected_get_kmers_tuples(entry, case)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Row N3: persistence.  Round trip through this repo's classes, and -- in the build container, where the
+# reference is mounted -- cross-loading with the REAL reference in a subprocess (both packages are named
+# genome_kmers, so they cannot share a process).  HDF5 needs h5py, which the image does not have.
+# ---------------------------------------------------------------------------------------------------
+REFERENCE_SRC = "/root/reference/src"
+
+
+def _sorted_kmers_on_host(strands="forward"):
+    case = golden_case("sl2_both_k3" if strands == "both" else "sl2_k3")
+    sc = SequenceCollection(sequence_list=SL2, strands_to_load=strands)
+    km = Kmers(sc, min_kmer_len=3, max_kmer_len=3, source_strand=strands)
+    km.kmer_sba_start_indices = case["sorted"].astype(np.uint32)
+    km._is_sorted = True
+    return sc, km, case
+
+
+@pytest.mark.parametrize("strands", ["forward", "both"])
+def test_kmers_shelve_round_trip(tmp_path, strands):
+    sc, km, case = _sorted_kmers_on_host(strands)
+    km.save(tmp_path / "km.db", include_sequence_collection=True, format="shelve")
+    back = Kmers()
+    back.load(tmp_path / "km.db", format="shelve")
+    assert back == km and back._is_sorted and back.seq_coll == sc
+    assert back.kmer_sba_start_indices.dtype == np.uint32
+    assert np.array_equal(back.kmer_sba_start_indices, case["sorted"])
+    other = Kmers()
+    other.load(tmp_path / "km.db", seq_coll=sc, format="shelve")
+    assert other.seq_coll is sc and other == km
+    with pytest.raises(ValueError, match="format \\(nope\\) not recognized"):
+        km.save(tmp_path / "x", format="nope")
+
+
+_REF_PRELUDE = """
+import sys, types, json
+import numpy as np
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+sys.path.insert(0, %r)
+from genome_kmers.kmers import Kmers
+from genome_kmers.sequence_collection import SequenceCollection
+""" % REFERENCE_SRC
+
+
+def _run_reference(script):
+    import subprocess
+    import sys
+
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    out = subprocess.run([sys.executable, "-c", _REF_PRELUDE + script], capture_output=True, text=True, env=env,
+                         cwd="/tmp", timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference is only mounted in the build container")
+def test_shelve_files_cross_load_with_the_reference(tmp_path):
+    import json
+
+    # ours -> reference
+    sc, km, case = _sorted_kmers_on_host("forward")
+    ours = str(tmp_path / "ours.db")
+    km.save(ours, include_sequence_collection=True, format="shelve")
+    got = json.loads(_run_reference("""
+km = Kmers()
+km.load(%r, format="shelve")
+sc = km.seq_coll
+print(json.dumps(dict(
+    min=int(km.min_kmer_len), max=int(km.max_kmer_len), strand=km.kmer_source_strand,
+    flags=[bool(km._is_initialized), bool(km._is_set), bool(km._is_sorted)],
+    idx=km.kmer_sba_start_indices.tolist(), idx_dtype=str(km.kmer_sba_start_indices.dtype),
+    sba=sc.forward_sba.tobytes().decode(), starts=sc._forward_sba_seg_starts.tolist(),
+    names=sc.forward_record_names, loaded=sc.strands_loaded(),
+    first=km.get_kmer_str(0, 3), text=str(sc))))
+""" % ours))
+    assert got["min"] == 3 and got["max"] == 3 and got["strand"] == "forward"
+    assert got["flags"] == [True, False, True] and got["idx_dtype"] == "uint32"
+    assert got["idx"] == case["sorted"].tolist()
+    assert got["sba"] == sc.forward_sba.tobytes().decode() and got["starts"] == [0, 11, 24]
+    assert got["names"] == ["chr1", "chr2", "chr3"] and got["loaded"] == "forward"
+    assert got["first"] == km.get_kmer_str(0, 3) and got["text"] == str(sc)
+
+    # reference -> ours
+    theirs = str(tmp_path / "theirs.db")
+    _run_reference("""
+sc = SequenceCollection(sequence_list=%r, strands_to_load="forward")
+km = Kmers(sc, min_kmer_len=3, max_kmer_len=3)
+km.kmer_sba_start_indices = np.array(%r, dtype=np.uint32)
+km._is_sorted = True
+km.save(%r, include_sequence_collection=True, format="shelve")
+""" % (SL2, case["sorted"].tolist(), theirs))
+    back = Kmers()
+    back.load(theirs, format="shelve")
+    assert back == km and back.seq_coll == sc
+    assert back.get_kmer_str(0, 3) == km.get_kmer_str(0, 3)
