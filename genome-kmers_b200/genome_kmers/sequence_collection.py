@@ -11,6 +11,7 @@ The arrays are built with vectorised NumPy instead of per-record Python loops, a
 constructors (`from_arrays`, `from_sba`) accept uint8 data directly, because materialising a
 multi-gigabase Python `str` costs more than sorting its k-mers on a B200.
 """
+import re
 import shelve
 from collections import Counter
 from pathlib import Path
@@ -82,13 +83,14 @@ class SequenceCollection:
 
         if fasta_file_path is not None:
             self._fasta_file_path = fasta_file_path
-            names, chunks = _read_fasta(fasta_file_path)
-            source = str(fasta_file_path)
-        else:
-            names = [name for name, _ in sequence_list]
-            chunks = [np.frombuffer(seq.encode("utf-8"), dtype=np.uint8) for _, seq in sequence_list]
-            source = None
-        self._set_from_records(names, chunks, strands_to_load, source)
+            names, sba, starts = _read_fasta(fasta_file_path)
+            _check_alphabet(sba)
+            self._verify_record_names_are_unique(names)
+            self._finish(sba, starts, names, strands_to_load)
+            return
+        names = [name for name, _ in sequence_list]
+        chunks = [np.frombuffer(seq.encode("utf-8"), dtype=np.uint8) for _, seq in sequence_list]
+        self._set_from_records(names, chunks, strands_to_load, None)
 
     # ------------------------------------------------------------------ extra constructors
     @classmethod
@@ -408,26 +410,188 @@ def get_forward_seq_idx(sba_idx: int, sba_strand: str, seg_sba_start_idx: int, s
     return seq_idx + (1 if one_based else 0)
 
 
+_ALLOWED_BYTES = bytes(int(v) for v in np.flatnonzero(_ALLOWED))
+
+
 def _check_alphabet(sba: np.ndarray) -> None:
-    present = np.flatnonzero(np.bincount(sba, minlength=256))
-    bad = {int(v) for v in present if not _ALLOWED[v]}
+    """Every byte must be one of the reference's allowed symbols (sequence_collection.py:441-459, :693-697).
+    Deleting the allowed bytes with bytes.translate leaves exactly the offenders (one C pass per chunk)."""
+    bad = set()
+    for lo in range(0, len(sba), 1 << 26):
+        bad.update(sba[lo:lo + (1 << 26)].tobytes().translate(None, _ALLOWED_BYTES))
     if bad:
         raise ValueError(f"Sequence contains non-allowed characters! ({bad})")
 
 
-def _read_fasta(path) -> Tuple[List[str], List[np.ndarray]]:
-    """FASTA -> record names (Bowtie rule, ref :497-515) and upper-cased uint8 sequences (ref :554)."""
+_FASTA_BLOCK = 64 << 20   # bytes of file text handled per vectorised step
+_STRIP_BYTES = np.zeros(256, dtype=bool)
+_STRIP_BYTES[[9, 10, 11, 12, 13, 28, 29, 30, 31, 32]] = True   # what str.strip() removes (ASCII range)
+_UPPER = np.arange(256, dtype=np.uint8)
+_UPPER[ord("a"):ord("z") + 1] -= 32
+
+
+def _fasta_block(data: np.ndarray):
+    """One block of whole lines -> (header names, kept sequence bytes, offsets into them where a record starts).
+
+    The reference walks the file line by line (sequence_collection.py:517-576): a line that starts with '>' opens
+    a record, every other line contributes line.strip().upper().  Here the same is done with array operations
+    over the block: line table from the newline positions, header lines masked out, leading/trailing whitespace
+    of each line peeled off (whitespace inside a line stays and fails the alphabet check, as in the reference).
+    """
+    n = len(data)
+    nl = np.flatnonzero(data == 10)
+    line_start = np.concatenate([[0], nl + 1])
+    line_end = np.concatenate([nl, [n]])              # exclusive
+    if line_start[-1] >= n:                           # the block ends with a newline
+        line_start, line_end = line_start[:-1], line_end[:-1]
+    is_hdr = data[line_start] == 62                   # '>'
+    lo, hi = line_start.copy(), line_end.copy()       # the stripped line is data[lo:hi]
+    strip = _STRIP_BYTES
+    active = np.flatnonzero(~is_hdr & (hi > lo))
+    while len(active):                                # trailing whitespace ('\r' of CRLF files, blanks)
+        active = active[strip[data[hi[active] - 1]]]
+        hi[active] -= 1
+        active = active[hi[active] > lo[active]]
+    active = np.flatnonzero(~is_hdr & (hi > lo))
+    while len(active):                                # leading whitespace
+        active = active[strip[data[lo[active]]]]
+        lo[active] += 1
+        active = active[hi[active] > lo[active]]
+    seq_lines = np.flatnonzero(~is_hdr & (hi > lo))
+    lengths = (hi - lo)[seq_lines]
+    # keep mask from a difference array: +1 at every kept line's first byte, -1 one past its last
+    delta = np.zeros(n + 1, dtype=np.int8)
+    delta[lo[seq_lines]] = 1
+    delta[hi[seq_lines]] -= 1                         # (hi of one line is never lo of another: a '\n' lies between)
+    keep = np.cumsum(delta[:-1], dtype=np.int8).view(bool)
+    kept = _UPPER[data[keep]]
+    # a record starts at the number of sequence bytes that precede its header line
+    line_off = np.concatenate([[0], np.cumsum(lengths)])
+    hdr_lines = np.flatnonzero(is_hdr)
+    cuts = line_off[np.searchsorted(seq_lines, hdr_lines)]
+    names = [SequenceCollection._get_fasta_record_name(
+        data[line_start[i]:line_end[i]].tobytes().decode("utf-8", errors="replace")) for i in hdr_lines]
+    return names, kept, cuts
+
+
+_UPPER_TABLE = bytes(_UPPER)
+_OTHER_STRIP_BYTES = [bytes([v]) for v in (9, 11, 12, 28, 29, 30, 31, 32)]   # str.strip() minus '\n', '\r'
+
+
+def _upper_inplace(seq: np.ndarray) -> None:
+    lower = (seq >= 97) & (seq <= 122)
+    if lower.any():                                    # soft-masked genomes: a..z -> A..Z, arithmetic passes
+        seq -= lower.view(np.uint8) << 5
+
+
+def _fasta_sequence(segment: bytes) -> np.ndarray:
+    """Sequence lines between two headers -> their stripped, upper-cased concatenation (uint8)."""
+    if any(ws in segment for ws in _OTHER_STRIP_BYTES):
+        # blanks or tabs somewhere: only those at the ends of a line may go (line.strip()), so take the
+        # line-table path
+        return _fasta_block(np.frombuffer(segment, dtype=np.uint8))[1]
+    width = segment.find(b"\n")
+    if width > 0 and b"\r" not in segment:
+        # the usual layout -- every line `width` bases long, the last one shorter: a strided copy
+        rows = len(segment) // (width + 1)
+        tail = len(segment) - rows * (width + 1)
+        tail_nl = 1 if (tail > 0 and segment.endswith(b"\n")) else 0
+        raw = np.frombuffer(segment, dtype=np.uint8)
+        if (segment.count(b"\n") == rows + tail_nl
+                and (raw[width:rows * (width + 1):width + 1] == 10).all()):
+            out = np.empty(rows * width + tail - tail_nl, dtype=np.uint8)
+            out[:rows * width].reshape(rows, width)[...] = raw[:rows * (width + 1)].reshape(rows, width + 1)[:, :width]
+            out[rows * width:] = raw[rows * (width + 1):len(raw) - tail_nl]
+            _upper_inplace(out)
+            return out
+    # anything else (ragged lines, blank lines, CRLF): one C pass that drops the line ends and upper-cases
+    return np.frombuffer(segment.translate(_UPPER_TABLE, b"\n\r"), dtype=np.uint8)
+
+
+def _read_fasta(path) -> Tuple[List[str], np.ndarray, np.ndarray]:
+    """FASTA -> (record names, forward byte array with '$' between records, uint32 segment starts).
+
+    Same result as the reference's two-pass line reader (sequence_collection.py:476-576: Bowtie-style record
+    names :497-515, line.strip().upper() :554), without a Python loop per line: the file is read in blocks of
+    whole lines, header lines are located with bytes.find, and the text between two headers is cleaned by one
+    strided copy (equal-width lines) or one bytes.translate call (NumPy line table when a line carries blanks
+    that strip() would trim).
+    """
     names: List[str] = []
-    parts: List[List[bytes]] = []
-    with open(path, "r") as handle:
-        for line in handle:
-            if line.startswith(">"):
-                names.append(SequenceCollection._get_fasta_record_name(line))
-                parts.append([])
-            elif parts:
-                parts[-1].append(line.strip().upper().encode("utf-8"))
-    chunks = [np.frombuffer(b"".join(p), dtype=np.uint8) for p in parts]
-    return names, chunks
+    pieces: List[np.ndarray] = []      # sequence bytes, in file order
+    starts_in_seq: List[int] = []      # for every record: sequence bytes that precede it in the whole file
+    total = 0
+
+    def take(segment: bytes):
+        nonlocal total
+        if segment:
+            seq = _fasta_sequence(segment)
+            if len(seq):
+                pieces.append(seq)
+                total += len(seq)
+
+    with open(path, "rb") as handle:
+        carry = b""
+        while True:
+            block = handle.read(_FASTA_BLOCK)
+            if not block:
+                text, carry = carry, b""
+            else:
+                cut = block.rfind(b"\n")
+                if cut < 0:                            # no line end yet: keep reading
+                    carry += block
+                    continue
+                text, carry = carry + block[:cut + 1], block[cut + 1:]
+            if text:
+                if b"\r" in text and re.search(rb"\r(?!\n)", text):
+                    # universal newlines, like the reference's text-mode open(): a lone '\r' ends a line
+                    # (a text never ends between '\r' and '\n')
+                    text = re.sub(rb"\r(?!\n)", b"\n", text)
+                pos = 0
+                hdr = 0 if text.startswith(b">") else text.find(b"\n>") + 1   # 0 from find() = -1: no header
+                if hdr == 0 and not text.startswith(b">"):
+                    hdr = -1
+                while hdr >= 0:
+                    take(text[pos:hdr])
+                    end = text.find(b"\n", hdr)
+                    end = len(text) if end < 0 else end
+                    names.append(SequenceCollection._get_fasta_record_name(
+                        text[hdr:end].decode("utf-8", errors="replace")))
+                    starts_in_seq.append(total)
+                    pos = min(end + 1, len(text))
+                    if text.startswith(b">", pos):
+                        hdr = pos
+                    else:
+                        nxt = text.find(b"\n>", pos)
+                        hdr = nxt + 1 if nxt >= 0 else -1
+                take(text[pos:])
+            if not block:
+                break
+    if not names:
+        raise ValueError("the collection must contain at least one sequence")
+    if starts_in_seq[0] != 0:
+        # sequence text before the first header: the reference's writer runs past its array (:555-562)
+        raise AssertionError("After parsing the fasta file, we expect sba to be full")
+    bounds = np.asarray(starts_in_seq + [total], dtype=np.int64)
+    lengths = np.diff(bounds)
+    if (lengths == 0).any():
+        raise ValueError(f"At least one empty sequence was found in the input file ({path})")
+    n_rec = len(names)
+    if total + n_rec - 1 > np.iinfo(np.uint32).max:
+        raise NotImplementedError("collections of 2^32 or more positions need 64-bit segment starts")
+    starts = bounds[:-1] + np.arange(n_rec)           # one '$' per earlier record
+    # pieces never straddle a record (a header closes the piece before it): write them behind each other and
+    # step over one '$' slot whenever a record is complete
+    sba = np.full(total + n_rec - 1, _SEP, dtype=np.uint8)
+    w, done, rec = 0, 0, 0                            # write position, sequence bytes written, current record
+    for piece in pieces:
+        while done >= bounds[rec + 1]:
+            rec += 1
+            w += 1
+        sba[w:w + len(piece)] = piece
+        w += len(piece)
+        done += len(piece)
+    return names, sba, starts.astype(np.uint32)
 
 
 def _require_h5py():

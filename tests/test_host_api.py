@@ -320,3 +320,94 @@ km.save(%r, include_sequence_collection=True, format="shelve")
     back.load(theirs, format="shelve")
     assert back == km and back.seq_coll == sc
     assert back.get_kmer_str(0, 3) == km.get_kmer_str(0, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Row N4: FASTA ingest.  The block-wise reader must give what the reference's line loop gives
+# (sequence_collection.py:517-576: a line starting with '>' opens a record, any other line contributes
+# line.strip().upper()), restated here line by line as the checker.
+# ---------------------------------------------------------------------------------------------------
+def _fasta_line_by_line(path):
+    names, parts = [], []
+    with open(path, "r") as handle:
+        for line in handle:
+            if line.startswith(">"):
+                names.append(line[1:].strip().split()[0])
+                parts.append([])
+            else:
+                parts[-1].append(line.strip().upper())
+    return names, ["".join(p) for p in parts]
+
+
+FASTA_TEXTS = {
+    "plain": ">chr1 some description\nATCGA\nattag\n>chr2\nGGATCTTGCATT\n>chr3\tx\nGTGATTGACCCCT\n",
+    "no_trailing_newline": ">a\nACGT\nAC\n>b\nGG",
+    "crlf": ">a desc\r\nACGT\r\nacgt\r\n>b\r\nNNRY\r\n",
+    "blank_lines_and_blanks_at_line_ends": ">a\n\nACGT  \n  \t\n\tACG\n\n>b  x y\n  TT\n\n",
+    "lone_cr_line_ends": ">a\rACGT\rAC\r>b\rGG\r",
+    "equal_width_lines": ">a\n" + "ACGTNRYKM\n" * 50 + "ACG\n>b\n" + "acgtacgtac\n" * 7,
+    "two_short_lines_fill_one_width": ">a\nACGTACGTAC\nACGT\nACGTA\nACGTACGTAC\nAC\n",
+    "many_small_records": "".join(f">r{i}\nACGTAC\nGT\n" for i in range(300)),
+    "vertical_tab_and_form_feed": ">a\nACGT\x0b\n\x0cAC\n",
+}
+
+
+@pytest.mark.parametrize("block", [7, 64, 64 << 20])
+@pytest.mark.parametrize("name", sorted(FASTA_TEXTS))
+def test_fasta_reader_matches_line_by_line_semantics(tmp_path, monkeypatch, name, block):
+    from genome_kmers import sequence_collection as scm
+
+    path = tmp_path / "t.fa"
+    with open(path, "w", newline="") as f:
+        f.write(FASTA_TEXTS[name])
+    want_names, want_seqs = _fasta_line_by_line(path)
+    monkeypatch.setattr(scm, "_FASTA_BLOCK", block)
+    sc = SequenceCollection(fasta_file_path=path, strands_to_load="both")
+    assert sc.forward_record_names == want_names
+    assert sc.forward_sba.tobytes().decode().split("$") == want_seqs
+    assert sc._forward_sba_seg_starts.dtype == np.uint32
+    assert sc == SequenceCollection(sequence_list=list(zip(want_names, want_seqs)), strands_to_load="both")
+
+
+def test_fasta_reader_errors(tmp_path):
+    def load(text):
+        path = tmp_path / "e.fa"
+        path.write_text(text)
+        return SequenceCollection(fasta_file_path=path)
+
+    with pytest.raises(ValueError, match="At least one empty sequence was found in the input file"):
+        load(">a\n>b\nAC\n")
+    with pytest.raises(ValueError, match="At least one empty sequence was found in the input file"):
+        load(">a\nAC\n>b\n")
+    with pytest.raises(ValueError, match="non-allowed characters"):
+        load(">a\nAC GT\n")                      # strip() trims the ends of a line only
+    with pytest.raises(ValueError, match="non-allowed characters"):
+        load(">a\nAC>GT\n")
+    with pytest.raises(ValueError, match="sequence_list contains 1 repeated record_names"):
+        load(">a x\nAC\n>a y\nGT\n")
+    with pytest.raises(AssertionError, match="we expect sba to be full"):
+        load("ACGT\n>a\nAC\n")                   # text before the first header (ref :555-569)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference is only mounted in the build container")
+def test_fasta_reader_matches_the_reference_loader(tmp_path):
+    import json
+
+    paths = {}
+    for name, text in FASTA_TEXTS.items():
+        paths[name] = str(tmp_path / f"{name}.fa")
+        with open(paths[name], "w", newline="") as f:
+            f.write(text)
+    got = json.loads(_run_reference("""
+out = {}
+for name, path in %r.items():
+    sc = SequenceCollection(fasta_file_path=path, strands_to_load="both")
+    out[name] = [sc.forward_sba.tobytes().decode(), sc._forward_sba_seg_starts.tolist(), sc.forward_record_names,
+                 sc.revcomp_sba.tobytes().decode(), sc._revcomp_sba_seg_starts.tolist(), sc.revcomp_record_names]
+print(json.dumps(out))
+""" % paths))
+    for name, path in paths.items():
+        sc = SequenceCollection(fasta_file_path=path, strands_to_load="both")
+        ours = [sc.forward_sba.tobytes().decode(), sc._forward_sba_seg_starts.tolist(), sc.forward_record_names,
+                sc.revcomp_sba.tobytes().decode(), sc._revcomp_sba_seg_starts.tolist(), sc.revcomp_record_names]
+        assert ours == got[name], name
