@@ -56,6 +56,10 @@ def reverse_complement_sba(sba: np.ndarray, complement_mapping_arr: np.ndarray =
     return rc
 
 
+_UINT8_TO_U1 = np.array([chr(i) for i in range(256)], dtype="U1")
+_U1_TO_UINT8 = {chr(i): i for i in range(256)}
+
+
 class SequenceCollection:
     """Holds the records of a FASTA file as one '$'-joined byte array per strand."""
 
@@ -73,6 +77,9 @@ class SequenceCollection:
         self._complement_mapping_arr = _COMPLEMENT
         self._allowed_uint8 = {int(v) for v in np.flatnonzero(_ALLOWED)}
         self._allowed_bases = {chr(v) for v in self._allowed_uint8}
+        # byte <-> one-character string tables the reference keeps on the object (ref :463-474)
+        self._uint8_to_u1_mapping = _UINT8_TO_U1
+        self._u1_to_uint8_mapping = _U1_TO_UINT8
 
         if fasta_file_path is None and sequence_list is None:
             return
@@ -300,6 +307,23 @@ class SequenceCollection:
         seq_idx = get_forward_seq_idx(sba_idx, strand, seg_start, seg_end, one_based=one_based)
         return ("+" if strand == "forward" else "-", names[seg], seq_idx)
 
+    def generate_get_record_info_from_sba_index_func(self, one_based: bool = False):
+        """Closure sba_idx -> (segment number, segment start, segment end, strand symbol, record name,
+        forward sequence index) for the loaded strand (ref :1113-1187).  Errors as in the reference:
+        ValueError when the index lies outside every segment (e.g. on a '$')."""
+        strand = self._get_sba_strand_to_use(self.strands_loaded())
+        sba, starts, names = self._strand_arrays(strand)
+        names, len_sba = tuple(names), len(sba)
+        symbol = "+" if strand == "forward" else "-"
+
+        def get_record_info_from_sba_index(sba_idx: int):
+            seg = get_segment_num_from_sba_index(sba_idx, strand, starts)
+            seg_start, seg_end = get_sba_start_end_indices_for_segment(seg, strand, starts, len_sba)
+            seq_idx = get_forward_seq_idx(sba_idx, strand, seg_start, seg_end, one_based=one_based)
+            return seg, seg_start, seg_end, symbol, names[seg], seq_idx
+
+        return get_record_info_from_sba_index
+
     def locate_sba_indices(self, sba_indices: np.ndarray, sba_strand: str = None,
                            one_based: bool = False):
         """Vectorised get_record_loc_from_sba_index: (segment numbers, forward sequence indices)."""
@@ -387,6 +411,27 @@ class SequenceCollection:
                 self._fasta_file_path = Path(fasta) if fasta else None
         else:
             raise ValueError(f"format ({format}) not recognized")
+
+
+def bisect_right(a, x) -> int:
+    """Number of entries of the sorted sequence `a` that are <= x (module-level helper of the reference,
+    ref :16-40; NumPy's searchsorted does the work here)."""
+    return int(np.searchsorted(np.asarray(a), x, side="right"))
+
+
+def get_segment_num_from_sba_index(sba_idx: int, sba_strand: str, sba_seg_starts: np.ndarray) -> int:
+    """Segment (record) that holds a byte array index (ref :77-98); `sba_strand` is unused there too."""
+    return bisect_right(sba_seg_starts, sba_idx) - 1
+
+
+def get_sba_start_end_indices_for_segment(segment_num: int, sba_strand: str, sba_seg_starts: np.ndarray,
+                                          len_sba: int) -> Tuple[int, int]:
+    """First and last byte array index of a segment (ref :156-187)."""
+    if segment_num < 0 or segment_num >= len(sba_seg_starts):
+        raise ValueError(f"segment_num ({segment_num}) is out of bounds")
+    last = segment_num == len(sba_seg_starts) - 1
+    end = len_sba - 1 if last else int(sba_seg_starts[segment_num + 1]) - 2
+    return int(sba_seg_starts[segment_num]), end
 
 
 def get_forward_seq_idx(sba_idx: int, sba_strand: str, seg_sba_start_idx: int, seg_sba_end_idx: int,
