@@ -752,6 +752,12 @@ def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, me
                          "launches_per_step": passes, "pairs_on_rank0": int(n_shard),
                          "pair_bytes": pair_bytes},
             "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()), "mode": exchange_mode,
+                         # rank 0's exchange phase: fused partition + peer writes + the ordering all-reduce
+                         "exchange_ms_rank0": round(float(phase_ms.get("exchange", 0.0)), 3),
+                         "nvlink_gbs_per_gpu_outbound": (
+                             round(float(sent_all.item()) / world / (phase_ms["exchange"] * 1e-3) / 1e9, 1)
+                             if phase_ms.get("exchange", 0.0) > 0 else None),
+                         "nvlink_peak_gbs_per_direction": 900.0,
                          "note": "(G-1)/G of all (u64 key, u32 start) pairs cross NVLink once: written by the "
                                  "partition kernel into peer memory (mode peer) or one NCCL all-to-all (mode nccl)"},
             "cpu_baseline": None, "clocks": clock_info,
