@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, strands, k, out_dir):
+def _worker(rank, world, port, strands, k, out_dir, kind="mixed"):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "genome-kmers_b200"), HERE]
     import torch.distributed as dist
 
@@ -41,6 +41,10 @@ def _worker(rank, world, port, strands, k, out_dir):
             seq[rng.integers(0, n, 3)] = ord("R")
             recs.append(seq)
         recs.append(np.frombuffer(b"ACAC" * 60, dtype=np.uint8))     # a low-complexity record: big groups
+        if kind == "one_group":      # every k-mer is the same: one rank owns everything, the others get nothing
+            recs = [np.full(400, ord("A"), dtype=np.uint8), np.full(300, ord("A"), dtype=np.uint8)]
+        elif kind == "tiny":         # fewer k-mers than ranks can share evenly
+            recs = [np.frombuffer(b"ACGTTGCA"[:k + 1], dtype=np.uint8)]
         sba, starts = oracle.build_sba(recs)
         sk = ShardedKmers(sba, starts, k, strands, engine=NumpyEngine())
         sk.sort()
@@ -69,6 +73,18 @@ def test_sharded_sort_count_matches_oracle(tmp_path, world, strands, k):
     sizes = [len(np.load(tmp_path / f"shard{r}.npy")) for r in range(world)]
     assert sum(sizes) == int(np.load(tmp_path / "ok.npy")[0])
     assert min(sizes) > 0, f"a rank received nothing: {sizes}"
+
+
+@pytest.mark.parametrize("world,strands,k,kind", [(2, "forward", 7, "one_group"), (3, "both", 7, "one_group"),
+                                                  (2, "forward", 5, "tiny")])
+def test_sharded_sort_count_degenerate_inputs(tmp_path, world, strands, k, kind):
+    """A rank that receives nothing (one giant group, or almost no k-mers) must still take part in every
+    collective and report an empty shard."""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, strands, k, str(tmp_path), kind), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok.npy")
+    sizes = [len(np.load(tmp_path / f"shard{r}.npy")) for r in range(world)]
+    assert sum(sizes) == int(np.load(tmp_path / "ok.npy")[0])
 
 
 def test_splitters_and_slices():
