@@ -44,8 +44,9 @@ __device__ __forceinline__ uint32_t splitter_digit(const uint64_t *s_split, uint
 // ---- 1. histogram ------------------------------------------------------------------------------
 constexpr int kHistThreads = 512;
 
+template <typename KeyT>
 __global__ void __launch_bounds__(kHistThreads)
-digit_histogram_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_bit, int end_bit,
+digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit, int end_bit,
                        const uint64_t *__restrict__ splitters, uint32_t n_split,
                        unsigned long long *__restrict__ g_hist /* [passes][256] */)
 {
@@ -57,8 +58,9 @@ digit_histogram_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_
     if (splitters && threadIdx.x < n_split) s_split[threadIdx.x] = splitters[threadIdx.x];
     __syncthreads();
 
-    const uint64_t n2 = n / 2;
-    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
+    constexpr int kVec = 16 / (int)sizeof(KeyT);   // keys per 16-byte load
+    const uint64_t n_vec = n / kVec;
+    const uint4 *kv = reinterpret_cast<const uint4 *>(keys);
     const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
     auto add = [&](uint64_t key) {
         if (splitters) {
@@ -75,12 +77,17 @@ digit_histogram_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_
             }
         }
     };
-    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n2; i += stride) {
-        ulonglong2 v = k2[i];
-        add(v.x);
-        add(v.y);
+    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n_vec; i += stride) {
+        const uint4 v = kv[i];
+        if (sizeof(KeyT) == 8) {
+            add(((uint64_t)v.y << 32) | v.x);
+            add(((uint64_t)v.w << 32) | v.z);
+        } else {
+            add(v.x); add(v.y); add(v.z); add(v.w);
+        }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) add(keys[n - 1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = n_vec * kVec; i < n; ++i) add((uint64_t)keys[i]);
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) {
         uint32_t c = (&s_hist[0][0])[i];
@@ -135,11 +142,11 @@ struct PeerTable {
     void *vals[kMaxPeers];
 };
 
-template <typename ValT, int THREADS, int IPT>
+template <typename ValT, int THREADS, int IPT, typename KeyT = uint64_t>
 struct OnesweepSmem {
     static constexpr int kTile = THREADS * IPT;
     static constexpr int kWarps = THREADS / 32;
-    uint64_t keys[kTile];
+    KeyT keys[kTile];
     ValT vals[kTile];
     uint32_t warp_cnt[kWarps][kRadix];  // per-warp digit counts, then running tile positions
     unsigned long long global_off[kRadix];  // bin's global start minus its start inside the tile
@@ -192,19 +199,21 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
 //      slot in shared memory
 //   D  bin threads: decoupled look-back, several predecessor status words per round trip
 //   E  stream the tile out; consecutive threads write consecutive addresses inside each bin
-template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
+// KeyT = uint32_t: the same pass for 32-bit keys (8-byte pairs with 32-bit values); never with PARTITION.
+template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION, typename KeyT = uint64_t>
 __global__ void __launch_bounds__(THREADS, MINB)
-onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
+onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                 const ValT *__restrict__ vals_in, ValT *__restrict__ vals_out, uint64_t n,
                 int shift, uint32_t digit_mask, const uint64_t *__restrict__ splitters, uint32_t n_split,
                 const unsigned long long *__restrict__ bin_base, uint32_t *__restrict__ tile_counter,
                 StatusT *__restrict__ status, int *__restrict__ err, const PeerTable *__restrict__ peer)
 {
-    using Smem = OnesweepSmem<ValT, THREADS, IPT>;
+    using Smem = OnesweepSmem<ValT, THREADS, IPT, KeyT>;
     using ST = StatusTraits<StatusT>;
     constexpr int kTile = Smem::kTile;
     constexpr int kWarps = Smem::kWarps;
     static_assert(THREADS >= kRadix, "one thread per bin is needed for the look-back");
+    static_assert(!PARTITION || sizeof(KeyT) == 8, "splitters are 64-bit keys");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -220,8 +229,8 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         s.peer_vals[t] = reinterpret_cast<ValT *>(peer->vals[t]);
     }
     __syncthreads();
-    auto digit_of = [&](uint64_t k) -> uint32_t {
-        if (PARTITION) return splitter_digit(s.splitters, n_split, k);
+    auto digit_of = [&](KeyT k) -> uint32_t {
+        if (PARTITION) return splitter_digit(s.splitters, n_split, (uint64_t)k);
         return (uint32_t)(k >> shift) & digit_mask;
     };
     const uint64_t tile = s.tile;
@@ -230,7 +239,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
     const uint32_t tile_valid = full_tile ? (uint32_t)kTile : (uint32_t)(n - tile_base);
 
     // warp-striped inside a warp-contiguous chunk, so memory order == (j, lane)
-    uint64_t key[IPT];
+    KeyT key[IPT];
     ValT val[IPT];
     const uint64_t warp_base = tile_base + (uint64_t)warp * (32 * IPT);
     if (full_tile) {
@@ -243,7 +252,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         for (int j = 0; j < IPT; ++j) {
             const uint64_t g = warp_base + j * 32 + lane;
             const bool ok = g < n;
-            key[j] = ok ? keys_in[g] : ~0ull;  // pads rank last in the last bin of the last tile
+            key[j] = ok ? keys_in[g] : (KeyT)~(KeyT)0;  // pads rank last in the last bin of the last tile
             val[j] = ok ? vals_in[g] : (ValT)0;
         }
     }
@@ -348,10 +357,10 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         for (int j = 0; j < IPT; ++j) {
             const uint32_t p = t + j * THREADS;
             if (p < tile_valid) {
-                const uint64_t k = s.keys[p];
+                const KeyT k = s.keys[p];
                 const uint32_t d = digit_of(k);
                 const uint64_t dst = (uint64_t)(s.global_off[d] + p);
-                s.peer_keys[d][dst] = k;
+                s.peer_keys[d][dst] = (uint64_t)k;
                 s.peer_vals[d][dst] = s.vals[p];
             }
         }
@@ -361,7 +370,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const uint32_t p = t + j * THREADS;
-            const uint64_t k = s.keys[p];
+            const KeyT k = s.keys[p];
             const uint32_t d = digit_of(k);
             const uint64_t dst = kNarrow ? (uint64_t)(uint32_t)(s.global_off32[d] + p)
                                          : (uint64_t)(s.global_off[d] + p);
@@ -373,7 +382,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
         for (int j = 0; j < IPT; ++j) {
             const uint32_t p = t + j * THREADS;
             if (p < tile_valid) {
-                const uint64_t k = s.keys[p];
+                const KeyT k = s.keys[p];
                 const uint64_t dst = (uint64_t)(s.global_off[digit_of(k)] + p);
                 keys_out[dst] = k;
                 vals_out[dst] = s.vals[p];
@@ -384,24 +393,25 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ key
 
 // ---- host driver ---------------------------------------------------------------------------------
 struct PassArgs {
-    const uint64_t *kin; uint64_t *kout; const void *vin; void *vout; uint64_t n;
+    const void *kin; void *kout; const void *vin; void *vout; uint64_t n;
     int shift, bits; const uint64_t *splitters; uint32_t n_split;
     const unsigned long long *bin_base; uint32_t *tile_counter; void *status; int *err;
     const PeerTable *peer;
 };
 
-template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION>
+template <typename ValT, typename StatusT, int THREADS, int IPT, int MINB, bool PARTITION,
+          typename KeyT = uint64_t>
 static int launch_pass_impl(const PassArgs &a, cudaStream_t st)
 {
-    using Smem = OnesweepSmem<ValT, THREADS, IPT>;
-    auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT, MINB, PARTITION>;
+    using Smem = OnesweepSmem<ValT, THREADS, IPT, KeyT>;
+    auto kernel = onesweep_kernel<ValT, StatusT, THREADS, IPT, MINB, PARTITION, KeyT>;
     GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     GK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared));
     const uint64_t tiles = (a.n + Smem::kTile - 1) / Smem::kTile;
     kernel<<<(unsigned)tiles, THREADS, sizeof(Smem), st>>>(
-        a.kin, a.kout, (const ValT *)a.vin, (ValT *)a.vout, a.n, a.shift, (1u << a.bits) - 1u, a.splitters,
-        a.n_split, a.bin_base, a.tile_counter, (StatusT *)a.status, a.err, a.peer);
+        (const KeyT *)a.kin, (KeyT *)a.kout, (const ValT *)a.vin, (ValT *)a.vout, a.n, a.shift,
+        (1u << a.bits) - 1u, a.splitters, a.n_split, a.bin_base, a.tile_counter, (StatusT *)a.status, a.err, a.peer);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -574,6 +584,115 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     return GK_OK;
 }
 
+// ---- 32-bit keys ---------------------------------------------------------------------------------
+// The same stable LSD onesweep for (u32 key, u32/u64 value) pairs: 8 bytes per pair with 32-bit values, so a
+// pass moves 16 B per pair instead of 24 and a tile of the same shared-memory size holds 1.5x the pairs.
+// Tile shapes for this pair size; GK_SORT32_CFG selects one (read per call, tools/bench_sort.py --env).
+constexpr SortConfig kSort32Configs[] = {
+    {256, 32, 2},  // 0:  8192-pair tiles,  64 KB of pairs
+    {256, 40, 2},  // 1: 10240-pair tiles,  80 KB
+    {256, 48, 2},  // 2: 12288-pair tiles,  96 KB: as much shared memory as the 64-bit default
+    {256, 24, 3},  // 3:  6144-pair tiles,  48 KB, three CTAs per SM
+};
+constexpr int kNumSort32Configs = (int)(sizeof(kSort32Configs) / sizeof(kSort32Configs[0]));
+constexpr int kDefaultSort32Config = 0;
+
+static int sort32_config_id(int val_bytes)
+{
+    int id = kDefaultSort32Config;
+    const char *e = getenv("GK_SORT32_CFG");
+    if (e && *e) {
+        const int v = atoi(e);
+        if (v >= 0 && v < kNumSort32Configs) id = v;
+    }
+    // 64-bit values: 12 bytes per pair, the two largest tiles no longer fit two CTAs per SM
+    return (val_bytes == 8 && (id == 1 || id == 2)) ? 0 : id;
+}
+
+template <typename ValT, typename StatusT>
+static int dispatch_pass32(int cfg, const PassArgs &a, cudaStream_t st)
+{
+    if constexpr (sizeof(ValT) == 4) {  // (sort32_config_id never selects these for 64-bit values)
+        if (cfg == 1) return launch_pass_impl<ValT, StatusT, 256, 40, 2, false, uint32_t>(a, st);
+        if (cfg == 2) return launch_pass_impl<ValT, StatusT, 256, 48, 2, false, uint32_t>(a, st);
+    }
+    if (cfg == 3) return launch_pass_impl<ValT, StatusT, 256, 24, 3, false, uint32_t>(a, st);
+    return launch_pass_impl<ValT, StatusT, 256, 32, 2, false, uint32_t>(a, st);
+}
+
+int radix_sort_pairs32_device(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_vals, void *d_vals_alt, int val_bytes,
+                              uint64_t n, int begin_bit, int end_bit, int *result_in_alt, cudaStream_t st)
+{
+    if (val_bytes != 4 && val_bytes != 8) {
+        set_error("radix_sort_pairs32: val_bytes must be 4 or 8");
+        return GK_ERR_ARG;
+    }
+    if (begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {
+        set_error("radix_sort_pairs32: bad bit range [%d, %d)", begin_bit, end_bit);
+        return GK_ERR_ARG;
+    }
+    if (result_in_alt) *result_in_alt = 0;
+    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    if (n < 2 || passes == 0) return GK_OK;
+    if ((reinterpret_cast<uintptr_t>(d_keys) & 15u) || (reinterpret_cast<uintptr_t>(d_keys_alt) & 15u)) {
+        set_error("radix_sort_pairs32: key buffers must be 16-byte aligned");
+        return GK_ERR_ARG;
+    }
+    const int cfg = sort32_config_id(val_bytes);
+    const int tile = kSort32Configs[cfg].threads * kSort32Configs[cfg].ipt;
+    const uint64_t tiles = (n + tile - 1) / tile;
+    const bool wide = n >= (1ull << 30);
+    const size_t status_bytes = (size_t)tiles * kRadix * (wide ? 8 : 4);
+    const size_t hist_bytes = (size_t)kMaxPasses * kRadix * sizeof(unsigned long long);
+    // temp layout as in run_onesweep: [hist][base][counters (kMaxPasses u32) + err (int)][status]
+    DeviceBuffer temp;
+    const size_t ctr_bytes = 64;
+    GK_TRY(temp.alloc(2 * hist_bytes + ctr_bytes + status_bytes, st));
+    unsigned long long *d_hist = temp.as<unsigned long long>();
+    unsigned long long *d_base = d_hist + kMaxPasses * kRadix;
+    uint32_t *d_ctr = reinterpret_cast<uint32_t *>(d_base + kMaxPasses * kRadix);
+    int *d_err = reinterpret_cast<int *>(d_ctr + kMaxPasses);
+    void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
+    GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
+    int hist_grid = sm_count() * 2;
+    {
+        uint64_t need = (n / 4 + kHistThreads - 1) / kHistThreads;
+        if (need < 1) need = 1;
+        if ((uint64_t)hist_grid > need) hist_grid = (int)need;
+    }
+    digit_histogram_kernel<uint32_t><<<hist_grid, kHistThreads, 0, st>>>(d_keys, n, begin_bit, end_bit, nullptr, 0,
+                                                                         d_hist);
+    GK_LAUNCH_CHECK();
+    scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_hist, d_base);
+    GK_LAUNCH_CHECK();
+    uint32_t *kin = d_keys, *kout = d_keys_alt;
+    void *vin = d_vals, *vout = d_vals_alt;
+    for (int p = 0; p < passes; ++p) {
+        const int lo = begin_bit + p * kRadixBits;
+        const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
+        GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
+        PassArgs pa = {kin, kout, vin, vout, n, lo, bits, nullptr, 0, d_base + p * kRadix,
+                       d_ctr + p, d_status, d_err, nullptr};
+        int rc;
+        if (val_bytes == 4)
+            rc = wide ? dispatch_pass32<uint32_t, uint64_t>(cfg, pa, st) : dispatch_pass32<uint32_t, uint32_t>(cfg, pa, st);
+        else
+            rc = wide ? dispatch_pass32<uint64_t, uint64_t>(cfg, pa, st) : dispatch_pass32<uint64_t, uint32_t>(cfg, pa, st);
+        GK_TRY(rc);
+        uint32_t *tk = kin; kin = kout; kout = tk;
+        void *tv = vin; vin = vout; vout = tv;
+    }
+    if (result_in_alt) *result_in_alt = passes & 1;
+    int h_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("radix_sort_pairs32: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
+    return GK_OK;
+}
+
 int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                             int val_bytes, uint64_t n, int begin_bit, int end_bit,
                             int *result_in_alt, cudaStream_t st, SortTiming *timing,
@@ -705,6 +824,18 @@ extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void 
     }
     return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
                                    end_bit, result_in_alt, as_stream(stream), nullptr, nullptr);
+}
+
+extern "C" int gk_radix_sort_pairs32(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                                     int val_bytes, uint64_t n, int begin_bit, int end_bit, int *result_in_alt,
+                                     void *stream)
+{
+    if (n && (!d_keys || !d_keys_alt || !d_vals || !d_vals_alt)) {
+        set_error("gk_radix_sort_pairs32: null buffer");
+        return GK_ERR_ARG;
+    }
+    return radix_sort_pairs32_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit, end_bit,
+                                     result_in_alt, as_stream(stream));
 }
 
 extern "C" int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, void *d_vals_out,

@@ -69,6 +69,7 @@ SIGNATURES = {
     "gk_pack_keys": (_int, [_vp, _u64, _vp, _u32, _u32, _u32, _int, _u64, _u64, _vp, _int, _vp,
                             _u64, _p(_u64), _p(_u64), _vp]),
     "gk_radix_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _int, _int, _p(_int), _vp]),
+    "gk_radix_sort_pairs32": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _int, _int, _p(_int), _vp]),
     "gk_partition_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _vp, _u32, _vp, _vp]),
     "gk_partition_count": (_int, [_vp, _u64, _vp, _u32, _vp, _vp]),
     "gk_partition_pairs_peer": (_int, [_vp, _vp, _int, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),

@@ -122,6 +122,12 @@ int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_s
 int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                         int val_bytes, uint64_t n, int begin_bit, int end_bit,
                         int *result_in_alt, void *stream);
+/* The same sort for 32-bit keys on key bits [begin_bit, end_bit) of 32: with 32-bit values a pair is 8 bytes,
+ * so a pass moves 16 bytes per pair instead of 24 (the planned split-key path sorts
+ * (top key word, start index) pairs).  Same contract as gk_radix_sort_pairs. */
+int gk_radix_sort_pairs32(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_vals, void *d_vals_alt,
+                          int val_bytes, uint64_t n, int begin_bit, int end_bit,
+                          int *result_in_alt, void *stream);
 /* Multi-GPU partition step: stable split of the pairs by destination rank = number of splitters
  * (sorted, n_parts-1 of them, device memory) that are <= key.  One onesweep pass whose "digit" is
  * the destination.  Output in the *_out buffers; h_counts_out[d] = pairs for destination d. */

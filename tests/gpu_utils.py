@@ -51,6 +51,20 @@ def radix_sort_pairs(keys: np.ndarray, vals: np.ndarray, begin_bit: int, end_bit
     return host(kk, np.uint64), host(vv, vals.dtype)
 
 
+def radix_sort_pairs32(keys: np.ndarray, vals: np.ndarray, begin_bit: int, end_bit: int):
+    torch = torch_mod()
+    lib = _native.lib()
+    k0, v0 = dev(keys.astype(np.uint32)), dev(vals)
+    k1, v1 = torch.empty_like(k0), torch.empty_like(v0)
+    in_alt = ctypes.c_int(0)
+    _native.check(lib.gk_radix_sort_pairs32(k0.data_ptr(), k1.data_ptr(), v0.data_ptr(), v1.data_ptr(),
+                                            vals.dtype.itemsize, len(keys), begin_bit, end_bit,
+                                            ctypes.byref(in_alt), stream()))
+    torch.cuda.synchronize()
+    kk, vv = (k1, v1) if in_alt.value else (k0, v0)
+    return host(kk, np.uint32), host(vv, vals.dtype)
+
+
 def pack_keys(sba: np.ndarray, seg_starts, valid_len, key_len, class_bit, idx_dtype=np.uint32,
               first=0, end=None):
     torch = torch_mod()

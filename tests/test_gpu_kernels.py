@@ -123,6 +123,27 @@ def test_radix_sort_pairs_u64_values_and_skewed_digits():
     assert np.array_equal(got_k, keys[order]) and np.array_equal(got_v, vals[order])
 
 
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("n,bits,val_dtype", [
+    (1, (0, 32), np.uint32), (2, (0, 32), np.uint32), (8191, (0, 32), np.uint32), (8193, (0, 32), np.uint32),
+    (12289, (5, 21), np.uint32), (500_003, (0, 32), np.uint32), (500_003, (24, 32), np.uint32),
+    (300_001, (0, 32), np.uint64), (2_000_003, (0, 16), np.uint32),
+])
+def test_radix_sort_pairs32_is_a_stable_sort(n, bits, val_dtype, cfg, monkeypatch):
+    """The 32-bit-key variant of the onesweep sort, every tile shape (GK_SORT32_CFG is read per call)."""
+    monkeypatch.setenv("GK_SORT32_CFG", cfg)
+    rng = np.random.default_rng(n + bits[0] * 131 + bits[1])
+    keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[rng.integers(0, n, n // 3)] = keys[0]  # long ties exercise stability
+    vals = (np.arange(n, dtype=np.uint64) * np.uint64(3 if val_dtype == np.uint64 else 1)).astype(val_dtype)
+    got_k, got_v = gu.radix_sort_pairs32(keys, vals, bits[0], bits[1])
+    field = (keys >> np.uint32(bits[0])) & np.uint32((1 << (bits[1] - bits[0])) - 1)
+    order = np.argsort(field, kind="stable")
+    assert np.array_equal(got_v, vals[order])
+    assert np.array_equal(got_k, keys[order])
+
+
 @pytest.mark.parametrize("n", [1, 7, 8, 9, 4096, 100_000, 1_234_567])
 def test_rle_and_group_hist(n):
     torch = gu.torch_mod()

@@ -101,8 +101,45 @@ def variants(n, env_name, values):
         del keys, vals, k0, v0, k1, v1
 
 
+def keys32(n, cfgs):
+    """gk_radix_sort_pairs32 (u32 key, u32 value: 8-byte pairs), 4 passes over 32 bits, every tile shape."""
+    import torch
+    from genome_kmers import _native
+
+    lib = _native.lib()
+    sp = int(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    keys = torch.randint(-(1 << 31), 1 << 31, (n,), dtype=torch.int32, device="cuda", generator=g)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    k0, v0 = keys.clone(), vals.clone()
+    k1, v1 = torch.empty_like(keys), torch.empty_like(vals)
+    in_alt = ctypes.c_int(0)
+    for cfg in cfgs:
+        os.environ["GK_SORT32_CFG"] = cfg
+        times = []
+        for it in range(6):
+            k0.copy_(keys); v0.copy_(vals)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _native.check(lib.gk_radix_sort_pairs32(k0.data_ptr(), k1.data_ptr(), v0.data_ptr(), v1.data_ptr(), 4, n,
+                                                    0, 32, ctypes.byref(in_alt), sp))
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        out = k1 if in_alt.value else k0
+        u = out.long() & 0xFFFFFFFF
+        ok = bool((u[1:] >= u[:-1]).all())
+        best = min(times[2:])
+        print(f"keys32 cfg={cfg} n={n} sort_ms={best:.3f} per_pass_ms={best / 4:.3f} "
+              f"GBps_per_pass={16 * n / (best / 4) / 1e6:.0f} (incl. histogram) sorted={ok}", flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "--child":
+    if len(sys.argv) > 1 and sys.argv[1] == "--keys32":
+        # python tools/bench_sort.py --keys32 200000000 0 1 2 3
+        keys32(int(sys.argv[2]), sys.argv[3:] or ["0", "1", "2", "3"])
+    elif len(sys.argv) > 1 and sys.argv[1] == "--child":
         child(int(sys.argv[2]))
     elif len(sys.argv) > 1 and sys.argv[1] == "--env":
         # python tools/bench_sort.py --env GK_SORT_CFG 200000000 7 6 7 6
