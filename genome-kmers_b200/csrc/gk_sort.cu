@@ -58,9 +58,6 @@ digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit,
     if (splitters && threadIdx.x < n_split) s_split[threadIdx.x] = splitters[threadIdx.x];
     __syncthreads();
 
-    constexpr int kVec = 16 / (int)sizeof(KeyT);   // keys per 16-byte load
-    const uint64_t n_vec = n / kVec;
-    const uint4 *kv = reinterpret_cast<const uint4 *>(keys);
     const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
     auto add = [&](uint64_t key) {
         if (splitters) {
@@ -77,17 +74,25 @@ digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit,
             }
         }
     };
-    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n_vec; i += stride) {
-        const uint4 v = kv[i];
-        if (sizeof(KeyT) == 8) {
-            add(((uint64_t)v.y << 32) | v.x);
-            add(((uint64_t)v.w << 32) | v.z);
-        } else {
+    if constexpr (sizeof(KeyT) == 8) {  // two keys per 16-byte load
+        const uint64_t n2 = n / 2;
+        const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
+        for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n2; i += stride) {
+            ulonglong2 v = k2[i];
+            add(v.x);
+            add(v.y);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) add(keys[n - 1]);
+    } else {                            // four keys per 16-byte load
+        const uint64_t n4 = n / 4;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+        for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n4; i += stride) {
+            const uint4 v = k4[i];
             add(v.x); add(v.y); add(v.z); add(v.w);
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (uint64_t i = n4 * 4; i < n; ++i) add((uint64_t)keys[i]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (uint64_t i = n_vec * kVec; i < n; ++i) add((uint64_t)keys[i]);
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) {
         uint32_t c = (&s_hist[0][0])[i];
