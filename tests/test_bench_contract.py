@@ -38,7 +38,11 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_reference_arm_under_torchrun_only_rank0_reports():
-    port = 29000 + os.getpid() % 1000
+    import socket
+
+    with socket.socket() as sock:                      # a free port for the rendezvous
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     out = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
          "127.0.0.1", "--master-port", str(port), "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1",
