@@ -411,3 +411,20 @@ print(json.dumps(out))
         ours = [sc.forward_sba.tobytes().decode(), sc._forward_sba_seg_starts.tolist(), sc.forward_record_names,
                 sc.revcomp_sba.tobytes().decode(), sc._revcomp_sba_seg_starts.tolist(), sc.revcomp_record_names]
         assert ours == got[name], name
+
+
+def test_integration_md_stub_binds_the_library():
+    """The ctypes stub INTEGRATION.md shows a maintainer is real code: it loads libgkb200.so, binds
+    gk_sort_count_host with the documented argument list and defines sort_and_count (no compute call here)."""
+    import ctypes
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes, numpy as np\n.*?)```", text, flags=re.S).group(1)
+    lib_path = os.path.join(ROOT, "genome-kmers_b200", "lib", "libgkb200.so")
+    assert 'ctypes.CDLL("libgkb200.so")' in block
+    scope = {}
+    exec(block.replace('ctypes.CDLL("libgkb200.so")', f"ctypes.CDLL({lib_path!r})"), scope)
+    assert callable(scope["sort_and_count"])
+    bound = scope["_lib"].gk_sort_count_host
+    assert len(bound.argtypes) == len(_native.SIGNATURES["gk_sort_count_host"][1]) == 13
+    assert bound.restype is ctypes.c_int
