@@ -166,3 +166,41 @@ def test_oracle_group_walk_matches_reference_get_kmers(entry):
     assert first.tolist() == want_first
     assert size.tolist() == want_size
     assert total == sum(want_size)
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded random cross-check of the two independent oracles (comparator quicksort in C against the 4-bit rank
+# encoding + lexsort in NumPy) on inputs the golden cases do not enumerate: many short records, every IUPAC
+# letter, fixed and variable window lengths, both strands
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(24))
+def test_c_oracle_and_numpy_oracle_agree_on_random_collections(seed):
+    rng = np.random.default_rng(1000 + seed)
+    alphabet = np.frombuffer(b"ACGT" * 6 + b"RYSWKMBDHVN", dtype=np.uint8)     # mostly A/C/G/T
+    n_rec = int(rng.integers(1, 9))
+    lengths = rng.integers(1, 120, n_rec) if seed % 3 else rng.integers(40, 400, n_rec)
+    records = []
+    for n in lengths:
+        seq = alphabet[rng.integers(0, len(alphabet), int(n))].copy()
+        if n > 30 and seed % 2:
+            seq[5:5 + int(n) // 3] = ord("N")                                  # an N run
+        if n > 20 and seed % 4 == 0:
+            seq[:] = seq[int(rng.integers(0, n))]                              # a homopolymer record
+        records.append(seq)
+    sba, starts = oracle.build_sba(records)
+    starts = starts.astype(np.uint64)
+    if seed % 5 == 0:
+        sba, starts = oracle.both_strands(sba, starts)
+    shortest = int(min(len(r) for r in records))
+    min_len = int(rng.integers(1, shortest + 1))
+    max_len = [min_len, None, min_len + int(rng.integers(0, 40))][seed % 3]
+    init = oracle.init_indices(starts, len(sba), min_len)
+    got_c = oracle.sort_indices(sba, init, min_len, max_len, break_ties=True, threads=1 + seed % 3)
+    got_np = oracle_np.sort_indices(sba, init, starts, max_len)
+    assert np.array_equal(got_c, got_np)
+    for kmer_len in {min_len, max_len, max(1, min_len // 2)}:
+        hist_c, total_c, first, size = oracle.group_hist(sba, got_c, kmer_len, max_bin=12, want_groups=True)
+        sizes_np = oracle_np.group_sizes(sba, got_c, starts, kmer_len)
+        hist_np, total_np = oracle_np.group_hist(sizes_np, max_bin=12)
+        assert size.tolist() == sizes_np.tolist()
+        assert total_c == total_np == len(init) and np.array_equal(hist_c, hist_np)
