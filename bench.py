@@ -26,9 +26,7 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np

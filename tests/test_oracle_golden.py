@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from oracle import oracle_np
-from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
+from conftest import dense_hist, golden_case, golden_case_names
 
 ALL = golden_case_names()
 COMP = str.maketrans("ACGTRYSWKMBDHVN", "TGCAYRSWMKVHDBN")
