@@ -588,7 +588,7 @@ def _read_fasta(path) -> Tuple[List[str], np.ndarray, np.ndarray]:
                     continue
                 text, carry = carry + block[:cut + 1], block[cut + 1:]
             if text:
-                if b"\r" in text and re.search(rb"\r(?!\n)", text):
+                if b"\r" in text and text.count(b"\r") != text.count(b"\r\n"):
                     # universal newlines, like the reference's text-mode open(): a lone '\r' ends a line
                     # (a text never ends between '\r' and '\n')
                     text = re.sub(rb"\r(?!\n)", b"\n", text)
