@@ -87,11 +87,58 @@ struct DeviceBuffer {
     T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 
-// device time of one radix sort, split the way bench.py reports it
+// device time of one radix sort, split the way bench.py reports it.  A sort that runs without a
+// synchronise (deferred error word) leaves its events pending; the caller resolves them after its own
+// final synchronise.
 struct SortTiming {
-    float hist_ms;    // digit histogram + scan (one read of the keys)
-    float passes_ms;  // all onesweep passes (and their status memsets)
-    int passes;
+    float hist_ms = 0.f;    // digit histogram + scan (one read of the keys)
+    float passes_ms = 0.f;  // all onesweep passes (and their status memsets)
+    int passes = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool pending = false;
+    SortTiming() = default;
+    SortTiming(const SortTiming &) = delete;
+    SortTiming &operator=(const SortTiming &) = delete;
+    ~SortTiming() { drop(); }
+    void drop()
+    {
+        for (auto &e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        pending = false;
+    }
+    void resolve()  // after a synchronise of the stream the events were recorded on
+    {
+        if (pending) {
+            cudaEventElapsedTime(&hist_ms, ev[0], ev[1]);
+            cudaEventElapsedTime(&passes_ms, ev[1], ev[2]);
+        }
+        drop();
+    }
+};
+
+// Ambiguous-window fragments: the pack kernel lists every block of consecutive identical
+// non-ACGT windows (all windows inside an N run are one block per pack tile) as
+// (radix key, 4-bit rank words, first start, number of windows).  Unordered (slots come from an atomic
+// counter); entries beyond `capacity` are counted but not written.
+struct FragOut {
+    uint64_t *key = nullptr, *w0 = nullptr, *w1 = nullptr, *start = nullptr;
+    uint32_t *count = nullptr;
+    unsigned long long *counter = nullptr;
+    uint64_t capacity = 0;
+};
+
+// Sorted fragment list (device): what frag_sort_device leaves for frag_expand_device (gk_frag.cu).
+struct FragSorted {
+    DeviceBuffer skey_a, skey_b, perm_a, perm_b, sstart, off, whead, slot0;
+    const uint64_t *skey = nullptr;
+    uint64_t F = 0;
+    // the buffers are allocated and filled on a side stream and last used on the main stream: release them there
+    void rebind(cudaStream_t st)
+    {
+        for (DeviceBuffer *b : {&skey_a, &skey_b, &perm_a, &perm_b, &sstart, &off, &whead, &slot0}) b->stream = st;
+    }
 };
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -1,0 +1,228 @@
+// gk_frag.cu -- ambiguous windows as run-length blocks ("fragments"), from pack time to the final order
+// (DESIGN.md 4.2b).
+//
+// A window that holds a non-ACGT symbol gets a radix key that orders it exactly against every pure window
+// (gk_pack.cu), so the main sort puts the ambiguous windows into the right SLOTS as a set.  What is left is
+// their order among themselves, by the reference's raw byte comparison (kmers.py:381-388).  Real genomes and
+// the bench workload hold almost all of them in N runs -- millions of identical windows -- so they are never
+// handled as elements here:
+//   pack kernel        lists every block of consecutive identical ambiguous windows as one fragment
+//                      (key, 4-bit rank words w0/w1, first start, count): ~25 k fragments for 8.4 M windows
+//   frag_sort_device   orders the fragments by (key, w0, w1, start) -- a few single-CTA sorts, independent of
+//                      the main sort, so it runs beside it on a second stream
+//   frag_expand_device finds the slot range of every fragment (lower bound of its key in the sorted keys +
+//                      windows of earlier fragments with the same key) and writes starts and head flags
+// Nothing here reads or writes per-k-mer data except the final writes into the ambiguous slots.
+#include "gk_common.cuh"
+
+namespace gk {
+
+int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, int *, cudaStream_t,
+                            SortTiming *, const unsigned long long *d_pre_hist = nullptr, void *d_vals_final = nullptr);
+
+static int frag_grid(uint64_t items)
+{
+    uint64_t blocks = (items + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__global__ void __launch_bounds__(256)
+frag_iota_kernel(uint32_t *__restrict__ perm, uint64_t F)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < F; q += stride) perm[q] = (uint32_t)q;
+}
+
+__global__ void __launch_bounds__(256)
+frag_gather_kernel(const uint64_t *__restrict__ word, const uint32_t *__restrict__ perm, uint64_t F,
+                   uint64_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < F; q += stride) out[q] = word[perm[q]];
+}
+
+// sorted order -> dense arrays: first start, count, "first fragment of a group of equal k-mers"
+__global__ void __launch_bounds__(256)
+frag_finish_kernel(const uint64_t *__restrict__ skey, const uint64_t *__restrict__ w0,
+                   const uint64_t *__restrict__ w1, const uint64_t *__restrict__ start,
+                   const uint32_t *__restrict__ count, const uint32_t *__restrict__ perm, uint64_t F,
+                   uint64_t *__restrict__ sstart, unsigned long long *__restrict__ off, uint8_t *__restrict__ whead)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < F; q += stride) {
+        const uint32_t f = perm[q];
+        sstart[q] = start[f];
+        off[q] = count[f];
+        bool head = true;
+        if (q > 0) {
+            const uint32_t g = perm[q - 1];
+            head = skey[q] != skey[q - 1] || w0[f] != w0[g] || w1[f] != w1[g];
+        }
+        whead[q] = head ? 1 : 0;
+    }
+}
+
+// one CTA: in-place exclusive scan of F counts, total appended at [F]
+__global__ void __launch_bounds__(1024)
+frag_scan_kernel(unsigned long long *__restrict__ data, uint64_t F)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < F; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long c = (i < F) ? data[i] : 0;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+        if (i < F) data[i] = pre + inc - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) data[F] = s_carry;
+}
+
+__device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *__restrict__ a, uint64_t n, uint64_t x)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// First slot of every fragment in the sorted order.  All windows with an ambiguous key K sit in one run of
+// slots that starts at the lower bound of K in the sorted keys (no pure window shares a class-0 key);
+// inside the run the fragments follow each other in (w0, w1, start) order.
+// err bit 1: fragment windows != ambiguous windows counted by the pack kernel; bit 2: key not found.
+__global__ void __launch_bounds__(256)
+frag_slots_kernel(const uint64_t *__restrict__ skey, const unsigned long long *__restrict__ off, uint64_t F,
+                  const uint64_t *__restrict__ keys_sorted, uint64_t n, const unsigned int *__restrict__ descent,
+                  const unsigned long long *__restrict__ n_amb_expected, unsigned long long *__restrict__ slot0,
+                  int *__restrict__ err)
+{
+    if (*descent) return;   // the keys are not fully sorted: the caller takes the element-wise path instead
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0 && n_amb_expected && off[F] != *n_amb_expected) atomicOr(err, 2);
+    for (uint64_t q = tid; q < F; q += stride) {
+        const uint64_t kf = skey[q];
+        const uint64_t g = lower_bound_u64(skey, F, kf);
+        const uint64_t lb = lower_bound_u64(keys_sorted, n, kf);
+        if (lb >= n || keys_sorted[lb] != kf) atomicOr(err, 4);
+        slot0[q] = lb + (off[q] - off[g]);
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+frag_expand_kernel(const uint64_t *__restrict__ sstart, const unsigned long long *__restrict__ off,
+                   const unsigned long long *__restrict__ slot0, const uint8_t *__restrict__ whead, uint64_t F,
+                   uint64_t n, const unsigned int *__restrict__ descent, const int *__restrict__ err,
+                   IdxT *__restrict__ d_idx, uint8_t *__restrict__ d_flags)
+{
+    if (*descent || (*err & 6)) return;
+    const uint64_t m = off[F];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += stride) {
+        uint64_t lo = 0, hi = F;  // last fragment whose offset is <= o
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (o < off[mid]) hi = mid; else lo = mid + 1;
+        }
+        const uint64_t q = lo - 1;
+        const uint64_t i = o - off[q];
+        const uint64_t slot = slot0[q] + i;
+        if (slot < n) {
+            d_idx[slot] = (IdxT)(sstart[q] + i);
+            d_flags[slot] = kFlagAmb | ((i == 0 && whead[q]) ? kFlagHead : 0);
+        }
+    }
+}
+
+// Order F fragments by (key, w0, w1, start); stable LSD, least significant word first.  Only small sorts:
+// no synchronise (the look-back error word of larger lists is the caller's deferred one).
+int frag_sort_device(const FragOut &frag, uint64_t F, uint32_t key_len, int key_bits, int start_bits,
+                     FragSorted &out, cudaStream_t st)
+{
+    out.F = F;
+    if (F == 0) return GK_OK;
+    const size_t pad = (size_t)((F + 1) & ~1ull);  // (16-byte aligned key buffers)
+    GK_TRY(out.skey_a.alloc(pad * 8, st));
+    GK_TRY(out.skey_b.alloc(pad * 8, st));
+    GK_TRY(out.perm_a.alloc(pad * 4, st));
+    GK_TRY(out.perm_b.alloc(pad * 4, st));
+    GK_TRY(out.sstart.alloc((size_t)F * 8, st));
+    GK_TRY(out.off.alloc((size_t)(F + 1) * 8, st));
+    GK_TRY(out.whead.alloc((size_t)F, st));
+    GK_TRY(out.slot0.alloc((size_t)F * 8, st));
+    const int grid = frag_grid(F);
+    frag_iota_kernel<<<grid, 256, 0, st>>>(out.perm_a.as<uint32_t>(), F);
+    GK_LAUNCH_CHECK();
+    uint32_t *cur = out.perm_a.as<uint32_t>(), *alt = out.perm_b.as<uint32_t>();
+    uint64_t *ka = out.skey_a.as<uint64_t>(), *kb = out.skey_b.as<uint64_t>();
+    const uint64_t *sorted_word = ka;
+    auto sort_word = [&](const uint64_t *word, int begin_bit, int end_bit) -> int {
+        frag_gather_kernel<<<grid, 256, 0, st>>>(word, cur, F, ka);
+        GK_LAUNCH_CHECK();
+        int alt_has = 0;
+        if (F > 1)
+            GK_TRY(radix_sort_pairs_device(ka, kb, cur, alt, 4, F, begin_bit, end_bit, &alt_has, st, nullptr));
+        if (alt_has) { uint32_t *t = cur; cur = alt; alt = t; }
+        sorted_word = alt_has ? kb : ka;
+        return GK_OK;
+    };
+    GK_TRY(sort_word(frag.start, 0, start_bits));
+    if (key_len > 16) GK_TRY(sort_word(frag.w1, 64 - 4 * ((int)key_len - 16), 64));
+    GK_TRY(sort_word(frag.w0, 64 - 4 * ((int)key_len < 16 ? (int)key_len : 16), 64));
+    GK_TRY(sort_word(frag.key, 0, key_bits));
+    out.skey = sorted_word;
+    frag_finish_kernel<<<grid, 256, 0, st>>>(out.skey, frag.w0, frag.w1, frag.start, frag.count, cur, F,
+                                             out.sstart.as<uint64_t>(), out.off.as<unsigned long long>(),
+                                             out.whead.as<uint8_t>());
+    GK_LAUNCH_CHECK();
+    frag_scan_kernel<<<1, 1024, 0, st>>>(out.off.as<unsigned long long>(), F);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// Write the fragments into the ambiguous slots of the sorted order.  keys_sorted: the fully sorted radix keys
+// (the kernels do nothing when *d_descent != 0: the caller then repairs the order element-wise).
+// d_err (device int): bits 2/4 are set on inconsistency and make the caller fall back as well.
+int frag_expand_device(FragSorted &fs, const uint64_t *keys_sorted, uint64_t n, int idx_bytes, void *d_idx,
+                       uint8_t *d_flags, const unsigned int *d_descent, const unsigned long long *d_n_amb_expected,
+                       uint64_t n_amb_host, int *d_err, cudaStream_t st)
+{
+    if (fs.F == 0) return GK_OK;
+    frag_slots_kernel<<<frag_grid(fs.F), 256, 0, st>>>(fs.skey, fs.off.as<unsigned long long>(), fs.F, keys_sorted,
+                                                       n, d_descent, d_n_amb_expected,
+                                                       fs.slot0.as<unsigned long long>(), d_err);
+    GK_LAUNCH_CHECK();
+    const int grid = frag_grid(n_amb_host ? n_amb_host : 1);
+    if (idx_bytes == 4)
+        frag_expand_kernel<uint32_t><<<grid, 256, 0, st>>>(fs.sstart.as<uint64_t>(), fs.off.as<unsigned long long>(),
+                                                           fs.slot0.as<unsigned long long>(), fs.whead.as<uint8_t>(),
+                                                           fs.F, n, d_descent, d_err, (uint32_t *)d_idx, d_flags);
+    else
+        frag_expand_kernel<uint64_t><<<grid, 256, 0, st>>>(fs.sstart.as<uint64_t>(), fs.off.as<unsigned long long>(),
+                                                           fs.slot0.as<unsigned long long>(), fs.whead.as<uint8_t>(),
+                                                           fs.F, n, d_descent, d_err, (uint64_t *)d_idx, d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+}  // namespace gk

@@ -20,7 +20,19 @@ int kmer_count_host(const uint64_t *, uint32_t, uint64_t, uint32_t, uint64_t *);
 int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, void *, cudaStream_t);
 int pack_keys_device(const uint8_t *, uint64_t, const uint64_t *, uint32_t, uint32_t, uint32_t, int,
                      uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *, int, int,
-                     unsigned long long *, cudaStream_t);
+                     unsigned long long *, cudaStream_t, const FragOut *);
+int pack_keys_list_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, int, uint64_t *,
+                          unsigned long long *, cudaStream_t);
+int widen_indices_device(const void *, int, uint64_t, uint64_t *, cudaStream_t);
+int check_starts_device(const void *, int, uint64_t, const uint64_t *, uint32_t, uint64_t, uint32_t,
+                        unsigned long long *, cudaStream_t);
+int scan_alphabet_async(const uint8_t *, uint64_t, unsigned long long *, cudaStream_t);
+int verify_order_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const uint64_t *, uint32_t,
+                        uint32_t, const uint8_t *, uint64_t *, cudaStream_t);
+struct FragSorted;
+int frag_sort_device(const FragOut &, uint64_t, uint32_t, int, int, FragSorted &, cudaStream_t);
+int frag_expand_device(FragSorted &, const uint64_t *, uint64_t, int, void *, uint8_t *, const unsigned int *,
+                       const unsigned long long *, uint64_t, int *, cudaStream_t);
 int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
                             cudaStream_t);
 int gather2_u64_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, cudaStream_t);
@@ -30,7 +42,8 @@ int subset_expand_device(const void *, const void *, const uint64_t *, const uin
                          const void *, const void *, const unsigned long long *, uint64_t, uint64_t, int, int,
                          void *, uint8_t *, cudaStream_t);
 int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, int *,
-                            cudaStream_t, SortTiming *, const unsigned long long *d_pre_hist = nullptr);
+                            cudaStream_t, SortTiming *, const unsigned long long *d_pre_hist = nullptr,
+                            void *d_vals_final = nullptr);
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
 int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *,
                          unsigned long long *, cudaStream_t);
@@ -107,14 +120,14 @@ struct Owned {
 };
 
 struct EventTimer {
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[16];
     int n = 0;
     cudaStream_t st;
     explicit EventTimer(cudaStream_t s) : st(s) {}
     ~EventTimer() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
     int mark()
     {
-        if (n >= 8) return n - 1;
+        if (n >= 16) return n - 1;
         if (cudaEventCreate(&ev[n]) != cudaSuccess) return -1;
         cudaEventRecord(ev[n], st);
         return n++;
@@ -142,6 +155,7 @@ struct gk_index {
     uint64_t n = 0;
     Owned d_idx;                        // start indices (init order until sorted)
     bool idx_ready = false;
+    bool user_idx = false;              // d_idx was assigned by the caller (gk_index_set_indices)
     bool sorted = false;
     Owned d_flags;                      // head/amb flags of the sorted order for flags_kmer_len
     bool flags_valid = false;
@@ -176,11 +190,38 @@ static int ensure_indices(gk_index *ix, cudaStream_t st)
 // Stage timing marks of one sort; turned into milliseconds after the final synchronise.
 struct StageMarks {
     int pack0 = -1, pack1 = -1, fix0 = -1, fix1 = -1;
-    SortTiming main_sort = {0.f, 0.f, 0};
+    SortTiming main_sort;
     uint64_t n_amb = 0;
+    uint64_t n_frag = 0;
     int key_bits = 0;
     int levels = 1;
 };
+
+// A second stream for work that does not depend on the main sort (reading back the pack kernel's counters,
+// sorting the fragment list): one per host thread and device, created on first use.
+static int side_stream(cudaStream_t *out)
+{
+    static thread_local cudaStream_t streams[64] = {nullptr};
+    int dev = 0;
+    GK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return GK_ERR_ARG; }
+    if (!streams[dev]) GK_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    *out = streams[dev];
+    return GK_OK;
+}
+
+struct ScopedEvent {
+    cudaEvent_t ev = nullptr;
+    ~ScopedEvent() { if (ev) cudaEventDestroy(ev); }
+    int create() { GK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); return GK_OK; }
+};
+
+static bool fragments_enabled()
+{
+    const char *e = getenv("GK_FRAGMENTS");
+    return !(e && e[0] == '0');
+}
+constexpr uint64_t kFragCapacity = 1ull << 21;  // fragments listed by the pack kernel; beyond: element-wise path
 
 // First key bit the LSD passes of the main sort cover.  0 = plain LSD over the whole key.  Otherwise only
 // the top 8*ceil((log2(n)+4)/8) bits are sorted -- 16 times more prefix buckets than k-mers, so about one
@@ -319,57 +360,121 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
 }
 
 // Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
-// Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags.
-static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, bool has_amb, uint64_t n,
-                       Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm,
-                       cudaStream_t st)
+// Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags; synchronises once, at
+// the end.  d_alpha (optional): the three alphabet counters of a scan that is still in flight on `st`; they
+// come back with the other counters (h_alpha).  d_list != nullptr: sort these starts (ascending, n of them)
+// instead of every window of the byte array.
+//
+// Stream plan (nothing on the main stream ever waits for the host):
+//   main   pack (+ fragment list) | E1 | histogram scan, radix passes, tie repair + flags | wait E2 | expand
+//   side   wait E1 | counters -> host | fragment sort | E2
+// The host blocks on the side stream only: that copy completes when the pack kernel does, milliseconds
+// before the main stream runs dry, and tells how many fragments there are to sort.
+static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int class_bit, uint64_t n,
+                       Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm, cudaStream_t st,
+                       unsigned long long *d_alpha, unsigned long long *h_alpha, const void *d_list = nullptr)
 {
     const int ib = ix->idx_bytes;
-    const int class_bit = has_amb ? 1 : 0;
     // value <= 4^key_len needs 2*key_len+1 bits when ambiguous windows exist, plus the class bit
     const int key_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
     marks.key_bits = key_bits;
+    const bool terminated = valid_len < key_len;
 
-    DeviceBuffer keys_a, keys_b, n_amb_dev, pre_hist;
+    DeviceBuffer keys_a, keys_b, counters, pre_hist, frag_mem;
     Owned idx_b;
     GK_TRY(keys_a.alloc((size_t)n * 8, st));
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
     GK_TRY(idx_b.alloc((size_t)n * ib, st));
     GK_TRY(out_idx.alloc((size_t)n * ib, st));
-    GK_TRY(n_amb_dev.alloc(16, st));
-    GK_CUDA(cudaMemsetAsync(n_amb_dev.ptr, 0, 16, st));
+    // device counters: [0] ambiguous windows, [1] descent (u32), [2] fragments, [3] fragment error bits (int)
+    GK_TRY(counters.alloc(32, st));
+    GK_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, st));
+    unsigned long long *d_counters = counters.as<unsigned long long>();
+    unsigned int *d_descent = reinterpret_cast<unsigned int *>(d_counters + 1);
+    int *d_frag_err = reinterpret_cast<int *>(d_counters + 3);
     // the pack kernel counts the digits of the radix passes while it writes the keys
     const int begin_bit = prefix_begin_bit(n, key_bits);
     GK_TRY(pre_hist.alloc(8 * 256 * sizeof(unsigned long long), st));
     GK_CUDA(cudaMemsetAsync(pre_hist.ptr, 0, pre_hist.bytes, st));
+    // fragment list of the ambiguous windows (not for an arbitrary list of starts: no neighbours there)
+    FragOut frag;
+    const bool want_frag = class_bit && !d_list && fragments_enabled();
+    if (want_frag) {
+        const uint64_t cap = n < kFragCapacity ? n : kFragCapacity;
+        GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
+        uint64_t *base = frag_mem.as<uint64_t>();
+        frag.key = base; frag.w0 = base + cap; frag.w1 = base + 2 * cap; frag.start = base + 3 * cap;
+        frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
+        frag.counter = d_counters + 2;
+        frag.capacity = cap;
+    }
 
     marks.pack0 = tm.mark();
-    GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
-                            (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
-                            keys_a.as<uint64_t>(), ib, out_idx.ptr, n_amb_dev.as<unsigned long long>(),
-                            begin_bit, key_bits, pre_hist.as<unsigned long long>(), st));
+    if (d_list) {
+        GK_CUDA(cudaMemcpyAsync(out_idx.ptr, d_list, (size_t)n * ib, cudaMemcpyDeviceToDevice, st));
+        GK_TRY(pack_keys_list_device(ix->d_sba, ix->sba_len, d_list, ib, n, key_len, class_bit,
+                                     keys_a.as<uint64_t>(), d_counters, st));
+    } else {
+        GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
+                                (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
+                                keys_a.as<uint64_t>(), ib, out_idx.ptr, d_counters, begin_bit, key_bits,
+                                pre_hist.as<unsigned long long>(), st, want_frag ? &frag : nullptr));
+    }
     marks.pack1 = tm.mark();
+    ScopedEvent e_pack, e_frag;
+    GK_TRY(e_pack.create());
+    GK_TRY(e_frag.create());
+    GK_CUDA(cudaEventRecord(e_pack.ev, st));
+
     int in_alt = 0;
     GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
-    unsigned long long *d_counters = n_amb_dev.as<unsigned long long>();  // [0] ambiguous windows, [1] descent
     GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
-                               key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt,
-                               reinterpret_cast<unsigned int *>(d_counters + 1), &marks.main_sort, st,
-                               pre_hist.as<unsigned long long>()));
+                               key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt, d_descent,
+                               &marks.main_sort, st, d_list ? nullptr : pre_hist.as<unsigned long long>()));
     const uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
     if (in_alt) out_idx.swap(idx_b);
-    idx_b.reset();
 
-    unsigned long long h_counters[2] = {0, 0};
-    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaStreamSynchronize(st));
-    const uint64_t n_amb = h_counters[0];
+    // ---- side stream: the pack kernel's counters, then the fragment sort -------------------------------------
+    cudaStream_t side = nullptr;
+    GK_TRY(side_stream(&side));
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    GK_CUDA(cudaStreamWaitEvent(side, e_pack.ev, 0));
+    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, side));
+    GK_CUDA(cudaStreamSynchronize(side));
+    const uint64_t n_amb = h_counters[0], n_frag = h_counters[2];
     marks.n_amb = n_amb;
-
+    marks.n_frag = n_frag;
+    const bool use_frag = want_frag && n_amb > 0 && n_frag > 0 && n_frag <= frag.capacity;
+    FragSorted fs;
     marks.fix0 = tm.mark();
-    GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
-                         n_amb, (h_counters[1] & 0xffffffffull) != 0, valid_len < key_len, st));
+    if (use_frag) {
+        int start_bits = 1;
+        while (start_bits < 64 && (ix->sba_len >> start_bits)) ++start_bits;
+        GK_TRY(frag_sort_device(frag, n_frag, key_len, key_bits, start_bits, fs, side));
+        GK_CUDA(cudaEventRecord(e_frag.ev, side));
+        GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
+        GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr, d_descent,
+                                  d_counters, n_amb, d_frag_err, st));
+        fs.rebind(st);
+    }
     marks.fix1 = tm.mark();
+
+    // ---- the one synchronise: descent word, fragment check, alphabet counters ---------------------------------
+    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
+    if (d_alpha) GK_CUDA(cudaMemcpyAsync(h_alpha, d_alpha, 24, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    const bool descent = (h_counters[1] & 0xffffffffull) != 0;
+    const int frag_err = (int)(h_counters[3] & 0xffffffffull);
+    if (descent || (n_amb > 0 && (!use_frag || frag_err))) {
+        // element-wise repair (gk_refine.cu): a long prefix run is out of order (repeat-rich input), or the
+        // fragment list was not available
+        const int f0 = tm.mark();
+        GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
+                             n_amb, descent, terminated, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        marks.fix0 = f0;
+        marks.fix1 = tm.mark();
+    }
     return GK_OK;
 }
 
@@ -558,9 +663,50 @@ int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_by
     GK_CUDA(cudaStreamSynchronize(st));
     ix->n = n;
     ix->idx_ready = true;
+    ix->user_idx = true;
     ix->sorted = sorted != 0;
     ix->flags_valid = false;
     ix->flags_mark_amb = false;
+    return GK_OK;
+}
+
+// Start indices assigned by the caller (gk_index_set_indices): order them by value, check that every one
+// starts a k-mer of at least min_kmer_len symbols (the reference's sort raises through its validation
+// otherwise, kmers.py:1716-1727), and tell whether they are exactly the full set of the index.
+static int prepare_user_indices(gk_index *ix, Owned &list, bool *is_full_set, cudaStream_t st)
+{
+    const int ib = ix->idx_bytes;
+    const uint64_t n = ix->n;
+    *is_full_set = false;
+    uint64_t n_full = 0;
+    GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, ix->min_len, &n_full));
+    DeviceBuffer keys_a, keys_b, vals_b, report;
+    const size_t pad = (size_t)((n + 1) & ~1ull);
+    GK_TRY(keys_a.alloc(pad * 8, st));
+    GK_TRY(keys_b.alloc(pad * 8, st));
+    GK_TRY(vals_b.alloc((size_t)n * ib, st));
+    GK_TRY(list.alloc((size_t)n * ib, st));
+    GK_CUDA(cudaMemcpyAsync(list.ptr, ix->d_idx.ptr, (size_t)n * ib, cudaMemcpyDeviceToDevice, st));
+    GK_TRY(widen_indices_device(list.ptr, ib, n, keys_a.as<uint64_t>(), st));
+    int bits = 1;
+    while (bits < 64 && (ix->sba_len >> bits)) ++bits;
+    int in_alt = 0;
+    GK_TRY(radix_sort_pairs_device(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), list.ptr, vals_b.ptr, ib, n, 0,
+                                   ib == 4 ? (bits < 32 ? bits : 32) : 64, &in_alt, st, nullptr));
+    if (in_alt) GK_CUDA(cudaMemcpyAsync(list.ptr, vals_b.ptr, (size_t)n * ib, cudaMemcpyDeviceToDevice, st));
+    GK_TRY(report.alloc(16, st));
+    GK_CUDA(cudaMemsetAsync(report.ptr, 0, 16, st));
+    GK_TRY(check_starts_device(list.ptr, ib, n, (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
+                               ix->sba_len, ix->min_len, report.as<unsigned long long>(), st));
+    unsigned long long h_report[2] = {0, 0};  // [0] starts that begin no k-mer of min_len symbols, [1] not ascending
+    GK_CUDA(cudaMemcpyAsync(h_report, report.ptr, 16, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (h_report[0]) {
+        set_error("kmers compared were less than min_kmer_len (%u).  Was kmer_sba_start_indices "
+                  "initialized correctly?", ix->min_len);
+        return GK_ERR_INVALID_KMERS;
+    }
+    *is_full_set = (n == n_full && h_report[1] == 0);
     return GK_OK;
 }
 
@@ -574,7 +720,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     EventTimer tm(st);
     StageMarks marks;
     const int t0 = tm.mark();
-    // one device error word for every small sort of this call, checked once at the end
+    // one device error word for every sort of this call, checked once at the end
     DeviceBuffer sort_err;
     GK_TRY(sort_err.alloc(4, st));
     GK_CUDA(cudaMemsetAsync(sort_err.ptr, 0, 4, st));
@@ -583,41 +729,77 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         ~ErrWordGuard() { set_deferred_sort_error_word(nullptr); }
     } err_guard(sort_err.as<int>());
 
-    GK_TRY(ensure_alphabet(ix, st));
-    if (ix->n_sep != ix->h_segs.size() - 1) {
-        // a '$' inside a record: the reference's sort raises through its validation
-        set_error("kmers compared were less than min_kmer_len (%u).  Was kmer_sba_start_indices "
-                  "initialized correctly?", ix->min_len);
-        return GK_ERR_INVALID_KMERS;
-    }
     const bool fixed = ix->max_len != 0 && ix->max_len == ix->min_len;
-    const bool has_amb = ix->n_amb_letters > 0 || ix->n_bad > 0;
     const uint32_t k = ix->min_len;
-    stats.n_windows = ix->n;
-    int t_ref0 = -1, t_ref1 = -1;
     const uint32_t max_len = ix->max_len;  // 0 = None
-    if (ix->n == 0) {
-        ix->sorted = true;
-    } else if (fixed && (k <= 31 || (k == 32 && !has_amb))) {
-        GK_TRY(sort_level1(ix, k, k, has_amb, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
-        ix->flags_mark_amb = true;
-    } else if (!fixed && max_len != 0 && max_len <= 31) {
-        // Variable-length mode inside one key word: compare up to max_kmer_len symbols, a window that reaches
-        // its record's '$' first sorts first (kmers.py:360-378).  '$' is one more non-ACGT symbol for the
-        // two-class keys.
-        ix->flags_mark_amb = false;
-        GK_TRY(sort_level1(ix, ix->min_len, max_len, true, ix->n, ix->d_idx, ix->d_flags, marks, tm, st));
+    // Modes that fit one key word always carry the class bit, so nothing has to wait for the alphabet scan:
+    // it runs at the head of the stream and its counters come back with the sort's own.
+    const bool one_word = (fixed && k <= 31) || (!fixed && max_len != 0 && max_len <= 31);
+    DeviceBuffer alpha;
+    unsigned long long h_alpha[3] = {0, 0, 0};
+    const bool alpha_async = one_word && !ix->alphabet_known;
+    if (alpha_async) {
+        GK_TRY(alpha.alloc(24, st));
+        GK_TRY(scan_alphabet_async(ix->d_sba, ix->sba_len, alpha.as<unsigned long long>(), st));
+    } else {
+        GK_TRY(ensure_alphabet(ix, st));
+    }
+    auto check_separators = [&]() -> int {
+        if (ix->n_sep != ix->h_segs.size() - 1) {
+            // a '$' inside a record: the reference's sort raises through its validation
+            set_error("kmers compared were less than min_kmer_len (%u).  Was kmer_sba_start_indices "
+                      "initialized correctly?", ix->min_len);
+            return GK_ERR_INVALID_KMERS;
+        }
+        return GK_OK;
+    };
+    if (!alpha_async) GK_TRY(check_separators());
+
+    // start indices assigned by the caller: the reference sorts whatever the array holds (kmers.py:1648)
+    Owned user_list;
+    bool subset = false;
+    if (ix->user_idx && ix->n > 0) {
+        bool full = false;
+        GK_TRY(prepare_user_indices(ix, user_list, &full, st));
+        subset = !full;
+    }
+    uint64_t n_sort = ix->n;
+    if (ix->user_idx && !subset)   // the full set (or an empty array): sort every window of the byte array
+        GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, ix->min_len, &n_sort));
+    if (ix->user_idx && ix->n == 0) n_sort = 0;
+    stats.n_windows = n_sort;
+
+    // the new order is built in local buffers and adopted only when everything has succeeded
+    Owned new_idx, new_flags;
+    bool new_mark_amb = false;
+    int t_ref0 = -1, t_ref1 = -1;
+    if (n_sort == 0) {
+        // nothing to sort
+    } else if (one_word) {
+        const uint32_t key_len = fixed ? k : max_len;
+        new_mark_amb = fixed;
+        GK_TRY(sort_level1(ix, k, key_len, 1, n_sort, new_idx, new_flags, marks, tm, st,
+                           alpha_async ? alpha.as<unsigned long long>() : nullptr, h_alpha,
+                           subset ? user_list.ptr : nullptr));
+    } else if (fixed && k == 32 && ix->n_amb_letters == 0 && ix->n_bad == 0) {
+        new_mark_amb = true;
+        GK_TRY(sort_level1(ix, k, k, 0, n_sort, new_idx, new_flags, marks, tm, st, nullptr, nullptr,
+                           subset ? user_list.ptr : nullptr));
     } else {
         // Longer than one key word -- fixed k > 32, max_kmer_len > 31, or None (suffix order inside each
         // record).  Sort EVERY start of every record by its first 31 symbols, terminator-aware, so that
         // every position has a rank; double the compared length until the target is covered or nothing is
         // tied any more; finally drop the windows shorter than min_kmer_len.
+        if (subset) {
+            set_error("sorting an assigned subset of start indices is available for k-mers of one key word "
+                      "(max_kmer_len <= 31) only");
+            return GK_ERR_UNSUPPORTED;
+        }
         if (ix->idx_bytes != 4) {
             set_error("k-mers longer than one key word on a byte array of 2^32 or more positions are not "
                       "available yet");
             return GK_ERR_UNSUPPORTED;
         }
-        ix->flags_mark_amb = false;
         uint64_t longest = 0;
         for (size_t r = 0; r < ix->h_segs.size(); ++r) {
             const uint64_t e = (r + 1 < ix->h_segs.size()) ? ix->h_segs[r + 1] - 1 : ix->sba_len;
@@ -626,32 +808,45 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         const uint64_t target = (max_len != 0 && max_len < longest) ? max_len : longest;
         uint64_t n_cur = 0;
         GK_TRY(kmer_count_host(ix->h_segs.data(), (uint32_t)ix->h_segs.size(), ix->sba_len, 1, &n_cur));
-        Owned cur_idx, cur_flags;
-        GK_TRY(sort_level1(ix, 1, 31, true, n_cur, cur_idx, cur_flags, marks, tm, st));
+        GK_TRY(sort_level1(ix, 1, 31, 1, n_cur, new_idx, new_flags, marks, tm, st, nullptr, nullptr));
         t_ref0 = tm.mark();
-        GK_TRY(doubling_rounds(ix, cur_idx, cur_flags, n_cur, 31, target, &marks.levels, st));
-        if (ix->min_len > 1) GK_TRY(drop_short_windows(ix, ix->min_len, cur_idx, cur_flags, n_cur, st));
+        GK_TRY(doubling_rounds(ix, new_idx, new_flags, n_cur, 31, target, &marks.levels, st));
+        if (ix->min_len > 1) GK_TRY(drop_short_windows(ix, ix->min_len, new_idx, new_flags, n_cur, st));
         t_ref1 = tm.mark();
-        if (n_cur != ix->n) {
+        if (n_cur != n_sort) {
             set_error("doubling kept %llu windows, expected %llu", (unsigned long long)n_cur,
-                      (unsigned long long)ix->n);
+                      (unsigned long long)n_sort);
             return GK_ERR_INTERNAL;
         }
-        ix->d_idx.swap(cur_idx);
-        ix->d_flags.swap(cur_flags);
     }
-    ix->idx_ready = true;
-    ix->flags_valid = ix->n > 0;
-    ix->flags_kmer_len = fixed ? k : ix->max_len;  // (None -> 0: such queries take the comparator path)
-    ix->sorted = true;
     const int t1 = tm.mark();
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    marks.main_sort.resolve();
     if (h_sort_err) {
         set_error("radix sort: decoupled look-back timed out");
         return GK_ERR_INTERNAL;
     }
+    if (alpha_async) {
+        ix->n_bad = h_alpha[0];
+        ix->n_sep = h_alpha[1];
+        ix->n_amb_letters = h_alpha[2];
+        ix->alphabet_known = true;
+        GK_TRY(check_separators());   // (the index keeps its previous order)
+    }
+    // adopt the result
+    if (n_sort > 0) {
+        ix->d_idx.swap(new_idx);
+        ix->d_flags.swap(new_flags);
+    }
+    ix->n = n_sort;
+    ix->user_idx = subset;
+    ix->idx_ready = true;
+    ix->flags_mark_amb = new_mark_amb;
+    ix->flags_valid = n_sort > 0;
+    ix->flags_kmer_len = fixed ? k : ix->max_len;  // (None -> 0: such queries take the comparator path)
+    ix->sorted = true;
     stats.pack_ms = tm.ms(marks.pack0, marks.pack1);
     stats.hist_ms = marks.main_sort.hist_ms;
     stats.sort_ms = marks.main_sort.passes_ms;
@@ -660,6 +855,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     stats.key_bits = marks.key_bits;
     stats.levels = marks.levels;
     stats.n_ambiguous = marks.n_amb;
+    stats.n_fragments = marks.n_frag;
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;
@@ -690,7 +886,7 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     const int t0 = tm.mark();
     const int ib = ix->idx_bytes;
     const int key_bits = 2 * (int)k + (class_bit ? 2 : 0);
-    SortTiming timing = {0.f, 0.f, 0};
+    SortTiming timing;
     int in_alt = 0;
     ix->n = n_local;
     GK_TRY(ix->d_idx.alloc((size_t)n_local * ib, st));
@@ -959,6 +1155,17 @@ int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *f
                 h_sizes_out[g] = ((g + 1 < n_groups) ? h_offsets_out[g + 1] : m) - h_offsets_out[g];
     }
     return GK_OK;
+}
+
+int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, void *stream)
+{
+    if (!ix || !h_report8) return GK_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_indices(ix, st));
+    const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
+    return verify_order_device(ix->d_sba, ix->sba_len, ix->d_idx.ptr, ix->idx_bytes, ix->n, kmer_len,
+                               (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->min_len,
+                               cached ? (const uint8_t *)ix->d_flags.ptr : nullptr, h_report8, st);
 }
 
 int gk_sort_count_host(const uint8_t *h_sba, uint64_t sba_len, const uint64_t *h_seg_starts,

@@ -38,12 +38,14 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                  uint32_t key_len, int class_bit, uint64_t first_start, uint64_t end_start,
                  uint64_t out_base, uint64_t *__restrict__ keys_out, IdxT *__restrict__ idx_out,
                  unsigned long long *__restrict__ n_amb_out, uint64_t n_tiles, int hist_begin_bit,
-                 int hist_end_bit, unsigned long long *__restrict__ g_hist /* [passes][256] or null */)
+                 int hist_end_bit, unsigned long long *__restrict__ g_hist /* [passes][256] or null */,
+                 const FragOut frag /* frag.key == nullptr: no fragment list */)
 {
     __shared__ __align__(16) uint8_t s_bytes[kPackChunks * 16];
     __shared__ uint32_t s_codes[kPackChunks];
     __shared__ __align__(4) uint16_t s_amb[kPackChunks + 2];
     __shared__ __align__(4) uint16_t s_sep[kPackChunks + 2];
+    __shared__ __align__(4) uint16_t s_ne[kPackChunks + 2];  // bit i: byte i differs from byte i + 1
     __shared__ uint32_t s_sep_pre[kPackChunks / 2 + 2];
     __shared__ uint32_t s_valid[kPackTile / 32];  // bit b of word w: a window may start at 32w + b
     __shared__ uint32_t s_seg0;
@@ -59,6 +61,7 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // tiles are aligned to the byte array, not to first_start, so 128-bit loads stay aligned
     const uint64_t tile0 = (first_start / kPackTile + tile) * (uint64_t)kPackTile;
+    uint32_t any_amb = 0;
 
     // ---- stage bytes, convert to streams ----------------------------------------------------
     const bool aligned = (reinterpret_cast<uintptr_t>(sba) & 15u) == 0;
@@ -93,10 +96,29 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
         s_codes[c] = codes;
         s_amb[c] = (uint16_t)amb;
         s_sep[c] = (uint16_t)sep;
+        any_amb |= amb;   // ('$' included: a terminated window is a non-ACGT window too)
     }
-    if (t < 2) { s_amb[kPackChunks + t] = 0xFFFFu; s_sep[kPackChunks + t] = 0xFFFFu; }
+    if (t < 2) { s_amb[kPackChunks + t] = 0xFFFFu; s_sep[kPackChunks + t] = 0xFFFFu; s_ne[kPackChunks + t] = 0xFFFFu; }
     if (t == 0) s_seg0 = upper_seg(seg_starts, n_seg, tile0 < sba_len ? tile0 : sba_len - 1);
-    __syncthreads();
+    // (barrier + vote) does this tile hold any non-ACGT symbol besides '$'?  Nearly all tiles do not.
+    const bool tile_frags = __syncthreads_or((int)any_amb) != 0 && frag.key != nullptr;
+    if (tile_frags) {
+        // "next byte differs" bits: a window equals the window one position to its left iff its key_len + 1
+        // bytes from that position on are all the same symbol
+        for (uint32_t c = t; c < kPackChunks; c += kPackThreads) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(s_bytes + 16 * c);
+            const uint32_t nxt = (c + 1 < kPackChunks) ? (uint32_t)s_bytes[16 * c + 16] : 0x100u;  // unknown: differs
+            const uint32_t w[5] = {q.x, q.y, q.z, q.w, nxt};
+            uint32_t ne = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t a = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                const uint32_t b = (i == 15) ? nxt : ((w[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xFFu);
+                ne |= (a != b ? 1u : 0u) << i;
+            }
+            s_ne[c] = (uint16_t)ne;
+        }
+    }
 
     // exclusive prefix of '$' counts per 32-position word (one warp, kPackChunks/2 words)
     const uint32_t *amb32 = reinterpret_cast<const uint32_t *>(s_amb);
@@ -186,6 +208,47 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
         const uint64_t pos = tile_pos0 + q - (uint64_t)valid_len * seg_rel;
         keys_out[pos] = key;
         idx_out[pos] = (IdxT)i;
+        if (!pure && tile_frags) {
+            // head of a block of identical windows?  (the window at q - 1 must be one this launch emits too)
+            const uint32_t *ne32 = reinterpret_cast<const uint32_t *>(s_ne);
+            bool cont = false;
+            if (q > q_lo) {
+                const uint32_t u = q - 1;
+                const uint64_t ne64 = (((uint64_t)ne32[(u >> 5) + 1] << 32) | ne32[u >> 5]) >> (u & 31u);
+                cont = (ne64 & key_mask) == 0;
+            }
+            if (!cont) {
+                // the block runs until the first differing byte pair at p*: windows q .. p* - key_len + 1
+                uint32_t word = q >> 5;
+                uint32_t bits = ne32[word] & ~((1u << (q & 31u)) - 1u);
+                while (bits == 0) bits = ne32[++word];   // (the pad words are all ones)
+                const int p_star = (int)(word * 32u + (uint32_t)__ffs((int)bits) - 1u);
+                int cnt = p_star - (int)q - (int)key_len + 2;
+                if (cnt < 1) cnt = 1;
+                if (cnt > (int)(q_hi - q)) cnt = (int)(q_hi - q);
+                if (valid_len > key_len) {  // identical key prefixes, but the record may end first
+                    const uint32_t seg = seg0 + seg_rel;
+                    const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;
+                    const uint64_t left = seg_end - valid_len - i + 1;   // valid starts from i on
+                    if ((uint64_t)cnt > left) cnt = (int)left;
+                }
+                uint64_t w0 = 0, w1 = 0;
+                for (uint32_t j = 0; j < key_len; ++j) {
+                    const uint64_t code = rank4(s_bytes[q + j]);
+                    if (code == 0) break;   // '$' / end of array: the k-mer ends here (kmers.py:360-378)
+                    if (j < 16) w0 |= code << (4u * (15u - j));
+                    else w1 |= code << (4u * (31u - j));
+                }
+                const unsigned long long slot = atomicAdd(frag.counter, 1ull);
+                if (slot < frag.capacity) {
+                    frag.key[slot] = key;
+                    frag.w0[slot] = w0;
+                    frag.w1[slot] = w1;
+                    frag.start[slot] = i;
+                    frag.count[slot] = (uint32_t)cnt;
+                }
+            }
+        }
         // HP >= 0: the number of counted digit positions is a compile-time constant (no branches)
 #pragma unroll
         for (int p = 0; p < kPackHistPasses; ++p) {
@@ -351,7 +414,7 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
                      uint64_t first_start, uint64_t end_start, uint64_t out_base,
                      uint64_t *d_keys_out, int idx_bytes, void *d_idx_out,
                      unsigned long long *d_n_amb, int hist_begin_bit, int hist_end_bit,
-                     unsigned long long *d_hist, cudaStream_t st)
+                     unsigned long long *d_hist, cudaStream_t st, const FragOut *frag)
 {
     // valid_len < key_len is the variable-length mode: windows shorter than the key end at their record's
     // '$', which the key treats like any other non-ACGT symbol (it sorts below A); needs the class bit
@@ -374,10 +437,11 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
     uint64_t grid = (uint64_t)sm_count() * 8;
     if (grid > n_tiles) grid = n_tiles;
     const int hp = d_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
+    const FragOut fr = frag ? *frag : FragOut();
 #define GK_PACK_LAUNCH(IDX, HPV)                                                                       \
     pack_keys_kernel<IDX, HPV><<<(unsigned)grid, kPackThreads, 0, st>>>(                               \
         d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start, end_start,   \
-        out_base, d_keys_out, (IDX *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit, hist_end_bit, d_hist)
+        out_base, d_keys_out, (IDX *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit, hist_end_bit, d_hist, fr)
     if (idx_bytes == 4) {
         if (hp == 0) GK_PACK_LAUNCH(uint32_t, 0);
         else if (hp == 4) GK_PACK_LAUNCH(uint32_t, 4);
@@ -390,6 +454,131 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
         else GK_PACK_LAUNCH(uint64_t, -1);
     }
 #undef GK_PACK_LAUNCH
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// ---- keys for an arbitrary list of starts -------------------------------------------------------------------
+// Kmers.kmer_sba_start_indices may be assigned by the caller and sort() orders whatever the array holds
+// (kmers.py:1648).  Same key definition as pack_keys_kernel, one thread per start, bytes read in place; a
+// window that meets its record's '$' (or the end of the array) inside the key is a non-ACGT window whose
+// first non-ACGT symbol sorts below 'A'.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pack_keys_list_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const IdxT *__restrict__ idx, uint64_t n,
+                      uint32_t key_len, int class_bit, uint64_t *__restrict__ keys_out,
+                      unsigned long long *__restrict__ n_amb_out)
+{
+    uint32_t n_amb = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const uint64_t s = (uint64_t)idx[r];
+        uint64_t value = 0;
+        bool pure = true;
+        for (uint32_t j = 0; j < key_len; ++j) {
+            const uint32_t b = (s + j < sba_len) ? sba[s + j] : kSep;
+            if (is_acgt(b)) {
+                value = (value << 2) | code2(b);
+            } else {
+                const uint32_t rem = 2u * (key_len - j);
+                value = ((rem >= 64) ? 0ull : (value << rem)) + ((uint64_t)acgt_below(b) << (rem - 2));
+                pure = false;
+                break;
+            }
+        }
+        if (!pure) ++n_amb;
+        keys_out[r] = class_bit ? ((value << 1) | (pure ? 1ull : 0ull)) : value;
+    }
+    if (n_amb_out) {
+        n_amb = warp_sum(n_amb);
+        if (lane_id() == 0 && n_amb) atomicAdd(n_amb_out, (unsigned long long)n_amb);
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+widen_indices_kernel(const IdxT *__restrict__ idx, uint64_t n, uint64_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) out[r] = (uint64_t)idx[r];
+}
+
+// report[0] += starts that do not begin a k-mer of min_len symbols inside one record,
+// report[1] += positions r > 0 with idx[r] <= idx[r - 1] (the list is not strictly ascending)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+check_starts_kernel(const IdxT *__restrict__ idx, uint64_t n, const uint64_t *__restrict__ seg_starts,
+                    uint32_t n_seg, uint64_t sba_len, uint32_t min_len, unsigned long long *__restrict__ report)
+{
+    uint32_t bad = 0, unordered = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const uint64_t s = (uint64_t)idx[r];
+        bool ok = s < sba_len;
+        if (ok) {
+            const uint32_t seg = upper_seg(seg_starts, n_seg, s);
+            const uint64_t seg_end = (seg + 1 < n_seg) ? seg_starts[seg + 1] - 1 : sba_len;  // position of '$'
+            ok = s + min_len <= seg_end;
+        }
+        if (!ok) ++bad;
+        if (r > 0 && (uint64_t)idx[r - 1] >= s) ++unordered;
+    }
+    bad = warp_sum(bad);
+    unordered = warp_sum(unordered);
+    if (lane_id() == 0) {
+        if (bad) atomicAdd(&report[0], (unsigned long long)bad);
+        if (unordered) atomicAdd(&report[1], (unsigned long long)unordered);
+    }
+}
+
+static unsigned list_grid(uint64_t n)
+{
+    uint64_t blocks = (n + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+int pack_keys_list_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes, uint64_t n,
+                          uint32_t key_len, int class_bit, uint64_t *d_keys_out, unsigned long long *d_n_amb,
+                          cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    if (key_len < 1 || key_len > 32 || (class_bit && key_len > 31)) {
+        set_error("pack_keys_list: key_len %u / class_bit %d out of range", key_len, class_bit);
+        return GK_ERR_ARG;
+    }
+    if (idx_bytes == 4)
+        pack_keys_list_kernel<uint32_t><<<list_grid(n), 256, 0, st>>>(d_sba, sba_len, (const uint32_t *)d_idx, n,
+                                                                      key_len, class_bit, d_keys_out, d_n_amb);
+    else
+        pack_keys_list_kernel<uint64_t><<<list_grid(n), 256, 0, st>>>(d_sba, sba_len, (const uint64_t *)d_idx, n,
+                                                                      key_len, class_bit, d_keys_out, d_n_amb);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int widen_indices_device(const void *d_idx, int idx_bytes, uint64_t n, uint64_t *d_out, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    if (idx_bytes == 4)
+        widen_indices_kernel<uint32_t><<<list_grid(n), 256, 0, st>>>((const uint32_t *)d_idx, n, d_out);
+    else
+        widen_indices_kernel<uint64_t><<<list_grid(n), 256, 0, st>>>((const uint64_t *)d_idx, n, d_out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int check_starts_device(const void *d_idx, int idx_bytes, uint64_t n, const uint64_t *d_seg_starts, uint32_t n_seg,
+                        uint64_t sba_len, uint32_t min_len, unsigned long long *d_report, cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    if (idx_bytes == 4)
+        check_starts_kernel<uint32_t><<<list_grid(n), 256, 0, st>>>((const uint32_t *)d_idx, n, d_seg_starts, n_seg,
+                                                                    sba_len, min_len, d_report);
+    else
+        check_starts_kernel<uint64_t><<<list_grid(n), 256, 0, st>>>((const uint64_t *)d_idx, n, d_seg_starts, n_seg,
+                                                                    sba_len, min_len, d_report);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -442,7 +631,7 @@ extern "C" int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64
     GK_CUDA(cudaMemsetAsync(amb.ptr, 0, 8, st));
     GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, valid_len, key_len,
                             class_bit, first_start, end_start, base, d_keys_out, idx_bytes,
-                            d_idx_out, amb.as<unsigned long long>(), 0, 0, nullptr, st));
+                            d_idx_out, amb.as<unsigned long long>(), 0, 0, nullptr, st, nullptr));
     uint64_t n_amb = 0;
     GK_CUDA(cudaMemcpyAsync(&n_amb, amb.ptr, 8, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));

@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(256) scan_alphabet_kernel(const uint8_t *__res
 }
 
 // ---- reverse complement (sequence_collection.py:42-73) -------------------------------------
-// One thread produces 16 consecutive output bytes (one aligned 16-byte store when possible) from
-// 16 reversed input bytes; the complement table sits in shared memory.
+// One thread produces 16 consecutive output bytes with one aligned 16-byte store.  Their 16 source bytes are
+// contiguous too (the mirror image), but not aligned: two aligned 16-byte loads and funnel shifts cut them
+// out, PRMT reverses each word, and the complement table sits in shared memory.
 __global__ void __launch_bounds__(256) revcomp_kernel(const uint8_t *__restrict__ in,
                                                       uint64_t len, uint8_t *__restrict__ out)
 {
@@ -57,20 +58,53 @@ __global__ void __launch_bounds__(256) revcomp_kernel(const uint8_t *__restrict_
     const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u;
     const uint64_t n_chunks = 1 + (len > head ? (len - head + 15) / 16 : 0);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uintptr_t in_addr = reinterpret_cast<uintptr_t>(in);
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
         uint64_t o0 = (c == 0) ? 0 : head + (c - 1) * 16;
         uint64_t o1 = (c == 0) ? (head < len ? head : len) : (o0 + 16 < len ? o0 + 16 : len);
         if (c != 0 && o1 - o0 == 16) {
-            uint32_t w[4];
+            // source bytes [lo, lo + 16), lo = len - 16 - o0; out[o0 + i] = comp(in[lo + 15 - i])
+            const uint64_t lo = len - 16 - o0;
+            const uint32_t off = (uint32_t)((in_addr + lo) & 15u);
+            uint32_t r[4];
+            // the second load may reach past the last source byte but stays inside the array unless the
+            // source window ends in the array's last 16-byte line: those few chunks go byte by byte
+            if (off == 0) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(in + lo);
+                r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+            } else if (lo >= off && lo - off + 32 <= len) {
+                const uint8_t *base = in + lo - off;              // 16-byte aligned
+                const uint4 q0 = *reinterpret_cast<const uint4 *>(base);
+                const uint4 q1 = *reinterpret_cast<const uint4 *>(base + 16);
+                const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                const uint32_t ws = off >> 2, bs = (off & 3u) * 8u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t a = 0, b2 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {   // (register-only selection: no local-memory indexing)
+                        if ((uint32_t)j == ws + i) a = w[j];
+                        if ((uint32_t)j == ws + i + 1) b2 = w[j];
+                    }
+                    r[i] = __funnelshift_r(a, b2, bs);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x |= (uint32_t)in[lo + 4 * i + j] << (8 * j);
+                    r[i] = x;
+                }
+            }
+            uint32_t w_out[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                uint32_t x = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    x |= (uint32_t)lut[in[len - 1 - (o0 + 4 * i + j)]] << (8 * j);
-                w[i] = x;
+                const uint32_t x = __byte_perm(r[3 - i], 0, 0x0123);   // reverse the four bytes
+                w_out[i] = (uint32_t)lut[x & 0xFFu] | ((uint32_t)lut[(x >> 8) & 0xFFu] << 8) |
+                           ((uint32_t)lut[(x >> 16) & 0xFFu] << 16) | ((uint32_t)lut[x >> 24] << 24);
             }
-            *reinterpret_cast<uint4 *>(out + o0) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(out + o0) = make_uint4(w_out[0], w_out[1], w_out[2], w_out[3]);
         } else {
             for (uint64_t o = o0; o < o1; ++o) out[o] = lut[in[len - 1 - o]];
         }
@@ -104,6 +138,17 @@ static int grid_for(uint64_t work_items, int block)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+// alphabet counters left on the device (zeroed here), no synchronise: for callers that read them back later
+int scan_alphabet_async(const uint8_t *d_sba, uint64_t len, unsigned long long *d_counts3, cudaStream_t st)
+{
+    GK_CUDA(cudaMemsetAsync(d_counts3, 0, 3 * sizeof(unsigned long long), st));
+    if (len) {
+        scan_alphabet_kernel<<<grid_for(len / 16 + 1, 256), 256, 0, st>>>(d_sba, len, d_counts3);
+        GK_LAUNCH_CHECK();
+    }
+    return GK_OK;
 }
 
 int kmer_count_host(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t sba_len, uint32_t k,

@@ -7,7 +7,7 @@
 //   2. scan_histogram_kernel: exclusive scan per digit position -> global bin bases.
 //   3. onesweep_kernel, once per 8-bit digit, least significant first.  A CTA claims the next
 //      tile with an atomic ticket (so look-back never waits on an unscheduled tile), ranks its
-//      keys with warp-level match_any (stable: items are visited in memory order), publishes
+//      keys with eight warp ballots per digit (stable: items are visited in memory order), publishes
 //      its per-bin counts, resolves its global bin offsets by decoupled look-back over the
 //      preceding tiles' status words, reorders the tile in shared memory and streams it out so
 //      consecutive threads write consecutive addresses inside each bin.
@@ -396,6 +396,112 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
     }
 }
 
+
+// ---- small inputs: the whole sort in ONE launch ------------------------------------------------------
+// The refinement stages sort lists of a few ten thousand elements by up to four 64-bit words.  Through
+// onesweep_kernel that is one launch (plus a status memset) per digit, each far too small to fill the GPU:
+// the time is launch latency.  One CTA does every digit pass of such a sort here: each warp owns a contiguous
+// segment (so memory order == (warp, row, lane)), counts its digits into a private row of shared counters,
+// the rows are scanned across warps and bins, and every warp then ranks its rows with the same ballot
+// matching as the big kernel.  A digit that is the same for all elements costs a copy instead of a scatter,
+// so the ping-pong parity stays a host-side constant.  Global data is read with ld.cg: the buffers are
+// rewritten by this CTA between passes and must not be served from a stale L1 line.
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallWarps = kSmallThreads / 32;
+constexpr uint64_t kSmallSortMax = 1ull << 16;
+
+template <typename ValT>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b, uint32_t n, int begin_bit,
+                  int end_bit)
+{
+    __shared__ uint32_t s_cnt[kSmallWarps][kRadix];
+    __shared__ uint32_t s_wsum[kRadix / 32];
+    __shared__ int s_skip;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t rows = (n + kSmallThreads - 1) / kSmallThreads;  // rows of 32 elements per warp
+    const uint32_t seg0 = warp * rows * 32u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint64_t *kin = keys_a, *kout = keys_b;
+    ValT *vin = vals_a, *vout = vals_b;
+    for (int lo = begin_bit; lo < end_bit; lo += kRadixBits) {
+        const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
+        const uint32_t mask = (1u << bits) - 1u;
+        for (int i = t; i < kSmallWarps * kRadix; i += kSmallThreads) (&s_cnt[0][0])[i] = 0;
+        if (t == 0) s_skip = 0;
+        __syncthreads();
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t i = seg0 + r * 32u + lane;
+            if (i < n) atomicAdd(&s_cnt[warp][(uint32_t)(__ldcg(kin + i) >> lo) & mask], 1u);
+        }
+        __syncthreads();
+        uint32_t total = 0;
+        if (t < kRadix) {
+            uint32_t sum = 0;
+#pragma unroll 8
+            for (int w = 0; w < kSmallWarps; ++w) {
+                const uint32_t c = s_cnt[w][t];
+                s_cnt[w][t] = sum;
+                sum += c;
+            }
+            total = sum;
+            if (total == n) s_skip = 1;  // every element has this digit: the pass is the identity
+        }
+        uint32_t inc = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (t < kRadix && lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        if (t < kRadix) {
+            uint32_t pre = 0;
+            for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
+            const uint32_t excl = pre + inc - total;
+#pragma unroll 8
+            for (int w = 0; w < kSmallWarps; ++w) s_cnt[w][t] += excl;
+        }
+        __syncthreads();
+        if (s_skip) {
+            for (uint32_t i = t; i < n; i += kSmallThreads) {
+                kout[i] = __ldcg(kin + i);
+                vout[i] = __ldcg(vin + i);
+            }
+        } else {
+            uint32_t *my_cnt = s_cnt[warp];
+            for (uint32_t r = 0; r < rows; ++r) {
+                const uint32_t i = seg0 + r * 32u + lane;
+                const bool ok = i < n;
+                const uint64_t key = ok ? __ldcg(kin + i) : 0ull;
+                const uint32_t d = (uint32_t)(key >> lo) & mask;
+                const uint32_t live = __ballot_sync(0xffffffffu, ok);
+                if (live == 0) break;  // (uniform: rows past the end of the array)
+                const uint32_t peers = digit_peers(d) & live;
+                const uint32_t before = peers & lt_mask;
+                const uint32_t base = ok ? my_cnt[d] : 0u;
+                __syncwarp();
+                if (ok && before == 0) my_cnt[d] = base + __popc(peers);
+                __syncwarp();
+                if (ok) {
+                    const uint32_t pos = base + __popc(before);
+                    kout[pos] = key;
+                    vout[pos] = __ldcg(vin + i);
+                }
+            }
+        }
+        __syncthreads();  // orders this pass's global writes before the next pass's reads (same CTA)
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        ValT *tv = vin; vin = vout; vout = tv;
+    }
+}
+
+static bool small_sort_enabled()
+{
+    const char *e = getenv("GK_SMALL_SORT");
+    return !(e && e[0] == '0');
+}
+
 // ---- host driver ---------------------------------------------------------------------------------
 struct PassArgs {
     const void *kin; void *kout; const void *vin; void *vout; uint64_t n;
@@ -486,14 +592,16 @@ void set_deferred_sort_error_word(int *d_err) { g_deferred_err = d_err; }
 
 // Shared driver: histogram(s) + scan + `passes` onesweep launches.  splitters != nullptr selects
 // the single partition pass (digit = destination rank); h_bin_counts (256 entries, optional)
-// receives the first pass's histogram.
+// receives the first pass's histogram.  d_vals_final (optional): a third value buffer that receives the
+// sorted values whatever the number of passes (the outputs alternate final / alt counting back from the
+// last pass, so the input buffer is only read by the first pass).
 static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                         int val_bytes, uint64_t n, int begin_bit, int end_bit,
                         const uint64_t *d_splitters, uint32_t n_split, int *result_in_alt,
                         unsigned long long *h_bin_counts, cudaStream_t st, SortTiming *timing,
-                        const unsigned long long *d_pre_hist = nullptr)
+                        const unsigned long long *d_pre_hist = nullptr, void *d_vals_final = nullptr)
 {
-    if (timing) { timing->hist_ms = 0.f; timing->passes_ms = 0.f; timing->passes = 0; }
+    if (timing) { timing->drop(); timing->hist_ms = 0.f; timing->passes_ms = 0.f; timing->passes = 0; }
     if (val_bytes != 4 && val_bytes != 8) {
         set_error("radix_sort_pairs: val_bytes must be 4 or 8");
         return GK_ERR_ARG;
@@ -505,11 +613,40 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     if (result_in_alt) *result_in_alt = 0;
     if (h_bin_counts) memset(h_bin_counts, 0, kRadix * sizeof(unsigned long long));
     const int passes = d_splitters ? 1 : (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
-    if (n == 0 || passes == 0) return GK_OK;
-    if (n == 1 && !d_splitters) return GK_OK;
+    if (n == 0 || passes == 0 || (n == 1 && !d_splitters)) {
+        if (d_vals_final && n) GK_CUDA(cudaMemcpyAsync(d_vals_final, d_vals, (size_t)n * val_bytes,
+                                                       cudaMemcpyDeviceToDevice, st));
+        return GK_OK;
+    }
     if ((reinterpret_cast<uintptr_t>(d_keys) & 15u) || (reinterpret_cast<uintptr_t>(d_keys_alt) & 15u)) {
         set_error("radix_sort_pairs: key buffers must be 16-byte aligned");
         return GK_ERR_ARG;
+    }
+    const bool deferred = g_deferred_err && !h_bin_counts;
+    if (timing) {
+        for (auto &e : timing->ev) GK_CUDA(cudaEventCreate(&e));
+        timing->pending = true;
+        timing->passes = passes;
+    }
+
+    // ---- a list this small is sorted by one CTA in one launch ----------------------------------------------
+    if (!d_splitters && !h_bin_counts && !d_pre_hist && !d_vals_final && n <= kSmallSortMax && small_sort_enabled()) {
+        if (timing) { GK_CUDA(cudaEventRecord(timing->ev[0], st)); GK_CUDA(cudaEventRecord(timing->ev[1], st)); }
+        if (val_bytes == 4)
+            small_sort_kernel<uint32_t><<<1, kSmallThreads, 0, st>>>(d_keys, d_keys_alt, (uint32_t *)d_vals,
+                                                                     (uint32_t *)d_vals_alt, (uint32_t)n, begin_bit,
+                                                                     end_bit);
+        else
+            small_sort_kernel<uint64_t><<<1, kSmallThreads, 0, st>>>(d_keys, d_keys_alt, (uint64_t *)d_vals,
+                                                                     (uint64_t *)d_vals_alt, (uint32_t)n, begin_bit,
+                                                                     end_bit);
+        GK_LAUNCH_CHECK();
+        if (result_in_alt) *result_in_alt = passes & 1;
+        if (timing) {
+            GK_CUDA(cudaEventRecord(timing->ev[2], st));
+            if (!deferred) { GK_CUDA(cudaStreamSynchronize(st)); timing->resolve(); }
+        }
+        return GK_OK;
     }
 
     const int cfg = sort_config_id(val_bytes);
@@ -525,15 +662,11 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     unsigned long long *d_hist = temp.as<unsigned long long>();
     unsigned long long *d_base = d_hist + kMaxPasses * kRadix;
     uint32_t *d_ctr = reinterpret_cast<uint32_t *>(d_base + kMaxPasses * kRadix);
-    const bool deferred = g_deferred_err && !timing && !h_bin_counts;
     int *d_err = deferred ? g_deferred_err : reinterpret_cast<int *>(d_ctr + kMaxPasses);
     void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
     GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
 
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    if (timing)
-        for (auto &e : ev) GK_CUDA(cudaEventCreate(&e));
-    if (timing) GK_CUDA(cudaEventRecord(ev[0], st));
+    if (timing) GK_CUDA(cudaEventRecord(timing->ev[0], st));
     int hist_grid = sm_count() * 2;
     {
         uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
@@ -547,13 +680,16 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     }
     scan_histogram_kernel<<<passes, kRadix, 0, st>>>(d_pre_hist ? d_pre_hist : d_hist, d_base);
     GK_LAUNCH_CHECK();
-    if (timing) GK_CUDA(cudaEventRecord(ev[1], st));
+    if (timing) GK_CUDA(cudaEventRecord(timing->ev[1], st));
 
     uint64_t *kin = d_keys, *kout = d_keys_alt;
-    void *vin = d_vals, *vout = d_vals_alt;
+    void *vin = d_vals;
     for (int p = 0; p < passes; ++p) {
         const int lo = begin_bit + p * kRadixBits;
         const int bits = d_splitters ? kRadixBits : ((end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits);
+        void *vout;
+        if (d_vals_final) vout = ((passes - 1 - p) & 1) ? d_vals_alt : d_vals_final;
+        else vout = (vin == d_vals) ? d_vals_alt : d_vals;
         GK_CUDA(cudaMemsetAsync(d_status, 0, status_bytes, st));
         PassArgs pa = {kin, kout, vin, vout, n, lo, bits, d_splitters, n_split, d_base + p * kRadix,
                        d_ctr + p, d_status, d_err, nullptr};
@@ -564,10 +700,10 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
             rc = wide ? dispatch_pass<uint64_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint64_t, uint32_t>(cfg, pa, st);
         GK_TRY(rc);
         uint64_t *tk = kin; kin = kout; kout = tk;
-        void *tv = vin; vin = vout; vout = tv;
+        vin = vout;
     }
     if (result_in_alt) *result_in_alt = passes & 1;
-    if (timing) GK_CUDA(cudaEventRecord(ev[2], st));
+    if (timing) GK_CUDA(cudaEventRecord(timing->ev[2], st));
     if (deferred) return GK_OK;  // scratch is released in stream order; the caller checks the error word
 
     int h_err = 0;
@@ -576,12 +712,7 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         GK_CUDA(cudaMemcpyAsync(h_bin_counts, d_hist, kRadix * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
-    if (timing) {
-        cudaEventElapsedTime(&timing->hist_ms, ev[0], ev[1]);
-        cudaEventElapsedTime(&timing->passes_ms, ev[1], ev[2]);
-        timing->passes = passes;
-        for (auto &e : ev) cudaEventDestroy(e);
-    }
+    if (timing) timing->resolve();
     if (h_err) {
         set_error("radix_sort_pairs: decoupled look-back timed out");
         return GK_ERR_INTERNAL;
@@ -701,10 +832,10 @@ int radix_sort_pairs32_device(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_va
 int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, void *d_vals_alt,
                             int val_bytes, uint64_t n, int begin_bit, int end_bit,
                             int *result_in_alt, cudaStream_t st, SortTiming *timing,
-                            const unsigned long long *d_pre_hist)
+                            const unsigned long long *d_pre_hist, void *d_vals_final)
 {
     return run_onesweep(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit, end_bit, nullptr,
-                        0, result_in_alt, nullptr, st, timing, d_pre_hist);
+                        0, result_in_alt, nullptr, st, timing, d_pre_hist, d_vals_final);
 }
 
 // Stable partition of the pairs by destination = number of splitters <= key.  Output always lands
@@ -828,7 +959,7 @@ extern "C" int gk_radix_sort_pairs(uint64_t *d_keys, uint64_t *d_keys_alt, void 
         return GK_ERR_ARG;
     }
     return radix_sort_pairs_device(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit,
-                                   end_bit, result_in_alt, as_stream(stream), nullptr, nullptr);
+                                   end_bit, result_in_alt, as_stream(stream), nullptr, nullptr, nullptr);
 }
 
 extern "C" int gk_radix_sort_pairs32(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_vals, void *d_vals_alt,

@@ -38,6 +38,7 @@ class GkSortStats(ctypes.Structure):
         ("sort_passes", ctypes.c_int32), ("key_bits", ctypes.c_int32), ("levels", ctypes.c_int32),
         ("gpu_launches", ctypes.c_int32), ("n_windows", ctypes.c_uint64),
         ("n_ambiguous", ctypes.c_uint64),
+        ("n_fragments", ctypes.c_uint64),
     ]
 
     def as_dict(self):
@@ -98,6 +99,7 @@ SIGNATURES = {
                                             _p(_u64), _p(ctypes.c_int64), _vp]),
     "gk_index_groups": (_int, [_vp, _u32, _p(_u64), _vp, _vp, _vp]),
     "gk_index_groups_filtered": (_int, [_vp, _u32, _p(GkFilter), _p(_u64), _p(_u64), _vp, _vp, _vp, _vp]),
+    "gk_index_verify": (_int, [_vp, _u32, _vp, _vp]),
     "gk_sort_count_host": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _int, _vp, _u64, _vp,
                                   _p(ctypes.c_int64), _p(_u64), _p(GkSortStats)]),
 }

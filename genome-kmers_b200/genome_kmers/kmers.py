@@ -452,6 +452,24 @@ class Kmers:
                                               self._stream()))
         return offsets, sizes
 
+    def verify_order(self, kmer_len: Union[int, None] = None) -> dict:
+        """Self-check of the current order on the device, straight from the sequence bytes (gk_index_verify):
+        neighbours compared with the reference's '$'-terminated comparator, ties in ascending start order,
+        every start a valid and distinct k-mer start.  `ok` is True for a correctly sorted index."""
+        self._ensure_device()
+        self._push_host_indices()
+        if kmer_len is None:
+            kmer_len = self.max_kmer_len
+        report = np.zeros(8, dtype=np.uint64)
+        _native.check(_native.lib().gk_index_verify(self._ix, kmer_len or 0, _native.host_ptr(report),
+                                                    self._stream()))
+        names = ("kmers", "out_of_order", "tie_order", "invalid_starts", "duplicate_starts", "groups",
+                 "flag_mismatches", "flags_compared")
+        out = {k: int(v) for k, v in zip(names, report)}
+        out["ok"] = not any(out[k] for k in ("out_of_order", "tie_order", "invalid_starts", "duplicate_starts",
+                                             "flag_mismatches"))
+        return out
+
     # ------------------------------------------------------------------ host-side accessors
     def get_kmers(self, kmer_len: Union[int, None], one_based_seq_index: bool = False,
                   kmer_filter_func: Callable = kmer_filter_keep_all, kmer_info_to_yield: str = "minimum",

@@ -73,6 +73,7 @@ typedef struct {
     int32_t gpu_launches; /* kernels launched by the call */
     uint64_t n_windows;   /* k-mers sorted */
     uint64_t n_ambiguous; /* windows holding a non-ACGT symbol within the key */
+    uint64_t n_fragments; /* blocks of identical ambiguous windows listed by the pack kernel (0: not used) */
 } gk_sort_stats;
 
 typedef struct gk_index gk_index;
@@ -224,6 +225,15 @@ int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups,
 int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *filter, uint64_t *h_n_kept,
                              uint64_t *h_n_groups, uint64_t *h_kept_pos_out, uint64_t *h_offsets_out,
                              uint64_t *h_sizes_out, void *stream);
+
+/* Self-check of the current order against the sequence bytes, independent of how it was produced: the
+ * reference's '$'-terminated comparator (kmers.py:306-397) on every pair of neighbours, ties in ascending
+ * start order (kmers.py:1710-1711), every start a valid, distinct k-mer start (kmers.py:814-826).
+ * h_report8: [0] k-mers checked, [1] neighbours out of order, [2] ties not in ascending start order,
+ * [3] invalid starts, [4] duplicate starts, [5] groups of equal k-mers counted from the bytes,
+ * [6] cached head flags that disagree with the bytes, [7] 1 when cached flags were compared.
+ * A correct sort of the init set has [1..4] == 0, [6] == 0 and [0] == gk_kmer_count(). kmer_len 0 = None. */
+int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, void *stream);
 
 /* ---- one-shot host entry point (host buffers in, host buffers out) ------------------------ */
 /* sba (forward strand, records joined by '$') -> sorted start indices + histogram.  strands:

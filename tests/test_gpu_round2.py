@@ -1,0 +1,172 @@
+"""
+GPU tests of the round-2 paths: ambiguous-window fragments (pack-time run-length blocks) against the
+element-wise refinement, the single-CTA small sort, sorting an assigned subset of start indices
+(reference kmers.py:1648), the device-side order check (gk_index_verify), reverse complement on unaligned
+buffers.  Bit-exact against the CPU oracle / the golden vectors of the real reference.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import dense_hist, golden_case, golden_case_names, is_fixed_k
+from genome_kmers import _native
+from genome_kmers.kmers import Kmers, gen_no_ambiguous_bases_filter, kmer_filter_keep_all
+from genome_kmers.sequence_collection import SequenceCollection
+import gpu_utils as gu
+
+pytestmark = pytest.mark.gpu
+
+AMBIGUOUS_GOLDEN = [n for n in golden_case_names(is_fixed_k)
+                    if any(t in n for t in ("iupac", "repeatN", "rand120kN", "amb", "N_both", "every"))]
+
+
+def _oracle_sorted(recs, k, strands, min_len=None, max_len=None):
+    sc = SequenceCollection.from_arrays(recs, strands_to_load=strands)
+    fwd, starts = sc.forward_sba, sc._forward_sba_seg_starts.astype(np.uint64)
+    if strands == "both":
+        sba, seg = oracle.both_strands(fwd, starts)
+    else:
+        sba, seg = fwd, starts
+    lo, hi = (k, k) if min_len is None else (min_len, max_len)
+    init = oracle.init_indices(seg, len(sba), lo)
+    want = oracle.sort_indices(sba, init, lo, hi, threads=min(8, oracle.max_threads()))
+    return sc, sba, seg, want
+
+
+@pytest.mark.parametrize("frag", ["0", "1"])
+@pytest.mark.parametrize("name", AMBIGUOUS_GOLDEN)
+def test_golden_ambiguous_cases_with_and_without_fragments(name, frag, monkeypatch):
+    monkeypatch.setenv("GK_FRAGMENTS", frag)
+    case = golden_case(name)
+    sc = SequenceCollection(sequence_list=[tuple(r) for r in case["seq_list"]], strands_to_load=case["strands"])
+    km = Kmers(sc, case["min_len"], case["max_len"], source_strand=case["strands"])
+    km.sort()
+    got = km.kmer_sba_start_indices
+    bad = np.flatnonzero(got != case["sorted"])
+    assert len(bad) == 0, f"{name}: first mismatches at {bad[:8]}"
+    if frag == "1" and km.last_sort_stats["n_ambiguous"]:
+        assert km.last_sort_stats["n_fragments"] > 0
+    for qu, ans in zip(case["queries"], case["answers"]):
+        flt = kmer_filter_keep_all if qu["filter"] is None else gen_no_ambiguous_bases_filter(qu["filter"][1])
+        hist, total = km.get_kmer_group_counts(qu["kmer_len"], flt, qu["min_group"], qu["max_group"], qu["max_bin"])
+        assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"])), (name, qu)
+    assert km.verify_order(case["max_len"])["ok"]
+
+
+@pytest.mark.parametrize("k,strands", [(31, "both"), (12, "forward"), (5, "both"), (17, "both")])
+def test_fragments_on_long_runs_of_every_kind(k, strands):
+    """N runs longer than several pack tiles, runs of other IUPAC letters, runs that touch record ends, runs
+    shorter than k, and scattered single letters: the fragment path against the oracle."""
+    rng = np.random.default_rng(100 + k)
+    recs = gu.random_genome(rng, 260_000, 3, n_runs=0)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for name, seq in recs:
+        n = len(seq)
+        seq[0:9000] = ord("N")                       # run at the start of a record, > 2 pack tiles
+        seq[n - 5000:n] = ord("N")                   # run at the end of a record
+        seq[20_000:20_000 + k - 1] = ord("N")        # shorter than k: no all-N window
+        seq[30_000:30_000 + k] = ord("N")            # exactly one all-N window
+        seq[40_000:40_000 + k + 1] = ord("R")        # two identical windows of another letter
+        seq[50_000:50_700] = ord("Y")
+        seq[60_000:60_300] = ord("N")
+        seq[60_300:60_600] = ord("R")                # two runs back to back
+        seq[rng.integers(0, n, 30)] = ord("W")
+        seq[70_000:70_000 + 3 * k] = acgt[0]         # a pure homopolymer: never a fragment
+    sc, sba, seg, want = _oracle_sorted(recs, k, strands)
+    km = Kmers(sc, k, k, source_strand=strands)
+    km.sort()
+    got = km.kmer_sba_start_indices.astype(np.uint64)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, f"first mismatches at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
+    st = km.last_sort_stats
+    assert st["n_fragments"] > 0 and st["n_fragments"] < st["n_ambiguous"]
+    hist, total = km.get_kmer_group_counts(k, max_counts_bin=50)
+    o_hist, o_total = oracle.group_hist(sba, want, k, max_bin=50)
+    assert total == o_total and np.array_equal(hist, o_hist)
+    rep = km.verify_order(k)
+    assert rep["ok"] and rep["groups"] == int(hist.sum()) and rep["flags_compared"] == 1
+
+
+@pytest.mark.parametrize("n", [2, 31, 33, 1000, 1025, 40_000, 65_536])
+@pytest.mark.parametrize("val_dtype", [np.uint32, np.uint64])
+def test_small_sort_matches_stable_numpy(n, val_dtype, monkeypatch):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 63, n, dtype=np.uint64)
+    keys[rng.integers(0, n, n // 3)] &= np.uint64(0xFF00FF)          # many ties and constant digits
+    vals = np.arange(n).astype(val_dtype)
+    for begin, end in ((0, 64), (8, 40), (3, 21)):
+        order = np.argsort((keys >> np.uint64(begin)) & np.uint64((1 << (end - begin)) - 1), kind="stable")
+        for small in ("1", "0"):
+            monkeypatch.setenv("GK_SMALL_SORT", small)
+            k_out, v_out = gu.radix_sort_pairs(keys, vals, begin, end)
+            assert np.array_equal(v_out, vals[order]), (n, begin, end, small)
+            assert np.array_equal(k_out, keys[order])
+
+
+def test_sort_of_an_assigned_subset_of_start_indices():
+    """reference kmers.py:1648: sort() orders whatever kmer_sba_start_indices holds."""
+    rng = np.random.default_rng(5)
+    recs = gu.random_genome(rng, 50_000, 3, n_runs=4, run_lo=40, run_hi=400, n_scatter=10)
+    k = 21
+    sc, sba, seg, want_all = _oracle_sorted(recs, k, "forward")
+    init = oracle.init_indices(seg, len(sba), k)
+    subset = rng.permutation(init)[:7000].astype(np.uint32)          # arbitrary order, no duplicates
+    km = Kmers(sc, k, k)
+    km.kmer_sba_start_indices = subset
+    km.sort()
+    want = oracle.sort_indices(sba, np.sort(subset).astype(np.uint64), k, k, threads=1)
+    got = km.kmer_sba_start_indices
+    assert len(got) == len(subset) and np.array_equal(got.astype(np.uint64), want)
+    hist, total = km.get_kmer_group_counts(k, max_counts_bin=20)
+    o_hist, o_total = oracle.group_hist(sba, want, k, max_bin=20)
+    assert total == o_total == len(subset) and np.array_equal(hist, o_hist)
+    # sorting again is idempotent; assigning the whole set (shuffled) gives the full order
+    km.sort()
+    assert np.array_equal(km.kmer_sba_start_indices.astype(np.uint64), want)
+    km.kmer_sba_start_indices = rng.permutation(init).astype(np.uint32)
+    km.sort()
+    assert np.array_equal(km.kmer_sba_start_indices.astype(np.uint64), want_all)
+    # a start that begins no k-mer of min_kmer_len symbols: the reference's validation raises
+    bad = subset.copy()
+    bad[3] = np.uint32(int(seg[1]) - 2)                               # last base of record 0
+    km.kmer_sba_start_indices = bad
+    with pytest.raises(Exception, match="less than min_kmer_len"):
+        km.sort()
+
+
+def test_verify_order_reports_what_is_wrong():
+    rng = np.random.default_rng(11)
+    recs = gu.random_genome(rng, 30_000, 2, n_runs=2, run_lo=50, run_hi=200)
+    k = 15
+    sc = SequenceCollection.from_arrays(recs)
+    km = Kmers(sc, k, k)
+    assert not km.verify_order(k)["ok"]                                # init order is not sorted
+    km.sort()
+    rep = km.verify_order(k)
+    assert rep["ok"] and rep["kmers"] == len(km) and rep["flags_compared"] == 1
+    good = km.kmer_sba_start_indices.copy()
+    swapped = good.copy()
+    swapped[[100, 20_000]] = swapped[[20_000, 100]]
+    km2 = Kmers(sc, k, k)
+    km2.kmer_sba_start_indices = swapped
+    km2._is_sorted = True
+    rep = km2.verify_order(k)
+    assert not rep["ok"] and rep["out_of_order"] >= 1
+    dup = good.copy()
+    dup[5] = dup[6]
+    km2.kmer_sba_start_indices = dup
+    rep = km2.verify_order(k)
+    assert rep["duplicate_starts"] == 1
+
+
+@pytest.mark.parametrize("n,shift", [(100003, 1), (4099, 7), (65, 3), (1 << 20, 5)])
+def test_revcomp_on_unaligned_input(n, shift):
+    torch = gu.torch_mod()
+    rng = np.random.default_rng(n)
+    sba = np.frombuffer(b"ACGTRYSWKMBDHVN$", dtype=np.uint8)[rng.integers(0, 16, n + shift)].copy()
+    d_in = gu.dev(sba)[shift:]
+    d_out = torch.zeros(n + 11, dtype=torch.uint8, device="cuda")
+    _native.check(_native.lib().gk_sba_revcomp(d_in.data_ptr(), n, d_out[11:].data_ptr(), gu.stream()))
+    assert np.array_equal(d_out[11:].cpu().numpy(), oracle.revcomp(sba[shift:]))
