@@ -18,6 +18,8 @@ constexpr uint8_t kFlagPass = 4;   // element passes a filter / validity test (s
 constexpr uint8_t kFlagMulti = 8;  // member of a group with more than one element (scratch arrays)
 constexpr uint8_t kFlagLong = 16;  // member of a prefix run too long for the in-place tie repair
 
+constexpr int kDescentCap = 4096;  // out-of-order positions of long prefix runs listed for the bucket-wise repair
+
 // ---- error plumbing ------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

@@ -91,7 +91,8 @@ template <typename ValT, typename PreT>
 __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent,
-                     unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */)
+                     unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */,
+                     unsigned long long *__restrict__ descent_list /* nullable: first kDescentCap positions */)
 {
     // bit (i + 32) of s_cont: slot i (tile-relative, -8 <= i < kTieTile + 8) has the same prefix as slot i - 1
     constexpr int kContWords = kTieTile / 32 + 2;
@@ -247,7 +248,10 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             const uint64_t kp = ph ? 0 : keys[p - 1];
             const bool head = ph || kp != k;
             const bool amb = class_bit && !(k & 1ull);
-            if (!ph && k < kp) atomicOr(descent, 1u);
+            if (!ph && k < kp) {   // *descent counts them; the first kDescentCap positions are listed
+                const unsigned int s_ = atomicAdd(descent, 1u);
+                if (descent_list && s_ < (unsigned int)kDescentCap) descent_list[s_] = p;
+            }
             flags[p] = (amb ? kFlagAmb : (head ? kFlagHead : 0)) | kFlagLong;
         } else if (ph) {  // a short run that starts in this tile: slot and length - 1
             s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)(i | (f << 11));
@@ -317,6 +321,68 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             }
         }
     }
+}
+
+// ---- bucket-wise repair of out-of-order long prefix runs -----------------------------------------------
+// For every listed descent position: the slot range [lo, hi) of its prefix bucket (the array is sorted by
+// prefix, so two binary searches on key >> lo_bits find it).  ranges[2 * i], ranges[2 * i + 1].
+__global__ void __launch_bounds__(256)
+bucket_ranges_kernel(const uint64_t *__restrict__ keys, uint64_t n, int lo_bits,
+                     const unsigned long long *__restrict__ positions, uint32_t count,
+                     unsigned long long *__restrict__ ranges)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t pre = keys[positions[i]] >> lo_bits;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {   // first slot whose prefix is >= pre
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> lo_bits) < pre) lo = mid + 1; else hi = mid;
+    }
+    const uint64_t first = lo;
+    hi = n;
+    while (lo < hi) {   // first slot whose prefix is > pre
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> lo_bits) <= pre) lo = mid + 1; else hi = mid;
+    }
+    ranges[2 * i] = first;
+    ranges[2 * i + 1] = lo;
+}
+
+// head / ambiguous flags of the fully sorted slots [lo, hi) of each range (a bucket start is always a head)
+__global__ void __launch_bounds__(256)
+range_key_flags_kernel(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ ranges,
+                       int class_bit, uint8_t *__restrict__ flags)
+{
+    const uint64_t lo = ranges[2 * blockIdx.y], hi = ranges[2 * blockIdx.y + 1];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += stride) {
+        const uint64_t k = keys[p];
+        const bool amb = class_bit && !(k & 1ull);
+        const bool head = (p == lo) || keys[p - 1] != k;
+        flags[p] = amb ? kFlagAmb : (head ? kFlagHead : 0);
+    }
+}
+
+int bucket_ranges_device(const uint64_t *d_keys, uint64_t n, int lo_bits, const unsigned long long *d_positions,
+                         uint32_t count, unsigned long long *d_ranges, cudaStream_t st)
+{
+    if (count == 0) return GK_OK;
+    bucket_ranges_kernel<<<(count + 255) / 256, 256, 0, st>>>(d_keys, n, lo_bits, d_positions, count, d_ranges);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int range_key_flags_device(const uint64_t *d_keys, const unsigned long long *d_ranges, uint32_t n_ranges,
+                           uint64_t longest, int class_bit, uint8_t *d_flags, cudaStream_t st)
+{
+    if (n_ranges == 0) return GK_OK;
+    uint64_t bx = (longest + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    range_key_flags_kernel<<<dim3((unsigned)bx, n_ranges), 256, 0, st>>>(d_keys, d_ranges, class_bit, d_flags);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
 }
 
 // ---- head flags from the sequence bytes (reference comparator) ------------------------------------
@@ -696,7 +762,7 @@ int key_flags_device(const uint64_t *d_keys, uint64_t n, int class_bit, uint8_t 
 // *d_descent (zeroed by the caller) becomes 1 when a kFlagLong run is out of order
 int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t n, int lo_bits,
                          int class_bit, uint8_t *d_flags, unsigned int *d_descent,
-                         unsigned long long *d_n_amb, cudaStream_t st)
+                         unsigned long long *d_n_amb, cudaStream_t st, unsigned long long *d_descent_list)
 {
     if (n == 0) return GK_OK;
     const uint64_t tiles = (n + kTieTile - 1) / kTieTile;
@@ -704,16 +770,16 @@ int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t
     const unsigned grid = (unsigned)tiles;
     if (val_bytes == 4 && narrow)
         tie_fix_flags_kernel<uint32_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
     else if (val_bytes == 4)
         tie_fix_flags_kernel<uint32_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
     else if (narrow)
         tie_fix_flags_kernel<uint64_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
     else
         tie_fix_flags_kernel<uint64_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb);
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

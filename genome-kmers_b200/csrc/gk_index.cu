@@ -46,7 +46,13 @@ int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_
                             void *d_vals_final = nullptr);
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
 int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *,
-                         unsigned long long *, cudaStream_t);
+                         unsigned long long *, cudaStream_t, unsigned long long *d_descent_list = nullptr);
+int bucket_ranges_device(const uint64_t *, uint64_t, int, const unsigned long long *, uint32_t, unsigned long long *,
+                         cudaStream_t);
+int range_key_flags_device(const uint64_t *, const unsigned long long *, uint32_t, uint64_t, int, uint8_t *,
+                           cudaStream_t);
+int sort_segments_device(uint64_t *, uint64_t *, void *, void *, int, const unsigned long long *,
+                         const unsigned long long *, uint32_t, int, cudaStream_t);
 int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
 int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &, int, void *, const uint64_t *,
                        uint64_t *, const void *, void *, cudaStream_t);
@@ -193,6 +199,7 @@ struct StageMarks {
     SortTiming main_sort;
     uint64_t n_amb = 0;
     uint64_t n_frag = 0;
+    uint32_t refine_flags = 0;  // 1 fragment path, 2 element-wise repair ran, 4 descent, fragment error bits << 8
     int key_bits = 0;
     int levels = 1;
 };
@@ -250,13 +257,15 @@ static int prefix_begin_bit(uint64_t n, int key_bits)
 
 // Stable sort of the (key, start) pairs by key bits [0, key_bits), up to the slots that refine_subset
 // repairs afterwards, and head/ambiguous flags of that order.  The pair buffers ping-pong; *in_alt tells
-// where the result is.  *d_descent (device word, zeroed here) becomes non-zero when a long prefix run is
-// out of order; the caller reads it back together with whatever else it needs (no synchronise here).
+// where the result is.  *d_descent (device word, zeroed here) counts the slots of long prefix runs that are
+// out of order (the first kDescentCap positions go to d_descent_list); the caller reads it back together with
+// whatever else it needs (no synchronise here).
 static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, void *idx_b, int ib,
                                uint64_t n, int key_bits, int class_bit, uint8_t *d_flags, int *in_alt,
                                unsigned int *d_descent, SortTiming *timing, cudaStream_t st,
                                const unsigned long long *d_pre_hist = nullptr,
-                               unsigned long long *d_n_amb = nullptr, bool *n_amb_counted = nullptr)
+                               unsigned long long *d_n_amb = nullptr, bool *n_amb_counted = nullptr,
+                               unsigned long long *d_descent_list = nullptr)
 {
     // d_n_amb (zeroed by the caller): the tie-repair pass also counts the ambiguous slots on request, for
     // callers that did not pack the keys themselves (*n_amb_counted tells whether it ran)
@@ -270,7 +279,7 @@ static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, 
     void *is = *in_alt ? idx_b : idx_a;
     if (begin == 0) return key_flags_device(ks, n, class_bit, d_flags, st);
     if (n_amb_counted) *n_amb_counted = d_n_amb != nullptr;
-    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, d_n_amb, st);
+    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, d_n_amb, st, d_descent_list);
 }
 
 // After the main sort and its flags pass, two kinds of slots may still hold the wrong element:
@@ -359,6 +368,42 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     return GK_OK;  // the scratch above is released in stream order (cudaFreeAsync): no synchronise needed
 }
 
+// Long prefix runs that the flags pass found out of order (a pure k-mer in the middle of a run of equal
+// ambiguous keys; diverged repeats that share their first 16 symbols): sort each such bucket by its low key
+// bits, in place, and recompute its flags.  The buckets are found from the listed descent positions; the
+// rest of the array is not touched.  Synchronises (the bucket list comes back to the host).
+static int repair_buckets(uint64_t *keys, uint64_t *keys_tmp, void *idx, void *idx_tmp, int ib, uint64_t n,
+                          int lo_bits, int class_bit, uint8_t *d_flags, const unsigned long long *d_positions,
+                          uint32_t count, uint64_t *n_slots_out, cudaStream_t st)
+{
+    DeviceBuffer ranges;
+    GK_TRY(ranges.alloc((size_t)count * 16, st));
+    GK_TRY(bucket_ranges_device(keys, n, lo_bits, d_positions, count, ranges.as<unsigned long long>(), st));
+    std::vector<unsigned long long> h((size_t)count * 2);
+    GK_CUDA(cudaMemcpyAsync(h.data(), ranges.ptr, (size_t)count * 16, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    std::vector<std::pair<unsigned long long, unsigned long long>> uniq;
+    for (uint32_t i = 0; i < count; ++i) uniq.emplace_back(h[2 * i], h[2 * i + 1]);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    uint64_t longest = 0, total = 0;
+    for (size_t i = 0; i < uniq.size(); ++i) {
+        h[2 * i] = uniq[i].first;
+        h[2 * i + 1] = uniq[i].second;
+        const uint64_t len = uniq[i].second - uniq[i].first;
+        longest = len > longest ? len : longest;
+        total += len;
+    }
+    const uint32_t n_ranges = (uint32_t)uniq.size();
+    GK_CUDA(cudaMemcpyAsync(ranges.ptr, h.data(), (size_t)n_ranges * 16, cudaMemcpyHostToDevice, st));
+    GK_TRY(sort_segments_device(keys, keys_tmp, idx, idx_tmp, ib, ranges.as<unsigned long long>(), h.data(), n_ranges,
+                                lo_bits, st));
+    GK_TRY(range_key_flags_device(keys, ranges.as<unsigned long long>(), n_ranges, longest, class_bit, d_flags, st));
+    GK_CUDA(cudaStreamSynchronize(st));   // h is pageable and must outlive the upload
+    if (n_slots_out) *n_slots_out = total;
+    return GK_OK;
+}
+
 // Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
 // Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags; synchronises once, at
 // the end.  d_alpha (optional): the three alphabet counters of a scan that is still in flight on `st`; they
@@ -386,8 +431,9 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
     GK_TRY(idx_b.alloc((size_t)n * ib, st));
     GK_TRY(out_idx.alloc((size_t)n * ib, st));
-    // device counters: [0] ambiguous windows, [1] descent (u32), [2] fragments, [3] fragment error bits (int)
-    GK_TRY(counters.alloc(32, st));
+    // device counters: [0] ambiguous windows, [1] descents (u32), [2] fragments, [3] fragment error bits (int),
+    // [4 ...] the first kDescentCap descent positions
+    GK_TRY(counters.alloc(32 + (size_t)kDescentCap * 8, st));
     GK_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, st));
     unsigned long long *d_counters = counters.as<unsigned long long>();
     unsigned int *d_descent = reinterpret_cast<unsigned int *>(d_counters + 1);
@@ -430,8 +476,10 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
     GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
                                key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt, d_descent,
-                               &marks.main_sort, st, d_list ? nullptr : pre_hist.as<unsigned long long>()));
-    const uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
+                               &marks.main_sort, st, d_list ? nullptr : pre_hist.as<unsigned long long>(), nullptr,
+                               nullptr, d_counters + 4));
+    uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
+    uint64_t *keys_other = in_alt ? keys_a.as<uint64_t>() : keys_b.as<uint64_t>();
     if (in_alt) out_idx.swap(idx_b);
 
     // ---- side stream: the pack kernel's counters, then the fragment sort -------------------------------------
@@ -463,17 +511,49 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
     if (d_alpha) GK_CUDA(cudaMemcpyAsync(h_alpha, d_alpha, 24, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
-    const bool descent = (h_counters[1] & 0xffffffffull) != 0;
+    const uint32_t n_descent = (uint32_t)(h_counters[1] & 0xffffffffull);
     const int frag_err = (int)(h_counters[3] & 0xffffffffull);
-    if (descent || (n_amb > 0 && (!use_frag || frag_err))) {
-        // element-wise repair (gk_refine.cu): a long prefix run is out of order (repeat-rich input), or the
-        // fragment list was not available
+    marks.refine_flags = (use_frag ? 1u : 0u) | (n_descent ? 4u : 0u) | ((uint32_t)frag_err << 8);
+    if (getenv("GK_TRACE"))
+        fprintf(stderr, "[gk trace] level1: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u frag_err=%d\n",
+                (unsigned long long)n, (unsigned long long)n_amb, (unsigned long long)n_frag, (int)use_frag,
+                n_descent, frag_err);
+    const bool frag_ok = use_frag && !frag_err;
+    bool need_elementwise = n_amb > 0 && !frag_ok;   // ambiguous windows without a usable fragment list
+    bool elementwise_long = false;
+    if (n_descent) {
         const int f0 = tm.mark();
-        GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
-                             n_amb, descent, terminated, st));
-        GK_CUDA(cudaStreamSynchronize(st));
+        if (n_descent <= (uint32_t)kDescentCap && begin_bit > 0) {
+            // a handful of long prefix runs are out of order: sort those buckets, nothing else
+            uint64_t repaired = 0;
+            GK_TRY(repair_buckets(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, n, begin_bit, class_bit,
+                                  (uint8_t *)out_flags.ptr, d_counters + 4, n_descent, &repaired, st));
+            marks.refine_flags |= 16u;
+            if (frag_ok) {   // the fragment kernels did nothing while the keys were out of order: run them now
+                GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
+                GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr, d_descent,
+                                          d_counters, n_amb, d_frag_err, st));
+                GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
+                GK_CUDA(cudaStreamSynchronize(st));
+                if ((int)(h_counters[3] & 0xffffffffull)) need_elementwise = true;
+            }
+        } else {
+            need_elementwise = true;   // too many to list: element-wise repair of every long run
+            elementwise_long = true;
+        }
         marks.fix0 = f0;
         marks.fix1 = tm.mark();
+    }
+    if (need_elementwise) {
+        // element-wise repair (gk_refine.cu): the ambiguous windows by their 4-bit rank words when there is no
+        // fragment list for them, and the members of every long prefix run when too many are out of order
+        const int f0 = tm.mark();
+        GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
+                             n_amb, elementwise_long, terminated, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        if (!n_descent) marks.fix0 = f0;
+        marks.fix1 = tm.mark();
+        marks.refine_flags |= 2u;
     }
     return GK_OK;
 }
@@ -856,6 +936,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     stats.levels = marks.levels;
     stats.n_ambiguous = marks.n_amb;
     stats.n_fragments = marks.n_frag;
+    stats.refine_flags = marks.refine_flags;
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;

@@ -409,12 +409,19 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
 constexpr int kSmallThreads = 1024;
 constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr uint64_t kSmallSortMax = 1ull << 16;
+constexpr int kSmallBatch = 8;
 
 template <typename ValT>
 __global__ void __launch_bounds__(kSmallThreads, 1)
 small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b, uint32_t n, int begin_bit,
-                  int end_bit)
+                  int end_bit, const unsigned long long *__restrict__ ranges /* nullable: one segment per CTA */)
 {
+    if (ranges) {   // segment mode: sort slots [lo, hi) of the arrays in place (result lands in the *_a arrays)
+        const unsigned long long lo_ = ranges[2 * blockIdx.x], hi_ = ranges[2 * blockIdx.x + 1];
+        if (hi_ - lo_ > kSmallSortMax || hi_ - lo_ < 2) return;   // (larger segments are sorted by the host driver)
+        n = (uint32_t)(hi_ - lo_);
+        keys_a += lo_; keys_b += lo_; vals_a += lo_; vals_b += lo_;
+    }
     __shared__ uint32_t s_cnt[kSmallWarps][kRadix];
     __shared__ uint32_t s_wsum[kRadix / 32];
     __shared__ int s_skip;
@@ -430,9 +437,18 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
         for (int i = t; i < kSmallWarps * kRadix; i += kSmallThreads) (&s_cnt[0][0])[i] = 0;
         if (t == 0) s_skip = 0;
         __syncthreads();
-        for (uint32_t r = 0; r < rows; ++r) {
-            const uint32_t i = seg0 + r * 32u + lane;
-            if (i < n) atomicAdd(&s_cnt[warp][(uint32_t)(__ldcg(kin + i) >> lo) & mask], 1u);
+        for (uint32_t r0 = 0; r0 < rows; r0 += kSmallBatch) {   // several rows in flight per L2 round trip
+            uint64_t kk[kSmallBatch];
+#pragma unroll
+            for (int u = 0; u < kSmallBatch; ++u) {
+                const uint32_t i = seg0 + (r0 + u) * 32u + lane;
+                kk[u] = (r0 + u < rows && i < n) ? __ldcg(kin + i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kSmallBatch; ++u) {
+                const uint32_t i = seg0 + (r0 + u) * 32u + lane;
+                if (r0 + u < rows && i < n) atomicAdd(&s_cnt[warp][(uint32_t)(kk[u] >> lo) & mask], 1u);
+            }
         }
         __syncthreads();
         uint32_t total = 0;
@@ -470,29 +486,46 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
             }
         } else {
             uint32_t *my_cnt = s_cnt[warp];
-            for (uint32_t r = 0; r < rows; ++r) {
-                const uint32_t i = seg0 + r * 32u + lane;
-                const bool ok = i < n;
-                const uint64_t key = ok ? __ldcg(kin + i) : 0ull;
-                const uint32_t d = (uint32_t)(key >> lo) & mask;
-                const uint32_t live = __ballot_sync(0xffffffffu, ok);
-                if (live == 0) break;  // (uniform: rows past the end of the array)
-                const uint32_t peers = digit_peers(d) & live;
-                const uint32_t before = peers & lt_mask;
-                const uint32_t base = ok ? my_cnt[d] : 0u;
-                __syncwarp();
-                if (ok && before == 0) my_cnt[d] = base + __popc(peers);
-                __syncwarp();
-                if (ok) {
-                    const uint32_t pos = base + __popc(before);
-                    kout[pos] = key;
-                    vout[pos] = __ldcg(vin + i);
+            for (uint32_t r0 = 0; r0 < rows; r0 += kSmallBatch) {
+                uint64_t kk[kSmallBatch];
+                ValT vv[kSmallBatch];
+#pragma unroll
+                for (int u = 0; u < kSmallBatch; ++u) {
+                    const uint32_t i = seg0 + (r0 + u) * 32u + lane;
+                    const bool ok = r0 + u < rows && i < n;
+                    kk[u] = ok ? __ldcg(kin + i) : 0ull;
+                    vv[u] = ok ? __ldcg(vin + i) : (ValT)0;
+                }
+#pragma unroll
+                for (int u = 0; u < kSmallBatch; ++u) {
+                    const uint32_t i = seg0 + (r0 + u) * 32u + lane;
+                    const bool ok = r0 + u < rows && i < n;
+                    const uint32_t live = __ballot_sync(0xffffffffu, ok);
+                    if (live == 0) break;  // (uniform: rows past the end of the array)
+                    const uint32_t d = (uint32_t)(kk[u] >> lo) & mask;
+                    const uint32_t peers = digit_peers(d) & live;
+                    const uint32_t before = peers & lt_mask;
+                    const uint32_t base = ok ? my_cnt[d] : 0u;
+                    __syncwarp();
+                    if (ok && before == 0) my_cnt[d] = base + __popc(peers);
+                    __syncwarp();
+                    if (ok) {
+                        const uint32_t pos = base + __popc(before);
+                        kout[pos] = kk[u];
+                        vout[pos] = vv[u];
+                    }
                 }
             }
         }
         __syncthreads();  // orders this pass's global writes before the next pass's reads (same CTA)
         uint64_t *tk = kin; kin = kout; kout = tk;
         ValT *tv = vin; vin = vout; vout = tv;
+    }
+    if (ranges && kin != keys_a) {   // odd number of passes: bring the segment home
+        for (uint32_t i = t; i < n; i += kSmallThreads) {
+            keys_a[i] = __ldcg(kin + i);
+            vals_a[i] = __ldcg(vin + i);
+        }
     }
 }
 
@@ -635,11 +668,11 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
         if (val_bytes == 4)
             small_sort_kernel<uint32_t><<<1, kSmallThreads, 0, st>>>(d_keys, d_keys_alt, (uint32_t *)d_vals,
                                                                      (uint32_t *)d_vals_alt, (uint32_t)n, begin_bit,
-                                                                     end_bit);
+                                                                     end_bit, nullptr);
         else
             small_sort_kernel<uint64_t><<<1, kSmallThreads, 0, st>>>(d_keys, d_keys_alt, (uint64_t *)d_vals,
                                                                      (uint64_t *)d_vals_alt, (uint32_t)n, begin_bit,
-                                                                     end_bit);
+                                                                     end_bit, nullptr);
         GK_LAUNCH_CHECK();
         if (result_in_alt) *result_in_alt = passes & 1;
         if (timing) {
@@ -836,6 +869,44 @@ int radix_sort_pairs_device(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals
 {
     return run_onesweep(d_keys, d_keys_alt, d_vals, d_vals_alt, val_bytes, n, begin_bit, end_bit, nullptr,
                         0, result_in_alt, nullptr, st, timing, d_pre_hist, d_vals_final);
+}
+
+// Stable sort of disjoint slot ranges of (keys, vals) on key bits [0, end_bit), in place (the *_tmp arrays of
+// the same size are scratch).  h_ranges: n_ranges (lo, hi) pairs, also on the device (d_ranges).  Ranges of up
+// to kSmallSortMax slots share one launch (one CTA each); larger ones go through the onesweep passes.
+int sort_segments_device(uint64_t *d_keys, uint64_t *d_keys_tmp, void *d_vals, void *d_vals_tmp, int val_bytes,
+                         const unsigned long long *d_ranges, const unsigned long long *h_ranges, uint32_t n_ranges,
+                         int end_bit, cudaStream_t st)
+{
+    if (n_ranges == 0) return GK_OK;
+    bool any_small = false;
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+        const uint64_t lo = h_ranges[2 * i], hi = h_ranges[2 * i + 1];
+        if (hi - lo <= kSmallSortMax) { any_small = true; continue; }
+        // 16-byte aligned key pointers are required: an odd start takes the slot before it along, whose larger
+        // prefix bits keep it first when all 64 bits are sorted
+        const uint64_t a = lo & ~1ull;
+        const int eb = (a == lo) ? end_bit : 64;
+        int in_alt = 0;
+        unsigned char *v = (unsigned char *)d_vals, *vt = (unsigned char *)d_vals_tmp;
+        GK_TRY(run_onesweep(d_keys + a, d_keys_tmp + a, v + a * val_bytes, vt + a * val_bytes, val_bytes, hi - a, 0,
+                            eb, nullptr, 0, &in_alt, nullptr, st, nullptr));
+        if (in_alt) {
+            GK_CUDA(cudaMemcpyAsync(d_keys + a, d_keys_tmp + a, (size_t)(hi - a) * 8, cudaMemcpyDeviceToDevice, st));
+            GK_CUDA(cudaMemcpyAsync(v + a * val_bytes, vt + a * val_bytes, (size_t)(hi - a) * val_bytes,
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (any_small) {
+        if (val_bytes == 4)
+            small_sort_kernel<uint32_t><<<n_ranges, kSmallThreads, 0, st>>>(
+                d_keys, d_keys_tmp, (uint32_t *)d_vals, (uint32_t *)d_vals_tmp, 0, 0, end_bit, d_ranges);
+        else
+            small_sort_kernel<uint64_t><<<n_ranges, kSmallThreads, 0, st>>>(
+                d_keys, d_keys_tmp, (uint64_t *)d_vals, (uint64_t *)d_vals_tmp, 0, 0, end_bit, d_ranges);
+        GK_LAUNCH_CHECK();
+    }
+    return GK_OK;
 }
 
 // Stable partition of the pairs by destination = number of splitters <= key.  Output always lands

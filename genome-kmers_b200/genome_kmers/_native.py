@@ -39,6 +39,7 @@ class GkSortStats(ctypes.Structure):
         ("gpu_launches", ctypes.c_int32), ("n_windows", ctypes.c_uint64),
         ("n_ambiguous", ctypes.c_uint64),
         ("n_fragments", ctypes.c_uint64),
+        ("refine_flags", ctypes.c_uint64),
     ]
 
     def as_dict(self):

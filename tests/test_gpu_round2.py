@@ -82,6 +82,7 @@ def test_fragments_on_long_runs_of_every_kind(k, strands):
     assert len(bad) == 0, f"first mismatches at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
     st = km.last_sort_stats
     assert st["n_fragments"] > 0 and st["n_fragments"] < st["n_ambiguous"]
+    assert st["refine_flags"] & 1 and not st["refine_flags"] & 2, st   # fragment path, no element-wise repair
     hist, total = km.get_kmer_group_counts(k, max_counts_bin=50)
     o_hist, o_total = oracle.group_hist(sba, want, k, max_bin=50)
     assert total == o_total and np.array_equal(hist, o_hist)
@@ -170,3 +171,50 @@ def test_revcomp_on_unaligned_input(n, shift):
     d_out = torch.zeros(n + 11, dtype=torch.uint8, device="cuda")
     _native.check(_native.lib().gk_sba_revcomp(d_in.data_ptr(), n, d_out[11:].data_ptr(), gu.stream()))
     assert np.array_equal(d_out[11:].cpu().numpy(), oracle.revcomp(sba[shift:]))
+
+
+def test_pure_kmer_inside_a_run_of_equal_ambiguous_keys_is_repaired_bucket_wise():
+    """Every window 'A' + 30 x 'N' has the radix key of the pure 31-mer 'AT' + 29 x 'A' minus the class bit,
+    so they share a prefix bucket; a pure k-mer that starts before them leaves that long bucket out of order.
+    Only that bucket is re-sorted (refine_flags bit 16), and the fragments fill the ambiguous slots."""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = acgt[rng.integers(0, 4, 150_000)].copy()
+    seq[1000:1031] = np.frombuffer(b"AT" + b"A" * 29, dtype=np.uint8)
+    for i in range(12):                                   # twelve 'A' + N-run edges: a long bucket of equal keys
+        p = 20_000 + 9_000 * i
+        seq[p] = ord("A")
+        seq[p + 1:p + 200] = ord("N")
+    sc, sba, seg, want = _oracle_sorted([("chr0", seq)], 31, "forward")
+    km = Kmers(sc, 31, 31)
+    km.sort()
+    got = km.kmer_sba_start_indices.astype(np.uint64)
+    assert np.array_equal(got, want)
+    st = km.last_sort_stats
+    assert st["refine_flags"] & 4 and st["refine_flags"] & 16 and st["refine_flags"] & 1, st
+    assert not st["refine_flags"] & 2, st
+    hist, total = km.get_kmer_group_counts(31, max_counts_bin=300)
+    o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=300)
+    assert total == o_total and np.array_equal(hist, o_hist)
+    assert km.verify_order(31)["ok"]
+
+
+def test_repeat_rich_input_is_repaired_without_the_elementwise_path():
+    """Diverged copies of one unit: many prefix buckets longer than eight, some out of order."""
+    rng = np.random.default_rng(78)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, 900)]
+    parts = []
+    for _ in range(150):
+        c = unit.copy()
+        c[rng.integers(0, 900, 4)] = acgt[rng.integers(0, 4, 4)]
+        parts += [c, acgt[rng.integers(0, 4, int(rng.integers(10, 200)))]]
+    seq = np.concatenate(parts)
+    sc, sba, seg, want = _oracle_sorted([("chr0", seq[:70_000]), ("chr1", seq[70_000:])], 31, "both")
+    km = Kmers(sc, 31, 31, source_strand="both")
+    km.sort()
+    assert np.array_equal(km.kmer_sba_start_indices.astype(np.uint64), want)
+    assert km.verify_order(31)["ok"]
+    hist, total = km.get_kmer_group_counts(31, max_counts_bin=400)
+    o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=400)
+    assert total == o_total and np.array_equal(hist, o_hist)
