@@ -18,6 +18,7 @@ constexpr uint8_t kFlagPass = 4;   // element passes a filter / validity test (s
 constexpr uint8_t kFlagMulti = 8;  // member of a group with more than one element (scratch arrays)
 constexpr uint8_t kFlagLong = 16;  // member of a prefix run too long for the in-place tie repair
 
+constexpr int kBigBucketCap = 15;  // out-of-order buckets too long for one CTA, listed for the host
 constexpr int kDescentCap = 4096;  // out-of-order positions of long prefix runs listed for the bucket-wise repair
 
 // ---- error plumbing ------------------------------------------------------------------------
@@ -135,8 +136,25 @@ struct FragOut {
 struct FragSorted {
     DeviceBuffer skey_a, skey_b, perm_a, perm_b, sstart, off, whead, slot0;
     const uint64_t *skey = nullptr;
-    uint64_t F = 0;
-    // the buffers are allocated and filled on a side stream and last used on the main stream: release them there
+    uint64_t F = 0, cap = 0;
+    // Room for up to `f` fragments.  Called on the MAIN stream before the side stream forks, so that the pool
+    // never has to hand memory from one stream to the other (that costs a fresh device allocation).
+    int reserve(uint64_t f, cudaStream_t st)
+    {
+        if (f <= cap) return GK_OK;
+        const size_t pad = (size_t)((f + 1) & ~1ull);  // (16-byte aligned key buffers)
+        GK_TRY(skey_a.alloc(pad * 8, st));
+        GK_TRY(skey_b.alloc(pad * 8, st));
+        GK_TRY(perm_a.alloc(pad * 4, st));
+        GK_TRY(perm_b.alloc(pad * 4, st));
+        GK_TRY(sstart.alloc((size_t)f * 8, st));
+        GK_TRY(off.alloc((size_t)(f + 1) * 8, st));
+        GK_TRY(whead.alloc((size_t)f, st));
+        GK_TRY(slot0.alloc((size_t)f * 8, st));
+        cap = f;
+        return GK_OK;
+    }
+    // buffers that were (re)allocated on a side stream are last used on the main stream: release them there
     void rebind(cudaStream_t st)
     {
         for (DeviceBuffer *b : {&skey_a, &skey_b, &perm_a, &perm_b, &sstart, &off, &whead, &slot0}) b->stream = st;

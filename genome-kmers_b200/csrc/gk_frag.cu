@@ -108,14 +108,14 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *__restrict__
 // First slot of every fragment in the sorted order.  All windows with an ambiguous key K sit in one run of
 // slots that starts at the lower bound of K in the sorted keys (no pure window shares a class-0 key);
 // inside the run the fragments follow each other in (w0, w1, start) order.
-// err bit 1: fragment windows != ambiguous windows counted by the pack kernel; bit 2: key not found.
+// err value 2: fragment windows != ambiguous windows counted by the pack kernel; 4: key not found.
 __global__ void __launch_bounds__(256)
 frag_slots_kernel(const uint64_t *__restrict__ skey, const unsigned long long *__restrict__ off, uint64_t F,
                   const uint64_t *__restrict__ keys_sorted, uint64_t n, const unsigned int *__restrict__ descent,
                   const unsigned long long *__restrict__ n_amb_expected, unsigned long long *__restrict__ slot0,
                   int *__restrict__ err)
 {
-    if (*descent) return;   // the keys are not fully sorted: the caller takes the element-wise path instead
+    if (*descent) return;   // the keys are not fully sorted yet: the caller repairs them and calls again
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid == 0 && n_amb_expected && off[F] != *n_amb_expected) atomicOr(err, 2);
@@ -161,15 +161,7 @@ int frag_sort_device(const FragOut &frag, uint64_t F, uint32_t key_len, int key_
 {
     out.F = F;
     if (F == 0) return GK_OK;
-    const size_t pad = (size_t)((F + 1) & ~1ull);  // (16-byte aligned key buffers)
-    GK_TRY(out.skey_a.alloc(pad * 8, st));
-    GK_TRY(out.skey_b.alloc(pad * 8, st));
-    GK_TRY(out.perm_a.alloc(pad * 4, st));
-    GK_TRY(out.perm_b.alloc(pad * 4, st));
-    GK_TRY(out.sstart.alloc((size_t)F * 8, st));
-    GK_TRY(out.off.alloc((size_t)(F + 1) * 8, st));
-    GK_TRY(out.whead.alloc((size_t)F, st));
-    GK_TRY(out.slot0.alloc((size_t)F * 8, st));
+    GK_TRY(out.reserve(F, st));
     const int grid = frag_grid(F);
     frag_iota_kernel<<<grid, 256, 0, st>>>(out.perm_a.as<uint32_t>(), F);
     GK_LAUNCH_CHECK();

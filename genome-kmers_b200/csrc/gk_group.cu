@@ -323,32 +323,7 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     }
 }
 
-// ---- bucket-wise repair of out-of-order long prefix runs -----------------------------------------------
-// For every listed descent position: the slot range [lo, hi) of its prefix bucket (the array is sorted by
-// prefix, so two binary searches on key >> lo_bits find it).  ranges[2 * i], ranges[2 * i + 1].
-__global__ void __launch_bounds__(256)
-bucket_ranges_kernel(const uint64_t *__restrict__ keys, uint64_t n, int lo_bits,
-                     const unsigned long long *__restrict__ positions, uint32_t count,
-                     unsigned long long *__restrict__ ranges)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint64_t pre = keys[positions[i]] >> lo_bits;
-    uint64_t lo = 0, hi = n;
-    while (lo < hi) {   // first slot whose prefix is >= pre
-        const uint64_t mid = (lo + hi) >> 1;
-        if ((keys[mid] >> lo_bits) < pre) lo = mid + 1; else hi = mid;
-    }
-    const uint64_t first = lo;
-    hi = n;
-    while (lo < hi) {   // first slot whose prefix is > pre
-        const uint64_t mid = (lo + hi) >> 1;
-        if ((keys[mid] >> lo_bits) <= pre) lo = mid + 1; else hi = mid;
-    }
-    ranges[2 * i] = first;
-    ranges[2 * i + 1] = lo;
-}
-
+// ---- flags of re-sorted prefix buckets (the bucket-wise repair lives in gk_sort.cu / gk_index.cu) ------------
 // head / ambiguous flags of the fully sorted slots [lo, hi) of each range (a bucket start is always a head)
 __global__ void __launch_bounds__(256)
 range_key_flags_kernel(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ ranges,
@@ -362,15 +337,6 @@ range_key_flags_kernel(const uint64_t *__restrict__ keys, const unsigned long lo
         const bool head = (p == lo) || keys[p - 1] != k;
         flags[p] = amb ? kFlagAmb : (head ? kFlagHead : 0);
     }
-}
-
-int bucket_ranges_device(const uint64_t *d_keys, uint64_t n, int lo_bits, const unsigned long long *d_positions,
-                         uint32_t count, unsigned long long *d_ranges, cudaStream_t st)
-{
-    if (count == 0) return GK_OK;
-    bucket_ranges_kernel<<<(count + 255) / 256, 256, 0, st>>>(d_keys, n, lo_bits, d_positions, count, d_ranges);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
 }
 
 int range_key_flags_device(const uint64_t *d_keys, const unsigned long long *d_ranges, uint32_t n_ranges,

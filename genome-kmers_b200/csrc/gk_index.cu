@@ -47,12 +47,13 @@ int radix_sort_pairs_device(uint64_t *, uint64_t *, void *, void *, int, uint64_
 int key_flags_device(const uint64_t *, uint64_t, int, uint8_t *, cudaStream_t);
 int tie_fix_flags_device(uint64_t *, void *, int, uint64_t, int, int, uint8_t *, unsigned int *,
                          unsigned long long *, cudaStream_t, unsigned long long *d_descent_list = nullptr);
-int bucket_ranges_device(const uint64_t *, uint64_t, int, const unsigned long long *, uint32_t, unsigned long long *,
-                         cudaStream_t);
 int range_key_flags_device(const uint64_t *, const unsigned long long *, uint32_t, uint64_t, int, uint8_t *,
                            cudaStream_t);
 int sort_segments_device(uint64_t *, uint64_t *, void *, void *, int, const unsigned long long *,
                          const unsigned long long *, uint32_t, int, cudaStream_t);
+int repair_buckets_on_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, uint8_t *,
+                             const unsigned int *, const unsigned long long *, int *, unsigned long long *,
+                             cudaStream_t);
 int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
 int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &, int, void *, const uint64_t *,
                        uint64_t *, const void *, void *, cudaStream_t);
@@ -228,7 +229,8 @@ static bool fragments_enabled()
     const char *e = getenv("GK_FRAGMENTS");
     return !(e && e[0] == '0');
 }
-constexpr uint64_t kFragCapacity = 1ull << 21;  // fragments listed by the pack kernel; beyond: element-wise path
+constexpr uint64_t kFragCapacity = 1ull << 21;
+constexpr uint64_t kFragReserve = 1ull << 17;   // fragment-sort scratch reserved on the main stream up front  // fragments listed by the pack kernel; beyond: element-wise path
 
 // First key bit the LSD passes of the main sort cover.  0 = plain LSD over the whole key.  Otherwise only
 // the top 8*ceil((log2(n)+4)/8) bits are sorted -- 16 times more prefix buckets than k-mers, so about one
@@ -368,39 +370,20 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     return GK_OK;  // the scratch above is released in stream order (cudaFreeAsync): no synchronise needed
 }
 
-// Long prefix runs that the flags pass found out of order (a pure k-mer in the middle of a run of equal
-// ambiguous keys; diverged repeats that share their first 16 symbols): sort each such bucket by its low key
-// bits, in place, and recompute its flags.  The buckets are found from the listed descent positions; the
-// rest of the array is not touched.  Synchronises (the bucket list comes back to the host).
-static int repair_buckets(uint64_t *keys, uint64_t *keys_tmp, void *idx, void *idx_tmp, int ib, uint64_t n,
-                          int lo_bits, int class_bit, uint8_t *d_flags, const unsigned long long *d_positions,
-                          uint32_t count, uint64_t *n_slots_out, cudaStream_t st)
+// Out-of-order prefix buckets that were too long for the device-side repair (one CTA per bucket): sort each
+// by its low key bits with the radix passes, in place, and recompute its flags.  h_ranges: n_ranges (lo, hi)
+// slot ranges as listed by repair_buckets_kernel.  No synchronise.
+static int repair_big_buckets(uint64_t *keys, uint64_t *keys_tmp, void *idx, void *idx_tmp, int ib, int lo_bits,
+                              int class_bit, uint8_t *d_flags, const unsigned long long *d_ranges,
+                              const unsigned long long *h_ranges, uint32_t n_ranges, cudaStream_t st)
 {
-    DeviceBuffer ranges;
-    GK_TRY(ranges.alloc((size_t)count * 16, st));
-    GK_TRY(bucket_ranges_device(keys, n, lo_bits, d_positions, count, ranges.as<unsigned long long>(), st));
-    std::vector<unsigned long long> h((size_t)count * 2);
-    GK_CUDA(cudaMemcpyAsync(h.data(), ranges.ptr, (size_t)count * 16, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaStreamSynchronize(st));
-    std::vector<std::pair<unsigned long long, unsigned long long>> uniq;
-    for (uint32_t i = 0; i < count; ++i) uniq.emplace_back(h[2 * i], h[2 * i + 1]);
-    std::sort(uniq.begin(), uniq.end());
-    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-    uint64_t longest = 0, total = 0;
-    for (size_t i = 0; i < uniq.size(); ++i) {
-        h[2 * i] = uniq[i].first;
-        h[2 * i + 1] = uniq[i].second;
-        const uint64_t len = uniq[i].second - uniq[i].first;
+    uint64_t longest = 0;
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+        const uint64_t len = h_ranges[2 * i + 1] - h_ranges[2 * i];
         longest = len > longest ? len : longest;
-        total += len;
     }
-    const uint32_t n_ranges = (uint32_t)uniq.size();
-    GK_CUDA(cudaMemcpyAsync(ranges.ptr, h.data(), (size_t)n_ranges * 16, cudaMemcpyHostToDevice, st));
-    GK_TRY(sort_segments_device(keys, keys_tmp, idx, idx_tmp, ib, ranges.as<unsigned long long>(), h.data(), n_ranges,
-                                lo_bits, st));
-    GK_TRY(range_key_flags_device(keys, ranges.as<unsigned long long>(), n_ranges, longest, class_bit, d_flags, st));
-    GK_CUDA(cudaStreamSynchronize(st));   // h is pageable and must outlive the upload
-    if (n_slots_out) *n_slots_out = total;
+    GK_TRY(sort_segments_device(keys, keys_tmp, idx, idx_tmp, ib, d_ranges, h_ranges, n_ranges, lo_bits, st));
+    GK_TRY(range_key_flags_device(keys, d_ranges, n_ranges, longest, class_bit, d_flags, st));
     return GK_OK;
 }
 
@@ -431,12 +414,15 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_TRY(keys_b.alloc((size_t)n * 8, st));
     GK_TRY(idx_b.alloc((size_t)n * ib, st));
     GK_TRY(out_idx.alloc((size_t)n * ib, st));
-    // device counters: [0] ambiguous windows, [1] descents (u32), [2] fragments, [3] fragment error bits (int),
-    // [4 ...] the first kDescentCap descent positions
-    GK_TRY(counters.alloc(32 + (size_t)kDescentCap * 8, st));
-    GK_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, st));
+    // device counters: [0] ambiguous windows, [1] low half: descents, high half: repair status (0 = the order
+    // is final), [2] fragments, [3] fragment error bits (int), [4] number of big out-of-order buckets, then
+    // their kBigBucketCap (lo, hi) ranges, [kCounterWords ...] the first kDescentCap descent positions
+    constexpr int kCounterWords = 5 + 2 * kBigBucketCap;
+    GK_TRY(counters.alloc((size_t)(kCounterWords + kDescentCap) * 8, st));
+    GK_CUDA(cudaMemsetAsync(counters.ptr, 0, (size_t)kCounterWords * 8, st));
     unsigned long long *d_counters = counters.as<unsigned long long>();
     unsigned int *d_descent = reinterpret_cast<unsigned int *>(d_counters + 1);
+    int *d_status = reinterpret_cast<int *>(d_descent + 1);
     int *d_frag_err = reinterpret_cast<int *>(d_counters + 3);
     // the pack kernel counts the digits of the radix passes while it writes the keys
     const int begin_bit = prefix_begin_bit(n, key_bits);
@@ -444,6 +430,7 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_CUDA(cudaMemsetAsync(pre_hist.ptr, 0, pre_hist.bytes, st));
     // fragment list of the ambiguous windows (not for an arbitrary list of starts: no neighbours there)
     FragOut frag;
+    FragSorted fs;
     const bool want_frag = class_bit && !d_list && fragments_enabled();
     if (want_frag) {
         const uint64_t cap = n < kFragCapacity ? n : kFragCapacity;
@@ -453,6 +440,7 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
         frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
         frag.counter = d_counters + 2;
         frag.capacity = cap;
+        GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
     }
 
     marks.pack0 = tm.mark();
@@ -477,15 +465,21 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
                                key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt, d_descent,
                                &marks.main_sort, st, d_list ? nullptr : pre_hist.as<unsigned long long>(), nullptr,
-                               nullptr, d_counters + 4));
+                               nullptr, d_counters + kCounterWords));
     uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
     uint64_t *keys_other = in_alt ? keys_a.as<uint64_t>() : keys_b.as<uint64_t>();
     if (in_alt) out_idx.swap(idx_b);
+    marks.fix0 = tm.mark();
+    // long prefix runs that came out of order are re-sorted bucket by bucket, driven from the device list
+    if (begin_bit > 0)
+        GK_TRY(repair_buckets_on_device(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, n, begin_bit, class_bit,
+                                        (uint8_t *)out_flags.ptr, d_descent, d_counters + kCounterWords, d_status,
+                                        d_counters + 4, st));
 
     // ---- side stream: the pack kernel's counters, then the fragment sort -------------------------------------
     cudaStream_t side = nullptr;
     GK_TRY(side_stream(&side));
-    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    unsigned long long h_counters[kCounterWords] = {0};
     GK_CUDA(cudaStreamWaitEvent(side, e_pack.ev, 0));
     GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, side));
     GK_CUDA(cudaStreamSynchronize(side));
@@ -493,65 +487,64 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     marks.n_amb = n_amb;
     marks.n_frag = n_frag;
     const bool use_frag = want_frag && n_amb > 0 && n_frag > 0 && n_frag <= frag.capacity;
-    FragSorted fs;
-    marks.fix0 = tm.mark();
     if (use_frag) {
         int start_bits = 1;
         while (start_bits < 64 && (ix->sba_len >> start_bits)) ++start_bits;
         GK_TRY(frag_sort_device(frag, n_frag, key_len, key_bits, start_bits, fs, side));
         GK_CUDA(cudaEventRecord(e_frag.ev, side));
         GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
-        GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr, d_descent,
-                                  d_counters, n_amb, d_frag_err, st));
+        GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr,
+                                  reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb, d_frag_err, st));
         fs.rebind(st);
     }
     marks.fix1 = tm.mark();
 
-    // ---- the one synchronise: descent word, fragment check, alphabet counters ---------------------------------
-    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
+    // ---- the one synchronise: descents, repair status, fragment check, alphabet counters -----------------------
+    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     if (d_alpha) GK_CUDA(cudaMemcpyAsync(h_alpha, d_alpha, 24, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_descent = (uint32_t)(h_counters[1] & 0xffffffffull);
-    const int frag_err = (int)(h_counters[3] & 0xffffffffull);
-    marks.refine_flags = (use_frag ? 1u : 0u) | (n_descent ? 4u : 0u) | ((uint32_t)frag_err << 8);
+    const int status = (int)(h_counters[1] >> 32);
+    int frag_err = (int)(h_counters[3] & 0xffffffffull);
+    marks.refine_flags = (use_frag ? 1u : 0u) | (n_descent ? 4u : 0u) | (n_descent && !status ? 16u : 0u) |
+                         ((uint32_t)frag_err << 8);
     if (getenv("GK_TRACE"))
-        fprintf(stderr, "[gk trace] level1: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u frag_err=%d\n",
-                (unsigned long long)n, (unsigned long long)n_amb, (unsigned long long)n_frag, (int)use_frag,
-                n_descent, frag_err);
-    const bool frag_ok = use_frag && !frag_err;
-    bool need_elementwise = n_amb > 0 && !frag_ok;   // ambiguous windows without a usable fragment list
+        fprintf(stderr, "[gk trace] level1: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u status=%d "
+                        "frag_err=%d\n", (unsigned long long)n, (unsigned long long)n_amb, (unsigned long long)n_frag,
+                (int)use_frag, n_descent, status, frag_err);
     bool elementwise_long = false;
-    if (n_descent) {
+    if (status) {
+        // the device-side repair left work behind: a bucket too long for one CTA (sorted from here with the
+        // radix passes), or more descents than the list holds (element-wise repair of every long run)
         const int f0 = tm.mark();
-        if (n_descent <= (uint32_t)kDescentCap && begin_bit > 0) {
-            // a handful of long prefix runs are out of order: sort those buckets, nothing else
-            uint64_t repaired = 0;
-            GK_TRY(repair_buckets(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, n, begin_bit, class_bit,
-                                  (uint8_t *)out_flags.ptr, d_counters + 4, n_descent, &repaired, st));
-            marks.refine_flags |= 16u;
-            if (frag_ok) {   // the fragment kernels did nothing while the keys were out of order: run them now
-                GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
-                GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr, d_descent,
-                                          d_counters, n_amb, d_frag_err, st));
-                GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
-                GK_CUDA(cudaStreamSynchronize(st));
-                if ((int)(h_counters[3] & 0xffffffffull)) need_elementwise = true;
+        if (!(status & 2)) {
+            const uint32_t n_big = (uint32_t)h_counters[4];
+            GK_TRY(repair_big_buckets(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, begin_bit, class_bit,
+                                      (uint8_t *)out_flags.ptr, d_counters + 5, h_counters + 5, n_big, st));
+            marks.refine_flags |= 32u;
+            if (use_frag && !frag_err) {   // the fragment kernels did nothing while the keys were out of order
+                GK_CUDA(cudaMemsetAsync(d_status, 0, 4, st));
+                GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr,
+                                          reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb,
+                                          d_frag_err, st));
             }
+            GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaStreamSynchronize(st));
+            frag_err = (int)(h_counters[3] & 0xffffffffull);
         } else {
-            need_elementwise = true;   // too many to list: element-wise repair of every long run
             elementwise_long = true;
         }
         marks.fix0 = f0;
         marks.fix1 = tm.mark();
     }
-    if (need_elementwise) {
+    if (elementwise_long || (n_amb > 0 && !(use_frag && !frag_err))) {
         // element-wise repair (gk_refine.cu): the ambiguous windows by their 4-bit rank words when there is no
         // fragment list for them, and the members of every long prefix run when too many are out of order
         const int f0 = tm.mark();
         GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
                              n_amb, elementwise_long, terminated, st));
         GK_CUDA(cudaStreamSynchronize(st));
-        if (!n_descent) marks.fix0 = f0;
+        if (!status) marks.fix0 = f0;
         marks.fix1 = tm.mark();
         marks.refine_flags |= 2u;
     }

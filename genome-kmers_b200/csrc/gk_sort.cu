@@ -411,20 +411,19 @@ constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr uint64_t kSmallSortMax = 1ull << 16;
 constexpr int kSmallBatch = 8;
 
+struct SmallSortSmem {
+    uint32_t cnt[kSmallWarps][kRadix];
+    uint32_t wsum[kRadix / 32];
+    int skip;
+};
+
+// Body shared by the kernels below: sort n <= kSmallSortMax pairs on key bits [begin_bit, end_bit) by
+// ping-ponging between the a and b arrays; with land_in_a the result is brought back to the a arrays when the
+// number of passes is odd.  All threads of the CTA call it.
 template <typename ValT>
-__global__ void __launch_bounds__(kSmallThreads, 1)
-small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b, uint32_t n, int begin_bit,
-                  int end_bit, const unsigned long long *__restrict__ ranges /* nullable: one segment per CTA */)
+__device__ __forceinline__ void small_sort_body(SmallSortSmem &sm, uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a,
+                                                ValT *vals_b, uint32_t n, int begin_bit, int end_bit, bool land_in_a)
 {
-    if (ranges) {   // segment mode: sort slots [lo, hi) of the arrays in place (result lands in the *_a arrays)
-        const unsigned long long lo_ = ranges[2 * blockIdx.x], hi_ = ranges[2 * blockIdx.x + 1];
-        if (hi_ - lo_ > kSmallSortMax || hi_ - lo_ < 2) return;   // (larger segments are sorted by the host driver)
-        n = (uint32_t)(hi_ - lo_);
-        keys_a += lo_; keys_b += lo_; vals_a += lo_; vals_b += lo_;
-    }
-    __shared__ uint32_t s_cnt[kSmallWarps][kRadix];
-    __shared__ uint32_t s_wsum[kRadix / 32];
-    __shared__ int s_skip;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t rows = (n + kSmallThreads - 1) / kSmallThreads;  // rows of 32 elements per warp
     const uint32_t seg0 = warp * rows * 32u;
@@ -434,8 +433,8 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
     for (int lo = begin_bit; lo < end_bit; lo += kRadixBits) {
         const int bits = (end_bit - lo < kRadixBits) ? end_bit - lo : kRadixBits;
         const uint32_t mask = (1u << bits) - 1u;
-        for (int i = t; i < kSmallWarps * kRadix; i += kSmallThreads) (&s_cnt[0][0])[i] = 0;
-        if (t == 0) s_skip = 0;
+        for (int i = t; i < kSmallWarps * kRadix; i += kSmallThreads) (&sm.cnt[0][0])[i] = 0;
+        if (t == 0) sm.skip = 0;
         __syncthreads();
         for (uint32_t r0 = 0; r0 < rows; r0 += kSmallBatch) {   // several rows in flight per L2 round trip
             uint64_t kk[kSmallBatch];
@@ -447,7 +446,7 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
 #pragma unroll
             for (int u = 0; u < kSmallBatch; ++u) {
                 const uint32_t i = seg0 + (r0 + u) * 32u + lane;
-                if (r0 + u < rows && i < n) atomicAdd(&s_cnt[warp][(uint32_t)(kk[u] >> lo) & mask], 1u);
+                if (r0 + u < rows && i < n) atomicAdd(&sm.cnt[warp][(uint32_t)(kk[u] >> lo) & mask], 1u);
             }
         }
         __syncthreads();
@@ -456,12 +455,12 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
             uint32_t sum = 0;
 #pragma unroll 8
             for (int w = 0; w < kSmallWarps; ++w) {
-                const uint32_t c = s_cnt[w][t];
-                s_cnt[w][t] = sum;
+                const uint32_t c = sm.cnt[w][t];
+                sm.cnt[w][t] = sum;
                 sum += c;
             }
             total = sum;
-            if (total == n) s_skip = 1;  // every element has this digit: the pass is the identity
+            if (total == n) sm.skip = 1;  // every element has this digit: the pass is the identity
         }
         uint32_t inc = total;
 #pragma unroll
@@ -469,23 +468,23 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (uint32_t)o) inc += v;
         }
-        if (t < kRadix && lane == 31) s_wsum[warp] = inc;
+        if (t < kRadix && lane == 31) sm.wsum[warp] = inc;
         __syncthreads();
         if (t < kRadix) {
             uint32_t pre = 0;
-            for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
+            for (uint32_t w = 0; w < warp; ++w) pre += sm.wsum[w];
             const uint32_t excl = pre + inc - total;
 #pragma unroll 8
-            for (int w = 0; w < kSmallWarps; ++w) s_cnt[w][t] += excl;
+            for (int w = 0; w < kSmallWarps; ++w) sm.cnt[w][t] += excl;
         }
         __syncthreads();
-        if (s_skip) {
+        if (sm.skip) {
             for (uint32_t i = t; i < n; i += kSmallThreads) {
                 kout[i] = __ldcg(kin + i);
                 vout[i] = __ldcg(vin + i);
             }
         } else {
-            uint32_t *my_cnt = s_cnt[warp];
+            uint32_t *my_cnt = sm.cnt[warp];
             for (uint32_t r0 = 0; r0 < rows; r0 += kSmallBatch) {
                 uint64_t kk[kSmallBatch];
                 ValT vv[kSmallBatch];
@@ -521,11 +520,96 @@ small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b
         uint64_t *tk = kin; kin = kout; kout = tk;
         ValT *tv = vin; vin = vout; vout = tv;
     }
-    if (ranges && kin != keys_a) {   // odd number of passes: bring the segment home
+    if (land_in_a && kin != keys_a) {   // odd number of passes: bring the result home
         for (uint32_t i = t; i < n; i += kSmallThreads) {
             keys_a[i] = __ldcg(kin + i);
             vals_a[i] = __ldcg(vin + i);
         }
+        __syncthreads();
+    }
+}
+
+// ranges == nullptr: one list of n pairs.  Otherwise one CTA per (lo, hi) slot range of the arrays, sorted in
+// place (ranges longer than kSmallSortMax are left to the host driver).
+template <typename ValT>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+small_sort_kernel(uint64_t *keys_a, uint64_t *keys_b, ValT *vals_a, ValT *vals_b, uint32_t n, int begin_bit,
+                  int end_bit, const unsigned long long *__restrict__ ranges)
+{
+    __shared__ SmallSortSmem sm;
+    if (ranges) {
+        const unsigned long long lo_ = ranges[2 * blockIdx.x], hi_ = ranges[2 * blockIdx.x + 1];
+        if (hi_ - lo_ > kSmallSortMax || hi_ - lo_ < 2) return;
+        n = (uint32_t)(hi_ - lo_);
+        keys_a += lo_; keys_b += lo_; vals_a += lo_; vals_b += lo_;
+    }
+    small_sort_body<ValT>(sm, keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, ranges != nullptr);
+}
+
+// Device-driven repair of the long prefix runs that the flags pass found out of order (gk_group.cu:
+// tie_fix_flags_kernel lists the positions).  CTA b takes listed position b: finds the slot range of its
+// prefix bucket (the array is sorted by prefix), drops out if an earlier list entry lies in the same bucket,
+// sorts the bucket by its low key bits in place and rewrites its head / ambiguous flags.  Nothing comes back
+// to the host unless *status ends up non-zero: bit 1 a bucket is longer than kSmallSortMax, bit 2 more
+// positions than the list holds.
+template <typename ValT>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+repair_buckets_kernel(uint64_t *keys, uint64_t *keys_tmp, ValT *vals, ValT *vals_tmp, uint64_t n, int lo_bits,
+                      int class_bit, uint8_t *__restrict__ flags, const unsigned int *__restrict__ count,
+                      const unsigned long long *__restrict__ list, int *__restrict__ status,
+                      unsigned long long *__restrict__ big /* [0] count, then up to kBigBucketCap (lo, hi) pairs */)
+{
+    __shared__ SmallSortSmem sm;
+    __shared__ unsigned long long s_range[2];
+    const unsigned int total = *count;
+    if (total > (unsigned int)kDescentCap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 2);
+        return;
+    }
+    for (unsigned int b = blockIdx.x; b < total; b += gridDim.x) {
+        if (threadIdx.x == 0) {
+            const uint64_t pre = keys[list[b]] >> lo_bits;
+            uint64_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if ((__ldcg(keys + mid) >> lo_bits) < pre) lo = mid + 1; else hi = mid;
+            }
+            s_range[0] = lo;
+            hi = n;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if ((__ldcg(keys + mid) >> lo_bits) <= pre) lo = mid + 1; else hi = mid;
+            }
+            s_range[1] = lo;
+        }
+        __syncthreads();
+        const uint64_t lo = s_range[0], hi = s_range[1];
+        int dup = 0;
+        for (unsigned int j = threadIdx.x; j < b; j += kSmallThreads) dup |= (list[j] >= lo && list[j] < hi) ? 1 : 0;
+        dup = __syncthreads_or(dup);   // (also orders the reads of s_range before the next iteration's write)
+        if (dup) continue;
+        if (hi - lo > kSmallSortMax) {   // too long for one CTA: listed for the host, which runs the radix passes
+            if (threadIdx.x == 0) {
+                const unsigned long long slot = atomicAdd(&big[0], 1ull);
+                if (slot < (unsigned long long)kBigBucketCap) {
+                    big[1 + 2 * slot] = lo;
+                    big[2 + 2 * slot] = hi;
+                    atomicOr(status, 1);
+                } else {
+                    atomicOr(status, 2);
+                }
+            }
+            continue;
+        }
+        const uint32_t len = (uint32_t)(hi - lo);
+        small_sort_body<ValT>(sm, keys + lo, keys_tmp + lo, vals + lo, vals_tmp + lo, len, 0, lo_bits, true);
+        for (uint32_t i = threadIdx.x; i < len; i += kSmallThreads) {
+            const uint64_t k = __ldcg(keys + lo + i);
+            const bool amb = class_bit && !(k & 1ull);
+            const bool head = (i == 0) || __ldcg(keys + lo + i - 1) != k;
+            flags[lo + i] = amb ? kFlagAmb : (head ? kFlagHead : 0);
+        }
+        __syncthreads();
     }
 }
 
@@ -906,6 +990,25 @@ int sort_segments_device(uint64_t *d_keys, uint64_t *d_keys_tmp, void *d_vals, v
                 d_keys, d_keys_tmp, (uint64_t *)d_vals, (uint64_t *)d_vals_tmp, 0, 0, end_bit, d_ranges);
         GK_LAUNCH_CHECK();
     }
+    return GK_OK;
+}
+
+int repair_buckets_on_device(uint64_t *d_keys, uint64_t *d_keys_tmp, void *d_vals, void *d_vals_tmp, int val_bytes,
+                             uint64_t n, int lo_bits, int class_bit, uint8_t *d_flags, const unsigned int *d_count,
+                             const unsigned long long *d_list, int *d_status, unsigned long long *d_big,
+                             cudaStream_t st)
+{
+    if (n == 0) return GK_OK;
+    const int grid = 64;
+    if (val_bytes == 4)
+        repair_buckets_kernel<uint32_t><<<grid, kSmallThreads, 0, st>>>(d_keys, d_keys_tmp, (uint32_t *)d_vals,
+                                                                        (uint32_t *)d_vals_tmp, n, lo_bits, class_bit,
+                                                                        d_flags, d_count, d_list, d_status, d_big);
+    else
+        repair_buckets_kernel<uint64_t><<<grid, kSmallThreads, 0, st>>>(d_keys, d_keys_tmp, (uint64_t *)d_vals,
+                                                                        (uint64_t *)d_vals_tmp, n, lo_bits, class_bit,
+                                                                        d_flags, d_count, d_list, d_status, d_big);
+    GK_LAUNCH_CHECK();
     return GK_OK;
 }
 
