@@ -522,7 +522,7 @@ def run_single_gpu(args):
         handle = device_step(keep=True)
         try:
             report = np.zeros(8, dtype=np.uint64)
-            _native.check(lib.gk_index_verify(handle, K, _native.host_ptr(report), sp))
+            _native.check(lib.gk_index_verify(handle, K, _native.host_ptr(report), None, sp))
         finally:
             lib.gk_index_destroy(handle)
         rep = dict(zip(("kmers", "out_of_order", "tie_order", "invalid_starts", "duplicate_starts", "groups",

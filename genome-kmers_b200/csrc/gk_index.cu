@@ -28,7 +28,7 @@ int check_starts_device(const void *, int, uint64_t, const uint64_t *, uint32_t,
                         unsigned long long *, cudaStream_t);
 int scan_alphabet_async(const uint8_t *, uint64_t, unsigned long long *, cudaStream_t);
 int verify_order_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, const uint64_t *, uint32_t,
-                        uint32_t, const uint8_t *, uint64_t *, cudaStream_t);
+                        uint32_t, const uint8_t *, uint64_t *, uint32_t *, cudaStream_t);
 struct FragSorted;
 int frag_sort_device(const FragOut &, uint64_t, uint32_t, int, int, FragSorted &, cudaStream_t);
 int frag_expand_device(FragSorted &, const uint64_t *, uint64_t, int, void *, uint8_t *, const unsigned int *,
@@ -1231,7 +1231,7 @@ int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *f
     return GK_OK;
 }
 
-int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, void *stream)
+int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, uint32_t *d_seen_bitmap, void *stream)
 {
     if (!ix || !h_report8) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
@@ -1239,7 +1239,7 @@ int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, void *
     const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
     return verify_order_device(ix->d_sba, ix->sba_len, ix->d_idx.ptr, ix->idx_bytes, ix->n, kmer_len,
                                (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->min_len,
-                               cached ? (const uint8_t *)ix->d_flags.ptr : nullptr, h_report8, st);
+                               cached ? (const uint8_t *)ix->d_flags.ptr : nullptr, h_report8, d_seen_bitmap, st);
 }
 
 int gk_sort_count_host(const uint8_t *h_sba, uint64_t sba_len, const uint64_t *h_seg_starts,

@@ -68,16 +68,20 @@ verify_order_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const Idx
 
 int verify_order_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes, uint64_t n,
                         uint32_t kmer_len, const uint64_t *d_seg_starts, uint32_t n_seg, uint32_t min_len,
-                        const uint8_t *d_flags, uint64_t *h_report8, cudaStream_t st)
+                        const uint8_t *d_flags, uint64_t *h_report8, uint32_t *d_seen_out, cudaStream_t st)
 {
     for (int i = 0; i < 8; ++i) h_report8[i] = 0;
     h_report8[0] = n;
     if (n == 0) return GK_OK;
     DeviceBuffer seen, report;
     const size_t words = (size_t)(sba_len / 32 + 1);
-    GK_TRY(seen.alloc(words * 4, st));
+    uint32_t *d_seen = d_seen_out;   // caller's bitmap (already zero) or a scratch one
+    if (!d_seen) {
+        GK_TRY(seen.alloc(words * 4, st));
+        GK_CUDA(cudaMemsetAsync(seen.ptr, 0, words * 4, st));
+        d_seen = seen.as<uint32_t>();
+    }
     GK_TRY(report.alloc(64, st));
-    GK_CUDA(cudaMemsetAsync(seen.ptr, 0, words * 4, st));
     GK_CUDA(cudaMemsetAsync(report.ptr, 0, 64, st));
     uint64_t blocks = (n + 255) / 256;
     const uint64_t cap = (uint64_t)sm_count() * 32;
@@ -85,11 +89,11 @@ int verify_order_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_id
     if (idx_bytes == 4)
         verify_order_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(
             d_sba, sba_len, (const uint32_t *)d_idx, n, kmer_len, d_seg_starts, n_seg, min_len, d_flags,
-            seen.as<uint32_t>(), report.as<unsigned long long>());
+            d_seen, report.as<unsigned long long>());
     else
         verify_order_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>(
             d_sba, sba_len, (const uint64_t *)d_idx, n, kmer_len, d_seg_starts, n_seg, min_len, d_flags,
-            seen.as<uint32_t>(), report.as<unsigned long long>());
+            d_seen, report.as<unsigned long long>());
     GK_LAUNCH_CHECK();
     unsigned long long h[8];
     GK_CUDA(cudaMemcpyAsync(h, report.ptr, 64, cudaMemcpyDeviceToHost, st));
@@ -100,4 +104,35 @@ int verify_order_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_id
     return GK_OK;
 }
 
+__global__ void __launch_bounds__(256)
+popcount_words_kernel(const uint32_t *__restrict__ words, uint64_t n_words, unsigned long long *__restrict__ out)
+{
+    unsigned long long c = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) c += __popc(words[i]);
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(out, c);
+}
+
 }  // namespace gk
+
+using namespace gk;
+
+extern "C" int gk_popcount_words(const uint32_t *d_words, uint64_t n_words, uint64_t *h_count_out, void *stream)
+{
+    if (!h_count_out || (n_words && !d_words)) return GK_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    *h_count_out = 0;
+    if (n_words == 0) return GK_OK;
+    DeviceBuffer out;
+    GK_TRY(out.alloc(8, st));
+    GK_CUDA(cudaMemsetAsync(out.ptr, 0, 8, st));
+    uint64_t blocks = (n_words + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    popcount_words_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_words, n_words, out.as<unsigned long long>());
+    GK_LAUNCH_CHECK();
+    GK_CUDA(cudaMemcpyAsync(h_count_out, out.ptr, 8, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    return GK_OK;
+}

@@ -100,7 +100,8 @@ SIGNATURES = {
                                             _p(_u64), _p(ctypes.c_int64), _vp]),
     "gk_index_groups": (_int, [_vp, _u32, _p(_u64), _vp, _vp, _vp]),
     "gk_index_groups_filtered": (_int, [_vp, _u32, _p(GkFilter), _p(_u64), _p(_u64), _vp, _vp, _vp, _vp]),
-    "gk_index_verify": (_int, [_vp, _u32, _vp, _vp]),
+    "gk_index_verify": (_int, [_vp, _u32, _vp, _vp, _vp]),
+    "gk_popcount_words": (_int, [_vp, _u64, _p(_u64), _vp]),
     "gk_sort_count_host": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _int, _vp, _u64, _vp,
                                   _p(ctypes.c_int64), _p(_u64), _p(GkSortStats)]),
 }

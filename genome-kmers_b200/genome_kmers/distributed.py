@@ -31,6 +31,7 @@ import numpy as np
 from genome_kmers import _native
 
 SAMPLES_PER_RANK = 2048
+HIST_PAIRS_PER_MESSAGE = 512   # occupied histogram bins per rank in the first all-gather round
 
 
 def _torch():
@@ -194,6 +195,31 @@ class NativeEngine:
             _native.check(rc)
             return bins[:n_pairs.value], counts[:n_pairs.value], int(total.value)
 
+    def shard_verify(self, sk, k):
+        """(report8, first k-mer bytes, last k-mer bytes, bits set in the summed start bitmaps)."""
+        torch, lib = self.torch, self.lib
+        shard = sk.shard
+        words = sk.total_len // 32 + 1
+        seen = torch.zeros(words, dtype=torch.int32, device=self.device)
+        report = np.zeros(8, dtype=np.uint64)
+        _native.check(lib.gk_index_verify(shard["handle"], k, _native.host_ptr(report), seen.data_ptr(),
+                                          self.stream()))
+        if sk.world > 1:
+            sk.dist.all_reduce(seen, group=sk.group)     # disjoint bitmaps add without carries
+        bits = ctypes.c_uint64(0)
+        _native.check(lib.gk_popcount_words(seen.data_ptr(), words, ctypes.byref(bits), self.stream()))
+        first = last = bytes(k)
+        if shard["n"]:
+            ptr = ctypes.c_void_p()
+            _native.check(lib.gk_index_device_indices(shard["handle"], ctypes.byref(ptr), self.stream()))
+            from genome_kmers.kmers import _tensor_from_ptr
+
+            idx = _tensor_from_ptr(torch, ptr.value, shard["n"], shard["idx_bytes"])
+            ends = idx[[0, shard["n"] - 1]].to(torch.int64).cpu().numpy()
+            first = sk.d_sba[int(ends[0]):int(ends[0]) + k].cpu().numpy().tobytes()
+            last = sk.d_sba[int(ends[1]):int(ends[1]) + k].cpu().numpy().tobytes()
+        return [int(v) for v in report], first, last, int(bits.value)
+
     def shard_indices_host(self, shard):
         torch = self.torch
         wide = shard["idx_bytes"] == 8
@@ -215,67 +241,134 @@ class NativeEngine:
         return self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
 
 
+def backend_is_nccl(dist, group) -> bool:
+    try:
+        return str(dist.get_backend(group)).lower() == "nccl"
+    except Exception:
+        return False
+
+
+def gather_small(dist, group, engine, arr: np.ndarray) -> np.ndarray:
+    """All-gather of a small host array (same shape and dtype on every rank) -> [world, ...] on the host.
+    NCCL moves it through device tensors; any other backend (gloo in the CPU tests and in the
+    two-ranks-on-one-GPU test) through CPU tensors."""
+    torch = _torch()
+    arr = np.ascontiguousarray(arr)
+    world = dist.get_world_size(group)
+    flat = torch.from_numpy(arr.reshape(-1).view(np.uint8).copy())
+    if backend_is_nccl(dist, group):
+        flat = flat.to(engine.device)
+    out = torch.empty(world * flat.numel(), dtype=torch.uint8, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    host = out.cpu().numpy().view(arr.dtype)
+    return host.reshape((world,) + arr.shape)
+
+
 class PeerExchange:
     """Receive buffers of every rank, mapped into every rank (CUDA IPC over NVLink peer memory).
 
     The fused partition kernel (gk_partition_pairs_peer) writes each (key, start) pair directly into the
     buffer of the rank that owns its key range.  Buffers are allocated once per (group, capacity) and
-    reused by later sorts; `capacity` counts pairs."""
+    reused by later sorts; `capacity` counts pairs.  The mapping is only attempted when every rank sits on
+    one host and the group has at most 16 ranks (the kernel's destination table); get() returns None when
+    any rank fails to map a peer's buffers, and every rank then takes the NCCL all-to-all path."""
 
     _cache = {}
     MAX_BYTES = 64 << 30   # per rank; beyond this the NCCL all-to-all path is used
+    MAX_RANKS = 16         # kMaxPeers in csrc/gk_sort.cu
 
     def __init__(self, engine, dist, group, capacity: int, idx_bytes: int):
-        torch, lib = engine.torch, engine.lib
+        lib = engine.lib
         self.lib, self.capacity, self.idx_bytes = lib, int(capacity), idx_bytes
+        self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.my_keys, self.my_idx = ctypes.c_void_p(), ctypes.c_void_p()
-        _native.check(lib.gk_peer_alloc(self.capacity * 8, ctypes.byref(self.my_keys)))
-        _native.check(lib.gk_peer_alloc(self.capacity * idx_bytes, ctypes.byref(self.my_idx)))
+        self._opened = []
+        self.ok = False
+        ok = 1
         handles = np.zeros(128, dtype=np.uint8)
-        _native.check(lib.gk_peer_export(self.my_keys, _native.host_ptr(handles)))
-        _native.check(lib.gk_peer_export(self.my_idx, _native.host_ptr(handles[64:])))
-        mine = torch.from_numpy(handles).to(engine.device)
-        gathered = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(gathered, mine, group=group)
+        try:
+            _native.check(lib.gk_peer_alloc(self.capacity * 8, ctypes.byref(self.my_keys)))
+            _native.check(lib.gk_peer_alloc(self.capacity * idx_bytes, ctypes.byref(self.my_idx)))
+            _native.check(lib.gk_peer_export(self.my_keys, _native.host_ptr(handles)))
+            _native.check(lib.gk_peer_export(self.my_idx, _native.host_ptr(handles[64:])))
+        except Exception:
+            ok = 0
+        gathered = gather_small(dist, group, engine, handles)
         self.key_ptrs = np.zeros(self.world, dtype=np.uint64)
         self.idx_ptrs = np.zeros(self.world, dtype=np.uint64)
-        self._opened = []
-        for r, g in enumerate(gathered):
+        for r in range(self.world):
+            if not ok:
+                break
             if r == self.rank:
                 self.key_ptrs[r], self.idx_ptrs[r] = self.my_keys.value, self.my_idx.value
                 continue
-            h = np.ascontiguousarray(g.cpu().numpy())
+            h = np.ascontiguousarray(gathered[r])
             pk, pi = ctypes.c_void_p(), ctypes.c_void_p()
-            _native.check(lib.gk_peer_open(_native.host_ptr(h), ctypes.byref(pk)))
-            _native.check(lib.gk_peer_open(_native.host_ptr(h[64:]), ctypes.byref(pi)))
-            self._opened += [pk, pi]
+            try:
+                _native.check(lib.gk_peer_open(_native.host_ptr(h), ctypes.byref(pk)))
+                self._opened.append(pk)
+                _native.check(lib.gk_peer_open(_native.host_ptr(h[64:]), ctypes.byref(pi)))
+                self._opened.append(pi)
+            except Exception:
+                ok = 0
+                break
             self.key_ptrs[r], self.idx_ptrs[r] = pk.value, pi.value
+        # every rank must be able to reach every other one, or nobody uses the mapping
+        self.ok = bool(gather_small(dist, group, engine, np.array([ok], dtype=np.int64)).min())
+
+    @staticmethod
+    def available(engine, dist, group) -> bool:
+        """One host, at most MAX_RANKS ranks (agreed by all ranks)."""
+        import socket
+        import zlib
+
+        world = dist.get_world_size(group)
+        if world > PeerExchange.MAX_RANKS:
+            return False
+        host = np.array([zlib.crc32(socket.gethostname().encode())], dtype=np.int64)
+        hosts = gather_small(dist, group, engine, host)
+        return bool((hosts == hosts[0]).all())
 
     @classmethod
     def get(cls, engine, dist, group, capacity: int, idx_bytes: int):
         key = (id(group), dist.get_world_size(group), idx_bytes)
+        if key in cls._cache and cls._cache[key] is None:
+            return None                                # the mapping failed before: stay on the NCCL path
         px = cls._cache.get(key)
         if px is None or px.capacity < capacity:   # every rank computes the same capacity: collective-safe
             if px is not None:
                 px.close()
+            elif not cls.available(engine, dist, group):
+                cls._cache[key] = None
+                return None
             px = cls(engine, dist, group, capacity, idx_bytes)
+            if not px.ok:
+                px.close()
+                px = None
             cls._cache[key] = px
         return px
 
     def close(self):
+        """Collective: unmap every peer's buffers, wait until every rank has done so, then free the local ones
+        (freeing exported memory that another process still has open is undefined in CUDA IPC)."""
+        _torch().cuda.synchronize()
         for p in self._opened:
             self.lib.gk_peer_close(p)
         self._opened = []
+        self.dist.barrier(group=self.group)
         if self.my_keys:
             self.lib.gk_peer_free(self.my_keys)
+            self.my_keys = None
+        if self.my_idx:
             self.lib.gk_peer_free(self.my_idx)
-            self.my_keys = self.my_idx = None
+            self.my_idx = None
 
     @classmethod
     def close_all(cls):
         for px in cls._cache.values():
-            px.close()
+            if px is not None:
+                px.close()
         cls._cache.clear()
 
 
@@ -406,6 +499,19 @@ class ShardedKmers:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 
+    # ---- small collectives through the host (see gather_small) -------------------------------------------
+    def _gather(self, arr) -> np.ndarray:
+        return gather_small(self.dist, self.group, self.engine, np.asarray(arr))
+
+    def _order_after_peer_writes(self):
+        """Every rank's peer writes have landed behind this point of the current stream."""
+        if backend_is_nccl(self.dist, self.group):
+            token = self.engine.from_host_i64(np.zeros(1, dtype=np.int64))
+            self.dist.all_reduce(token, group=self.group)      # stream-ordered: no host synchronise
+        else:
+            _torch().cuda.synchronize()
+            self.dist.barrier(group=self.group)
+
     def sort(self):
         eng, dist = self.engine, self.dist
         k, world, rank = self.k, self.world, self.rank
@@ -419,9 +525,7 @@ class ShardedKmers:
         b16 = (end // 16) * 16 if rank < world - 1 else self.total_len
         counts = eng.alphabet(self.d_sba[a16:b16] if world > 1 else self.d_sba)
         if world > 1:   # every rank scans its own slice of the byte array; the three counters are summed
-            tot = eng.from_host_i64(counts.astype(np.int64))
-            dist.all_reduce(tot, group=self.group)
-            counts = self._to_host_i64(tot).astype(np.uint64)
+            counts = self._gather(counts.astype(np.int64)).sum(axis=0).astype(np.uint64)
         n_sep_expected = len(self.seg_starts) - 1
         if int(counts[1]) != n_sep_expected:
             raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
@@ -434,17 +538,13 @@ class ShardedKmers:
         # ---- splitters from evenly spaced samples --------------------------------------------------
         if world > 1:
             step = max(1, n_local_in // SAMPLES_PER_RANK)
-            sample = keys[::step][:SAMPLES_PER_RANK]
-            padded = eng.empty_like_n(keys, SAMPLES_PER_RANK + 1)
-            padded[0] = int(sample.numel())
-            padded[1:1 + sample.numel()] = sample
-            if sample.numel() < SAMPLES_PER_RANK:
-                padded[1 + sample.numel():] = 0
-            gathered = [eng.empty_like_n(keys, SAMPLES_PER_RANK + 1) for _ in range(world)]
-            dist.all_gather(gathered, padded, group=self.group)
-            # one device-to-host copy of all samples; 32 k keys are sorted faster on the host than through
-            # eight tiny radix passes and their synchronisations
-            table = self._to_host_u64(self._cat(gathered)).reshape(world, SAMPLES_PER_RANK + 1)
+            sample = self._to_host_u64(keys[::step][:SAMPLES_PER_RANK])
+            padded = np.zeros(SAMPLES_PER_RANK + 1, dtype=np.uint64)
+            padded[0] = len(sample)
+            padded[1:1 + len(sample)] = sample
+            # one small all-gather; 32 k keys are sorted faster on the host than through eight tiny radix
+            # passes and their synchronisations
+            table = self._gather(padded)
             pooled = np.sort(np.concatenate([row[1:1 + int(row[0])] for row in table]))
             splitters_host = choose_splitters(pooled, world, class_bit)
             splitters = eng.from_host_i64(splitters_host.view(np.int64))
@@ -461,36 +561,31 @@ class ShardedKmers:
             # fused: counts first (placement), then ONE kernel partitions and writes every pair straight
             # into its destination rank's receive buffer over NVLink peer memory
             send_counts = eng.partition_count(keys, splitters, world)
-            mine = eng.from_host_i64(send_counts)
-            rows = [eng.empty_like_n(mine, world) for _ in range(world)]
-            dist.all_gather(rows, mine, group=self.group)
-            matrix = np.stack([self._to_host_i64(r) for r in rows])          # [source, destination]
+            matrix = self._gather(send_counts.astype(np.int64))             # [source, destination]
             recv_total = matrix.sum(axis=0)
             # every rank sees the same matrix, so every rank computes the same capacity: the largest
             # receive count plus 10 % head-room (the buffers are cached and only ever grow)
             capacity = int(1.1 * int(recv_total.max())) + (1 << 20)
             self._mark("partition")
+            px = None
             if capacity * (8 + self.idx_bytes) <= PeerExchange.MAX_BYTES:
                 px = eng.peer_exchange(dist, self.group, capacity, self.idx_bytes)
+            if px is not None:
                 offsets = matrix[:rank, :].sum(axis=0)
                 eng.partition_peer(keys, idx, splitters, world, px, offsets)
-                token = eng.from_host_i64(np.zeros(1, dtype=np.int64))
-                dist.all_reduce(token, group=self.group)     # every rank's writes have landed behind this
+                self._order_after_peer_writes()
                 recv_ptrs = (px.my_keys, px.my_idx, int(recv_total[rank]))
                 self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank]) * (8 + self.idx_bytes))
                 del keys, idx
                 self._mark("exchange")
             else:
-                use_peer = False                             # skew beyond the buffers: NCCL path below
+                use_peer = False         # skew beyond the buffers, several hosts, or no peer access: NCCL path
         if not use_peer:
             keys_p, idx_p, send_counts = eng.partition(keys, idx, splitters, world)
             del keys, idx
             self._mark("partition")
             if world > 1:
-                send_t = eng.from_host_i64(send_counts)
-                recv_t = eng.empty_like_n(send_t, world)
-                dist.all_to_all_single(recv_t, send_t, group=self.group)
-                recv_counts = self._to_host_i64(recv_t)
+                recv_counts = self._gather(send_counts.astype(np.int64))[:, rank]
                 n_recv = int(recv_counts.sum())
                 keys_r = eng.empty_like_n(keys_p, n_recv)
                 idx_r = eng.empty_like_n(idx_p, n_recv)
@@ -543,25 +638,67 @@ class ShardedKmers:
         if self.world == 1:
             hist[bins.astype(np.int64)] = counts
             return hist, total
-        # the occupied bins of every rank are all-gathered as (bin, count) pairs: a few hundred bytes,
-        # instead of all-reducing the 8 MB table the reference's default max_counts_bin implies
-        head = self.engine.from_host_i64(np.array([len(bins), total], dtype=np.int64))
-        heads = [self.engine.empty_like_n(head, 2) for _ in range(self.world)]
-        self.dist.all_gather(heads, head, group=self.group)
-        heads = np.stack([self._to_host_i64(h) for h in heads])
-        width = int(heads[:, 0].max())
-        total = int(heads[:, 1].sum())
-        if width:
-            mine = np.zeros(2 * width, dtype=np.int64)
-            mine[:len(bins)] = bins.astype(np.int64)
-            mine[width:width + len(bins)] = counts
-            mine_t = self.engine.from_host_i64(mine)
-            parts = [self.engine.empty_like_n(mine_t, 2 * width) for _ in range(self.world)]
-            self.dist.all_gather(parts, mine_t, group=self.group)
-            for r, part in enumerate(parts):
-                arr, m = self._to_host_i64(part), int(heads[r, 0])
-                np.add.at(hist, arr[:m], arr[width:width + m])
-        return hist, total
+        # the occupied bins of every rank are all-gathered as (bin, count) pairs in ONE fixed-size message
+        # (a few KB), instead of all-reducing the 8 MB table the reference's default max_counts_bin implies;
+        # a rank with more occupied bins than the message holds triggers a second, wider round
+        width = HIST_PAIRS_PER_MESSAGE
+        while True:
+            mine = np.zeros(2 + 2 * width, dtype=np.int64)
+            mine[0], mine[1] = len(bins), total
+            m = min(len(bins), width)
+            mine[2:2 + m] = bins[:m].astype(np.int64)
+            mine[2 + width:2 + width + m] = counts[:m]
+            table = self._gather(mine)
+            widest = int(table[:, 0].max())
+            if widest <= width:
+                break
+            width = widest
+        for row in table:
+            m = int(row[0])
+            np.add.at(hist, row[2:2 + m], row[2 + width:2 + width + m])
+        return hist, int(table[:, 1].sum())
+
+    def verify(self, hist=None, n_total: Optional[int] = None) -> dict:
+        """Check the sharded order against the sequence bytes (collective; gk_index_verify per shard):
+        every shard sorted with ties in ascending start order and valid, distinct starts; shard boundaries in
+        strictly increasing k-mer order; all shards together hold every window start exactly once (their start
+        bitmaps add up without a carry to n_total bits); the global histogram counts the groups the bytes show.
+        Returns {"checked": True, "checks": {name: bool}, "report": ...}; every rank gets the same answer."""
+        eng, k = self.engine, self.k
+        rep, first_kmer, last_kmer, bits_total = eng.shard_verify(self, k)
+        reports = self._gather(np.array([rep[i] for i in range(8)], dtype=np.int64))
+        edges = self._gather(np.frombuffer(first_kmer + last_kmer, dtype=np.uint8))   # [world, 2k]
+        n_shards = reports[:, 0]
+        total = int(n_shards.sum())
+        boundaries_ok = True
+        prev_last = None
+        for r in range(self.world):
+            if n_shards[r] == 0:
+                continue
+            f, l = edges[r, :k].tobytes(), edges[r, k:].tobytes()
+            if prev_last is not None and not prev_last < f:
+                boundaries_ok = False                 # a group would straddle two ranks, or order is broken
+            prev_last = l
+        checks = {
+            "every shard: neighbours in non-decreasing order under the reference's byte comparator":
+                int(reports[:, 1].sum()) == 0,
+            "every shard: equal k-mers in ascending start order (break_ties=True order)": int(reports[:, 2].sum()) == 0,
+            "every shard: starts valid and distinct": int(reports[:, 3].sum()) == 0 and int(reports[:, 4].sum()) == 0,
+            "every shard: head flags of the sort agree with the bytes":
+                int(reports[:, 6].sum()) == 0 and bool((reports[n_shards > 0, 7] == 1).all()),
+            "shard boundaries: last k-mer of a rank < first k-mer of the next (no group straddles ranks)":
+                boundaries_ok,
+            "all shards together hold every window start exactly once (summed start bitmaps)":
+                bits_total == total,
+        }
+        if n_total is not None:
+            checks["number of k-mers over all shards"] = total == int(n_total)
+        if hist is not None:
+            checks["histogram: number of groups equals the groups counted from the bytes"] = \
+                int(np.asarray(hist).sum()) == int(reports[n_shards > 0, 5].sum())
+        return {"checked": True, "checks": checks,
+                "report": {"kmers_per_rank": [int(v) for v in n_shards], "groups": int(reports[n_shards > 0, 5].sum()),
+                           "start_bits_set": int(bits_total)}}
 
     def local_start_indices(self) -> np.ndarray:
         """This rank's shard of the globally sorted start indices (host array)."""
@@ -598,178 +735,3 @@ class ShardedKmers:
     @staticmethod
     def _to_host_u64(t) -> np.ndarray:
         return t.detach().cpu().numpy().view(np.uint64)
-
-
-# ---------------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): weak scaling, 100 Mbp of genome per GPU, one index over all of it
-# ---------------------------------------------------------------------------------------------------
-def bench_main(args, rank, world, make_genome, workload_config, ClockSampler, metric, unit, k, n_records,
-               runs_per_record, max_bin, measured_hbm_peak):
-    import json
-    import os
-    import time
-
-    import torch
-    import torch.distributed as dist
-
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = NativeEngine()
-    n_bases = args.bases
-
-    # every rank generates its own 100 Mbp (10 records) and the ranks all-gather the forward byte array;
-    # the trailing '$' of a rank's chunk separates it from the next rank's first record
-    chunk_len = n_bases + n_records
-    pinned = torch.empty(chunk_len, dtype=torch.uint8).pin_memory()
-    host = pinned.numpy()
-    sba, starts, _ = make_genome(n_bases, n_records, runs_per_record, 42 + rank, out=host[:chunk_len - 1])
-    host[chunk_len - 1] = ord("$")
-    all_starts = np.concatenate([starts + np.uint64(r * chunk_len) for r in range(world)])
-    total_fwd = world * chunk_len - 1
-    n_total = 2 * (n_bases * world - n_records * world * (k - 1))
-
-    def load_inputs():
-        d_chunk = pinned.to("cuda", non_blocking=True)
-        d_all = torch.empty(world * chunk_len, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(d_all, d_chunk)
-        return d_all[:total_fwd]
-
-    d_fwd = load_inputs()
-    hist = None
-
-    def step(d_forward):
-        m0 = eng.mark()
-        sk = ShardedKmers(d_forward, all_starts, k, "both", engine=eng)
-        m1 = eng.mark()
-        sk.sort()
-        m2 = eng.mark()
-        h, total = sk.get_kmer_group_counts(k, max_counts_bin=max_bin)
-        assert total == n_total, (total, n_total)
-        stats, sent = dict(sk.stats), sk.exchange_bytes_sent
-        stats["_mode"] = sk.exchange_mode
-        sk.close()
-        m3 = eng.mark()
-        stats["_sk_marks"] = [("begin", m0), ("both_strands", m1)] + sk._marks[1:] + [("count_allreduce", m3)]
-        del m2
-        return h, stats, sent
-
-    for _ in range(args.warmup):
-        step(d_fwd)
-    launches0 = _native.launch_count(reset=True)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    stream = torch.cuda.current_stream()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    per_step = []
-    for _ in range(args.steps):
-        hist, stats, sent = step(d_fwd)
-        if rank == 0:
-            clocks.sample()
-        per_step.append((stats, sent))
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = _native.launch_count()
-    ms_per_step = float(ms.item()) / args.steps
-    clock_info = clocks.stop() if rank == 0 else None
-
-    # e2e: host chunk -> H2D -> all-gather -> sort/count -> shard of sorted starts back on the host
-    e2e = None
-    if not args.no_e2e:
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        shard_bytes = 0
-
-        def e2e_step():
-            d_in = load_inputs()
-            sk = ShardedKmers(d_in, all_starts, k, "both", engine=eng)
-            sk.sort()
-            h, total = sk.get_kmer_group_counts(k, max_counts_bin=max_bin)
-            local = sk.local_start_indices()     # D2H of this rank's shard of the sorted starts (pinned)
-            sk.close()
-            assert total == n_total
-            return int(local.nbytes)
-
-        for _ in range(2):                       # warm the pinned-buffer cache and the NCCL channels
-            e2e_step()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            shard_bytes = e2e_step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_total / float(dt.item()) / 1e9, "unit": unit, "ms_per_step": 1e3 * float(dt.item()),
-               "steps": e2e_steps, "h2d_bytes_per_step": int(chunk_len) * world,
-               "d2h_bytes_per_step": shard_bytes * world,
-               "api": "ShardedKmers(...).sort(); get_kmer_group_counts(); local_start_indices() on every rank"}
-
-    eng_idx_bytes = 8 if (2 * (world * chunk_len - 1) + 1 > 0xFFFFFFFF
-                          or os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0")) else 4
-    last = per_step[-1][0]
-    mine = [last.get("total_ms", 0.0), last.get("fixup_ms", 0.0), float(last.get("n_shard", 0)),
-            float(last.get("n_ambiguous", 0))]
-    per_rank = [None] * world
-    dist.all_gather_object(per_rank, mine)
-    sent_all = torch.tensor([float(np.mean([s for _, s in per_step]))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(sent_all, op=dist.ReduceOp.SUM)
-    phase_ms = {}
-    exchange_mode = per_step[-1][0].pop("_mode", "nccl")
-    for stats, _ in per_step:
-        stats.pop("_mode", None)
-        marks = stats.pop("_sk_marks", [])
-        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
-            phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b) / len(per_step)
-    if rank == 0:
-        passes = per_step[-1][0]["sort_passes"]
-        pass_ms = float(np.mean([s["sort_ms"] for s, _ in per_step])) / max(passes, 1)
-        n_shard = per_step[-1][0]["n_shard"]
-        peak, peak_src = measured_hbm_peak()
-        pair_bytes = 8 + eng_idx_bytes
-        achieved = 2 * pair_bytes * n_shard / (pass_ms * 1e-3) / 1e9
-        line = {
-            "metric": metric, "value": n_total / (ms_per_step * 1e-3) / 1e9, "unit": unit, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": dict(workload_config(world), **({} if n_bases == 100_000_000 else {
-                "workload": f"NOT the bench workload: {n_bases} bp per GPU x {world} GPUs = "
-                            f"{n_bases * world / 1e9:.2f} Gbp, {n_records} records per GPU, N runs, both strands, "
-                            f"k={k} (BASELINE.json configs[2] size when bases x GPUs = 3.1e9)",
-                "bases_per_gpu": n_bases, "kmers_total": int(n_total)})),
-            "e2e": e2e, "gpu_launches": int(launches - 0),
-            "roofline": {"bound": "hbm", "kernel": "gk::onesweep_kernel on rank 0's key range",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": pass_ms,
-                         "launches_per_step": passes, "pairs_on_rank0": int(n_shard),
-                         "pair_bytes": pair_bytes},
-            "exchange": {"bytes_over_nvlink_per_step": float(sent_all.item()), "mode": exchange_mode,
-                         # rank 0's exchange phase: fused partition + peer writes + the ordering all-reduce
-                         "exchange_ms_rank0": round(float(phase_ms.get("exchange", 0.0)), 3),
-                         "nvlink_gbs_per_gpu_outbound": (
-                             round(float(sent_all.item()) / world / (phase_ms["exchange"] * 1e-3) / 1e9, 1)
-                             if phase_ms.get("exchange", 0.0) > 0 else None),
-                         "nvlink_peak_gbs_per_direction": 900.0,
-                         "note": "(G-1)/G of all (u64 key, u32 start) pairs cross NVLink once: written by the "
-                                 "partition kernel into peer memory (mode peer) or one NCCL all-to-all (mode nccl)"},
-            "cpu_baseline": None, "clocks": clock_info,
-            "phase_ms_rank0": {k_: round(v, 3) for k_, v in phase_ms.items()},
-            "per_rank_local_sort": {"total_ms": [round(r[0], 3) for r in per_rank],
-                                    "refine_ms": [round(r[1], 3) for r in per_rank],
-                                    "pairs": [int(r[2]) for r in per_rank],
-                                    "ambiguous": [int(r[3]) for r in per_rank]},
-            "local_sort_stats_rank0": {k_: v for k_, v in per_step[-1][0].items()},
-            "result": {"kmers": int(n_total), "distinct_kmers": int(hist.sum())},
-        }
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    PeerExchange.close_all()
-    dist.destroy_process_group()

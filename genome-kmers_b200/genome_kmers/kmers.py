@@ -461,7 +461,7 @@ class Kmers:
         if kmer_len is None:
             kmer_len = self.max_kmer_len
         report = np.zeros(8, dtype=np.uint64)
-        _native.check(_native.lib().gk_index_verify(self._ix, kmer_len or 0, _native.host_ptr(report),
+        _native.check(_native.lib().gk_index_verify(self._ix, kmer_len or 0, _native.host_ptr(report), None,
                                                     self._stream()))
         names = ("kmers", "out_of_order", "tie_order", "invalid_starts", "duplicate_starts", "groups",
                  "flag_mismatches", "flags_compared")

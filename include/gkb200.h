@@ -234,8 +234,12 @@ int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *f
  * h_report8: [0] k-mers checked, [1] neighbours out of order, [2] ties not in ascending start order,
  * [3] invalid starts, [4] duplicate starts, [5] groups of equal k-mers counted from the bytes,
  * [6] cached head flags that disagree with the bytes, [7] 1 when cached flags were compared.
- * A correct sort of the init set has [1..4] == 0, [6] == 0 and [0] == gk_kmer_count(). kmer_len 0 = None. */
-int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, void *stream);
+ * A correct sort of the init set has [1..4] == 0, [6] == 0 and [0] == gk_kmer_count(). kmer_len 0 = None.
+ * d_seen_bitmap (optional): a zeroed device bitmap of sba_len / 32 + 1 words that receives one bit per start
+ * seen; the shards of a multi-GPU index sum their bitmaps (disjoint bitmaps add without carries) and count
+ * the bits with gk_popcount_words to prove that together they hold every start exactly once. */
+int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, uint32_t *d_seen_bitmap, void *stream);
+int gk_popcount_words(const uint32_t *d_words, uint64_t n_words, uint64_t *h_count_out, void *stream);
 
 /* ---- one-shot host entry point (host buffers in, host buffers out) ------------------------ */
 /* sba (forward strand, records joined by '$') -> sorted start indices + histogram.  strands:

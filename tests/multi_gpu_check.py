@@ -30,8 +30,15 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    same_gpu = "--same-gpu" in sys.argv
+    if same_gpu:
+        # every rank on cuda:0 (the driver's single-GPU box): gloo carries the small collectives (NCCL refuses two
+        # ranks on one device), CUDA IPC carries the pairs exactly as it does between GPUs
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     world = dist.get_world_size()
     failures = []
     cases = [(31, 600_000, 6, 8, False), (21, 400_000, 3, 0, False), (12, 300_000, 2, 3, False),
@@ -56,17 +63,23 @@ def main():
             hist, total = sk.get_kmer_group_counts(k, max_counts_bin=1000)
             got = sk.gather_start_indices(0)
             used = sk.exchange_mode
+            ver = sk.verify(hist, total)
             sk.close()
             if rank == 0:
                 ok = (len(got) == len(want) and np.array_equal(got.astype(np.uint64), want)
-                      and total == total_want and np.array_equal(hist, hist_want))
+                      and total == total_want and np.array_equal(hist, hist_want)
+                      and all(ver["checks"].values()))
+                if not all(ver["checks"].values()):
+                    print("verify failed:", [name for name, v in ver["checks"].items() if not v], flush=True)
                 print(f"k={k} world={world} exchange={used} idx64={wide}: {'ok' if ok else 'MISMATCH'} "
                       f"({len(got)} k-mers, {int(hist.sum())} distinct)", flush=True)
                 if not ok:
                     failures.append((k, used))
                 if mode == "1" and used != "peer":
                     failures.append((k, "peer exchange was not used"))
-    flag = torch.tensor([len(failures)], device="cuda")
+    flag = torch.tensor([len(failures)])
+    if not same_gpu:
+        flag = flag.cuda()
     dist.broadcast(flag, 0)
     gkd.PeerExchange.close_all()
     dist.barrier()
