@@ -217,4 +217,116 @@ int frag_expand_device(FragSorted &fs, const uint64_t *keys_sorted, uint64_t n, 
     return GK_OK;
 }
 
+// ---- multi-GPU: the fragments of a shard ---------------------------------------------------------------------
+// Every rank lists the fragments of its slice of the byte array (gk_pack_slice) and the lists are all-gathered;
+// a rank keeps those whose key falls into its key range [key_lo, key_hi) (key_hi == 0: no upper bound), with
+// the key made relative to key_lo like the pairs it received.  Order does not matter (the list is sorted later).
+__global__ void __launch_bounds__(256)
+frag_filter_kernel(const unsigned char *__restrict__ gathered, const unsigned long long *__restrict__ counts,
+                   uint32_t world, uint64_t cap, uint64_t key_lo, uint64_t key_hi, FragOut out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total = (uint64_t)world * cap;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t src = (uint32_t)(t / cap);
+        const uint64_t j = t - (uint64_t)src * cap;
+        if (j >= counts[src]) continue;
+        const uint64_t *b = reinterpret_cast<const uint64_t *>(gathered + (size_t)src * cap * 36);
+        const uint64_t key = b[j];
+        if (key < key_lo || (key_hi && key >= key_hi)) continue;
+        const unsigned long long slot = atomicAdd(out.counter, 1ull);
+        if (slot < out.capacity) {
+            out.key[slot] = key - key_lo;
+            out.w0[slot] = b[cap + j];
+            out.w1[slot] = b[2 * cap + j];
+            out.start[slot] = b[3 * cap + j];
+            out.count[slot] = reinterpret_cast<const uint32_t *>(b + 4 * cap)[j];
+        }
+    }
+}
+
+// one CTA: off[q] = sum of count[0 .. q), off[F] = total, F read from the device
+__global__ void __launch_bounds__(1024)
+frag_scan_counts_kernel(const uint32_t *__restrict__ count, const unsigned long long *__restrict__ n_frag,
+                        uint64_t capacity, unsigned long long *__restrict__ off)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const uint64_t F = *n_frag < capacity ? *n_frag : capacity;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < F; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long c = (i < F) ? count[i] : 0;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+        if (i < F) off[i] = pre + inc - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[F] = s_carry;
+}
+
+// The ambiguous windows of the shard as (key, start) pairs behind the n_pure received ones: they go through the
+// local sort like any other pair and so mark the slots that frag_expand_device fills in afterwards.
+// err |= 8 when the fragments do not add up to the n_amb windows the ranks counted for this key range.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+frag_placeholders_kernel(FragOut frag, const unsigned long long *__restrict__ off, uint64_t n_pure, uint64_t n_amb,
+                         uint64_t *__restrict__ keys, IdxT *__restrict__ idx, int *__restrict__ err)
+{
+    const uint64_t F = *frag.counter < frag.capacity ? *frag.counter : frag.capacity;
+    const uint64_t m = off[F];
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0 && (m != n_amb || *frag.counter > frag.capacity)) atomicOr(err, 8);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t lim = m < n_amb ? m : n_amb;
+    for (uint64_t o = tid; o < lim; o += stride) {
+        uint64_t lo = 0, hi = F;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (o < off[mid]) hi = mid; else lo = mid + 1;
+        }
+        const uint64_t q = lo - 1;
+        keys[n_pure + o] = frag.key[q];
+        idx[n_pure + o] = (IdxT)(frag.start[q] + (o - off[q]));
+    }
+}
+
+int frag_filter_device(const void *d_gathered, const unsigned long long *d_counts, uint32_t world, uint64_t cap,
+                       uint64_t key_lo, uint64_t key_hi, const FragOut &out, cudaStream_t st)
+{
+    if (world == 0 || cap == 0) return GK_OK;
+    frag_filter_kernel<<<frag_grid((uint64_t)world * cap), 256, 0, st>>>((const unsigned char *)d_gathered, d_counts,
+                                                                         world, cap, key_lo, key_hi, out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int frag_placeholders_device(const FragOut &frag, unsigned long long *d_off, uint64_t n_pure, uint64_t n_amb,
+                             uint64_t *d_keys, void *d_idx, int idx_bytes, int *d_err, cudaStream_t st)
+{
+    frag_scan_counts_kernel<<<1, 1024, 0, st>>>(frag.count, frag.counter, frag.capacity, d_off);
+    GK_LAUNCH_CHECK();
+    const int grid = frag_grid(n_amb ? n_amb : 1);
+    if (idx_bytes == 4)
+        frag_placeholders_kernel<uint32_t><<<grid, 256, 0, st>>>(frag, d_off, n_pure, n_amb, d_keys, (uint32_t *)d_idx,
+                                                                 d_err);
+    else
+        frag_placeholders_kernel<uint64_t><<<grid, 256, 0, st>>>(frag, d_off, n_pure, n_amb, d_keys, (uint64_t *)d_idx,
+                                                                 d_err);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
 }  // namespace gk

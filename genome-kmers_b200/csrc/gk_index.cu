@@ -33,6 +33,10 @@ struct FragSorted;
 int frag_sort_device(const FragOut &, uint64_t, uint32_t, int, int, FragSorted &, cudaStream_t);
 int frag_expand_device(FragSorted &, const uint64_t *, uint64_t, int, void *, uint8_t *, const unsigned int *,
                        const unsigned long long *, uint64_t, int *, cudaStream_t);
+int frag_filter_device(const void *, const unsigned long long *, uint32_t, uint64_t, uint64_t, uint64_t,
+                       const FragOut &, cudaStream_t);
+int frag_placeholders_device(const FragOut &, unsigned long long *, uint64_t, uint64_t, uint64_t *, void *, int, int *,
+                             cudaStream_t);
 int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
                             cudaStream_t);
 int gather2_u64_device(const uint64_t *, const void *, const void *, uint64_t, int, uint64_t *, cudaStream_t);
@@ -257,33 +261,6 @@ static int prefix_begin_bit(uint64_t n, int key_bits)
     return key_bits - 8 * prefix_passes;
 }
 
-// Stable sort of the (key, start) pairs by key bits [0, key_bits), up to the slots that refine_subset
-// repairs afterwards, and head/ambiguous flags of that order.  The pair buffers ping-pong; *in_alt tells
-// where the result is.  *d_descent (device word, zeroed here) counts the slots of long prefix runs that are
-// out of order (the first kDescentCap positions go to d_descent_list); the caller reads it back together with
-// whatever else it needs (no synchronise here).
-static int sort_pairs_and_flag(uint64_t *keys_a, uint64_t *keys_b, void *idx_a, void *idx_b, int ib,
-                               uint64_t n, int key_bits, int class_bit, uint8_t *d_flags, int *in_alt,
-                               unsigned int *d_descent, SortTiming *timing, cudaStream_t st,
-                               const unsigned long long *d_pre_hist = nullptr,
-                               unsigned long long *d_n_amb = nullptr, bool *n_amb_counted = nullptr,
-                               unsigned long long *d_descent_list = nullptr)
-{
-    // d_n_amb (zeroed by the caller): the tie-repair pass also counts the ambiguous slots on request, for
-    // callers that did not pack the keys themselves (*n_amb_counted tells whether it ran)
-    if (n_amb_counted) *n_amb_counted = false;
-    // d_pre_hist: digit histograms of bits [prefix_begin_bit(n, key_bits), key_bits) counted by the producer
-    const int begin = prefix_begin_bit(n, key_bits);
-    GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
-    GK_TRY(radix_sort_pairs_device(keys_a, keys_b, idx_a, idx_b, ib, n, begin, key_bits, in_alt, st, timing,
-                                   d_pre_hist));
-    uint64_t *ks = *in_alt ? keys_b : keys_a;
-    void *is = *in_alt ? idx_b : idx_a;
-    if (begin == 0) return key_flags_device(ks, n, class_bit, d_flags, st);
-    if (n_amb_counted) *n_amb_counted = d_n_amb != nullptr;
-    return tie_fix_flags_device(ks, is, ib, n, begin, class_bit, d_flags, d_descent, d_n_amb, st, d_descent_list);
-}
-
 // After the main sort and its flags pass, two kinds of slots may still hold the wrong element:
 //   * ambiguous windows: in the right slots as a set, ordered by `value` only -> order them by their
 //     terminator-aware 4-bit rank words (16 symbols per word);
@@ -387,129 +364,136 @@ static int repair_big_buckets(uint64_t *keys, uint64_t *keys_tmp, void *idx, voi
     return GK_OK;
 }
 
-// Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
-// Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags; synchronises once, at
-// the end.  d_alpha (optional): the three alphabet counters of a scan that is still in flight on `st`; they
-// come back with the other counters (h_alpha).  d_list != nullptr: sort these starts (ascending, n of them)
-// instead of every window of the byte array.
+// device counters of one sort: [0] ambiguous windows, [1] low half: descents, high half: repair status (0 = the
+// order is final), [2] fragments, [3] fragment error bits (int), [4] number of big out-of-order buckets, then
+// their kBigBucketCap (lo, hi) ranges, [kCounterWords ...] the first kDescentCap descent positions
+constexpr int kCounterWords = 5 + 2 * kBigBucketCap;
+constexpr size_t kCounterBytes = (size_t)(kCounterWords + kDescentCap) * 8;
+
+// (key, start) pairs ready to be sorted, and what is known about them.
+struct PackedPairs {
+    uint64_t *keys_a = nullptr, *keys_b = nullptr;   // ping-pong key buffers, keys in keys_a
+    void *idx_a = nullptr, *idx_b = nullptr;         // ping-pong start buffers, starts in idx_a
+    void *idx_final = nullptr;     // optional third buffer that must receive the sorted starts
+    uint64_t n = 0;
+    uint32_t key_len = 0;
+    int key_bits = 0, class_bit = 0;
+    bool terminated = false;       // windows may end at a '$' inside the key (variable-length mode)
+    const unsigned long long *d_pre_hist = nullptr;   // digit histograms counted by the producer, or null
+    FragOut frag;                  // fragment list of the ambiguous windows (counter = d_counters + 2)
+    bool want_frag = false;
+    FragSorted *fs = nullptr;
+    unsigned long long *d_counters = nullptr;   // kCounterBytes, zeroed before the producer ran
+    bool producer_counted_amb = true;   // d_counters[0] is final when e_producer fires (else the flags pass counts)
+    cudaEvent_t e_producer = nullptr;   // recorded on the stream behind the producer of keys and fragments
+    int start_bits = 32;
+    unsigned long long *d_alpha = nullptr, *h_alpha = nullptr;   // alphabet counters still in flight (optional)
+    const int *d_extra_err = nullptr;   // optional device int that must be zero at the end (partition look-back)
+    // results
+    uint64_t *keys_sorted = nullptr;
+    void *idx_sorted = nullptr;
+};
+
+// Sort packed pairs, repair what the prefix sort leaves open, expand the fragments, leave starts and flags in
+// their final order.  Synchronises once, at the end.
 //
 // Stream plan (nothing on the main stream ever waits for the host):
-//   main   pack (+ fragment list) | E1 | histogram scan, radix passes, tie repair + flags | wait E2 | expand
+//   main   producer (pack + fragment list) | E1 | histogram scan, radix passes, tie repair + flags,
+//          bucket-wise repair | wait E2 | fragment expand
 //   side   wait E1 | counters -> host | fragment sort | E2
-// The host blocks on the side stream only: that copy completes when the pack kernel does, milliseconds
-// before the main stream runs dry, and tells how many fragments there are to sort.
-static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int class_bit, uint64_t n,
-                       Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm, cudaStream_t st,
-                       unsigned long long *d_alpha, unsigned long long *h_alpha, const void *d_list = nullptr)
+// The host blocks on the side stream only: that copy completes when the producer does, milliseconds before the
+// main stream runs dry, and tells how many fragments there are to sort.
+static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, StageMarks &marks, EventTimer &tm,
+                             cudaStream_t st)
 {
     const int ib = ix->idx_bytes;
-    // value <= 4^key_len needs 2*key_len+1 bits when ambiguous windows exist, plus the class bit
-    const int key_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
-    marks.key_bits = key_bits;
-    const bool terminated = valid_len < key_len;
-
-    DeviceBuffer keys_a, keys_b, counters, pre_hist, frag_mem;
-    Owned idx_b;
-    GK_TRY(keys_a.alloc((size_t)n * 8, st));
-    GK_TRY(keys_b.alloc((size_t)n * 8, st));
-    GK_TRY(idx_b.alloc((size_t)n * ib, st));
-    GK_TRY(out_idx.alloc((size_t)n * ib, st));
-    // device counters: [0] ambiguous windows, [1] low half: descents, high half: repair status (0 = the order
-    // is final), [2] fragments, [3] fragment error bits (int), [4] number of big out-of-order buckets, then
-    // their kBigBucketCap (lo, hi) ranges, [kCounterWords ...] the first kDescentCap descent positions
-    constexpr int kCounterWords = 5 + 2 * kBigBucketCap;
-    GK_TRY(counters.alloc((size_t)(kCounterWords + kDescentCap) * 8, st));
-    GK_CUDA(cudaMemsetAsync(counters.ptr, 0, (size_t)kCounterWords * 8, st));
-    unsigned long long *d_counters = counters.as<unsigned long long>();
+    const uint64_t n = pp.n;
+    unsigned long long *d_counters = pp.d_counters;
     unsigned int *d_descent = reinterpret_cast<unsigned int *>(d_counters + 1);
     int *d_status = reinterpret_cast<int *>(d_descent + 1);
     int *d_frag_err = reinterpret_cast<int *>(d_counters + 3);
-    // the pack kernel counts the digits of the radix passes while it writes the keys
-    const int begin_bit = prefix_begin_bit(n, key_bits);
-    GK_TRY(pre_hist.alloc(8 * 256 * sizeof(unsigned long long), st));
-    GK_CUDA(cudaMemsetAsync(pre_hist.ptr, 0, pre_hist.bytes, st));
-    // fragment list of the ambiguous windows (not for an arbitrary list of starts: no neighbours there)
-    FragOut frag;
-    FragSorted fs;
-    const bool want_frag = class_bit && !d_list && fragments_enabled();
-    if (want_frag) {
-        const uint64_t cap = n < kFragCapacity ? n : kFragCapacity;
-        GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
-        uint64_t *base = frag_mem.as<uint64_t>();
-        frag.key = base; frag.w0 = base + cap; frag.w1 = base + 2 * cap; frag.start = base + 3 * cap;
-        frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
-        frag.counter = d_counters + 2;
-        frag.capacity = cap;
-        GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
-    }
-
-    marks.pack0 = tm.mark();
-    if (d_list) {
-        GK_CUDA(cudaMemcpyAsync(out_idx.ptr, d_list, (size_t)n * ib, cudaMemcpyDeviceToDevice, st));
-        GK_TRY(pack_keys_list_device(ix->d_sba, ix->sba_len, d_list, ib, n, key_len, class_bit,
-                                     keys_a.as<uint64_t>(), d_counters, st));
-    } else {
-        GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
-                                (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
-                                keys_a.as<uint64_t>(), ib, out_idx.ptr, d_counters, begin_bit, key_bits,
-                                pre_hist.as<unsigned long long>(), st, want_frag ? &frag : nullptr));
-    }
-    marks.pack1 = tm.mark();
-    ScopedEvent e_pack, e_frag;
-    GK_TRY(e_pack.create());
-    GK_TRY(e_frag.create());
-    GK_CUDA(cudaEventRecord(e_pack.ev, st));
+    const int begin_bit = prefix_begin_bit(n, pp.key_bits);
+    marks.key_bits = pp.key_bits;
 
     int in_alt = 0;
-    GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
-    GK_TRY(sort_pairs_and_flag(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), out_idx.ptr, idx_b.ptr, ib, n,
-                               key_bits, class_bit, (uint8_t *)out_flags.ptr, &in_alt, d_descent,
-                               &marks.main_sort, st, d_list ? nullptr : pre_hist.as<unsigned long long>(), nullptr,
-                               nullptr, d_counters + kCounterWords));
-    uint64_t *keys_sorted = in_alt ? keys_b.as<uint64_t>() : keys_a.as<uint64_t>();
-    uint64_t *keys_other = in_alt ? keys_a.as<uint64_t>() : keys_b.as<uint64_t>();
-    if (in_alt) out_idx.swap(idx_b);
+    bool amb_counted = false;
+    // (inlined sort_pairs_and_flag: the third start buffer needs the passes' own bookkeeping)
+    GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
+    GK_TRY(radix_sort_pairs_device(pp.keys_a, pp.keys_b, pp.idx_a, pp.idx_b, ib, n, begin_bit, pp.key_bits, &in_alt, st,
+                                   &marks.main_sort, pp.d_pre_hist, pp.idx_final));
+    uint64_t *keys_sorted = in_alt ? pp.keys_b : pp.keys_a;
+    uint64_t *keys_other = in_alt ? pp.keys_a : pp.keys_b;
+    void *idx_sorted = pp.idx_final ? pp.idx_final : (in_alt ? pp.idx_b : pp.idx_a);
+    // scratch of the same size for the in-place repairs: a start buffer that does not hold the result
+    void *idx_other = (idx_sorted == pp.idx_b) ? pp.idx_a : pp.idx_b;
+    pp.keys_sorted = keys_sorted;
+    pp.idx_sorted = idx_sorted;
+    unsigned long long *d_n_amb = pp.producer_counted_amb ? nullptr : d_counters;
+    if (begin_bit == 0) {
+        GK_TRY(key_flags_device(keys_sorted, n, pp.class_bit, d_flags, st));
+    } else {
+        GK_TRY(tie_fix_flags_device(keys_sorted, idx_sorted, ib, n, begin_bit, pp.class_bit, d_flags, d_descent,
+                                    d_n_amb, st, d_counters + kCounterWords));
+        amb_counted = d_n_amb != nullptr;
+    }
     marks.fix0 = tm.mark();
     // long prefix runs that came out of order are re-sorted bucket by bucket, driven from the device list
     if (begin_bit > 0)
-        GK_TRY(repair_buckets_on_device(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, n, begin_bit, class_bit,
-                                        (uint8_t *)out_flags.ptr, d_descent, d_counters + kCounterWords, d_status,
+        GK_TRY(repair_buckets_on_device(keys_sorted, keys_other, idx_sorted, idx_other, ib, n, begin_bit,
+                                        pp.class_bit, d_flags, d_descent, d_counters + kCounterWords, d_status,
                                         d_counters + 4, st));
 
-    // ---- side stream: the pack kernel's counters, then the fragment sort -------------------------------------
-    cudaStream_t side = nullptr;
-    GK_TRY(side_stream(&side));
+    // ---- side stream: the producer's counters, then the fragment sort -----------------------------------------
     unsigned long long h_counters[kCounterWords] = {0};
-    GK_CUDA(cudaStreamWaitEvent(side, e_pack.ev, 0));
-    GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, side));
-    GK_CUDA(cudaStreamSynchronize(side));
-    const uint64_t n_amb = h_counters[0], n_frag = h_counters[2];
-    marks.n_amb = n_amb;
-    marks.n_frag = n_frag;
-    const bool use_frag = want_frag && n_amb > 0 && n_frag > 0 && n_frag <= frag.capacity;
-    if (use_frag) {
-        int start_bits = 1;
-        while (start_bits < 64 && (ix->sba_len >> start_bits)) ++start_bits;
-        GK_TRY(frag_sort_device(frag, n_frag, key_len, key_bits, start_bits, fs, side));
-        GK_CUDA(cudaEventRecord(e_frag.ev, side));
-        GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
-        GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr,
-                                  reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb, d_frag_err, st));
-        fs.rebind(st);
+    uint64_t n_amb = 0, n_frag = 0;
+    bool use_frag = false;
+    ScopedEvent e_frag;
+    if (pp.want_frag) {
+        cudaStream_t side = nullptr;
+        GK_TRY(side_stream(&side));
+        GK_TRY(e_frag.create());
+        GK_CUDA(cudaStreamWaitEvent(side, pp.e_producer, 0));
+        GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, side));
+        GK_CUDA(cudaStreamSynchronize(side));
+        n_amb = h_counters[0];
+        n_frag = h_counters[2];
+        use_frag = n_amb > 0 && n_frag > 0 && n_frag <= pp.frag.capacity;
+        if (use_frag) {
+            GK_TRY(frag_sort_device(pp.frag, n_frag, pp.key_len, pp.key_bits, pp.start_bits, *pp.fs, side));
+            GK_CUDA(cudaEventRecord(e_frag.ev, side));
+            GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
+            GK_TRY(frag_expand_device(*pp.fs, keys_sorted, n, ib, idx_sorted, d_flags,
+                                      reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb, d_frag_err,
+                                      st));
+            pp.fs->rebind(st);
+        }
     }
     marks.fix1 = tm.mark();
 
     // ---- the one synchronise: descents, repair status, fragment check, alphabet counters -----------------------
+    int h_extra_err = 0;
     GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-    if (d_alpha) GK_CUDA(cudaMemcpyAsync(h_alpha, d_alpha, 24, cudaMemcpyDeviceToHost, st));
+    if (pp.d_alpha) GK_CUDA(cudaMemcpyAsync(pp.h_alpha, pp.d_alpha, 24, cudaMemcpyDeviceToHost, st));
+    if (pp.d_extra_err) GK_CUDA(cudaMemcpyAsync(&h_extra_err, pp.d_extra_err, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    if (h_extra_err) {
+        set_error("partition: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
+    if (!pp.want_frag) {
+        n_amb = h_counters[0];
+        if (pp.class_bit && n && !pp.producer_counted_amb && !amb_counted)   // plain LSD: count the marked slots
+            GK_TRY(select_flagged(d_flags, n, kFlagAmb, ib, nullptr, nullptr, nullptr, nullptr, nullptr, &n_amb, st));
+    }
+    marks.n_amb = n_amb;
+    marks.n_frag = n_frag;
     const uint32_t n_descent = (uint32_t)(h_counters[1] & 0xffffffffull);
     const int status = (int)(h_counters[1] >> 32);
     int frag_err = (int)(h_counters[3] & 0xffffffffull);
     marks.refine_flags = (use_frag ? 1u : 0u) | (n_descent ? 4u : 0u) | (n_descent && !status ? 16u : 0u) |
                          ((uint32_t)frag_err << 8);
     if (getenv("GK_TRACE"))
-        fprintf(stderr, "[gk trace] level1: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u status=%d "
+        fprintf(stderr, "[gk trace] sort: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u status=%d "
                         "frag_err=%d\n", (unsigned long long)n, (unsigned long long)n_amb, (unsigned long long)n_frag,
                 (int)use_frag, n_descent, status, frag_err);
     bool elementwise_long = false;
@@ -519,12 +503,12 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
         const int f0 = tm.mark();
         if (!(status & 2)) {
             const uint32_t n_big = (uint32_t)h_counters[4];
-            GK_TRY(repair_big_buckets(keys_sorted, keys_other, out_idx.ptr, idx_b.ptr, ib, begin_bit, class_bit,
-                                      (uint8_t *)out_flags.ptr, d_counters + 5, h_counters + 5, n_big, st));
+            GK_TRY(repair_big_buckets(keys_sorted, keys_other, idx_sorted, idx_other, ib, begin_bit, pp.class_bit,
+                                      d_flags, d_counters + 5, h_counters + 5, n_big, st));
             marks.refine_flags |= 32u;
             if (use_frag && !frag_err) {   // the fragment kernels did nothing while the keys were out of order
                 GK_CUDA(cudaMemsetAsync(d_status, 0, 4, st));
-                GK_TRY(frag_expand_device(fs, keys_sorted, n, ib, out_idx.ptr, (uint8_t *)out_flags.ptr,
+                GK_TRY(frag_expand_device(*pp.fs, keys_sorted, n, ib, idx_sorted, d_flags,
                                           reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb,
                                           d_frag_err, st));
             }
@@ -541,13 +525,90 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
         // element-wise repair (gk_refine.cu): the ambiguous windows by their 4-bit rank words when there is no
         // fragment list for them, and the members of every long prefix run when too many are out of order
         const int f0 = tm.mark();
-        GK_TRY(refine_subset(ix, keys_sorted, out_idx.ptr, (uint8_t *)out_flags.ptr, n, class_bit, key_len, key_bits,
-                             n_amb, elementwise_long, terminated, st));
+        GK_TRY(refine_subset(ix, keys_sorted, idx_sorted, d_flags, n, pp.class_bit, pp.key_len, pp.key_bits, n_amb,
+                             elementwise_long, pp.terminated, st));
         GK_CUDA(cudaStreamSynchronize(st));
         if (!status) marks.fix0 = f0;
         marks.fix1 = tm.mark();
         marks.refine_flags |= 2u;
     }
+    return GK_OK;
+}
+
+// Level 1: every window of valid_len symbols, ordered by its first key_len <= 32 symbols.
+// Leaves the sorted starts in out_idx and the head flags (for key_len) in out_flags; synchronises once, at
+// the end.  d_alpha (optional): the three alphabet counters of a scan that is still in flight on `st`; they
+// come back with the other counters (h_alpha).  d_list != nullptr: sort these starts (ascending, n of them)
+// instead of every window of the byte array.
+static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int class_bit, uint64_t n,
+                       Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm, cudaStream_t st,
+                       unsigned long long *d_alpha, unsigned long long *h_alpha, const void *d_list = nullptr)
+{
+    const int ib = ix->idx_bytes;
+    PackedPairs pp;
+    pp.n = n;
+    pp.key_len = key_len;
+    pp.class_bit = class_bit;
+    // value <= 4^key_len needs 2*key_len+1 bits when ambiguous windows exist, plus the class bit
+    pp.key_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
+    pp.terminated = valid_len < key_len;
+    pp.d_alpha = d_alpha;
+    pp.h_alpha = h_alpha;
+
+    DeviceBuffer keys_a, keys_b, counters, pre_hist, frag_mem;
+    Owned idx_b;
+    FragSorted fs;
+    GK_TRY(keys_a.alloc((size_t)n * 8, st));
+    GK_TRY(keys_b.alloc((size_t)n * 8, st));
+    GK_TRY(idx_b.alloc((size_t)n * ib, st));
+    GK_TRY(out_idx.alloc((size_t)n * ib, st));
+    GK_TRY(counters.alloc(kCounterBytes, st));
+    GK_CUDA(cudaMemsetAsync(counters.ptr, 0, (size_t)kCounterWords * 8, st));
+    pp.d_counters = counters.as<unsigned long long>();
+    pp.keys_a = keys_a.as<uint64_t>();
+    pp.keys_b = keys_b.as<uint64_t>();
+    pp.idx_a = out_idx.ptr;
+    pp.idx_b = idx_b.ptr;
+    pp.fs = &fs;
+    // the pack kernel counts the digits of the radix passes while it writes the keys
+    const int begin_bit = prefix_begin_bit(n, pp.key_bits);
+    GK_TRY(pre_hist.alloc(8 * 256 * sizeof(unsigned long long), st));
+    GK_CUDA(cudaMemsetAsync(pre_hist.ptr, 0, pre_hist.bytes, st));
+    // fragment list of the ambiguous windows (not for an arbitrary list of starts: no neighbours there)
+    pp.want_frag = class_bit && !d_list && fragments_enabled();
+    if (pp.want_frag) {
+        const uint64_t cap = n < kFragCapacity ? n : kFragCapacity;
+        GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
+        uint64_t *base = frag_mem.as<uint64_t>();
+        pp.frag.key = base; pp.frag.w0 = base + cap; pp.frag.w1 = base + 2 * cap; pp.frag.start = base + 3 * cap;
+        pp.frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
+        pp.frag.counter = pp.d_counters + 2;
+        pp.frag.capacity = cap;
+        GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
+    }
+    pp.start_bits = 1;
+    while (pp.start_bits < 64 && (ix->sba_len >> pp.start_bits)) ++pp.start_bits;
+
+    marks.pack0 = tm.mark();
+    if (d_list) {
+        GK_CUDA(cudaMemcpyAsync(out_idx.ptr, d_list, (size_t)n * ib, cudaMemcpyDeviceToDevice, st));
+        GK_TRY(pack_keys_list_device(ix->d_sba, ix->sba_len, d_list, ib, n, key_len, class_bit, pp.keys_a,
+                                     pp.d_counters, st));
+    } else {
+        GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
+                                (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
+                                pp.keys_a, ib, out_idx.ptr, pp.d_counters, begin_bit, pp.key_bits,
+                                pre_hist.as<unsigned long long>(), st, pp.want_frag ? &pp.frag : nullptr));
+        pp.d_pre_hist = pre_hist.as<unsigned long long>();
+    }
+    marks.pack1 = tm.mark();
+    ScopedEvent e_pack;
+    GK_TRY(e_pack.create());
+    GK_CUDA(cudaEventRecord(e_pack.ev, st));
+    pp.e_producer = e_pack.ev;
+    GK_TRY(out_flags.alloc((size_t)((n + 15) & ~15ull), st));
+    GK_TRY(sort_packed_pairs(ix, pp, (uint8_t *)out_flags.ptr, marks, tm, st));
+    if (pp.idx_sorted == idx_b.ptr) out_idx.swap(idx_b);
     return GK_OK;
 }
 
@@ -937,76 +998,149 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     return GK_OK;
 }
 
-// Multi-GPU shard: adopt (key, start) pairs that the caller received from the exchange (keys made by
-// gk_pack_keys with the same key_len / class_bit), sort them and build the same state gk_index_sort
-// leaves behind, for this rank's key range only.  The pair buffers are scratch (ping-pong).
-int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
-                        uint64_t n_local, int class_bit, gk_sort_stats *stats_out, void *stream)
+// Multi-GPU shard: adopt the (key, start) pairs this rank received from the exchange (keys made by gk_pack_keys /
+// gk_pack_slice with key_len = valid_len = min_kmer_len, possibly relative to the start of this rank's key
+// range), sort them and build the same state gk_index_sort leaves behind, for this rank's key range only.
+// With a gathered fragment list the ambiguous windows of the range did not travel as pairs: they are generated
+// here from the fragments (n_ambiguous of them, appended behind the n_pure received pairs) and ordered by the
+// fragment path.  The pair buffers are scratch; the sorted starts land in the index's own buffer.
+int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
+                        uint64_t n_pure, uint64_t n_ambiguous, int class_bit, int key_bits,
+                        const void *d_frag_gathered, const uint64_t *d_frag_counts, uint32_t n_sources,
+                        uint64_t frag_capacity, uint64_t key_lo, uint64_t key_hi, const int *d_err,
+                        gk_sort_stats *stats_out, void *stream)
 {
+    const uint64_t n_local = n_pure + n_ambiguous;
     if (!ix || (n_local && (!d_keys || !d_keys_alt || !d_idx || !d_idx_alt))) {
-        set_error("gk_index_sort_pairs: null buffer");
+        set_error("gk_index_sort_shard: null buffer");
         return GK_ERR_ARG;
     }
     const uint32_t k = ix->min_len;
     if (!(ix->max_len == ix->min_len && (k <= 31 || (k == 32 && !class_bit)))) {
-        set_error("gk_index_sort_pairs: only single-word k-mers (k <= 31, or 32 without ambiguous bases)");
+        set_error("gk_index_sort_shard: only single-word k-mers (k <= 31, or 32 without ambiguous bases)");
         return GK_ERR_UNSUPPORTED;
+    }
+    const int full_bits = 2 * (int)k + (class_bit ? 2 : 0);
+    if (key_bits <= 0 || key_bits > full_bits) key_bits = full_bits;
+    const bool with_frag = d_frag_gathered != nullptr && class_bit && n_sources > 0 && frag_capacity > 0;
+    if (!with_frag && n_ambiguous) {
+        set_error("gk_index_sort_shard: ambiguous windows to generate but no fragment list");
+        return GK_ERR_ARG;
     }
     cudaStream_t st = as_stream(stream);
     gk_sort_stats stats;
     memset(&stats, 0, sizeof(stats));
     const uint64_t launches0 = gk_launch_count(0);
     EventTimer tm(st);
+    StageMarks marks;
     const int t0 = tm.mark();
     const int ib = ix->idx_bytes;
-    const int key_bits = 2 * (int)k + (class_bit ? 2 : 0);
-    SortTiming timing;
-    int in_alt = 0;
-    ix->n = n_local;
-    GK_TRY(ix->d_idx.alloc((size_t)n_local * ib, st));
-    GK_TRY(ix->d_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
-    DeviceBuffer descent;  // [0..3] descent word, [8..15] count of ambiguous slots
-    GK_TRY(descent.alloc(16, st));
-    GK_CUDA(cudaMemsetAsync(descent.ptr, 0, 16, st));
-    bool amb_counted = false;
-    GK_TRY(sort_pairs_and_flag(d_keys, d_keys_alt, d_idx, d_idx_alt, ib, n_local, key_bits, class_bit,
-                               (uint8_t *)ix->d_flags.ptr, &in_alt, descent.as<unsigned int>(), &timing, st,
-                               nullptr, descent.as<unsigned long long>() + 1, &amb_counted));
-    const uint64_t *keys_sorted = in_alt ? d_keys_alt : d_keys;
-    const void *idx_sorted = in_alt ? d_idx_alt : d_idx;
-    if (n_local)
-        GK_CUDA(cudaMemcpyAsync(ix->d_idx.ptr, idx_sorted, (size_t)n_local * ib, cudaMemcpyDeviceToDevice, st));
-    const int f0 = tm.mark();
-    unsigned long long h_words[2] = {0, 0};
-    GK_CUDA(cudaMemcpyAsync(h_words, descent.ptr, 16, cudaMemcpyDeviceToHost, st));
+    DeviceBuffer sort_err;
+    GK_TRY(sort_err.alloc(4, st));
+    GK_CUDA(cudaMemsetAsync(sort_err.ptr, 0, 4, st));
+    struct ErrWordGuard {
+        explicit ErrWordGuard(int *p) { set_deferred_sort_error_word(p); }
+        ~ErrWordGuard() { set_deferred_sort_error_word(nullptr); }
+    } err_guard(sort_err.as<int>());
+
+    Owned new_idx, new_flags;
+    DeviceBuffer counters, frag_mem, frag_off;
+    FragSorted fs;
+    PackedPairs pp;
+    if (n_local) {
+        GK_TRY(new_idx.alloc((size_t)n_local * ib, st));
+        GK_TRY(new_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
+        GK_TRY(counters.alloc(kCounterBytes, st));
+        GK_CUDA(cudaMemsetAsync(counters.ptr, 0, (size_t)kCounterWords * 8, st));
+        pp.n = n_local;
+        pp.key_len = k;
+        pp.key_bits = key_bits;
+        pp.class_bit = class_bit;
+        pp.keys_a = d_keys; pp.keys_b = d_keys_alt;
+        pp.idx_a = d_idx; pp.idx_b = d_idx_alt;
+        pp.idx_final = new_idx.ptr;
+        pp.d_counters = counters.as<unsigned long long>();
+        pp.d_extra_err = d_err;
+        pp.fs = &fs;
+        pp.start_bits = 1;
+        while (pp.start_bits < 64 && (ix->sba_len >> pp.start_bits)) ++pp.start_bits;
+        ScopedEvent e_ready;
+        GK_TRY(e_ready.create());
+        marks.pack0 = tm.mark();
+        if (with_frag) {
+            // the fragments of this key range, keys relative like the received pairs; then their windows as
+            // placeholder pairs behind the received ones
+            uint64_t cap = (uint64_t)n_sources * frag_capacity;
+            if (cap > kFragCapacity) cap = kFragCapacity;
+            GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
+            GK_TRY(frag_off.alloc((size_t)(cap + 1) * 8, st));
+            uint64_t *base = frag_mem.as<uint64_t>();
+            pp.frag.key = base; pp.frag.w0 = base + cap; pp.frag.w1 = base + 2 * cap; pp.frag.start = base + 3 * cap;
+            pp.frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
+            pp.frag.counter = pp.d_counters + 2;
+            pp.frag.capacity = cap;
+            pp.want_frag = fragments_enabled() || n_ambiguous > 0;
+            GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
+            GK_TRY(frag_filter_device(d_frag_gathered, reinterpret_cast<const unsigned long long *>(d_frag_counts),
+                                      n_sources, frag_capacity, key_lo, key_hi, pp.frag, st));
+            GK_TRY(frag_placeholders_device(pp.frag, frag_off.as<unsigned long long>(), n_pure, n_ambiguous, d_keys,
+                                            d_idx, ib, reinterpret_cast<int *>(pp.d_counters + 3), st));
+            // d_counters[0] = ambiguous windows of the shard: known to the caller, the expand step checks it
+            GK_CUDA(cudaMemcpyAsync(pp.d_counters, &n_ambiguous, 8, cudaMemcpyHostToDevice, st));
+            pp.producer_counted_amb = true;
+        } else {
+            pp.producer_counted_amb = false;   // ambiguous windows are among the pairs: the flags pass counts them
+        }
+        marks.pack1 = tm.mark();
+        GK_CUDA(cudaEventRecord(e_ready.ev, st));
+        pp.e_producer = e_ready.ev;
+        GK_TRY(sort_packed_pairs(ix, pp, (uint8_t *)new_flags.ptr, marks, tm, st));
+    }
+    const int t1 = tm.mark();
+    int h_sort_err = 0;
+    GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
-    const unsigned int h_descent = (unsigned int)(h_words[0] & 0xffffffffull);
-    uint64_t n_amb = h_words[1];
-    if (class_bit && n_local && !amb_counted)  // plain LSD path: count the slots the flags pass marked
-        GK_TRY(select_flagged((const uint8_t *)ix->d_flags.ptr, n_local, kFlagAmb, ib, nullptr, nullptr, nullptr,
-                              nullptr, nullptr, &n_amb, st));
-    GK_TRY(refine_subset(ix, keys_sorted, ix->d_idx.ptr, (uint8_t *)ix->d_flags.ptr, n_local, class_bit, k,
-                         key_bits, n_amb, h_descent != 0, false, st));
-    const int f1 = tm.mark();
+    marks.main_sort.resolve();
+    if (h_sort_err) {
+        set_error("radix sort: decoupled look-back timed out");
+        return GK_ERR_INTERNAL;
+    }
+    if (marks.refine_flags & (8u << 8)) {
+        set_error("gk_index_sort_shard: the fragments of this key range do not add up to %llu ambiguous windows",
+                  (unsigned long long)n_ambiguous);
+        return GK_ERR_INTERNAL;
+    }
+    ix->d_idx.swap(new_idx);
+    ix->d_flags.swap(new_flags);
+    ix->n = n_local;
+    ix->user_idx = false;
     ix->idx_ready = true;
     ix->flags_mark_amb = true;
     ix->flags_valid = n_local > 0;
     ix->flags_kmer_len = k;
     ix->sorted = true;
-    const int t1 = tm.mark();
-    GK_CUDA(cudaStreamSynchronize(st));
-    stats.hist_ms = timing.hist_ms;
-    stats.sort_ms = timing.passes_ms;
-    stats.sort_passes = timing.passes;
-    stats.fixup_ms = tm.ms(f0, f1);
+    stats.pack_ms = tm.ms(marks.pack0, marks.pack1);
+    stats.hist_ms = marks.main_sort.hist_ms;
+    stats.sort_ms = marks.main_sort.passes_ms;
+    stats.sort_passes = marks.main_sort.passes;
+    stats.fixup_ms = tm.ms(marks.fix0, marks.fix1);
     stats.key_bits = key_bits;
     stats.levels = 1;
     stats.n_windows = n_local;
-    stats.n_ambiguous = n_amb;
+    stats.n_ambiguous = marks.n_amb;
+    stats.n_fragments = marks.n_frag;
+    stats.refine_flags = marks.refine_flags;
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;
     return GK_OK;
+}
+
+int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
+                        uint64_t n_local, int class_bit, gk_sort_stats *stats_out, void *stream)
+{
+    return gk_index_sort_shard(ix, d_keys, d_keys_alt, d_idx, d_idx_alt, n_local, 0, class_bit, 0, nullptr, nullptr, 0,
+                               0, 0, 0, nullptr, stats_out, stream);
 }
 
 int gk_index_device_indices(gk_index *ix, const void **d_idx_out, void *stream)

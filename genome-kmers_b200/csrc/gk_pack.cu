@@ -531,6 +531,39 @@ check_starts_kernel(const IdxT *__restrict__ idx, uint64_t n, const uint64_t *__
     }
 }
 
+// Keys of evenly spaced windows of a slice (the multi-GPU driver picks its splitters from them): sample j is
+// window number base + j * n_slice / n_samples of the index; its start comes from the same slot rule as
+// init_indices_kernel, its key from the same definition as pack_keys_kernel.
+__global__ void __launch_bounds__(256)
+sample_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const uint64_t *__restrict__ seg_starts,
+                   uint32_t n_seg, uint32_t k, int class_bit, uint64_t base, uint64_t n_slice, uint32_t n_samples,
+                   uint64_t *__restrict__ keys_out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_samples) return;
+    const uint64_t p = base + (uint64_t)(((unsigned __int128)j * n_slice) / n_samples);
+    uint32_t lo = 0, hi = n_seg;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p < seg_starts[mid] - (uint64_t)mid * k) hi = mid; else lo = mid + 1;
+    }
+    const uint64_t s = p + (uint64_t)(lo - 1) * k;
+    uint64_t value = 0;
+    bool pure = true;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t b = (s + i < sba_len) ? sba[s + i] : kSep;
+        if (is_acgt(b)) {
+            value = (value << 2) | code2(b);
+        } else {
+            const uint32_t rem = 2u * (k - i);
+            value = ((rem >= 64) ? 0ull : (value << rem)) + ((uint64_t)acgt_below(b) << (rem - 2));
+            pure = false;
+            break;
+        }
+    }
+    keys_out[j] = class_bit ? ((value << 1) | (pure ? 1ull : 0ull)) : value;
+}
+
 static unsigned list_grid(uint64_t n)
 {
     uint64_t blocks = (n + 255) / 256;
@@ -637,5 +670,78 @@ extern "C" int gk_pack_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64
     GK_CUDA(cudaStreamSynchronize(st));
     if (h_n_out) *h_n_out = n;
     if (h_n_ambiguous) *h_n_ambiguous = n_amb;
+    return GK_OK;
+}
+
+/* Multi-GPU producer (no synchronise): pack the windows whose start lies in [first_start, end_start) and list
+ * the ambiguous-window fragments of that slice.  d_frag: frag_capacity * 36 bytes laid out as
+ * key[cap] w0[cap] w1[cap] start[cap] (u64) then count[cap] (u32); d_counters: 4 x u64, zeroed here:
+ * [0] ambiguous windows, [2] fragments found (may exceed the capacity: the list is then incomplete). */
+extern "C" int gk_pack_slice(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts, uint32_t n_seg,
+                             uint32_t kmer_len, int class_bit, uint64_t first_start, uint64_t end_start,
+                             uint64_t *d_keys_out, int idx_bytes, void *d_idx_out, uint64_t out_capacity,
+                             uint64_t *h_n_out, void *d_frag, uint64_t frag_capacity, uint64_t *d_counters,
+                             void *stream)
+{
+    if (!d_sba || !h_seg_starts || !d_keys_out || !d_idx_out || !d_counters || n_seg == 0 ||
+        (idx_bytes != 4 && idx_bytes != 8)) {
+        set_error("gk_pack_slice: bad argument");
+        return GK_ERR_ARG;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (end_start > sba_len) end_start = sba_len;
+    const uint64_t base = windows_before(h_seg_starts, n_seg, sba_len, kmer_len, first_start);
+    const uint64_t upto = windows_before(h_seg_starts, n_seg, sba_len, kmer_len, end_start);
+    const uint64_t n = upto - base;
+    if (n > out_capacity) {
+        set_error("gk_pack_slice: %llu windows do not fit the output capacity %llu", (unsigned long long)n,
+                  (unsigned long long)out_capacity);
+        return GK_ERR_ARG;
+    }
+    DeviceBuffer segs;
+    GK_TRY(segs.alloc((size_t)n_seg * 8, st));
+    GK_CUDA(cudaMemcpyAsync(segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemsetAsync(d_counters, 0, 32, st));
+    FragOut frag;
+    if (d_frag && frag_capacity && class_bit) {
+        uint64_t *b = reinterpret_cast<uint64_t *>(d_frag);
+        frag.key = b; frag.w0 = b + frag_capacity; frag.w1 = b + 2 * frag_capacity; frag.start = b + 3 * frag_capacity;
+        frag.count = reinterpret_cast<uint32_t *>(b + 4 * frag_capacity);
+        frag.counter = reinterpret_cast<unsigned long long *>(d_counters) + 2;
+        frag.capacity = frag_capacity;
+    }
+    GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, kmer_len, kmer_len, class_bit, first_start,
+                            end_start, base, d_keys_out, idx_bytes, d_idx_out,
+                            reinterpret_cast<unsigned long long *>(d_counters), 0, 0, nullptr, st,
+                            frag.key ? &frag : nullptr));
+    if (h_n_out) *h_n_out = n;
+    return GK_OK;   // (the pageable segment table was staged by the runtime before cudaMemcpyAsync returned)
+}
+
+/* Keys of n_samples evenly spaced windows of the slice [first_start, end_start) (fewer when the slice holds
+ * fewer windows; *h_n_out tells).  No synchronise. */
+extern "C" int gk_sample_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts, uint32_t n_seg,
+                              uint32_t kmer_len, int class_bit, uint64_t first_start, uint64_t end_start,
+                              uint32_t n_samples, uint64_t *d_keys_out, uint32_t *h_n_out, void *stream)
+{
+    if (!d_sba || !h_seg_starts || !d_keys_out || n_seg == 0 || kmer_len < 1 || kmer_len > 32 ||
+        (class_bit && kmer_len > 31)) {
+        set_error("gk_sample_keys: bad argument");
+        return GK_ERR_ARG;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (end_start > sba_len) end_start = sba_len;
+    const uint64_t base = windows_before(h_seg_starts, n_seg, sba_len, kmer_len, first_start);
+    const uint64_t upto = windows_before(h_seg_starts, n_seg, sba_len, kmer_len, end_start);
+    const uint64_t n_slice = upto - base;
+    if ((uint64_t)n_samples > n_slice) n_samples = (uint32_t)n_slice;
+    if (h_n_out) *h_n_out = n_samples;
+    if (n_samples == 0) return GK_OK;
+    DeviceBuffer segs;
+    GK_TRY(segs.alloc((size_t)n_seg * 8, st));
+    GK_CUDA(cudaMemcpyAsync(segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    sample_keys_kernel<<<(n_samples + 255) / 256, 256, 0, st>>>(d_sba, sba_len, segs.as<uint64_t>(), n_seg, kmer_len,
+                                                                class_bit, base, n_slice, n_samples, d_keys_out);
+    GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -215,6 +215,15 @@ int gk_sba_scan_alphabet(const uint8_t *d_sba, uint64_t len, uint64_t *h_counts3
     return GK_OK;
 }
 
+int gk_sba_scan_alphabet_async(const uint8_t *d_sba, uint64_t len, uint64_t *d_counts3, void *stream)
+{
+    if (!d_counts3 || (!d_sba && len)) {
+        set_error("gk_sba_scan_alphabet_async: null pointer");
+        return GK_ERR_ARG;
+    }
+    return scan_alphabet_async(d_sba, len, reinterpret_cast<unsigned long long *>(d_counts3), as_stream(stream));
+}
+
 int gk_sba_revcomp(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream)
 {
     if ((!d_in || !d_out) && len) {

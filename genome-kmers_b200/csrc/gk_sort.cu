@@ -48,7 +48,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kHistThreads)
 digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit, int end_bit,
                        const uint64_t *__restrict__ splitters, uint32_t n_split,
-                       unsigned long long *__restrict__ g_hist /* [passes][256] */)
+                       unsigned long long *__restrict__ g_hist /* [passes][256] */, int split_amb = 0)
 {
     __shared__ uint32_t s_hist[kMaxPasses][kRadix];
     __shared__ uint64_t s_split[kRadix];
@@ -61,7 +61,9 @@ digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit,
     const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
     auto add = [&](uint64_t key) {
         if (splitters) {
-            atomicAdd(&s_hist[0][splitter_digit(s_split, n_split, key)], 1u);
+            // split_amb: keys of class 0 (ambiguous windows) are counted per destination in bins n_parts ...
+            const uint32_t d = splitter_digit(s_split, n_split, key);
+            atomicAdd(&s_hist[0][d + ((split_amb && !(key & 1ull)) ? n_split + 1 : 0u)], 1u);
             return;
         }
 #pragma unroll
@@ -141,10 +143,16 @@ constexpr int kLookbackBatch = 4;                  // predecessor status words l
 
 // Multi-GPU partition straight into the destination ranks' receive buffers (peer memory over NVLink):
 // digit d's pairs go to keys[d] / vals[d]; bin_base[d] holds the offset of this rank's segment there.
+// key_base[d] is subtracted from every key that goes to rank d (the rank's key range starts there, so its local
+// sort sees keys relative to its own range); with skip_amb, keys of class 0 (ambiguous windows, which travel as
+// run-length fragments instead) are counted in digit n_dest and written nowhere.
 constexpr int kMaxPeers = 16;
 struct PeerTable {
     uint64_t *keys[kMaxPeers];
     void *vals[kMaxPeers];
+    uint64_t key_base[kMaxPeers];
+    uint32_t n_dest;
+    uint32_t skip_amb;
 };
 
 template <typename ValT, int THREADS, int IPT, typename KeyT = uint64_t>
@@ -159,6 +167,8 @@ struct OnesweepSmem {
     uint64_t splitters[kRadix];
     uint64_t *peer_keys[kMaxPeers];
     ValT *peer_vals[kMaxPeers];
+    uint64_t peer_key_base[kMaxPeers];
+    uint32_t peer_n_dest, peer_skip_amb;
     uint32_t bin_excl[kRadix];
     uint32_t warp_sums[kRadix / 32];
     uint32_t tile;
@@ -229,13 +239,22 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
     for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;
     if (PARTITION && t < n_split) s.splitters[t] = splitters[t];
-    if (PARTITION && peer && t < kMaxPeers) {
-        s.peer_keys[t] = peer->keys[t];
-        s.peer_vals[t] = reinterpret_cast<ValT *>(peer->vals[t]);
+    if (PARTITION && t < kMaxPeers) {
+        s.peer_keys[t] = peer ? peer->keys[t] : nullptr;
+        s.peer_vals[t] = peer ? reinterpret_cast<ValT *>(peer->vals[t]) : nullptr;
+        s.peer_key_base[t] = peer ? peer->key_base[t] : 0ull;
+        if (t == 0) {
+            s.peer_n_dest = peer ? peer->n_dest : 0u;
+            s.peer_skip_amb = peer ? peer->skip_amb : 0u;
+        }
     }
     __syncthreads();
+    const uint32_t skip_amb_digit = (PARTITION && s.peer_skip_amb) ? s.peer_n_dest : 0xffffffffu;
     auto digit_of = [&](KeyT k) -> uint32_t {
-        if (PARTITION) return splitter_digit(s.splitters, n_split, (uint64_t)k);
+        if (PARTITION) {
+            if (skip_amb_digit != 0xffffffffu && !((uint64_t)k & 1ull)) return skip_amb_digit;
+            return splitter_digit(s.splitters, n_split, (uint64_t)k);
+        }
         return (uint32_t)(k >> shift) & digit_mask;
     };
     const uint64_t tile = s.tile;
@@ -364,9 +383,11 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
             if (p < tile_valid) {
                 const KeyT k = s.keys[p];
                 const uint32_t d = digit_of(k);
-                const uint64_t dst = (uint64_t)(s.global_off[d] + p);
-                s.peer_keys[d][dst] = (uint64_t)k;
-                s.peer_vals[d][dst] = s.vals[p];
+                if (d < s.peer_n_dest) {
+                    const uint64_t dst = (uint64_t)(s.global_off[d] + p);
+                    s.peer_keys[d][dst] = (uint64_t)k - s.peer_key_base[d];
+                    s.peer_vals[d][dst] = s.vals[p];
+                }
             }
         }
         return;
@@ -1058,12 +1079,40 @@ int partition_count_device(const uint64_t *d_keys, uint64_t n, const uint64_t *d
     return GK_OK;
 }
 
+// Destination counts left on the device, no synchronise: d_counts_out[d] = pure pairs for destination d,
+// d_counts_out[n_parts + d] = ambiguous ones (class bit 0; only split off when class_bit is set).
+int partition_count_split_device(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                                 int class_bit, unsigned long long *d_counts_out, cudaStream_t st)
+{
+    if (n_parts < 1 || n_parts > (uint32_t)kMaxPeers) {
+        set_error("partition_count_split: n_parts must be in [1, %d]", kMaxPeers);
+        return GK_ERR_ARG;
+    }
+    GK_CUDA(cudaMemsetAsync(d_counts_out, 0, (size_t)2 * n_parts * 8, st));
+    if (n == 0) return GK_OK;
+    DeviceBuffer hist;
+    GK_TRY(hist.alloc(kRadix * sizeof(unsigned long long), st));
+    GK_CUDA(cudaMemsetAsync(hist.ptr, 0, hist.bytes, st));
+    int grid = sm_count() * 2;
+    uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
+    if (need < 1) need = 1;
+    if ((uint64_t)grid > need) grid = (int)need;
+    digit_histogram_kernel<<<grid, kHistThreads, 0, st>>>(d_keys, n, 0, 8, d_splitters ? d_splitters : d_keys,
+                                                          n_parts - 1, hist.as<unsigned long long>(), class_bit);
+    GK_LAUNCH_CHECK();
+    GK_CUDA(cudaMemcpyAsync(d_counts_out, hist.ptr, (size_t)2 * n_parts * 8, cudaMemcpyDeviceToDevice, st));
+    return GK_OK;
+}
+
 // One stable partition pass whose output lands in the destination ranks' buffers.  h_dst_keys / h_dst_vals:
 // n_parts device pointers (local or peer-mapped); h_dst_offsets[d]: first element of this rank's segment
-// in destination d.  No synchronise: the caller orders the consumers behind the launch.
+// in destination d; h_key_base (optional): subtracted from the keys sent to d; skip_amb: pairs of class 0 are
+// dropped.  d_err (optional device word): receives the look-back guard's verdict and the call does not
+// synchronise; without it the call synchronises and reports the failure itself.
 int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
                                 const uint64_t *d_splitters, uint32_t n_parts, uint64_t *const *h_dst_keys,
-                                void *const *h_dst_vals, const uint64_t *h_dst_offsets, cudaStream_t st)
+                                void *const *h_dst_vals, const uint64_t *h_dst_offsets, const uint64_t *h_key_base,
+                                int skip_amb, int *d_err_out, cudaStream_t st)
 {
     if (n_parts < 1 || n_parts > (uint32_t)kMaxPeers) {
         set_error("partition_pairs_peer: n_parts must be in [1, %d]", kMaxPeers);
@@ -1080,7 +1129,8 @@ int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int 
     const bool wide = n >= (1ull << 30);
     const size_t status_bytes = (size_t)tiles * kRadix * (wide ? 8 : 4);
     // temp layout: [bin_base 256 x u64][counter + err, 64 B][peer table][status]
-    const size_t head_bytes = kRadix * 8 + 64 + sizeof(PeerTable);
+    const size_t table_bytes = (sizeof(PeerTable) + 15) & ~(size_t)15;
+    const size_t head_bytes = kRadix * 8 + 64 + table_bytes;
     DeviceBuffer temp;
     GK_TRY(temp.alloc(head_bytes + status_bytes, st));
     unsigned char *base = temp.as<unsigned char>();
@@ -1092,13 +1142,16 @@ int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int 
     for (uint32_t d = 0; d < n_parts; ++d) {
         h_peer.keys[d] = h_dst_keys[d];
         h_peer.vals[d] = h_dst_vals[d];
+        h_peer.key_base[d] = h_key_base ? h_key_base[d] : 0ull;
     }
-    GK_CUDA(cudaMemsetAsync(base + kRadix * 8, 0, 64 + status_bytes + sizeof(PeerTable), st));
+    h_peer.n_dest = n_parts;
+    h_peer.skip_amb = skip_amb ? 1u : 0u;
+    GK_CUDA(cudaMemsetAsync(base + kRadix * 8, 0, 64 + status_bytes + table_bytes, st));
     GK_CUDA(cudaMemcpyAsync(base, h_base, sizeof(h_base), cudaMemcpyHostToDevice, st));
     GK_CUDA(cudaMemcpyAsync(base + kRadix * 8 + 64, &h_peer, sizeof(h_peer), cudaMemcpyHostToDevice, st));
     // the two small uploads read pageable host memory: they have completed when the calls return
     uint32_t *d_ctr = reinterpret_cast<uint32_t *>(base + kRadix * 8);
-    int *d_err = reinterpret_cast<int *>(d_ctr + 8);
+    int *d_err = d_err_out ? d_err_out : reinterpret_cast<int *>(d_ctr + 8);
     PassArgs pa = {d_keys, nullptr, d_vals, nullptr, n, 0, kRadixBits, d_splitters ? d_splitters : d_keys,
                    n_parts - 1, reinterpret_cast<const unsigned long long *>(base), d_ctr,
                    base + head_bytes, d_err, reinterpret_cast<const PeerTable *>(base + kRadix * 8 + 64)};
@@ -1108,8 +1161,7 @@ int partition_pairs_peer_device(const uint64_t *d_keys, const void *d_vals, int 
     else
         rc = wide ? dispatch_pass<uint64_t, uint64_t>(cfg, pa, st) : dispatch_pass<uint64_t, uint32_t>(cfg, pa, st);
     GK_TRY(rc);
-    // the scratch is released in stream order (after the kernel); look-back failures surface as a hang
-    // guard only: report them on the next synchronising call of the caller
+    if (d_err_out) return GK_OK;   // the scratch is released in stream order; the caller reads the error word
     int h_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
@@ -1177,7 +1229,8 @@ extern "C" int gk_partition_count(const uint64_t *d_keys, uint64_t n, const uint
 extern "C" int gk_partition_pairs_peer(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
                                        const uint64_t *d_splitters, uint32_t n_parts,
                                        uint64_t *const *h_dst_keys, void *const *h_dst_vals,
-                                       const uint64_t *h_dst_offsets, void *stream)
+                                       const uint64_t *h_dst_offsets, const uint64_t *h_key_base, int skip_ambiguous,
+                                       int *d_err, void *stream)
 {
     if (!h_dst_keys || !h_dst_vals || !h_dst_offsets || (n && (!d_keys || !d_vals)) ||
         (n_parts > 1 && !d_splitters)) {
@@ -1185,5 +1238,17 @@ extern "C" int gk_partition_pairs_peer(const uint64_t *d_keys, const void *d_val
         return GK_ERR_ARG;
     }
     return partition_pairs_peer_device(d_keys, d_vals, val_bytes, n, d_splitters, n_parts, h_dst_keys,
-                                       h_dst_vals, h_dst_offsets, as_stream(stream));
+                                       h_dst_vals, h_dst_offsets, h_key_base, skip_ambiguous, d_err,
+                                       as_stream(stream));
+}
+
+extern "C" int gk_partition_count_split(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters,
+                                        uint32_t n_parts, int class_bit, uint64_t *d_counts_out, void *stream)
+{
+    if (!d_counts_out || (n && !d_keys) || (n_parts > 1 && !d_splitters)) {
+        set_error("gk_partition_count_split: null buffer");
+        return GK_ERR_ARG;
+    }
+    return partition_count_split_device(d_keys, n, d_splitters, n_parts, class_bit,
+                                        reinterpret_cast<unsigned long long *>(d_counts_out), as_stream(stream));
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gk_device_info": (_int, [_p(_int), _p(_int), _p(_int), _p(_u64)]),
     "gk_launch_count": (_u64, [_int]),
     "gk_sba_scan_alphabet": (_int, [_vp, _u64, _vp, _vp]),
+    "gk_sba_scan_alphabet_async": (_int, [_vp, _u64, _vp, _vp]),
     "gk_sba_revcomp": (_int, [_vp, _u64, _vp, _vp]),
     "gk_sba_both_strands": (_int, [_vp, _u64, _vp, _vp]),
     "gk_kmer_count": (_int, [_vp, _u32, _u64, _u32, _p(_u64)]),
@@ -74,7 +75,8 @@ SIGNATURES = {
     "gk_radix_sort_pairs32": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _int, _int, _p(_int), _vp]),
     "gk_partition_pairs": (_int, [_vp, _vp, _vp, _vp, _int, _u64, _vp, _u32, _vp, _vp]),
     "gk_partition_count": (_int, [_vp, _u64, _vp, _u32, _vp, _vp]),
-    "gk_partition_pairs_peer": (_int, [_vp, _vp, _int, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gk_partition_pairs_peer": (_int, [_vp, _vp, _int, _u64, _vp, _u32, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "gk_partition_count_split": (_int, [_vp, _u64, _vp, _u32, _int, _vp, _vp]),
     "gk_peer_alloc": (_int, [_u64, _p(_vp)]),
     "gk_peer_free": (_int, [_vp]),
     "gk_peer_export": (_int, [_vp, _vp]),
@@ -90,6 +92,11 @@ SIGNATURES = {
     "gk_index_set_indices": (_int, [_vp, _vp, _u64, _int, _int, _vp]),
     "gk_index_sort": (_int, [_vp, _p(GkSortStats), _vp]),
     "gk_index_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _int, _p(GkSortStats), _vp]),
+    "gk_index_sort_shard": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _int, _int, _vp, _vp, _u32, _u64, _u64, _u64,
+                                   _vp, _p(GkSortStats), _vp]),
+    "gk_pack_slice": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _u64, _u64, _vp, _int, _vp, _u64, _p(_u64), _vp, _u64,
+                             _vp, _vp]),
+    "gk_sample_keys": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _u64, _u64, _u32, _vp, _p(_u32), _vp]),
     "gk_index_device_indices": (_int, [_vp, _p(_vp), _vp]),
     "gk_index_copy_indices": (_int, [_vp, _vp, _vp]),
     "gk_index_group_counts": (_int, [_vp, _u32, _p(GkFilter), _u64, _u64, _u64, _vp,

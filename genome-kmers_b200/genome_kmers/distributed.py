@@ -5,19 +5,26 @@ NVLink/NVSwitch) for the plumbing, libgkb200 kernels for every compute step.
 The reference has no parallel code at all; this is new design.  The k-mer windows of the indexed byte
 array are range-partitioned by key so that equal k-mers always meet on one GPU:
 
-  1. every rank holds the whole byte array (a few GB at most) and packs the windows of ITS slice of
-     start positions into (key, start) pairs                                   gk_pack_keys
-  2. evenly spaced key samples are all-gathered; every rank sorts them and picks the same G-1 splitters
-  3. one stable partition pass groups the pairs by destination rank            gk_partition_pairs
-  4. pair counts are exchanged (tiny all-to-all), then the pairs themselves: ONE variable-size
-     all-to-all for the keys and one for the starts                            all_to_all_single
-  5. every rank sorts its key range, refines ambiguous windows, flags groups   gk_index_sort_pairs
-  6. histograms are summed with an all-reduce; the global sorted order is the concatenation of the
+  1. every rank holds the whole byte array (a few GB at most) and packs the windows of ITS slice of start
+     positions into (key, start) pairs; the ambiguous windows of the slice (N runs, IUPAC letters) are also
+     listed as run-length fragments                                                gk_pack_slice
+  2. meanwhile (second stream) keys of evenly spaced windows of the slice are sampled, all-gathered, and
+     every rank picks the same G-1 splitters                                       gk_sample_keys
+  3. destination counts (pure / ambiguous pairs per rank) are exchanged in ONE small all-gather together
+     with the fragment counts and the alphabet counters                            gk_partition_count_split
+  4. ONE kernel partitions the pure pairs and writes each straight into the receive buffer of the rank that
+     owns its key range, over NVLink peer memory, with the key made relative to the start of that range;
+     ambiguous pairs are not sent at all: the fragment lists are all-gathered (a few MB) while that kernel
+     runs, and each rank regenerates the ambiguous windows of its own key range    gk_partition_pairs_peer
+  5. every rank sorts its key range, repairs prefix buckets, expands the fragments gk_index_sort_shard
+  6. the occupied histogram bins are all-gathered; the global sorted order is the concatenation of the
      ranks' shards in rank order.
 Splitters are keys (not (key, start) pairs), so a group of equal k-mers never straddles two ranks and
 no boundary fix-up is needed; the price is that one giant group cannot be split (documented skew).
 Ties stay in ascending start order: source ranks hold ascending slices, the partition and the sort are
-stable, and all_to_all_single concatenates by source rank.
+stable, and segments are laid out by source rank.
+Without peer access (several hosts, more than 16 ranks) step 4 partitions into a local staging buffer and
+the pairs travel through one NCCL all-to-all per array.
 
 The compute steps go through an `engine` object.  The default engine calls the CUDA library and needs
 a GPU; tests on CPU (gloo, world_size 2) inject a NumPy engine to exercise the orchestration only.
@@ -32,6 +39,8 @@ from genome_kmers import _native
 
 SAMPLES_PER_RANK = 2048
 HIST_PAIRS_PER_MESSAGE = 512   # occupied histogram bins per rank in the first all-gather round
+FRAG_SHARE = 1 << 16           # fragments per rank that the fixed-size fragment all-gather carries
+FRAG_BYTES = 36                # key, w0, w1, start (u64) + count (u32)
 
 
 def _torch():
@@ -40,8 +49,18 @@ def _torch():
     return torch
 
 
+class PackedSlice:
+    """What pack_slice leaves on the device: the (key, start) pairs of a rank's slice, its fragment list and
+    the counters [ambiguous windows, -, fragments, -]."""
+
+    def __init__(self, keys, idx, n, frag=None, counters=None):
+        self.keys, self.idx, self.n, self.frag, self.counters = keys, idx, int(n), frag, counters
+
+
 class NativeEngine:
     """Compute steps on the current CUDA device through the C ABI."""
+
+    supports_fragments = True
 
     def __init__(self):
         torch = _torch()
@@ -50,6 +69,8 @@ class NativeEngine:
         self.torch = torch
         self.lib = _native.lib()
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.side = torch.cuda.Stream(device=self.device)
+        self.err_word = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def stream(self):
         return int(self.torch.cuda.current_stream().cuda_stream)
@@ -67,10 +88,11 @@ class NativeEngine:
         _native.check(self.lib.gk_sba_both_strands(d_fwd.data_ptr(), d_fwd.numel(), out.data_ptr(), self.stream()))
         return out
 
-    def alphabet(self, d_sba):
-        counts = np.zeros(3, dtype=np.uint64)
-        _native.check(self.lib.gk_sba_scan_alphabet(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(counts),
-                                                    self.stream()))
+    def alphabet_async(self, d_sba):
+        """Device tensor int64[3] (bad bytes, '$', ambiguous letters); no synchronise."""
+        counts = self.torch.empty(3, dtype=self.torch.int64, device=self.device)
+        _native.check(self.lib.gk_sba_scan_alphabet_async(d_sba.data_ptr(), d_sba.numel(), counts.data_ptr(),
+                                                          self.stream()))
         return counts
 
     def pack_slice(self, d_sba, seg_starts, k, class_bit, first, end, idx_bytes):
@@ -78,96 +100,122 @@ class NativeEngine:
         cap = max(1, end - first)
         keys = torch.empty(cap, dtype=torch.int64, device=self.device)
         idx = torch.empty(cap, dtype=torch.int32 if idx_bytes == 4 else torch.int64, device=self.device)
-        n_out, n_amb = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        _native.check(self.lib.gk_pack_keys(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
-                                            len(seg_starts), k, k, class_bit, first, end, keys.data_ptr(),
-                                            idx_bytes, idx.data_ptr(), cap, ctypes.byref(n_out),
-                                            ctypes.byref(n_amb), self.stream()))
-        return keys[:n_out.value], idx[:n_out.value]
+        frag = torch.empty(FRAG_SHARE * FRAG_BYTES, dtype=torch.uint8, device=self.device)
+        counters = torch.empty(4, dtype=torch.int64, device=self.device)
+        n_out = ctypes.c_uint64(0)
+        _native.check(self.lib.gk_pack_slice(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
+                                             len(seg_starts), k, class_bit, first, end, keys.data_ptr(), idx_bytes,
+                                             idx.data_ptr(), cap, ctypes.byref(n_out), frag.data_ptr(), FRAG_SHARE,
+                                             counters.data_ptr(), self.stream()))
+        return PackedSlice(keys[:n_out.value], idx[:n_out.value], n_out.value, frag, counters)
 
-    def sort_keys(self, keys):
-        """Ascending (unsigned) order of a small key tensor."""
+    def sample_keys_host(self, d_sba, seg_starts, k, class_bit, first, end, n_samples, after=None):
+        """Keys of evenly spaced windows of the slice, on the host.  Runs on the engine's second stream so that
+        the caller's stream (busy with the pack kernel) is not waited for."""
         torch = self.torch
-        n = keys.numel()
-        if n < 2:
-            return keys
-        a = torch.empty(n + (n & 1), dtype=torch.int64, device=self.device)
-        a[:n] = keys
-        b = torch.empty_like(a)
-        v0 = torch.zeros(n, dtype=torch.int32, device=self.device)
-        v1 = torch.empty_like(v0)
-        in_alt = ctypes.c_int(0)
-        _native.check(self.lib.gk_radix_sort_pairs(a.data_ptr(), b.data_ptr(), v0.data_ptr(), v1.data_ptr(), 4, n,
-                                                   0, 64, ctypes.byref(in_alt), self.stream()))
-        return (b if in_alt.value else a)[:n]
+        out = torch.empty(max(1, n_samples), dtype=torch.int64, device=self.device)
+        n_out = ctypes.c_uint32(0)
+        self.side.wait_stream(torch.cuda.current_stream())      # d_sba was produced on the caller's stream
+        with torch.cuda.stream(self.side):
+            _native.check(self.lib.gk_sample_keys(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
+                                                  len(seg_starts), k, class_bit, first, end, n_samples,
+                                                  out.data_ptr(), ctypes.byref(n_out), self.stream()))
+            host = out[:n_out.value].cpu()
+        return host.numpy().view(np.uint64)
 
-    def partition(self, keys, idx, splitters, n_parts):
+    def splitters_to_device(self, splitters_host):
+        return self.torch.from_numpy(np.ascontiguousarray(splitters_host).view(np.int64).copy()).to(self.device)
+
+    def partition_counts_host(self, pk, splitters, n_parts, class_bit, extra=()):
+        """[pure pairs per destination, ambiguous pairs per destination, fragments, ambiguous windows, *extra]
+        as int64 on the host: one device-to-host copy behind the pack kernel."""
         torch = self.torch
-        n = keys.numel()
-        k_out, i_out = torch.empty_like(keys), torch.empty_like(idx)
-        counts = np.zeros(n_parts, dtype=np.uint64)
+        counts = torch.empty(2 * n_parts, dtype=torch.int64, device=self.device)
         sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
-        _native.check(self.lib.gk_partition_pairs(keys.data_ptr(), k_out.data_ptr(), idx.data_ptr(),
-                                                  i_out.data_ptr(), idx.element_size(), n, sp, n_parts,
-                                                  _native.host_ptr(counts), self.stream()))
-        return k_out, i_out, counts.astype(np.int64)
+        _native.check(self.lib.gk_partition_count_split(pk.keys.data_ptr(), pk.n, sp, n_parts, class_bit,
+                                                        counts.data_ptr(), self.stream()))
+        parts = [counts, pk.counters[2:3], pk.counters[0:1]] + [e for e in extra]
+        return torch.cat(parts).cpu().numpy()
 
-    def empty_like_n(self, ref, n):
-        return self.torch.empty(n, dtype=ref.dtype, device=self.device)
-
-    # ---- fused partition + exchange over peer memory ------------------------------------------------
     def peer_exchange(self, dist, group, capacity, idx_bytes):
         return PeerExchange.get(self, dist, group, capacity, idx_bytes)
 
-    def partition_count(self, keys, splitters, n_parts):
-        counts = np.zeros(n_parts, dtype=np.uint64)
-        sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
-        _native.check(self.lib.gk_partition_count(keys.data_ptr(), keys.numel(), sp, n_parts,
-                                                  _native.host_ptr(counts), self.stream()))
-        return counts.astype(np.int64)
-
-    def partition_peer(self, keys, idx, splitters, n_parts, px, offsets):
+    def _partition(self, pk, splitters, n_parts, key_ptrs, idx_ptrs, offsets, key_base, skip_amb):
         sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        base = np.ascontiguousarray(key_base, dtype=np.uint64)
         _native.check(self.lib.gk_partition_pairs_peer(
-            keys.data_ptr(), idx.data_ptr(), idx.element_size(), keys.numel(), sp, n_parts,
-            _native.host_ptr(px.key_ptrs), _native.host_ptr(px.idx_ptrs), _native.host_ptr(off), self.stream()))
+            pk.keys.data_ptr(), pk.idx.data_ptr(), pk.idx.element_size(), pk.n, sp, n_parts,
+            _native.host_ptr(key_ptrs), _native.host_ptr(idx_ptrs), _native.host_ptr(off), _native.host_ptr(base),
+            int(bool(skip_amb)), self.err_word.data_ptr(), self.stream()))
 
-    def shard_index_ptr(self, d_sba, seg_starts, k, keys_ptr, idx_ptr, n, idx_bytes, class_bit):
-        """Sort pairs that already sit in library-owned buffers (the peer receive buffers)."""
+    def partition_to_peers(self, pk, splitters, n_parts, px, offsets, key_base, skip_amb):
+        """One kernel: every pair straight into its destination rank's receive buffer (peer memory)."""
+        self.err_word.zero_()
+        self._partition(pk, splitters, n_parts, px.key_ptrs, px.idx_ptrs, offsets, key_base, skip_amb)
+
+    def partition_to_staging(self, pk, splitters, n_parts, send_counts, key_base, skip_amb):
+        """The same kernel into a local staging buffer laid out by destination (for the all-to-all path)."""
+        torch = self.torch
+        total = int(np.sum(send_counts))
+        keys = torch.empty(max(1, total), dtype=torch.int64, device=self.device)
+        idx = torch.empty(max(1, total), dtype=pk.idx.dtype, device=self.device)
+        offsets = np.concatenate([[0], np.cumsum(send_counts)[:-1]]).astype(np.uint64)
+        key_ptrs = np.full(n_parts, keys.data_ptr(), dtype=np.uint64)
+        idx_ptrs = np.full(n_parts, idx.data_ptr(), dtype=np.uint64)
+        self.err_word.zero_()
+        self._partition(pk, splitters, n_parts, key_ptrs, idx_ptrs, offsets, key_base, skip_amb)
+        return keys[:total], idx[:total]
+
+    def gather_fragments(self, pk, dist, group):
+        """All ranks' fragment lists, back to back, on the device; issued on the second stream so that it runs
+        beside the partition kernel.  Returns (tensor, event to wait for)."""
+        torch = self.torch
+        world = dist.get_world_size(group)
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            if backend_is_nccl(dist, group):
+                out = torch.empty(world * pk.frag.numel(), dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(out, pk.frag, group=group)
+            else:   # gloo cannot gather CUDA tensors: through the host (tests with two ranks on one GPU)
+                mine = pk.frag.cpu()
+                host = torch.empty(world * mine.numel(), dtype=torch.uint8)
+                dist.all_gather_into_tensor(host, mine, group=group)
+                out = host.to(self.device)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        return out, ev
+
+    def recv_buffers(self, ref_idx, n):
+        torch = self.torch
+        return (torch.empty(max(1, n), dtype=torch.int64, device=self.device),
+                torch.empty(max(1, n), dtype=ref_idx.dtype, device=self.device))
+
+    def shard_sort(self, d_sba, seg_starts, k, keys_ptr, idx_ptr, idx_bytes, n_pure, n_amb, class_bit, key_bits,
+                   frag_all, frag_counts, key_lo, key_hi, keep_alive=()):
+        """Sort the received pairs (+ the ambiguous windows regenerated from the fragments) into a shard."""
         torch = self.torch
         handle = ctypes.c_void_p()
         _native.check(self.lib.gk_index_create(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
                                                len(seg_starts), k, k, ctypes.byref(handle)))
         stats = _native.GkSortStats()
+        n = n_pure + n_amb
         k_alt = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         i_alt = torch.empty(max(n, 1), dtype=torch.int32 if idx_bytes == 4 else torch.int64, device=self.device)
+        counts_dev = None
+        if frag_all is not None:
+            counts_dev = torch.from_numpy(np.ascontiguousarray(frag_counts, dtype=np.int64)).to(self.device)
         try:
-            _native.check(self.lib.gk_index_sort_pairs(handle, keys_ptr, k_alt.data_ptr(), idx_ptr,
-                                                       i_alt.data_ptr(), n, class_bit, ctypes.byref(stats),
-                                                       self.stream()))
+            _native.check(self.lib.gk_index_sort_shard(
+                handle, keys_ptr, k_alt.data_ptr(), idx_ptr, i_alt.data_ptr(), n_pure, n_amb, class_bit, key_bits,
+                frag_all.data_ptr() if frag_all is not None else None,
+                counts_dev.data_ptr() if counts_dev is not None else None,
+                len(frag_counts) if frag_all is not None else 0, FRAG_SHARE, int(key_lo), int(key_hi),
+                self.err_word.data_ptr(), ctypes.byref(stats), self.stream()))
         except Exception:
             self.lib.gk_index_destroy(handle)
             raise
         return {"handle": handle, "n": n, "stats": stats.as_dict(), "idx_bytes": idx_bytes}
-
-    def shard_index(self, d_sba, seg_starts, k, keys, idx, class_bit):
-        """Sort the received pairs and return an opaque shard handle."""
-        torch = self.torch
-        handle = ctypes.c_void_p()
-        _native.check(self.lib.gk_index_create(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
-                                               len(seg_starts), k, k, ctypes.byref(handle)))
-        stats = _native.GkSortStats()
-        n = keys.numel()
-        k_alt, i_alt = torch.empty_like(keys), torch.empty_like(idx)
-        try:
-            _native.check(self.lib.gk_index_sort_pairs(handle, keys.data_ptr(), k_alt.data_ptr(), idx.data_ptr(),
-                                                       i_alt.data_ptr(), n, class_bit, ctypes.byref(stats),
-                                                       self.stream()))
-        except Exception:
-            self.lib.gk_index_destroy(handle)
-            raise
-        return {"handle": handle, "n": n, "stats": stats.as_dict(), "idx_bytes": idx.element_size()}
 
     def shard_counts(self, shard, k, filt, min_group, max_group, max_bin):
         hist = np.zeros(max_bin + 1, dtype=np.int64)
@@ -234,11 +282,15 @@ class NativeEngine:
             self.lib.gk_index_destroy(shard["handle"])
             shard["handle"] = None
 
-    def as_dist_tensor(self, t):
-        return t
-
     def from_host_i64(self, arr):
         return self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
+
+    @staticmethod
+    def tensor_ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def wait_event(self, ev):
+        self.torch.cuda.current_stream().wait_event(ev)
 
 
 def backend_is_nccl(dist, group) -> bool:
@@ -372,21 +424,22 @@ class PeerExchange:
         cls._cache.clear()
 
 
-AMBIGUOUS_COST = 2.5   # local-sort cost of an ambiguous window relative to a pure one (refinement), measured
 
-
-def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 0) -> np.ndarray:
+def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 0,
+                     ambiguous_cost: float = 1.0) -> np.ndarray:
     """n_parts-1 splitters at the even quantiles of the pooled, sorted samples (uint64).
 
-    With class_bit the quantiles are taken over COST, not count: a key with class bit 0 is an ambiguous
-    window, which also goes through the refinement.  One N run makes millions of them with ONE key, which no
-    key splitter can cut, so the rank that gets that group is given correspondingly fewer other keys."""
+    With class_bit the parts are built from BLOCKS of equal keys: one N run makes millions of windows with ONE
+    key, which no key splitter can cut, so the rank that gets that group is given correspondingly fewer other
+    keys (bottleneck-optimal cuts).  ambiguous_cost weighs a key with class bit 0 against a pure one; it is 1
+    since the ambiguous windows travel and sort as run-length fragments (it was 2.5 when each of them went
+    through the element-wise refinement)."""
     m = len(sorted_samples)
     if n_parts <= 1 or m == 0:
         return np.zeros(0, dtype=np.uint64)
     if class_bit:
         # blocks of equal keys (a part can only begin where a key begins) and their costs
-        weight = np.where((sorted_samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
+        weight = np.where((sorted_samples & np.uint64(1)) == 0, float(ambiguous_cost), 1.0)
         first = np.flatnonzero(np.concatenate([[True], sorted_samples[1:] != sorted_samples[:-1]]))
         run = np.concatenate([[0.0], np.cumsum(weight)])      # run[i] = cost of samples [0, i)
         cum = np.concatenate([run[first], run[-1:]])          # cum[b] = cost of blocks [0, b)
@@ -484,6 +537,7 @@ class ShardedKmers:
         self.stats = {}
         self._marks = []
         self._is_sorted = False
+        self._keep = None
 
     # -------------------------------------------------------------------------------------------
     def _mark(self, name):
@@ -519,100 +573,111 @@ class ShardedKmers:
         self._mark("start")
         if k > 31:
             raise NotImplementedError("the multi-GPU path handles single-word k-mers (k <= 31)")
+        # every key carries the class bit, so nothing waits for the alphabet scan: its counters travel with the
+        # destination counts
+        class_bit = 1
+        full_bits = 2 * k + 2
         first, end = slice_bounds(self.total_len, world, rank)
         # (16-byte aligned cut points, so that the scan keeps its 128-bit loads)
         a16 = (first // 16) * 16 if rank > 0 else 0
         b16 = (end // 16) * 16 if rank < world - 1 else self.total_len
-        counts = eng.alphabet(self.d_sba[a16:b16] if world > 1 else self.d_sba)
-        if world > 1:   # every rank scans its own slice of the byte array; the three counters are summed
-            counts = self._gather(counts.astype(np.int64)).sum(axis=0).astype(np.uint64)
-        n_sep_expected = len(self.seg_starts) - 1
-        if int(counts[1]) != n_sep_expected:
-            raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
-        class_bit = 1 if (counts[2] > 0 or counts[0] > 0) else 0
-        self._mark("alphabet")
-        keys, idx = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
-        n_local_in = int(keys.numel())
+        alpha = eng.alphabet_async(self.d_sba[a16:b16] if world > 1 else self.d_sba)
+        pk = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
         self._mark("pack")
 
-        # ---- splitters from evenly spaced samples --------------------------------------------------
+        # ---- splitters from evenly spaced samples (second stream: runs beside the pack kernel) --------------
         if world > 1:
-            step = max(1, n_local_in // SAMPLES_PER_RANK)
-            sample = self._to_host_u64(keys[::step][:SAMPLES_PER_RANK])
+            sample = eng.sample_keys_host(self.d_sba, self.seg_starts, k, class_bit, first, end, SAMPLES_PER_RANK)
             padded = np.zeros(SAMPLES_PER_RANK + 1, dtype=np.uint64)
             padded[0] = len(sample)
             padded[1:1 + len(sample)] = sample
-            # one small all-gather; 32 k keys are sorted faster on the host than through eight tiny radix
-            # passes and their synchronisations
             table = self._gather(padded)
             pooled = np.sort(np.concatenate([row[1:1 + int(row[0])] for row in table]))
-            splitters_host = choose_splitters(pooled, world, class_bit)
-            splitters = eng.from_host_i64(splitters_host.view(np.int64))
+            # even splitters: a key range then starts at an even key, so subtracting it keeps the class bit
+            splitters_host = choose_splitters(pooled, world, class_bit) & ~np.uint64(1)
+            splitters = eng.splitters_to_device(splitters_host)
         else:
             splitters_host, splitters = np.zeros(0, dtype=np.uint64), None
         self.splitters = splitters_host
         self._mark("splitters")
 
-        # ---- partition by destination, exchange -----------------------------------------------------
-        use_peer = (world > 1 and hasattr(eng, "peer_exchange")
-                    and os.environ.get("GK_PEER_EXCHANGE", "1") != "0")
-        recv_ptrs = None
-        if use_peer:
-            # fused: counts first (placement), then ONE kernel partitions and writes every pair straight
-            # into its destination rank's receive buffer over NVLink peer memory
-            send_counts = eng.partition_count(keys, splitters, world)
-            matrix = self._gather(send_counts.astype(np.int64))             # [source, destination]
-            recv_total = matrix.sum(axis=0)
-            # every rank sees the same matrix, so every rank computes the same capacity: the largest
-            # receive count plus 10 % head-room (the buffers are cached and only ever grow)
-            capacity = int(1.1 * int(recv_total.max())) + (1 << 20)
-            self._mark("partition")
-            px = None
-            if capacity * (8 + self.idx_bytes) <= PeerExchange.MAX_BYTES:
-                px = eng.peer_exchange(dist, self.group, capacity, self.idx_bytes)
-            if px is not None:
-                offsets = matrix[:rank, :].sum(axis=0)
-                eng.partition_peer(keys, idx, splitters, world, px, offsets)
-                self._order_after_peer_writes()
-                recv_ptrs = (px.my_keys, px.my_idx, int(recv_total[rank]))
-                self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank]) * (8 + self.idx_bytes))
-                del keys, idx
-                self._mark("exchange")
-            else:
-                use_peer = False         # skew beyond the buffers, several hosts, or no peer access: NCCL path
-        if not use_peer:
-            keys_p, idx_p, send_counts = eng.partition(keys, idx, splitters, world)
-            del keys, idx
-            self._mark("partition")
-            if world > 1:
-                recv_counts = self._gather(send_counts.astype(np.int64))[:, rank]
-                n_recv = int(recv_counts.sum())
-                keys_r = eng.empty_like_n(keys_p, n_recv)
-                idx_r = eng.empty_like_n(idx_p, n_recv)
-                in_splits, out_splits = [int(c) for c in send_counts], [int(c) for c in recv_counts]
-                dist.all_to_all_single(keys_r, keys_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
-                                       group=self.group)
-                dist.all_to_all_single(idx_r, idx_p, output_split_sizes=out_splits, input_split_sizes=in_splits,
-                                       group=self.group)
-                self.exchange_bytes_sent = int((send_counts.sum() - send_counts[rank])
-                                               * (8 + idx_p.element_size()))
-            else:
-                keys_r, idx_r = keys_p, idx_p
-                self.exchange_bytes_sent = 0
-            del keys_p, idx_p
-            self._mark("exchange")
+        # ---- ONE small all-gather: destination counts, fragment count, ambiguous windows, alphabet counters -----
+        header = eng.partition_counts_host(pk, splitters, world, class_bit, extra=(alpha,))
+        table = self._gather(header.astype(np.int64))
+        alpha_all = table[:, 2 * world + 2:].sum(axis=0)
+        if int(alpha_all[1]) != len(self.seg_starts) - 1:
+            raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
+        n_frag_src = table[:, 2 * world]
+        frag_ok = (eng.supports_fragments and os.environ.get("GK_FRAGMENTS", "1") != "0"
+                   and int(n_frag_src.max()) <= FRAG_SHARE)
+        pure, amb = table[:, :world].copy(), table[:, world:2 * world].copy()     # [source, destination]
+        if not frag_ok:             # the ambiguous windows travel as pairs like everything else
+            pure += amb
+            amb[:] = 0
+        recv_pure, recv_amb = pure.sum(axis=0), amb.sum(axis=0)
+        n_pure, n_amb = int(recv_pure[rank]), int(recv_amb[rank])
+        key_lo = np.concatenate([[0], splitters_host]).astype(np.uint64)          # first key of every rank
+        key_hi = np.concatenate([splitters_host, [0]]).astype(np.uint64)          # (0: no upper bound)
+        hi_me = int(key_hi[rank]) if rank < world - 1 else (1 << full_bits)
+        key_bits = max(1, int(hi_me - int(key_lo[rank]) - 1).bit_length()) if world > 1 else full_bits
+        # every rank sees the same table, so every rank computes the same capacity: the largest shard plus
+        # 10 % head-room (the peer buffers are cached and only ever grow)
+        capacity = int(1.1 * int((recv_pure + recv_amb).max())) + (1 << 20)
+        self._mark("counts")
 
-        # ---- local sort + refinement + flags ------------------------------------------------------------
+        # ---- partition by destination + exchange -------------------------------------------------------------
+        px = None
+        if (world > 1 and hasattr(eng, "peer_exchange") and os.environ.get("GK_PEER_EXCHANGE", "1") != "0"
+                and capacity * (8 + self.idx_bytes) <= PeerExchange.MAX_BYTES):
+            px = eng.peer_exchange(dist, self.group, capacity, self.idx_bytes)
+        frag_all = frag_ev = None
+        if px is not None:
+            # fused: ONE kernel partitions and writes every pair straight into its destination rank's receive
+            # buffer over NVLink peer memory; the fragment lists are gathered beside it
+            eng.partition_to_peers(pk, splitters, world, px, pure[:rank, :].sum(axis=0), key_lo, frag_ok)
+            if frag_ok:
+                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group)
+            self._order_after_peer_writes()
+            keys_ptr, idx_ptr = px.my_keys, px.my_idx
+            self._keep = None
+            self.exchange_mode = "peer"
+        else:
+            # several hosts, no peer access, or a single rank: the same kernel into a local staging buffer, then
+            # one all-to-all per array
+            keys_s, idx_s = eng.partition_to_staging(pk, splitters, world, pure[rank], key_lo, frag_ok)
+            if frag_ok and world > 1:
+                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group)
+            elif frag_ok:
+                frag_all = pk.frag
+            keys_r, idx_r = eng.recv_buffers(idx_s, n_pure + n_amb)
+            if world > 1:
+                in_splits, out_splits = [int(c) for c in pure[rank]], [int(c) for c in pure[:, rank]]
+                dist.all_to_all_single(keys_r[:n_pure], keys_s, output_split_sizes=out_splits,
+                                       input_split_sizes=in_splits, group=self.group)
+                dist.all_to_all_single(idx_r[:n_pure], idx_s, output_split_sizes=out_splits,
+                                       input_split_sizes=in_splits, group=self.group)
+            else:
+                keys_r[:n_pure] = keys_s
+                idx_r[:n_pure] = idx_s
+            keys_ptr, idx_ptr = eng.tensor_ptr(keys_r), eng.tensor_ptr(idx_r)
+            self._keep = (keys_r, idx_r)
+            self.exchange_mode = "nccl"
+        self.exchange_bytes_sent = int((pure[rank].sum() - pure[rank, rank]) * (8 + self.idx_bytes))
+        del pk.keys, pk.idx
+        self._mark("exchange")
+
+        # ---- local sort: radix passes over the rank's own key range, bucket repair, fragments, flags ---------
         if self.shard is not None:
             eng.shard_free(self.shard)
-        if recv_ptrs is not None:
-            self.shard = eng.shard_index_ptr(self.d_sba, self.seg_starts, k, recv_ptrs[0], recv_ptrs[1],
-                                             recv_ptrs[2], self.idx_bytes, class_bit)
-        else:
-            self.shard = eng.shard_index(self.d_sba, self.seg_starts, k, keys_r, idx_r, class_bit)
-        self.exchange_mode = "peer" if recv_ptrs is not None else "nccl"
+        if frag_ev is not None:
+            eng.wait_event(frag_ev)
+        self.shard = eng.shard_sort(self.d_sba, self.seg_starts, k, keys_ptr, idx_ptr, self.idx_bytes, n_pure, n_amb,
+                                    class_bit, key_bits, frag_all, n_frag_src if frag_all is not None else None,
+                                    int(key_lo[rank]), int(key_hi[rank]))
+        self._keep = None
         self.stats = dict(self.shard["stats"])
-        self.stats.update(n_packed=n_local_in, n_shard=int(self.shard["n"]), class_bit=class_bit)
+        self.stats.update(n_packed=pk.n, n_shard=int(self.shard["n"]), class_bit=class_bit, key_bits_shard=key_bits,
+                          fragments=bool(frag_ok))
         self._mark("local_sort")
         self._is_sorted = True
 

@@ -93,6 +93,8 @@ uint64_t gk_launch_count(int reset);
 /* counts[0] = bytes outside the IUPAC+'$' alphabet (sequence_collection.py:441-459),
  * counts[1] = '$' bytes, counts[2] = ambiguous IUPAC letters (allowed, not A/C/G/T/'$'). */
 int gk_sba_scan_alphabet(const uint8_t *d_sba, uint64_t len, uint64_t *h_counts3, void *stream);
+/* the same counters left in device memory (zeroed by the call), no synchronise */
+int gk_sba_scan_alphabet_async(const uint8_t *d_sba, uint64_t len, uint64_t *d_counts3, void *stream);
 /* out[len-1-i] = complement(in[i]) (sequence_collection.py:42-73, :402-433); in != out. */
 int gk_sba_revcomp(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream);
 /* out = in || '$' || revcomp(in), 2*len+1 bytes: this library's definition of both strands. */
@@ -147,9 +149,18 @@ int gk_partition_pairs(uint64_t *d_keys, uint64_t *d_keys_out, void *d_vals, voi
  *                            by the caller (a stream-ordered collective). */
 int gk_partition_count(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
                        uint64_t *h_counts_out, void *stream);
+/* The same counts left on the DEVICE (no synchronise): d_counts_out[d] = pure pairs for destination d,
+ * d_counts_out[n_parts + d] = pairs of class 0 (ambiguous windows) when class_bit is set. */
+int gk_partition_count_split(const uint64_t *d_keys, uint64_t n, const uint64_t *d_splitters, uint32_t n_parts,
+                             int class_bit, uint64_t *d_counts_out, void *stream);
+/* h_key_base (optional, n_parts entries): subtracted from every key sent to destination d, so that a rank
+ * sorts keys relative to the start of its own key range.  skip_ambiguous: pairs of class 0 are dropped (their
+ * windows travel as run-length fragments, gk_pack_slice).  d_err (optional device int): receives the look-back
+ * guard's verdict and the call does not synchronise. */
 int gk_partition_pairs_peer(const uint64_t *d_keys, const void *d_vals, int val_bytes, uint64_t n,
                             const uint64_t *d_splitters, uint32_t n_parts, uint64_t *const *h_dst_keys,
-                            void *const *h_dst_vals, const uint64_t *h_dst_offsets, void *stream);
+                            void *const *h_dst_vals, const uint64_t *h_dst_offsets, const uint64_t *h_key_base,
+                            int skip_ambiguous, int *d_err, void *stream);
 /* Peer-visible device memory for those buffers: cudaMalloc + CUDA IPC handles (64 bytes), one process
  * per GPU on one box. */
 int gk_peer_alloc(uint64_t bytes, void **d_ptr_out);
@@ -184,12 +195,35 @@ int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_by
 /* seam 1: sort the start indices lexicographically by k-mer, ties by ascending start. */
 int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream);
 /* Multi-GPU shard of seam 1: adopt the (key, start) pairs this rank received from the exchange
- * (made by gk_pack_keys with key_len = valid_len = min_kmer_len and the same class_bit), sort them
- * and leave the index describing this rank's key range only (gk_index_size() == n_local).  The
+ * (made by gk_pack_keys / gk_pack_slice with key_len = valid_len = min_kmer_len and the same class_bit), sort
+ * them and leave the index describing this rank's key range only (gk_index_size() == n_local).  The
  * pair buffers are scratch. */
 int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx,
                         void *d_idx_alt, uint64_t n_local, int class_bit, gk_sort_stats *stats_out,
                         void *stream);
+/* The same with everything the sharded driver knows: key_bits = width of the received keys when they are
+ * relative to the start of this rank's key range (0: full width); d_frag_gathered: the all-gathered fragment
+ * lists of all n_sources ranks (gk_pack_slice layout, frag_capacity entries each, d_frag_counts[s] used), from
+ * which the n_ambiguous windows of the key range [key_lo, key_hi) (key_hi 0: unbounded) are generated behind
+ * the n_pure received pairs -- the four buffers hold n_pure + n_ambiguous pairs; d_err: the device word the
+ * partition step wrote its look-back verdict to (optional). */
+int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
+                        uint64_t n_pure, uint64_t n_ambiguous, int class_bit, int key_bits,
+                        const void *d_frag_gathered, const uint64_t *d_frag_counts, uint32_t n_sources,
+                        uint64_t frag_capacity, uint64_t key_lo, uint64_t key_hi, const int *d_err,
+                        gk_sort_stats *stats_out, void *stream);
+/* Multi-GPU producers (no synchronise).  gk_pack_slice: pack the windows whose start lies in
+ * [first_start, end_start) and list the ambiguous-window fragments of that slice; d_frag: frag_capacity * 36
+ * bytes laid out key[cap] w0[cap] w1[cap] start[cap] (u64) count[cap] (u32); d_counters: 4 x u64, zeroed by the
+ * call: [0] ambiguous windows, [2] fragments found (above the capacity the list is incomplete).
+ * gk_sample_keys: keys of n_samples evenly spaced windows of the slice, for the splitter choice. */
+int gk_pack_slice(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts, uint32_t n_seg,
+                  uint32_t kmer_len, int class_bit, uint64_t first_start, uint64_t end_start,
+                  uint64_t *d_keys_out, int idx_bytes, void *d_idx_out, uint64_t out_capacity,
+                  uint64_t *h_n_out, void *d_frag, uint64_t frag_capacity, uint64_t *d_counters, void *stream);
+int gk_sample_keys(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_seg_starts, uint32_t n_seg,
+                   uint32_t kmer_len, int class_bit, uint64_t first_start, uint64_t end_start,
+                   uint32_t n_samples, uint64_t *d_keys_out, uint32_t *h_n_out, void *stream);
 /* Device pointer to the current (init or sorted) start indices; owned by the index. */
 int gk_index_device_indices(gk_index *ix, const void **d_idx_out, void *stream);
 /* Copy the start indices to a host buffer of gk_index_size() * idx_bytes bytes. */

@@ -102,22 +102,24 @@ def test_splitters_and_slices():
 
 def test_cost_balanced_splitters_around_a_giant_group():
     """One N run = millions of ambiguous windows with ONE key (class bit 0).  A key splitter cannot cut that
-    group; the cost-weighted, bottleneck-optimal cuts give its owner fewer other keys instead."""
+    group; the block-aware, bottleneck-optimal cuts give its owner fewer other keys instead (with any weight
+    for an ambiguous window: 1 now that they sort as fragments, 2.5 when they were refined one by one)."""
     sys.path[:0] = [os.path.join(ROOT, "genome-kmers_b200")]
-    from genome_kmers.distributed import AMBIGUOUS_COST, choose_splitters
+    from genome_kmers.distributed import choose_splitters
 
     rng = np.random.default_rng(3)
     m, parts = 8 * 4096, 8
     pure = (np.sort(rng.integers(0, 1 << 62, m, dtype=np.uint64)) << np.uint64(1)) | np.uint64(1)
     giant = np.full(int(0.044 * m), np.uint64(3) << np.uint64(61), dtype=np.uint64)   # 4.4 % of the samples
     samples = np.sort(np.concatenate([pure, giant]))
-    sp = choose_splitters(samples, parts, class_bit=1)
-    assert len(sp) == parts - 1 and bool((sp[1:] >= sp[:-1]).all())
-    dest = np.searchsorted(sp, samples, side="right")
-    weight = np.where((samples & np.uint64(1)) == 0, AMBIGUOUS_COST, 1.0)
-    share = np.array([weight[dest == r].sum() for r in range(parts)]) / weight.sum() * parts
-    assert share.max() < 1.08, share                       # even quantiles by count give the owner 1.3+
-    assert len(set(dest[samples == giant[0]].tolist())) == 1    # the group stays on one rank
+    for cost in (1.0, 2.5):
+        sp = choose_splitters(samples, parts, class_bit=1, ambiguous_cost=cost)
+        assert len(sp) == parts - 1 and bool((sp[1:] >= sp[:-1]).all())
+        dest = np.searchsorted(sp, samples, side="right")
+        weight = np.where((samples & np.uint64(1)) == 0, cost, 1.0)
+        share = np.array([weight[dest == r].sum() for r in range(parts)]) / weight.sum() * parts
+        assert share.max() < 1.08, share                       # even quantiles by count give the owner 1.3+
+        assert len(set(dest[samples == giant[0]].tolist())) == 1    # the group stays on one rank
     # without heavy keys no part is more than 3 % above an even share
     sp0 = choose_splitters(pure, parts, class_bit=1)
     d0 = np.searchsorted(sp0, pure, side="right")
