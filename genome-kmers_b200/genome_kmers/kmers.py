@@ -169,7 +169,144 @@ def get_compare_sba_kmers_func(kmer_len):
         return compare_sba_kmers_lexicographically(
             sba_a, sba_b, kmer_sba_start_idx_a, kmer_sba_start_idx_b, max_kmer_len=kmer_len)
 
+    compare_sba_kmers_func.kmer_len = kmer_len      # the device group walk reads the length from here
     return compare_sba_kmers_func
+
+
+def compare_sba_kmers_always_less_than(sba_a, sba_b, kmer_sba_start_idx_a: int, kmer_sba_start_idx_b: int,
+                                       max_kmer_len: Union[int, None] = None):
+    """Every k-mer is its own group: what the reference passes for an unsorted index (kmers.py:295-303)."""
+    return -1, 0
+
+
+def get_kmer_info_minimal(kmer_num: int, kmer_sba_start_indices, sba, kmer_len: Union[int, None],
+                          group_size_yielded: int, group_size_total: int):
+    """(kmer_num, group_size_yielded, group_size_total) -- kmers.py:400-425."""
+    return kmer_num, group_size_yielded, group_size_total
+
+
+def get_kmer_info_group_size_only(kmer_num: int, kmer_sba_start_indices, sba, kmer_len: Union[int, None],
+                                  group_size_yielded: int, group_size_total: int):
+    """group_size_total only -- kmers.py:428-451."""
+    return group_size_total
+
+
+class _ArrayIndex:
+    """A native index over caller-supplied arrays (sequence byte array + start indices): what the module-level
+    seams of the reference take instead of a Kmers object (kmers.py:454-648).  Records are found from the '$'
+    separators.  The arrays are uploaded once; the group walk and the histogram run on the GPU."""
+
+    def __init__(self, sba: np.ndarray, kmer_start_indices: np.ndarray, is_sorted: bool):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("genome_kmers needs a CUDA device: the k-mer hot path has no CPU fallback")
+        self.lib = _native.lib()
+        sba = np.ascontiguousarray(sba, dtype=np.uint8)
+        self.d_sba = torch.from_numpy(sba).to("cuda")
+        seps = np.flatnonzero(sba == _SEP)
+        starts = np.ascontiguousarray(np.concatenate([[0], seps + 1]), dtype=np.uint64)
+        self.handle = ctypes.c_void_p()
+        _native.check(self.lib.gk_index_create(self.d_sba.data_ptr(), len(sba), _native.host_ptr(starts), len(starts),
+                                               1, 0, ctypes.byref(self.handle)))
+        want = np.uint32 if self.lib.gk_index_idx_bytes(self.handle) == 4 else np.uint64
+        idx = np.ascontiguousarray(kmer_start_indices, dtype=want)
+        _native.check(self.lib.gk_index_set_indices(self.handle, _native.host_ptr(idx), len(idx), idx.itemsize,
+                                                    int(is_sorted), self.stream()))
+
+    @staticmethod
+    def stream() -> int:
+        return int(_torch().cuda.current_stream().cuda_stream)
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.gk_index_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _comparison_mode(kmer_comparison_func, kmer_len):
+    """(is_sorted, kmer_len) for the device group walk from the reference's comparison-function argument."""
+    if kmer_comparison_func is compare_sba_kmers_always_less_than:
+        return False, kmer_len
+    if hasattr(kmer_comparison_func, "kmer_len"):
+        return True, kmer_comparison_func.kmer_len
+    raise NotImplementedError(
+        "kmer_comparison_func must be compare_sba_kmers_always_less_than or come from "
+        "get_compare_sba_kmers_func(kmer_len): arbitrary Python callables cannot run on the GPU")
+
+
+def _check_group_limits(min_group_size, max_group_size, yield_first_n=None):
+    if min_group_size < 1:
+        raise ValueError(f"min_group_size ({min_group_size}) must be >= 1")
+    if max_group_size is not None and max_group_size < min_group_size:
+        raise ValueError(
+            f"if max_group_size ({max_group_size}) is specified, it must be >= min_group_size ({min_group_size})")
+    if yield_first_n is not None and yield_first_n < 1:
+        raise ValueError(f"if yield_first_n ({yield_first_n}) is specified, it must be > 0")
+
+
+def get_kmer_group_size_hist(sba, sba_strand: str, kmer_len: Union[int, None], kmer_start_indices,
+                             kmer_comparison_func: Callable, kmer_filter_func: Callable, min_group_size: int = 1,
+                             max_group_size: Union[int, None] = None, max_counts_bin: int = 1000000):
+    """(counts_by_group_size, total_kmer_count) for caller-supplied arrays -- the reference's internal seam 2
+    (kmers.py:454-520), computed by gk_index_group_counts on the GPU."""
+    if max_counts_bin <= 0:
+        raise ValueError(f"max_counts_bin ({max_counts_bin}) must be >= 1")
+    _check_group_limits(min_group_size, max_group_size)
+    is_sorted, cmp_len = _comparison_mode(kmer_comparison_func, kmer_len)
+    flt = Kmers._native_filter(kmer_filter_func)
+    hist = np.zeros(max_counts_bin + 1, dtype=np.int64)
+    if len(kmer_start_indices) == 0:
+        return hist, 0
+    ai = _ArrayIndex(sba, kmer_start_indices, is_sorted)
+    try:
+        total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
+        _native.check(ai.lib.gk_index_group_counts_zeroed(
+            ai.handle, cmp_len or 0, ctypes.byref(flt), min_group_size, max_group_size or 0, max_counts_bin,
+            _native.host_ptr(hist), ctypes.byref(total), ctypes.byref(top), ai.stream()))
+    finally:
+        ai.close()
+    return hist, int(total.value)
+
+
+def kmer_info_by_group_generator(sba, sba_strand: str, kmer_len: Union[int, None], kmer_start_indices,
+                                 kmer_comparison_func: Callable, kmer_filter_func: Callable,
+                                 kmer_info_func: Callable, min_group_size: int = 1,
+                                 max_group_size: Union[int, None] = None, yield_first_n: Union[int, None] = None):
+    """The reference's group walk over caller-supplied arrays (kmers.py:523-648): k-mers that fail the filter are
+    skipped, a passing k-mer is compared with the previous PASSING one, and the first yield_first_n members of
+    every group within the size limits are passed to kmer_info_func.  The filter and the grouping run on the GPU
+    (gk_index_groups_filtered); only the calls of kmer_info_func are a host loop."""
+    _check_group_limits(min_group_size, max_group_size, yield_first_n)
+    is_sorted, cmp_len = _comparison_mode(kmer_comparison_func, kmer_len)
+    flt = Kmers._native_filter(kmer_filter_func)
+    if len(kmer_start_indices) == 0:
+        return
+    ai = _ArrayIndex(sba, kmer_start_indices, is_sorted)
+    try:
+        n_kept, n_groups = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _native.check(ai.lib.gk_index_groups_filtered(ai.handle, cmp_len or 0, ctypes.byref(flt), ctypes.byref(n_kept),
+                                                      ctypes.byref(n_groups), None, None, None, ai.stream()))
+        kept_pos = np.zeros(n_kept.value, dtype=np.uint64)
+        offsets = np.zeros(n_groups.value, dtype=np.uint64)
+        sizes = np.zeros(n_groups.value, dtype=np.uint64)
+        if n_kept.value:
+            _native.check(ai.lib.gk_index_groups_filtered(
+                ai.handle, cmp_len or 0, ctypes.byref(flt), ctypes.byref(n_kept), ctypes.byref(n_groups),
+                _native.host_ptr(kept_pos), _native.host_ptr(offsets), _native.host_ptr(sizes), ai.stream()))
+    finally:
+        ai.close()
+    for off, size in zip(offsets.tolist(), sizes.tolist()):
+        if size < min_group_size or (max_group_size is not None and size > max_group_size):
+            continue
+        n_yield = size if yield_first_n is None else min(size, yield_first_n)
+        for member in range(off, off + n_yield):
+            yield kmer_info_func(int(kept_pos[member]), kmer_start_indices, sba, kmer_len, n_yield, size)
 
 
 def _torch():
@@ -581,6 +718,60 @@ class Kmers:
             return "-" if rc else "+", names[rc][s], int(seq_idx[kmer_num]), int(ends[rc][s])
 
         return locate
+
+    def generate_get_kmer_info_func(self, one_based_seq_index: bool) -> Callable:
+        """get_kmer_info(kmer_num, kmer_sba_start_indices, sba, kmer_len, group_size_yielded, group_size_total) ->
+        (kmer_num, strand, chrom, seq_start_idx, kmer_len, yielded, total) -- kmers.py:1180-1264."""
+        get_record_info_from_sba_index = self.seq_coll.generate_get_record_info_from_sba_index_func(
+            one_based_seq_index)
+
+        def get_kmer_info(kmer_num, kmer_sba_start_indices, sba, kmer_len, group_size_yielded, group_size_total):
+            if kmer_num < 0:
+                raise ValueError(f"kmer_num ({kmer_num}) cannot be less than zero")
+            if kmer_num >= len(kmer_sba_start_indices):
+                raise ValueError(
+                    f"kmer_num ({kmer_num}) is out of bounds (num kmers = {len(kmer_sba_start_indices)})")
+            sba_idx = int(kmer_sba_start_indices[kmer_num])
+            _, _, seg_end, seq_strand, seq_chrom, seq_start_idx = get_record_info_from_sba_index(sba_idx)
+            if kmer_len is None:
+                kmer_len = seg_end - sba_idx + 1
+            elif sba_idx + kmer_len - 1 > seg_end:
+                raise ValueError(
+                    f"kmer_len ({kmer_len}) for kmer_num ({kmer_num}) extends beyond the end of the segment")
+            return kmer_num, seq_strand, seq_chrom, seq_start_idx, kmer_len, group_size_yielded, group_size_total
+
+        return get_kmer_info
+
+    def get_is_less_than_func(self, validate_kmers: bool = True, break_ties: bool = False) -> Callable:
+        """is_less_than(start_a, start_b) with the reference's semantics (kmers.py:1654-1731), one pair at a time
+        on the host: the scalar definition of the order that sort() produces on the GPU (with break_ties=True;
+        sort() does not call it)."""
+        if self.kmer_source_strand != "forward" or self.seq_coll.strands_loaded() != "forward":
+            raise NotImplementedError(
+                f"both kmer_source_strand ({self.kmer_source_strand}) and "
+                "sequence_collection.strands_loaded() must be 'forward'")
+        sba = self.seq_coll.forward_sba
+        min_kmer_len, max_kmer_len = self.min_kmer_len, self.max_kmer_len
+
+        def is_less_than(kmer_sba_start_idx_a: int, kmer_sba_start_idx_b: int) -> bool:
+            comparison, last = compare_sba_kmers_lexicographically(
+                sba, sba, kmer_sba_start_idx_a, kmer_sba_start_idx_b, max_kmer_len=max_kmer_len)
+            if comparison < 0:
+                a_lt_b = True
+            elif comparison > 0:
+                a_lt_b = False
+            else:
+                a_lt_b = bool(break_ties and kmer_sba_start_idx_a < kmer_sba_start_idx_b)
+            if validate_kmers:
+                rest = min_kmer_len - (last + 1)
+                if not (kmer_has_required_len(sba, kmer_sba_start_idx_a + last + 1, rest)
+                        and kmer_has_required_len(sba, kmer_sba_start_idx_b + last + 1, rest)):
+                    raise AssertionError(
+                        f"kmers compared were less than min_kmer_len ({min_kmer_len}).  Was "
+                        "kmer_sba_start_indices initialized correctly?")
+            return a_lt_b
+
+        return is_less_than
 
     def _indexed_bytes(self):
         host_sba, _, _ = self._strand_layout()
