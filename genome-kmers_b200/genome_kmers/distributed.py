@@ -490,6 +490,21 @@ def choose_splitters(sorted_samples: np.ndarray, n_parts: int, class_bit: int = 
     return np.ascontiguousarray(sorted_samples[pos], dtype=np.uint64)
 
 
+def key_ranges(splitters: np.ndarray, full_bits: int):
+    """(first key, end key (0: no upper bound), key width in bits) of every rank's key range, exact in uint64.
+    Rank d owns the keys in [splitters[d-1], splitters[d]); it receives them minus its first key, so its local
+    sort only covers the bits of its own range."""
+    sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+    zero = np.zeros(1, dtype=np.uint64)      # (a Python int would promote the concatenation to float64)
+    key_lo = np.concatenate([zero, sp])
+    key_hi = np.concatenate([sp, zero])
+    bits = []
+    for d in range(len(sp) + 1):
+        hi = int(key_hi[d]) if d < len(sp) else (1 << full_bits)
+        bits.append(max(1, (hi - int(key_lo[d]) - 1).bit_length()))
+    return key_lo, key_hi, bits
+
+
 def slice_bounds(total_len: int, world: int, rank: int):
     """Contiguous slice of start positions owned by `rank` (windows may read k-1 bytes past it)."""
     return (total_len * rank) // world, (total_len * (rank + 1)) // world
@@ -616,10 +631,8 @@ class ShardedKmers:
             amb[:] = 0
         recv_pure, recv_amb = pure.sum(axis=0), amb.sum(axis=0)
         n_pure, n_amb = int(recv_pure[rank]), int(recv_amb[rank])
-        key_lo = np.concatenate([[0], splitters_host]).astype(np.uint64)          # first key of every rank
-        key_hi = np.concatenate([splitters_host, [0]]).astype(np.uint64)          # (0: no upper bound)
-        hi_me = int(key_hi[rank]) if rank < world - 1 else (1 << full_bits)
-        key_bits = max(1, int(hi_me - int(key_lo[rank]) - 1).bit_length()) if world > 1 else full_bits
+        key_lo, key_hi, bits_of = key_ranges(splitters_host, full_bits)
+        key_bits = bits_of[rank] if world > 1 else full_bits
         # every rank sees the same table, so every rank computes the same capacity: the largest shard plus
         # 10 % head-room (the peer buffers are cached and only ever grow)
         capacity = int(1.1 * int((recv_pure + recv_amb).max())) + (1 << 20)

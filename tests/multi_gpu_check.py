@@ -77,6 +77,23 @@ def main():
                     failures.append((k, used))
                 if mode == "1" and used != "peer":
                     failures.append((k, "peer exchange was not used"))
+    # a larger case than the oracle can answer: checked on the devices against the bytes (ShardedKmers.verify)
+    os.environ["GK_FORCE_IDX64"] = "0"
+    os.environ["GK_PEER_EXCHANGE"] = "1"
+    sys.path.insert(0, ROOT)
+    import bench
+
+    big, big_starts, _ = bench.make_genome(12_000_000 * world, 4 * world, 6, 42)
+    sk = gkd.ShardedKmers(big, big_starts, 31, "both")
+    sk.sort()
+    hist, total = sk.get_kmer_group_counts(31)
+    ver = sk.verify(hist, 2 * (12_000_000 * world - 4 * world * 30))
+    sk.close()
+    if rank == 0:
+        bad = [name for name, v in ver["checks"].items() if not v]
+        print(f"verify at {total} k-mers over {world} ranks: {'ok' if not bad else bad} {ver['report']}", flush=True)
+        if bad:
+            failures.append(("verify", bad))
     flag = torch.tensor([len(failures)])
     if not same_gpu:
         flag = flag.cuda()

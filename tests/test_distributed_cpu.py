@@ -127,3 +127,19 @@ def test_cost_balanced_splitters_around_a_giant_group():
     # degenerate inputs
     assert choose_splitters(np.full(16, 5, dtype=np.uint64), 4, class_bit=1).size == 3
     assert choose_splitters(np.zeros(0, dtype=np.uint64), 4, class_bit=1).size == 0
+
+
+def test_key_ranges_are_exact_in_uint64():
+    """Splitters are 64-bit keys: the bounds must not pass through float64 (53 bits), or a key equal to its
+    rank's first key would wrap around when the first key is subtracted."""
+    sys.path[:0] = [os.path.join(ROOT, "genome-kmers_b200")]
+    from genome_kmers.distributed import key_ranges
+
+    sp = np.array([(1 << 61) + 2, (1 << 63) + 1022, (1 << 64) - 4], dtype=np.uint64)
+    lo, hi, bits = key_ranges(sp, 64)
+    assert lo.dtype == np.uint64 and hi.dtype == np.uint64
+    assert [int(v) for v in lo] == [0, (1 << 61) + 2, (1 << 63) + 1022, (1 << 64) - 4]
+    assert [int(v) for v in hi] == [(1 << 61) + 2, (1 << 63) + 1022, (1 << 64) - 4, 0]
+    assert bits == [62, 63, 63, 2]
+    lo1, hi1, bits1 = key_ranges(np.zeros(0, dtype=np.uint64), 44)
+    assert [int(v) for v in lo1] == [0] and bits1 == [44]

@@ -1,7 +1,5 @@
 set -x
-mkdir -p gpurun_out
-for i in 1 2; do
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['step_wall_ms'], d['roofline']['stage_ms'])"
+for env in "GK_FRAGMENTS=1" "GK_FRAGMENTS=0" "GK_PEER_EXCHANGE=0" "GK_SORT_HYBRID=0"; do
+echo "=== $env"
+env $env timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/shard_verify.py --same-gpu --bases 50000000 2>&1 | grep -E "rank [01]:" | cut -c1-420
 done
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --clock-mode off 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['step_wall_ms'], d['roofline']['stage_ms'])"
-GK_TRACE=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --clock-mode off 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['step_wall_ms'], d['roofline']['stage_ms'])"
