@@ -58,6 +58,8 @@ int sort_segments_device(uint64_t *, uint64_t *, void *, void *, int, const unsi
 int repair_buckets_on_device(uint64_t *, uint64_t *, void *, void *, int, uint64_t, int, int, uint8_t *,
                              const unsigned int *, const unsigned long long *, int *, unsigned long long *,
                              cudaStream_t);
+int repair_big_ambiguous_buckets_on_device(uint64_t *, void *, int, int, uint8_t *, unsigned long long *, int *,
+                                           cudaStream_t);
 int select_pairs_count(const uint8_t *, uint64_t, uint8_t, DeviceBuffer &, uint64_t *, cudaStream_t);
 int select_pairs_write(const uint8_t *, uint64_t, uint8_t, const DeviceBuffer &, int, void *, const uint64_t *,
                        uint64_t *, const void *, void *, cudaStream_t);
@@ -459,6 +461,11 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
         n_frag = h_counters[2];
         use_frag = n_amb > 0 && n_frag > 0 && n_frag <= pp.frag.capacity;
         if (use_frag) {
+            // big out-of-order buckets made of one ambiguous key and a few strangers (the all-N bucket): only the
+            // strangers move, the fragments rewrite the rest
+            if (begin_bit > 0)
+                GK_TRY(repair_big_ambiguous_buckets_on_device(keys_sorted, idx_sorted, ib, pp.class_bit, d_flags,
+                                                              d_counters + 4, d_status, st));
             GK_TRY(frag_sort_device(pp.frag, n_frag, pp.key_len, pp.key_bits, pp.start_bits, *pp.fs, side));
             GK_CUDA(cudaEventRecord(e_frag.ev, side));
             GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
@@ -496,6 +503,9 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
         fprintf(stderr, "[gk trace] sort: n=%llu ambiguous=%llu fragments=%llu use_frag=%d descents=%u status=%d "
                         "frag_err=%d\n", (unsigned long long)n, (unsigned long long)n_amb, (unsigned long long)n_frag,
                 (int)use_frag, n_descent, status, frag_err);
+    if (getenv("GK_TRACE") && status)
+        for (unsigned i = 0; i < (unsigned)h_counters[4] && i < (unsigned)kBigBucketCap; ++i)
+            fprintf(stderr, "[gk trace]   big bucket %u: [%llu, %llu)\n", i, h_counters[5 + 2 * i], h_counters[6 + 2 * i]);
     bool elementwise_long = false;
     if (status) {
         // the device-side repair left work behind: a bucket too long for one CTA (sorted from here with the

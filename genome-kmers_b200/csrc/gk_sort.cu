@@ -1014,6 +1014,169 @@ int sort_segments_device(uint64_t *d_keys, uint64_t *d_keys_tmp, void *d_vals, v
     return GK_OK;
 }
 
+// ---- big out-of-order buckets that are one ambiguous key plus a few strangers ---------------------------------
+// The bucket of the all-N windows holds millions of equal (class 0) keys; on a genome of any size a handful of
+// other k-mers share its 32-bit prefix (a pure "TAAAAAAAAAAAAAAA..." 31-mer lands among them) and leave the bucket
+// out of order.  Re-sorting millions of equal keys for that is wasteful: the strangers are collected (every
+// element whose key differs from the bucket's majority key M), sorted, and put where they belong -- those below
+// M at the front of the bucket, those above at its end; every other slot holds M.  The start indices of the M
+// slots are not moved: M is an ambiguous key, and frag_expand_device rewrites all ambiguous slots from the
+// fragment list anyway.  Buckets that do not fit this pattern (M pure, or more than kRareCap strangers) keep
+// their entry in the list for the host.
+constexpr int kRareCap = 8192;
+struct RareList {
+    unsigned long long count[kBigBucketCap];
+    unsigned long long majority[kBigBucketCap];
+    uint64_t key[kBigBucketCap][kRareCap];
+    uint64_t pos[kBigBucketCap][kRareCap];
+};
+
+// the key that most of seven evenly spaced probes of the bucket agree on (a single probe can hit a stranger)
+__device__ __forceinline__ uint64_t majority_probe(const uint64_t *__restrict__ keys, uint64_t lo, uint64_t hi)
+{
+    uint64_t probe[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) probe[i] = keys[lo + ((hi - lo) * (uint64_t)(2 * i + 1)) / 14];
+    uint64_t best = probe[0];
+    int best_votes = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        int votes = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) votes += (probe[j] == probe[i]) ? 1 : 0;
+        if (votes > best_votes) { best_votes = votes; best = probe[i]; }
+    }
+    return best;
+}
+
+template <typename ValT>
+__global__ void __launch_bounds__(256)
+collect_rare_kernel(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ big /* [0] count */,
+                    int class_bit, RareList *__restrict__ rare)
+{
+    const unsigned int n_big = (unsigned int)(big[0] < (unsigned long long)kBigBucketCap ? big[0] : kBigBucketCap);
+    for (unsigned int b = 0; b < n_big; ++b) {
+        const uint64_t lo = big[1 + 2 * b], hi = big[2 + 2 * b];
+        const uint64_t m = majority_probe(keys, lo, hi);
+        if (blockIdx.x == 0 && threadIdx.x == 0) rare->majority[b] = m;
+        if (!class_bit || (m & 1ull)) continue;   // a pure majority key: its start indices would have to move
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t p = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += stride) {
+            const uint64_t k = keys[p];
+            if (k != m) {
+                const unsigned long long s_ = atomicAdd(&rare->count[b], 1ull);
+                if (s_ < (unsigned long long)kRareCap) {
+                    rare->key[b][s_] = k;
+                    rare->pos[b][s_] = p;
+                }
+            }
+        }
+    }
+}
+
+// one CTA per big bucket: order the strangers by (key, old position), place them, restore M everywhere else
+template <typename ValT>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+place_rare_kernel(uint64_t *keys, ValT *vals, int class_bit, uint8_t *__restrict__ flags,
+                  unsigned long long *__restrict__ big, RareList *__restrict__ rare, uint64_t *__restrict__ scratch,
+                  int *__restrict__ status, int *__restrict__ handled_all)
+{
+    __shared__ SmallSortSmem sm;
+    __shared__ uint32_t s_below;
+    const unsigned int b = blockIdx.x;
+    const unsigned int n_big = (unsigned int)(big[0] < (unsigned long long)kBigBucketCap ? big[0] : kBigBucketCap);
+    if (b >= n_big) return;
+    const uint64_t lo = big[1 + 2 * b], hi = big[2 + 2 * b];
+    const uint64_t m = rare->majority[b];
+    const unsigned long long cnt = rare->count[b];
+    if (!class_bit || (m & 1ull) || cnt > (unsigned long long)kRareCap || cnt == 0) {   // not this kernel's case
+        if (threadIdx.x == 0) atomicExch(handled_all, 0);
+        return;
+    }
+    const uint32_t r = (uint32_t)cnt;
+    // scratch rows of this bucket: [0] old positions, [1] ping-pong, [2] the strangers' start indices, [3] ping-pong
+    uint64_t *pos_a = scratch + (size_t)b * 4 * kRareCap, *pos_b = pos_a + kRareCap;
+    uint64_t *val_a = pos_b + kRareCap, *val_b = val_a + kRareCap;
+    uint64_t *key_a = rare->key[b], *key_b = rare->pos[b];   // (pos is copied out first, then reused as ping-pong)
+    for (uint32_t i = threadIdx.x; i < r; i += kSmallThreads) pos_a[i] = rare->pos[b][i];
+    __syncthreads();
+    // 1. by old position (restores the stable order the atomics lost), the key rides along as the value
+    small_sort_body<uint64_t>(sm, pos_a, pos_b, key_a, key_b, r, 0, 40, true);
+    // 2. stable by key, the old position rides along
+    small_sort_body<uint64_t>(sm, key_a, key_b, pos_a, pos_b, r, 0, 64, true);
+    // start indices of the strangers, read before anything is overwritten
+    for (uint32_t i = threadIdx.x; i < r; i += kSmallThreads) val_a[i] = (uint64_t)vals[__ldcg(pos_a + i)];
+    if (threadIdx.x == 0) s_below = 0;
+    __syncthreads();
+    uint32_t below = 0;
+    for (uint32_t i = threadIdx.x; i < r; i += kSmallThreads) below += (__ldcg(key_a + i) < m) ? 1u : 0u;
+    below = warp_sum(below);
+    if ((threadIdx.x & 31u) == 0 && below) atomicAdd(&s_below, below);
+    __syncthreads();
+    const uint32_t n_lo = s_below, n_hi = r - n_lo;
+    // old slots of the strangers go back to M (those inside the two end zones are overwritten right after)
+    for (uint32_t i = threadIdx.x; i < r; i += kSmallThreads) {
+        const uint64_t p = __ldcg(pos_a + i);
+        keys[p] = m;
+        flags[p] = kFlagAmb;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < r; i += kSmallThreads) {
+        const uint64_t k = __ldcg(key_a + i);
+        const uint64_t slot = (i < n_lo) ? lo + i : hi - n_hi + (i - n_lo);
+        const bool amb = class_bit && !(k & 1ull);
+        const bool head = (i == 0 && n_lo > 0) || (i == n_lo) || __ldcg(key_a + i - 1) != k;
+        keys[slot] = k;
+        vals[slot] = (ValT)__ldcg(val_a + i);
+        flags[slot] = amb ? kFlagAmb : (head ? kFlagHead : 0);
+    }
+    (void)val_b;
+    __syncthreads();
+    if (threadIdx.x == 0) {   // this bucket is done: take it off the host's list
+        big[1 + 2 * b] = 0;
+        big[2 + 2 * b] = 0;
+    }
+}
+
+// after place_rare_kernel: when every listed big bucket was handled (and nothing else is pending), the order
+// is final and the fragment kernels may run
+__global__ void clear_status_kernel(int *status, const int *handled_all, unsigned long long *big)
+{
+    if (*handled_all && (*status & ~1) == 0 && (*status & 1)) {
+        *status = 0;
+        big[0] = 0;
+    }
+}
+
+int repair_big_ambiguous_buckets_on_device(uint64_t *d_keys, void *d_vals, int val_bytes, int class_bit, uint8_t *d_flags,
+                                           unsigned long long *d_big, int *d_status, cudaStream_t st)
+{
+    DeviceBuffer rare, scratch, handled;
+    GK_TRY(rare.alloc(sizeof(RareList), st));
+    GK_TRY(scratch.alloc((size_t)kBigBucketCap * 4 * kRareCap * 8, st));
+    GK_TRY(handled.alloc(4, st));
+    GK_CUDA(cudaMemsetAsync(rare.ptr, 0, 2 * kBigBucketCap * sizeof(unsigned long long), st));
+    GK_CUDA(cudaMemsetAsync(handled.ptr, 0xff, 4, st));
+    const int grid = sm_count() * 8;
+    if (val_bytes == 4) {
+        collect_rare_kernel<uint32_t><<<grid, 256, 0, st>>>(d_keys, d_big, class_bit, rare.as<RareList>());
+        GK_LAUNCH_CHECK();
+        place_rare_kernel<uint32_t><<<kBigBucketCap, kSmallThreads, 0, st>>>(
+            d_keys, (uint32_t *)d_vals, class_bit, d_flags, d_big, rare.as<RareList>(), scratch.as<uint64_t>(), d_status,
+            handled.as<int>());
+    } else {
+        collect_rare_kernel<uint64_t><<<grid, 256, 0, st>>>(d_keys, d_big, class_bit, rare.as<RareList>());
+        GK_LAUNCH_CHECK();
+        place_rare_kernel<uint64_t><<<kBigBucketCap, kSmallThreads, 0, st>>>(
+            d_keys, (uint64_t *)d_vals, class_bit, d_flags, d_big, rare.as<RareList>(), scratch.as<uint64_t>(), d_status,
+            handled.as<int>());
+    }
+    GK_LAUNCH_CHECK();
+    clear_status_kernel<<<1, 1, 0, st>>>(d_status, handled.as<int>(), d_big);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
 int repair_buckets_on_device(uint64_t *d_keys, uint64_t *d_keys_tmp, void *d_vals, void *d_vals_tmp, int val_bytes,
                              uint64_t n, int lo_bits, int class_bit, uint8_t *d_flags, const unsigned int *d_count,
                              const unsigned long long *d_list, int *d_status, unsigned long long *d_big,

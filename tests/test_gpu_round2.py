@@ -218,3 +218,32 @@ def test_repeat_rich_input_is_repaired_without_the_elementwise_path():
     hist, total = km.get_kmer_group_counts(31, max_counts_bin=400)
     o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=400)
     assert total == o_total and np.array_equal(hist, o_hist)
+
+
+@pytest.mark.parametrize("strands", ["forward", "both"])
+def test_stranger_in_the_all_n_bucket_is_moved_without_sorting_the_bucket(strands):
+    """A bucket of more than 65536 equal ambiguous keys (one long N run) with pure k-mers that share its 32-bit
+    prefix ('T' + A's: the all-N key is the count of pure k-mers below 'N...', i.e. 'TAAA...A'), some starting
+    before the run and some after it: the device-side repair moves only the strangers (no host round trip:
+    refine_flags bit 32 stays clear) and the fragments rewrite the ambiguous slots."""
+    rng = np.random.default_rng(79)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = acgt[rng.integers(0, 4, 400_000)].copy()
+    stranger = np.frombuffer(b"T" + b"A" * 17 + b"CCGTA" + b"ACGTACGTA", dtype=np.uint8)   # 32 symbols
+    seq[5_000:5_032] = stranger
+    seq[100_000:180_000] = ord("N")
+    seq[300_000:300_032] = stranger
+    seq[350_000:350_031] = np.frombuffer(b"T" + b"A" * 30, dtype=np.uint8)
+    sc, sba, seg, want = _oracle_sorted([("chr0", seq)], 31, strands)
+    km = Kmers(sc, 31, 31, source_strand=strands)
+    km.sort()
+    got = km.kmer_sba_start_indices.astype(np.uint64)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, f"first mismatches at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
+    st = km.last_sort_stats
+    assert st["refine_flags"] & 4 and st["refine_flags"] & 16 and st["refine_flags"] & 1, st
+    assert not st["refine_flags"] & (2 | 32), st
+    hist, total = km.get_kmer_group_counts(31, max_counts_bin=100)
+    o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=100)
+    assert total == o_total and np.array_equal(hist, o_hist)
+    assert km.verify_order(31)["ok"]
