@@ -441,3 +441,96 @@ def test_config2_full_size_properties():
     assert t2 == n and int(h2.sum()) <= n_groups
     pure_hist, pure_total = km.get_kmer_group_counts(31, gen_no_ambiguous_bases_filter(31))
     assert pure_total == n - km.last_sort_stats["n_ambiguous"]
+
+
+# ---- full-size property tests of the other BASELINE.json configs (no CPU oracle reaches these sizes: the order
+# ---- is checked on the device against the bytes, gk_index_verify) ------------------------------------------------
+def _device_genome(n_bases, n_records, seed, n_runs=0, plant=None):
+    """Records generated on the device (torch is the generator here, not the thing under test)."""
+    torch = gu.torch_mod()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    bases = lut[torch.randint(0, 4, (n_bases,), generator=gen, device="cuda")]
+    rng = np.random.default_rng(seed)
+    for _ in range(n_runs):
+        ln = int(np.exp(rng.uniform(np.log(1e3), np.log(1e5))))
+        st = int(rng.integers(0, n_bases - ln))
+        bases[st:st + ln] = ord("N")
+    if plant is not None:
+        plant(bases, rng)
+    host = bases.cpu().numpy()
+    avg = n_bases // n_records
+    bounds = [i * avg for i in range(n_records)] + [n_bases]
+    return [(f"chr{i}", host[bounds[i]:bounds[i + 1]]) for i in range(n_records)]
+
+
+def _plant_diverged_repeats(bases, rng):
+    """Copies of 3 kb units whose first differences lie 35..90 symbols apart: k-mers of 64 and 100 symbols tie
+    on their first 31 symbols and need the prefix-doubling rounds to be separated."""
+    torch = gu.torch_mod()
+    n = bases.numel()
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for _ in range(40):
+        unit = lut[rng.integers(0, 4, 3000)]
+        for _ in range(int(rng.integers(5, 40))):
+            copy = unit.copy()
+            pos = np.cumsum(rng.integers(35, 90, 60))
+            pos = pos[pos < 3000]
+            copy[pos] = lut[rng.integers(0, 4, len(pos))]
+            st = int(rng.integers(0, n - 3000))
+            bases[st:st + 3000] = torch.from_numpy(copy).to("cuda")
+
+
+@pytest.mark.parametrize("k", [64, 100])
+def test_config4_long_kmers_full_size_properties(k):
+    """BASELINE.json configs[3]: 100 Mbp, both strands, k = 64 / 100, with planted diverged repeats so that the
+    doubling rounds have ties to break."""
+    n_bases = int(os.environ.get("GK_TEST_C4_BASES", 100_000_000))
+    recs = _device_genome(n_bases, 10, 4, plant=_plant_diverged_repeats)
+    sc = SequenceCollection.from_arrays(recs, strands_to_load="both")
+    km = Kmers(sc, k, k, source_strand="both")
+    km.sort()
+    assert len(km) == 2 * (n_bases - 10 * (k - 1))
+    assert km.last_sort_stats["levels"] >= 2, "the doubling rounds did not run"
+    rep = km.verify_order(k)
+    assert rep["ok"] and rep["kmers"] == len(km), rep
+    hist, total = km.get_kmer_group_counts(k)
+    assert total == len(km) and int(hist.sum()) == rep["groups"]
+    assert int(hist[2:].sum()) > 100, "the planted repeats should give groups of equal k-mers"
+
+
+@pytest.mark.parametrize("k", [15, 31, 63])
+def test_config5_one_gbp_full_size_properties(k):
+    """BASELINE.json configs[4]: 1 Gbp, both strands, k from the sweep (15: more windows than possible k-mers,
+    the grouping stress case; 63: two key words)."""
+    n_bases = int(os.environ.get("GK_TEST_C5_BASES", 1_000_000_000))
+    recs = _device_genome(n_bases, 10, 5)
+    sc = SequenceCollection.from_arrays(recs, strands_to_load="both")
+    km = Kmers(sc, k, k, source_strand="both")
+    km.sort()
+    n = len(km)
+    assert n == 2 * (n_bases - 10 * (k - 1))
+    rep = km.verify_order(k)
+    assert rep["ok"] and rep["kmers"] == n, rep
+    hist, total = km.get_kmer_group_counts(k)
+    assert total == n and int(hist.sum()) == rep["groups"]
+    if k == 15:
+        assert rep["groups"] < 4 ** 15 and int(hist[1]) < n // 2      # heavy duplication
+
+
+def test_repeat_rich_workload_full_size_properties():
+    """100 Mbp with ~40 % of the bases in diverged repeat families and low-complexity tracts (bench.py
+    --workload repeats), both strands, k = 31: long prefix buckets everywhere."""
+    import bench
+
+    n_bases = int(os.environ.get("GK_TEST_REPEAT_BASES", 100_000_000))
+    sba, starts, names = bench.make_repeat_genome(n_bases, 10, 20, 42)
+    sc = SequenceCollection.from_sba(sba, starts.astype(np.uint32), names, strands_to_load="both", validate=False)
+    km = Kmers(sc, 31, 31, source_strand="both")
+    km.sort()
+    rep = km.verify_order(31)
+    assert rep["ok"] and rep["kmers"] == len(km), (rep, km.last_sort_stats)
+    hist, total = km.get_kmer_group_counts(31)
+    assert total == len(km) and int(hist.sum()) == rep["groups"]
+    assert int(hist[2:].sum()) > 100_000
