@@ -776,6 +776,11 @@ static thread_local std::vector<unsigned long long> g_last_pairs;  // (bin, coun
 static thread_local uint64_t g_last_top_bin = 0;
 uint64_t last_hist_top_bin() { return g_last_top_bin; }
 const std::vector<unsigned long long> &last_hist_pairs() { return g_last_pairs; }
+void set_last_hist_pairs(const std::vector<unsigned long long> &pairs, uint64_t top_bin)
+{
+    g_last_pairs = pairs;
+    g_last_top_bin = top_bin;
+}
 void set_last_hist_single(uint64_t bin, uint64_t count)
 {
     g_last_pairs.clear();
@@ -993,7 +998,9 @@ __global__ void __launch_bounds__(kGfThreads)
 flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n_tiles,
                        const unsigned long long *__restrict__ carry, uint8_t skip_mask,
                        uint64_t min_group, uint64_t max_group, uint64_t max_bin,
-                       unsigned long long *__restrict__ hist, unsigned long long *__restrict__ totals)
+                       unsigned long long *__restrict__ hist, unsigned long long *__restrict__ totals,
+                       unsigned long long *__restrict__ big_list /* nullable: [0] count, then sizes >= 2048 */,
+                       uint64_t big_capacity)
 {
     __shared__ uint32_t s_small[kHistSmallBins];
     __shared__ unsigned long long s_total[3];
@@ -1016,7 +1023,10 @@ flag_group_hist_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint64_t n
             if (bin == 1) ++ones;
             else if (bin == 2) ++twos;
             else if (bin < kHistSmallBins) atomicAdd(&s_small[bin], 1u);
-            else atomicAdd(&hist[bin], 1ull);
+            else if (big_list) {   // spectrum mode: the exact sizes of the few large groups are listed
+                const unsigned long long slot = atomicAdd(&big_list[0], 1ull);
+                if (slot < big_capacity) big_list[1 + slot] = size;
+            } else atomicAdd(&hist[bin], 1ull);
         }
     };
 
@@ -1128,10 +1138,40 @@ int flag_group_hist_device(const uint8_t *d_flags, uint64_t n, uint8_t skip_mask
     if (grid > tiles) grid = tiles;
     flag_group_hist_kernel<<<(unsigned)grid, kGfThreads, 0, st>>>(d_flags, n, tiles, d_carry, skip_mask,
                                                                    min_group, max_group, max_bin, d_hist,
-                                                                   d_totals);
+                                                                   d_totals, nullptr, 0);
     GK_LAUNCH_CHECK();
     return collect_hist(d_hist, max_bin, h_hist, h_total, h_counted, st);
 }
+
+// The whole group-size spectrum of a sorted order in one go, left on the device (no synchronise): d_out holds
+// kHistSmallBins counts for the sizes below 2048, then the number of larger groups, then up to big_capacity of
+// their exact sizes.  gk_index_sort computes it behind the sort so that every later group-count query with the
+// sort length and no filter is answered on the host (any min/max group size, any max_counts_bin).
+int flag_group_spectrum_device(const uint8_t *d_flags, uint64_t n, unsigned long long *d_out, uint64_t big_capacity,
+                               cudaStream_t st)
+{
+    GK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)(kHistSmallBins + 1) * 8, st));
+    if (n == 0) return GK_OK;
+    const uint64_t tiles = (n + kGfTile - 1) / kGfTile;
+    DeviceBuffer scan, totals;
+    GK_TRY(scan.alloc((size_t)tiles * 16, st));
+    GK_TRY(totals.alloc(32, st));
+    GK_CUDA(cudaMemsetAsync(totals.ptr, 0, 32, st));
+    unsigned long long *d_last = scan.as<unsigned long long>();
+    unsigned long long *d_carry = d_last + tiles;
+    flag_tile_last_head_kernel<<<(unsigned)tiles, kGfThreads, 0, st>>>(d_flags, n, d_last);
+    GK_LAUNCH_CHECK();
+    flag_tile_carry_kernel<<<1, 1024, 0, st>>>(d_last, tiles, d_carry);
+    GK_LAUNCH_CHECK();
+    uint64_t grid = (uint64_t)sm_count() * 8;
+    if (grid > tiles) grid = tiles;
+    flag_group_hist_kernel<<<(unsigned)grid, kGfThreads, 0, st>>>(d_flags, n, tiles, d_carry, 0, 1, 0, ~0ull, d_out,
+                                                                   totals.as<unsigned long long>(),
+                                                                   d_out + kHistSmallBins, big_capacity);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+int spectrum_small_bins() { return kHistSmallBins; }
 
 // ---- k-mer filters as device predicates (kmers.py:14-259) ------------------------------------------
 // returns 1 pass, 0 fail, -1 where the reference raises ValueError

@@ -75,6 +75,9 @@ int group_hist_device(const void *, int, uint64_t, uint64_t, uint64_t, uint64_t,
 uint64_t last_hist_top_bin();
 const std::vector<unsigned long long> &last_hist_pairs();
 void set_last_hist_single(uint64_t, uint64_t);
+void set_last_hist_pairs(const std::vector<unsigned long long> &, uint64_t);
+int flag_group_spectrum_device(const uint8_t *, uint64_t, unsigned long long *, uint64_t, cudaStream_t);
+int spectrum_small_bins();
 int flag_group_hist_device(const uint8_t *, uint64_t, uint8_t, uint64_t, uint64_t, uint64_t, int64_t *,
                            int64_t *, int64_t *, cudaStream_t);
 int filter_flags_device(const uint8_t *, uint64_t, const void *, int, uint64_t, const gk_filter &,
@@ -176,6 +179,48 @@ struct gk_index {
     uint32_t flags_kmer_len = 0;
     bool alphabet_known = false;
     uint64_t n_bad = 0, n_sep = 0, n_amb_letters = 0;
+    // group-size spectrum of the sorted order for flags_kmer_len: (size, number of groups), ascending size
+    std::vector<std::pair<uint64_t, uint64_t>> spectrum;
+    bool spectrum_valid = false;
+};
+
+// Group-size spectrum behind a sort: kernels and the device-to-host copy are enqueued (no synchronise); finish()
+// turns the copy into ix->spectrum after the caller's own synchronise.
+constexpr uint64_t kSpectrumBig = 4096;   // large groups listed with their exact size; more: no spectrum
+struct SpectrumPending {
+    DeviceBuffer dev;
+    std::vector<unsigned long long> host;
+    bool armed = false;
+    int start(const uint8_t *d_flags, uint64_t n, cudaStream_t st)
+    {
+        const size_t words = (size_t)spectrum_small_bins() + 1 + kSpectrumBig;
+        GK_TRY(dev.alloc(words * 8, st));
+        GK_TRY(flag_group_spectrum_device(d_flags, n, dev.as<unsigned long long>(), kSpectrumBig, st));
+        host.assign(words, 0);
+        GK_CUDA(cudaMemcpyAsync(host.data(), dev.ptr, words * 8, cudaMemcpyDeviceToHost, st));
+        armed = true;
+        return GK_OK;
+    }
+    void finish(gk_index *ix)
+    {
+        ix->spectrum.clear();
+        ix->spectrum_valid = false;
+        if (!armed) return;
+        const size_t small = (size_t)spectrum_small_bins();
+        const uint64_t n_big = host[small];
+        if (n_big > kSpectrumBig) return;   // too many large groups to list: queries take the device path
+        for (size_t i = 1; i < small; ++i)
+            if (host[i]) ix->spectrum.emplace_back((uint64_t)i, (uint64_t)host[i]);
+        std::vector<uint64_t> big(host.begin() + small + 1, host.begin() + small + 1 + n_big);
+        std::sort(big.begin(), big.end());
+        for (size_t i = 0; i < big.size();) {
+            size_t j = i;
+            while (j < big.size() && big[j] == big[i]) ++j;
+            ix->spectrum.emplace_back(big[i], (uint64_t)(j - i));
+            i = j;
+        }
+        ix->spectrum_valid = true;
+    }
 };
 
 static int ensure_alphabet(gk_index *ix, cudaStream_t st)
@@ -219,7 +264,13 @@ static int side_stream(cudaStream_t *out)
     int dev = 0;
     GK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return GK_ERR_ARG; }
-    if (!streams[dev]) GK_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    if (!streams[dev]) {
+        // highest priority: its few small kernels (fragment sort) must slip in between the CTAs of the main
+        // stream's radix passes instead of queueing behind whole kernels
+        int least = 0, greatest = 0;
+        GK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        GK_CUDA(cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking, greatest));
+    }
     *out = streams[dev];
     return GK_OK;
 }
@@ -230,6 +281,11 @@ struct ScopedEvent {
     int create() { GK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); return GK_OK; }
 };
 
+static bool spectrum_enabled()
+{
+    const char *e = getenv("GK_SPECTRUM");
+    return !(e && e[0] == '0');
+}
 static bool fragments_enabled()
 {
     const char *e = getenv("GK_FRAGMENTS");
@@ -811,6 +867,7 @@ int gk_index_set_indices(gk_index *ix, const void *h_idx, uint64_t n, int idx_by
     ix->sorted = sorted != 0;
     ix->flags_valid = false;
     ix->flags_mark_amb = false;
+    ix->spectrum_valid = false;
     return GK_OK;
 }
 
@@ -964,6 +1021,9 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         }
     }
     const int t1 = tm.mark();
+    // the group-size spectrum of the new order rides along with the final synchronise
+    SpectrumPending spectrum;
+    if (n_sort > 0 && spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_sort, st));
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
@@ -985,6 +1045,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         ix->d_flags.swap(new_flags);
     }
     ix->n = n_sort;
+    spectrum.finish(ix);
     ix->user_idx = subset;
     ix->idx_ready = true;
     ix->flags_mark_amb = new_mark_amb;
@@ -1107,6 +1168,8 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         GK_TRY(sort_packed_pairs(ix, pp, (uint8_t *)new_flags.ptr, marks, tm, st));
     }
     const int t1 = tm.mark();
+    SpectrumPending spectrum;
+    if (n_local > 0 && spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_local, st));
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
@@ -1123,6 +1186,7 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     ix->d_idx.swap(new_idx);
     ix->d_flags.swap(new_flags);
     ix->n = n_local;
+    spectrum.finish(ix);
     ix->user_idx = false;
     ix->idx_ready = true;
     ix->flags_mark_amb = true;
@@ -1206,6 +1270,27 @@ static int index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *
 
     // fast path: sorted, same kmer_len as the sort, filter uniform over a group of equal k-mers
     const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
+    if (cached && f.id == GK_FILTER_KEEP_ALL && ix->spectrum_valid) {
+        // the sort left the whole group-size spectrum on the host: any limits and any bin clamp from there
+        if (min_group < 1) { set_error("min_group_size (%llu) must be >= 1", (unsigned long long)min_group); return GK_ERR_ARG; }
+        if (max_group != 0 && max_group < min_group) { set_error("max_group_size must be >= min_group_size"); return GK_ERR_ARG; }
+        if (max_bin < 1) { set_error("max_counts_bin (%llu) must be >= 1", (unsigned long long)max_bin); return GK_ERR_ARG; }
+        std::vector<unsigned long long> pairs;
+        uint64_t total = 0, top = 0;
+        for (const auto &sc : ix->spectrum) {
+            const uint64_t size = sc.first, count = sc.second;
+            if (size < min_group || (max_group != 0 && size > max_group)) continue;
+            const uint64_t bin = size < max_bin ? size : max_bin;
+            total += size * count;
+            top = bin > top ? bin : top;
+            if (!pairs.empty() && pairs[pairs.size() - 2] == bin) pairs.back() += count;
+            else { pairs.push_back(bin); pairs.push_back(count); }
+            if (h_hist_out) h_hist_out[bin] += (int64_t)count;
+        }
+        if (h_total_out) *h_total_out = (int64_t)total;
+        set_last_hist_pairs(pairs, top);
+        return GK_OK;
+    }
     const bool no_amb_same_len =
         f.id == GK_FILTER_NO_AMBIGUOUS && (uint64_t)f.p0 == kmer_len && ix->flags_mark_amb;
     if (cached && (f.id == GK_FILTER_KEEP_ALL || no_amb_same_len))

@@ -69,7 +69,7 @@ class NativeEngine:
         self.torch = torch
         self.lib = _native.lib()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.side = torch.cuda.Stream(device=self.device)
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)   # ahead of the bulk kernels
         self.err_word = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def stream(self):

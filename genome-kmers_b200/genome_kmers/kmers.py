@@ -327,7 +327,7 @@ class Kmers:
     def __init__(self, seq_coll: Union[SequenceCollection, None] = None, min_kmer_len: int = 1,
                  max_kmer_len: Union[int, None] = None, source_strand: str = "forward",
                  track_strands_separately: bool = False, method: str = "single_pass",
-                 device: Optional[Union[int, str]] = None) -> None:
+                 device: Optional[Union[int, str]] = None, num_gpus: Optional[int] = None) -> None:
         if track_strands_separately:
             raise NotImplementedError(
                 f"This function has not been implemented for track_strands_separately = '{track_strands_separately}'")
@@ -351,6 +351,11 @@ class Kmers:
         self.last_sort_stats = None
 
         self._device = device
+        # num_gpus > 1 (or GK_NUM_GPUS): sort() and the group counts run key-range sharded over the ranks of the
+        # default torch.distributed process group, one rank per GPU (genome_kmers.distributed.ShardedKmers);
+        # every rank constructs the same Kmers and makes the same calls.  Default: this process's GPU only.
+        self._num_gpus = num_gpus
+        self._sk = None            # ShardedKmers once sort() took the multi-GPU path
         self._ix = None            # gk_index handle
         self._d_sba = None         # torch uint8 tensor the index borrows
         self._host_idx = None      # cached host copy of the start indices
@@ -464,6 +469,13 @@ class Kmers:
     def kmer_sba_start_indices(self):
         if not self._is_initialized and self._host_idx is None:
             return None
+        if self._host_idx is None and self._sk is not None:
+            # multi-GPU path: every rank receives the whole sorted array (the shards in rank order)
+            import torch.distributed as dist
+
+            parts = [None] * self._sk.world
+            dist.all_gather_object(parts, self._sk.local_start_indices())
+            self._host_idx = np.concatenate(parts)
         if self._host_idx is None:
             self._ensure_device()
             lib = _native.lib()
@@ -501,8 +513,52 @@ class Kmers:
         pass
 
     # ------------------------------------------------------------------ the hot path
+    def _sharded_world(self) -> int:
+        """Number of ranks when this object is to take the multi-GPU path, else 0."""
+        import os
+
+        n = self._num_gpus if self._num_gpus is not None else int(os.environ.get("GK_NUM_GPUS", "0") or 0)
+        if n <= 1:
+            return 0
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("num_gpus > 1 needs an initialised torch.distributed process group with one rank "
+                               "per GPU (launch with torchrun)")
+        if dist.get_world_size() != n:
+            raise ValueError(f"num_gpus ({n}) does not match the process group's world size ({dist.get_world_size()})")
+        return n
+
+    def _sort_sharded(self):
+        from genome_kmers.distributed import ShardedKmers
+
+        if self.max_kmer_len != self.min_kmer_len or self.min_kmer_len > 31:
+            raise NotImplementedError("the multi-GPU path sorts fixed-length k-mers of one key word (k <= 31)")
+        if self._host_idx_dirty:
+            raise NotImplementedError("assigned start indices cannot be sorted on the multi-GPU path")
+        sc = self.seq_coll
+        if self.kmer_source_strand == "reverse_complement":
+            sba, starts, strands = sc.revcomp_sba, sc._revcomp_sba_seg_starts, "forward"
+        else:
+            sba, starts = sc.forward_sba, sc._forward_sba_seg_starts
+            strands = "both" if self.kmer_source_strand == "both" else "forward"
+        if self._sk is not None:
+            self._sk.close()
+        self._sk = ShardedKmers(np.ascontiguousarray(sba), starts.astype(np.uint64), self.min_kmer_len, strands)
+        self._sk.sort()
+        self.last_sort_stats = dict(self._sk.stats)
+        self._host_idx = None
+        self._is_sorted = True
+
+    def local_start_indices(self) -> np.ndarray:
+        """Multi-GPU path: this rank's shard of the sorted start indices (the shards of ranks 0, 1, ... in that
+        order are the global order).  Single GPU: the whole array."""
+        return self._sk.local_start_indices() if self._sk is not None else self.kmer_sba_start_indices
+
     def sort(self):
         """Sort the start indices in place by k-mer (kmers.py:1624-1652).  Runs on the GPU."""
+        if self._sharded_world():
+            return self._sort_sharded()
         self._ensure_device()
         self._push_host_indices()
         stats = _native.GkSortStats()
@@ -540,6 +596,12 @@ class Kmers:
             raise ValueError(
                 f"if max_group_size ({max_group_size}) is specified, it must be >= min_group_size ({min_group_size})")
         flt = self._native_filter(kmer_filter_func)
+        if self._sk is not None and not self._host_idx_dirty:
+            if kmer_len != self.min_kmer_len:
+                raise NotImplementedError("the multi-GPU path counts groups for the sort length only")
+            hist, total = self._sk.get_kmer_group_counts(kmer_len, flt, min_group_size, max_group_size,
+                                                         max_counts_bin)
+            return (hist if want_hist else None), total
         self._ensure_device()
         self._push_host_indices()
         # np.zeros hands out untouched zero pages: the library writes the occupied bins only

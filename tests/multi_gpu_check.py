@@ -77,6 +77,30 @@ def main():
                     failures.append((k, used))
                 if mode == "1" and used != "peer":
                     failures.append((k, "peer exchange was not used"))
+    # the drop-in class itself with num_gpus: same answers as the oracle on every rank
+    from genome_kmers.kmers import Kmers, gen_no_ambiguous_bases_filter
+    from genome_kmers.sequence_collection import SequenceCollection
+
+    os.environ["GK_FORCE_IDX64"] = "0"
+    os.environ["GK_PEER_EXCHANGE"] = "1"
+    rng = np.random.default_rng(5)
+    recs = gu.random_genome(rng, 300_000, 3, n_runs=4, run_lo=50, run_hi=3000, n_scatter=10)
+    sc = SequenceCollection.from_arrays(recs, strands_to_load="both")
+    km = Kmers(sc, 21, 21, source_strand="both", num_gpus=world)
+    km.sort()
+    hist, total = km.get_kmer_group_counts(21, max_counts_bin=100)
+    p_hist, p_total = km.get_kmer_group_counts(21, gen_no_ambiguous_bases_filter(21), max_counts_bin=100)
+    got = km.kmer_sba_start_indices
+    both, both_starts = oracle.both_strands(sc.forward_sba, sc._forward_sba_seg_starts.astype(np.uint64))
+    want = oracle.sort_indices(both, oracle.init_indices(both_starts, len(both), 21), 21, 21,
+                               threads=min(8, oracle.max_threads()))
+    o_hist, o_total = oracle.group_hist(both, want, 21, max_bin=100)
+    q_hist, q_total = oracle.group_hist(both, want, 21, filt=(oracle.FILTER_NO_AMBIGUOUS, 21, 0, 0), max_bin=100)
+    ok = (np.array_equal(got.astype(np.uint64), want) and total == o_total and np.array_equal(hist, o_hist)
+          and p_total == q_total and np.array_equal(p_hist, q_hist) and len(km.local_start_indices()) <= len(want))
+    print(f"rank {rank}: Kmers(num_gpus={world}): {'ok' if ok else 'MISMATCH'}", flush=True)
+    if not ok:
+        failures.append(("Kmers num_gpus", rank))
     # a larger case than the oracle can answer: checked on the devices against the bytes (ShardedKmers.verify)
     os.environ["GK_FORCE_IDX64"] = "0"
     os.environ["GK_PEER_EXCHANGE"] = "1"
@@ -97,7 +121,7 @@ def main():
     flag = torch.tensor([len(failures)])
     if not same_gpu:
         flag = flag.cuda()
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag)
     gkd.PeerExchange.close_all()
     dist.barrier()
     dist.destroy_process_group()

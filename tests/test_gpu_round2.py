@@ -247,3 +247,23 @@ def test_stranger_in_the_all_n_bucket_is_moved_without_sorting_the_bucket(strand
     o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=100)
     assert total == o_total and np.array_equal(hist, o_hist)
     assert km.verify_order(31)["ok"]
+
+
+@pytest.mark.parametrize("spectrum", ["0", "1"])
+@pytest.mark.parametrize("name", ["sl2_k3", "rand5k_k21_count11", "lowcomplex_k8", "rand120kN_both_k31", "iupac4k_k15"])
+def test_group_counts_from_the_cached_spectrum_and_from_the_device_agree(name, spectrum, monkeypatch):
+    """sort() leaves the group-size spectrum on the host (GK_SPECTRUM=1, default) and later queries are answered
+    from it; GK_SPECTRUM=0 keeps every query on the device histogram kernels.  Same answers as the reference."""
+    monkeypatch.setenv("GK_SPECTRUM", spectrum)
+    case = golden_case(name)
+    sc = SequenceCollection(sequence_list=[tuple(r) for r in case["seq_list"]], strands_to_load=case["strands"])
+    km = Kmers(sc, case["min_len"], case["max_len"], source_strand=case["strands"])
+    km.sort()
+    for qu, ans in zip(case["queries"], case["answers"]):
+        flt = kmer_filter_keep_all if qu["filter"] is None else gen_no_ambiguous_bases_filter(qu["filter"][1])
+        hist, total = km.get_kmer_group_counts(qu["kmer_len"], flt, qu["min_group"], qu["max_group"], qu["max_bin"])
+        assert total == ans["total"] and np.array_equal(hist, dense_hist(ans, qu["max_bin"])), (name, qu)
+        assert km.get_kmer_count(qu["kmer_len"], flt, qu["min_group"], qu["max_group"]) == ans["total"]
+    for max_bin in (1, 2, 5, 1000):
+        h, t = km.get_kmer_group_counts(case["max_len"], max_counts_bin=max_bin)
+        assert t == len(km) and int((h * np.arange(max_bin + 1)).sum()) <= len(km)
