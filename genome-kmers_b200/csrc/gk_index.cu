@@ -269,7 +269,9 @@ static int side_stream(cudaStream_t *out)
         // stream's radix passes instead of queueing behind whole kernels
         int least = 0, greatest = 0;
         GK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        GK_CUDA(cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking, greatest));
+        const char *e = getenv("GK_SIDE_PRIORITY");
+        GK_CUDA(cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking,
+                                             (e && e[0] == '0') ? least : greatest));
     }
     *out = streams[dev];
     return GK_OK;

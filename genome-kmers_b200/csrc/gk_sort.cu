@@ -276,7 +276,10 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
         for (int j = 0; j < IPT; ++j) {
             const uint64_t g = warp_base + j * 32 + lane;
             const bool ok = g < n;
-            key[j] = ok ? keys_in[g] : (KeyT)~(KeyT)0;  // pads rank last in the last bin of the last tile
+            // pads must rank behind every real pair of the tile: all ones has the largest digit in a sorting
+            // pass and the last destination in a partition pass; when ambiguous pairs are dropped (digit n_dest,
+            // beyond the last destination) the pad is made even so that it lands in that discard digit too
+            key[j] = ok ? keys_in[g] : (KeyT)(~(KeyT)0 - (KeyT)(skip_amb_digit != 0xffffffffu ? 1 : 0));
             val[j] = ok ? vals_in[g] : (ValT)0;
         }
     }

@@ -69,7 +69,8 @@ class NativeEngine:
         self.torch = torch
         self.lib = _native.lib()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.side = torch.cuda.Stream(device=self.device, priority=-1)   # ahead of the bulk kernels
+        prio = 0 if os.environ.get("GK_SIDE_PRIORITY", "1") == "0" else -1
+        self.side = torch.cuda.Stream(device=self.device, priority=prio)   # ahead of the bulk kernels
         self.err_word = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def stream(self):

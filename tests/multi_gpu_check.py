@@ -100,6 +100,26 @@ def main():
           and p_total == q_total and np.array_equal(p_hist, q_hist) and len(km.local_start_indices()) <= len(want))
     print(f"rank {rank}: Kmers(num_gpus={world}): {'ok' if ok else 'MISMATCH'}", flush=True)
     if not ok:
+        print(f"rank {rank}: order {np.array_equal(got.astype(np.uint64), want)} ({len(got)} / {len(want)}), counts "
+              f"{total == o_total} {np.array_equal(hist, o_hist)}, pure counts {p_total == q_total} ({p_total} / {q_total}) "
+              f"{np.array_equal(p_hist, q_hist)}", flush=True)
+        if rank == 0:
+            bad = np.flatnonzero(got.astype(np.uint64) != want)
+            print(f"rank 0: {len(bad)} mismatching slots, first {bad[:6]}, last {bad[-3:]}", flush=True)
+            for b in bad[:6]:
+                print(f"   slot {b}: got {got[b]} {both[int(got[b]):int(got[b]) + 21].tobytes()} want {want[b]} "
+                      f"{both[int(want[b]):int(want[b]) + 21].tobytes()}", flush=True)
+            print(f"rank 0: stats {km.last_sort_stats}", flush=True)
+            x = int(want[bad[0]])
+            where = np.flatnonzero(got.astype(np.uint64) == x)
+            vals, cnts = np.unique(got, return_counts=True)
+            print(f"rank 0: start {x} sits at slots {where.tolist()} of got; duplicated starts {vals[cnts > 1][:5].tolist()}; "
+                  f"last slots got {got[-3:].tolist()} want {want[-3:].tolist()}; splitters {km._sk.splitters.tolist()}",
+                  flush=True)
+    print(f"rank {rank}: shard stats refine_flags {km.last_sort_stats.get('refine_flags')} n_shard "
+          f"{km.last_sort_stats.get('n_shard')} amb {km.last_sort_stats.get('n_ambiguous')} frag "
+          f"{km.last_sort_stats.get('n_fragments')} key_bits {km.last_sort_stats.get('key_bits')}", flush=True)
+    if not ok:
         failures.append(("Kmers num_gpus", rank))
     # a larger case than the oracle can answer: checked on the devices against the bytes (ShardedKmers.verify)
     os.environ["GK_FORCE_IDX64"] = "0"

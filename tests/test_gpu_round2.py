@@ -267,3 +267,52 @@ def test_group_counts_from_the_cached_spectrum_and_from_the_device_agree(name, s
     for max_bin in (1, 2, 5, 1000):
         h, t = km.get_kmer_group_counts(case["max_len"], max_counts_bin=max_bin)
         assert t == len(km) and int((h * np.arange(max_bin + 1)).sum()) <= len(km)
+
+
+@pytest.mark.parametrize("n", [5, 8192, 8195, 40_001])
+@pytest.mark.parametrize("skip", [0, 1])
+def test_partition_to_destination_buffers_with_key_base_and_dropped_ambiguous_pairs(n, skip):
+    """gk_partition_pairs_peer into local buffers: stable per destination, keys minus the destination's base,
+    class-0 pairs dropped when asked, and not one slot written beyond each destination's count -- also when the
+    last (partial) tile holds dropped pairs (its padding must not leak into a destination)."""
+    torch = gu.torch_mod()
+    lib = _native.lib()
+    rng = np.random.default_rng(n + skip)
+    keys = rng.integers(1 << 40, 1 << 62, n, dtype=np.uint64) | np.uint64(1)
+    amb = rng.random(n) < 0.2
+    amb[-3:] = True                                   # ambiguous pairs at the very end of the last tile
+    keys[amb] &= ~np.uint64(1)
+    vals = np.arange(n, dtype=np.uint32)
+    splitters = np.sort(rng.integers(1 << 40, 1 << 62, 3, dtype=np.uint64)) & ~np.uint64(1)
+    base = np.concatenate([np.zeros(1, dtype=np.uint64), splitters])
+    dest = np.searchsorted(splitters, keys, side="right")
+    keep = ~amb if skip else np.ones(n, dtype=bool)
+    counts = np.bincount(dest[keep], minlength=4)
+    SENT = np.uint64(0xDEADBEEFDEADBEEF)
+    d_keys, d_vals, d_split = gu.dev(keys), gu.dev(vals), gu.dev(splitters)
+    outs_k = [torch.full((int(c) + 8,), int(SENT.view(np.int64)), dtype=torch.int64, device="cuda") for c in counts]
+    outs_v = [torch.full((int(c) + 8,), -1, dtype=torch.int32, device="cuda") for c in counts]
+    kp = np.array([t.data_ptr() for t in outs_k], dtype=np.uint64)
+    vp = np.array([t.data_ptr() for t in outs_v], dtype=np.uint64)
+    off = np.zeros(4, dtype=np.uint64)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _native.check(lib.gk_partition_pairs_peer(d_keys.data_ptr(), d_vals.data_ptr(), 4, n, d_split.data_ptr(), 4,
+                                              _native.host_ptr(kp), _native.host_ptr(vp), _native.host_ptr(off),
+                                              _native.host_ptr(base), skip, err.data_ptr(), gu.stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    for d in range(4):
+        sel = keep & (dest == d)
+        got_k = gu.host(outs_k[d], np.uint64)
+        got_v = gu.host(outs_v[d], np.uint32)
+        c = int(counts[d])
+        assert np.array_equal(got_k[:c], keys[sel] - base[d]) and np.array_equal(got_v[:c], vals[sel]), (n, skip, d)
+        assert bool((got_k[c:] == SENT).all()) and bool((got_v[c:] == np.uint32(0xFFFFFFFF)).all()), \
+            f"destination {d}: slots beyond its {c} pairs were written"
+    # the split counts agree with what the partition does
+    d_counts = torch.zeros(8, dtype=torch.int64, device="cuda")
+    _native.check(lib.gk_partition_count_split(d_keys.data_ptr(), n, d_split.data_ptr(), 4, 1, d_counts.data_ptr(),
+                                               gu.stream()))
+    got_counts = d_counts.cpu().numpy()
+    assert np.array_equal(got_counts[:4], np.bincount(dest[~amb], minlength=4))
+    assert np.array_equal(got_counts[4:], np.bincount(dest[amb], minlength=4))
