@@ -475,7 +475,7 @@ def run_single_gpu(args):
         try:
             _native.check(lib.gk_index_sort(handle, ctypes.byref(stats), sp))
             t.append(time.perf_counter())
-            hist = np.zeros(MAX_BIN + 1, dtype=np.int64)   # fresh zero pages, as Kmers.get_kmer_group_counts does
+            hist = _native.zeros_int64(MAX_BIN + 1)        # fresh zero pages, as Kmers.get_kmer_group_counts does
             total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
             _native.check(lib.gk_index_group_counts_zeroed(handle, K, None, 1, 0, MAX_BIN, _native.host_ptr(hist),
                                                            ctypes.byref(total), ctypes.byref(top), sp))

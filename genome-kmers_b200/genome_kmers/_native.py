@@ -157,3 +157,17 @@ def host_ptr(arr: np.ndarray) -> int:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().gk_launch_count(1 if reset else 0))
+
+
+def zeros_int64(n: int):
+    """np.zeros(n, int64) whose pages are untouched zero pages even after many calls: glibc serves repeated
+    multi-megabyte calloc requests from its heap (and then clears them by hand, 0.3 ms for the reference's
+    default 8 MB histogram); an anonymous mapping is lazily zero every time."""
+    import mmap
+
+    import numpy as np
+
+    nbytes = int(n) * 8
+    if nbytes < (1 << 20):
+        return np.zeros(n, dtype=np.int64)
+    return np.frombuffer(mmap.mmap(-1, nbytes), dtype=np.int64)

@@ -713,7 +713,7 @@ class ShardedKmers:
                                                     max_counts_bin)
             bins = np.flatnonzero(dense).astype(np.uint64)
             counts = dense[bins.astype(np.int64)]
-        hist = np.zeros(max_counts_bin + 1, dtype=np.int64)
+        hist = _native.zeros_int64(max_counts_bin + 1)
         if self.world == 1:
             hist[bins.astype(np.int64)] = counts
             return hist, total

@@ -605,7 +605,7 @@ class Kmers:
         self._ensure_device()
         self._push_host_indices()
         # np.zeros hands out untouched zero pages: the library writes the occupied bins only
-        hist = np.zeros(max_counts_bin + 1, dtype=np.int64) if want_hist else None
+        hist = _native.zeros_int64(max_counts_bin + 1) if want_hist else None
         total, top = ctypes.c_int64(0), ctypes.c_uint64(0)
         _native.check(_native.lib().gk_index_group_counts_zeroed(
             self._ix, kmer_len or 0, ctypes.byref(flt), min_group_size, max_group_size or 0,
