@@ -13,6 +13,8 @@
 //                min_group <= size <= max_group (kmers.py:514-518, :612-614); small sizes are
 //                privatised in shared memory because a random genome puts almost every group in
 //                bin 1.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "gk_common.cuh"
@@ -75,8 +77,7 @@ key_flags_kernel(const uint64_t *__restrict__ keys, uint64_t n, int class_bit,
 //     passes.  A long run without a descent is already in final order.
 constexpr int kTieMaxRun = 8;
 constexpr int kTieThreads = 256;
-constexpr int kTiePerThread = 8;
-constexpr int kTieTile = kTieThreads * kTiePerThread;  // slots per CTA
+constexpr int kTieDefaultPer = 8;   // slots per thread (GK_TIE_PER overrides)
 constexpr int kTieHalo = kTieMaxRun;                   // keys staged either side of the tile
 
 // A CTA stages the PREFIXES of its tile of keys (plus a halo) in shared memory, so that every neighbour
@@ -87,13 +88,16 @@ constexpr int kTieHalo = kTieMaxRun;                   // keys staged either sid
 //   2  queued slots: bounded search for the run's ends; long run -> own flag (+ descent report),
 //      first slot of a short run -> queue the run
 //   3  queued runs: rank the run by the full key in registers, write keys, values and flags in place
-template <typename ValT, typename PreT>
+template <typename ValT, typename PreT, int kTiePerThread>
 __global__ void __launch_bounds__(kTieThreads)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent,
                      unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */,
                      unsigned long long *__restrict__ descent_list /* nullable: first kDescentCap positions */)
 {
+    constexpr int kTieTile = kTieThreads * kTiePerThread;  // slots per CTA
+    constexpr int kRunShift = kTiePerThread > 8 ? 12 : 11;  // s_run entry: slot | (length - 1) << kRunShift
+    static_assert(kTieTile <= (1 << kRunShift) && kRunShift + 3 <= 16, "run entries are 16 bits");
     // bit (i + 32) of s_cont: slot i (tile-relative, -8 <= i < kTieTile + 8) has the same prefix as slot i - 1
     constexpr int kContWords = kTieTile / 32 + 2;
     __shared__ PreT s_pre[kTieTile + 2 * kTieHalo];
@@ -254,7 +258,7 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
             }
             flags[p] = (amb ? kFlagAmb : (head ? kFlagHead : 0)) | kFlagLong;
         } else if (ph) {  // a short run that starts in this tile: slot and length - 1
-            s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)(i | (f << 11));
+            s_run[atomicAdd(&s_n_run, 1u)] = (uint16_t)(i | (f << kRunShift));
         }
     }
     __syncthreads();
@@ -262,8 +266,8 @@ tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint6
     // ---- 3 ---------------------------------------------------------------------------------------------
     const uint32_t n_runs = s_n_run;
     for (uint32_t r = t; r < n_runs; r += kTieThreads) {
-        const int h = s_run[r] & 2047;
-        const int len = (s_run[r] >> 11) + 1;
+        const int h = s_run[r] & ((1 << kRunShift) - 1);
+        const int len = (s_run[r] >> kRunShift) + 1;
         const uint64_t g = tile0 + (uint64_t)h;
         if (len == 2) {  // nearly every run: one compare, at most one swap
             const uint64_t k0 = keys[g], k1 = keys[g + 1];
@@ -726,28 +730,45 @@ int key_flags_device(const uint64_t *d_keys, uint64_t n, int class_bit, uint8_t 
 
 // head/ambiguous flags of keys sorted on bits [lo_bits, 64) only, repairing short prefix runs in place;
 // *d_descent (zeroed by the caller) becomes 1 when a kFlagLong run is out of order
+template <int PER>
+static int tie_fix_launch(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t n, int lo_bits, int class_bit,
+                          uint8_t *d_flags, unsigned int *d_descent, unsigned long long *d_n_amb,
+                          unsigned long long *d_descent_list, cudaStream_t st)
+{
+    constexpr int kTile = kTieThreads * PER;
+    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
+    const bool narrow = (64 - lo_bits) <= 32;  // the prefix fits 32 bits
+    if (val_bytes == 4 && narrow)
+        tie_fix_flags_kernel<uint32_t, uint32_t, PER><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
+    else if (val_bytes == 4)
+        tie_fix_flags_kernel<uint32_t, uint64_t, PER><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
+    else if (narrow)
+        tie_fix_flags_kernel<uint64_t, uint32_t, PER><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
+    else
+        tie_fix_flags_kernel<uint64_t, uint64_t, PER><<<grid, kTieThreads, 0, st>>>(
+            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// head/ambiguous flags of keys sorted on bits [lo_bits, 64) only, repairing short prefix runs in place;
+// *d_descent (zeroed by the caller) counts the slots of kFlagLong runs that are out of order.
+// GK_TIE_PER=8|16 selects the slots per thread (tuning runs).
 int tie_fix_flags_device(uint64_t *d_keys, void *d_vals, int val_bytes, uint64_t n, int lo_bits,
                          int class_bit, uint8_t *d_flags, unsigned int *d_descent,
                          unsigned long long *d_n_amb, cudaStream_t st, unsigned long long *d_descent_list)
 {
     if (n == 0) return GK_OK;
-    const uint64_t tiles = (n + kTieTile - 1) / kTieTile;
-    const bool narrow = (64 - lo_bits) <= 32;  // the prefix fits 32 bits
-    const unsigned grid = (unsigned)tiles;
-    if (val_bytes == 4 && narrow)
-        tie_fix_flags_kernel<uint32_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
-    else if (val_bytes == 4)
-        tie_fix_flags_kernel<uint32_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint32_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
-    else if (narrow)
-        tie_fix_flags_kernel<uint64_t, uint32_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
-    else
-        tie_fix_flags_kernel<uint64_t, uint64_t><<<grid, kTieThreads, 0, st>>>(
-            d_keys, (uint64_t *)d_vals, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb, d_descent_list);
-    GK_LAUNCH_CHECK();
-    return GK_OK;
+    const char *e = getenv("GK_TIE_PER");
+    const int per = (e && *e) ? atoi(e) : kTieDefaultPer;
+    if (per == 16)
+        return tie_fix_launch<16>(d_keys, d_vals, val_bytes, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb,
+                                  d_descent_list, st);
+    return tie_fix_launch<8>(d_keys, d_vals, val_bytes, n, lo_bits, class_bit, d_flags, d_descent, d_n_amb,
+                             d_descent_list, st);
 }
 
 int sba_flags_device(const uint8_t *d_sba, uint64_t sba_len, const void *d_idx, int idx_bytes,

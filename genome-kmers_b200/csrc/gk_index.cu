@@ -21,6 +21,7 @@ int init_indices_device(const uint64_t *, uint32_t, uint32_t, uint64_t, int, voi
 int pack_keys_device(const uint8_t *, uint64_t, const uint64_t *, uint32_t, uint32_t, uint32_t, int,
                      uint64_t, uint64_t, uint64_t, uint64_t *, int, void *, unsigned long long *, int, int,
                      unsigned long long *, cudaStream_t, const FragOut *);
+int pack_hist_passes_max();
 int pack_keys_list_device(const uint8_t *, uint64_t, const void *, int, uint64_t, uint32_t, int, uint64_t *,
                           unsigned long long *, cudaStream_t);
 int widen_indices_device(const void *, int, uint64_t, uint64_t *, cudaStream_t);
@@ -663,11 +664,15 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
         GK_TRY(pack_keys_list_device(ix->d_sba, ix->sba_len, d_list, ib, n, key_len, class_bit, pp.keys_a,
                                      pp.d_counters, st));
     } else {
+        // (more digit positions than the pack kernel has counters for -- plain LSD over a long key on a small
+        // input: the sort counts its digits itself)
+        const bool count_digits = (pp.key_bits - begin_bit + 7) / 8 <= pack_hist_passes_max();
         GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
                                 (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
                                 pp.keys_a, ib, out_idx.ptr, pp.d_counters, begin_bit, pp.key_bits,
-                                pre_hist.as<unsigned long long>(), st, pp.want_frag ? &pp.frag : nullptr));
-        pp.d_pre_hist = pre_hist.as<unsigned long long>();
+                                count_digits ? pre_hist.as<unsigned long long>() : nullptr, st,
+                                pp.want_frag ? &pp.frag : nullptr));
+        if (count_digits) pp.d_pre_hist = pre_hist.as<unsigned long long>();
     }
     marks.pack1 = tm.mark();
     ScopedEvent e_pack;

@@ -29,7 +29,8 @@ constexpr int kPackThreads = 256;
 constexpr int kPackPerThread = 16;
 constexpr int kPackTile = kPackThreads * kPackPerThread;  // window starts per CTA
 constexpr int kPackChunks = kPackTile / 16 + 2;           // 16-byte chunks staged (tile + 32 B halo)
-constexpr int kPackHistPasses = 8;                        // digit positions counted on the fly
+constexpr int kPackHistPasses = 5;                        // digit positions counted on the fly (see pack_hist_passes_max)
+constexpr int kPackKeyRow = kPackThreads + 1;             // padded row of the key staging buffer (bank-conflict free)
 
 template <typename IdxT, int HP>
 __global__ void __launch_bounds__(kPackThreads)
@@ -52,6 +53,9 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     // digit histograms of the keys this CTA emits, for the radix passes that follow (the sort would
     // otherwise read all keys once more just to count digits); flushed once per CTA
     __shared__ uint32_t s_hist[kPackHistPasses][256];
+    // keys of a whole tile, written by the thread that cuts 16 CONSECUTIVE windows out of three code words and
+    // read back position by position for coalesced stores: s_keys[j * kPackKeyRow + t] = key of position 16 t + j
+    __shared__ uint64_t s_keys[kPackPerThread * kPackKeyRow];
 
     const uint32_t t = threadIdx.x;
     const int hist_passes = g_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
@@ -85,13 +89,25 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
             }
         }
         *reinterpret_cast<uint4 *>(s_bytes + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+        // four bytes at a time (the kernel is bound by integer issue, not by memory)
         uint32_t codes = 0, amb = 0, sep = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            codes |= code2(b) << (30 - 2 * i);
-            amb |= (is_acgt(b) ? 0u : 1u) << i;
-            sep |= (b == kSep ? 1u : 0u) << i;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = w[i];
+            uint32_t c = (x >> 1) & 0x03030303u;              // 2-bit code of every byte (A<C<G<T) ...
+            c ^= (c >> 1) & 0x01010101u;
+            // ... the byte each code stands for, to tell A/C/G/T from everything else
+            const uint32_t sel = (c & 0x3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+            const uint32_t canon = __byte_perm(0x54474341u, 0u, sel);
+            const uint32_t d = x ^ canon;                     // non-zero byte: not A/C/G/T
+            const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+            const uint32_t e = x ^ 0x24242424u;               // zero byte: '$'
+            const uint32_t zs = ~(((e & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | e) & 0x80808080u;
+            const uint32_t nzb = nz >> 7, zsb = zs >> 7;      // one bit per byte at 0, 8, 16, 24 -> a nibble
+            amb |= ((nzb | (nzb >> 7) | (nzb >> 14) | (nzb >> 21)) & 0xFu) << (4 * i);
+            sep |= ((zsb | (zsb >> 7) | (zsb >> 14) | (zsb >> 21)) & 0xFu) << (4 * i);
+            const uint32_t r = __byte_perm(c, 0u, 0x0123);    // first byte on top: most significant symbol first
+            codes |= ((r | (r >> 6) | (r >> 12) | (r >> 18)) & 0xFFu) << (24 - 8 * i);
         }
         s_codes[c] = codes;
         s_amb[c] = (uint16_t)amb;
@@ -100,8 +116,48 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     }
     if (t < 2) { s_amb[kPackChunks + t] = 0xFFFFu; s_sep[kPackChunks + t] = 0xFFFFu; s_ne[kPackChunks + t] = 0xFFFFu; }
     if (t == 0) s_seg0 = upper_seg(seg_starts, n_seg, tile0 < sba_len ? tile0 : sba_len - 1);
-    // (barrier + vote) does this tile hold any non-ACGT symbol besides '$'?  Nearly all tiles do not.
-    const bool tile_frags = __syncthreads_or((int)any_amb) != 0 && frag.key != nullptr;
+    // (barrier + vote) does the staged range hold anything but A/C/G/T?  Nearly all tiles do not.
+    const bool dirty = __syncthreads_or((int)any_amb) != 0;
+    const bool tile_frags = dirty && frag.key != nullptr;
+    // tile-relative bounds of the requested range of starts
+    const uint32_t q_lo = first_start > tile0 ? (uint32_t)((first_start - tile0 < (uint64_t)kPackTile)
+                                                               ? first_start - tile0 : kPackTile) : 0u;
+    const uint32_t q_hi = end_start > tile0 ? (uint32_t)((end_start - tile0 < (uint64_t)kPackTile)
+                                                             ? end_start - tile0 : kPackTile) : 0u;
+    if (!dirty && q_lo == 0 && q_hi == (uint32_t)kPackTile && valid_len <= 32 && key_len <= valid_len) {
+        // ---- fast tile: every position starts a pure window inside one record -------------------------------
+        // (no '$' and no other symbol in the tile or its halo, so nothing to validate, classify or list).
+        // A thread cuts its 16 consecutive windows out of three code words in registers ...
+        const uint32_t c0 = s_codes[t], c1 = s_codes[t + 1], c2 = s_codes[t + 2];
+        const uint64_t hi64 = ((uint64_t)c0 << 32) | c1;
+        const uint32_t sh = 64u - 2u * key_len;
+#pragma unroll
+        for (int j = 0; j < kPackPerThread; ++j) {
+            const uint64_t x = (j == 0) ? hi64 : ((hi64 << (2 * j)) | ((uint64_t)c2 >> (32 - 2 * j)));
+            const uint64_t value = x >> sh;
+            const uint64_t key = class_bit ? ((value << 1) | 1ull) : value;
+            s_keys[j * kPackKeyRow + t] = key;
+#pragma unroll
+            for (int p = 0; p < kPackHistPasses; ++p) {
+                if (p < (HP >= 0 ? HP : hist_passes)) {
+                    const int lo = hist_begin_bit + 8 * p;
+                    const int bits = (hist_end_bit - lo < 8) ? hist_end_bit - lo : 8;
+                    atomicAdd(&s_hist[p][(uint32_t)(key >> lo) & ((1u << bits) - 1u)], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // ... and the tile leaves in position order: consecutive threads store consecutive pairs
+        const uint64_t pos0 = tile0 - (uint64_t)valid_len * s_seg0 - out_base;  // (modular arithmetic)
+#pragma unroll
+        for (int j = 0; j < kPackPerThread; ++j) {
+            const uint32_t q = t + j * kPackThreads;
+            keys_out[pos0 + q] = s_keys[(q & 15u) * kPackKeyRow + (q >> 4)];
+            idx_out[pos0 + q] = (IdxT)(tile0 + q);
+        }
+        __syncthreads();  // the staged streams and keys are rewritten by the next tile
+        continue;
+    }
     if (tile_frags) {
         // "next byte differs" bits: a window equals the window one position to its left iff its key_len + 1
         // bytes from that position on are all the same symbol
@@ -165,11 +221,7 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     // ---- cut windows ---------------------------------------------------------------------------
     const uint32_t seg0 = s_seg0;
     const uint64_t key_mask = (key_len >= 32) ? 0xFFFFFFFFull : ((1ull << key_len) - 1ull);
-    // tile-relative bounds of the requested range of starts, and the output slot of tile position 0
-    const uint32_t q_lo = first_start > tile0 ? (uint32_t)((first_start - tile0 < (uint64_t)kPackTile)
-                                                               ? first_start - tile0 : kPackTile) : 0u;
-    const uint32_t q_hi = end_start > tile0 ? (uint32_t)((end_start - tile0 < (uint64_t)kPackTile)
-                                                             ? end_start - tile0 : kPackTile) : 0u;
+    // the output slot of tile position 0
     const uint64_t tile_pos0 = tile0 - (uint64_t)valid_len * seg0 - out_base;  // (modular arithmetic)
 #pragma unroll 4
     for (int j = 0; j < kPackPerThread; ++j) {
@@ -409,6 +461,8 @@ int pack4_words_stream_device(const uint64_t *d_stream, const void *d_idx, int i
     return GK_OK;
 }
 
+int pack_hist_passes_max() { return kPackHistPasses; }
+
 int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_seg_starts,
                      uint32_t n_seg, uint32_t valid_len, uint32_t key_len, int class_bit,
                      uint64_t first_start, uint64_t end_start, uint64_t out_base,
@@ -433,8 +487,9 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
         set_error("pack_keys: at most %d digit positions can be counted", kPackHistPasses);
         return GK_ERR_ARG;
     }
-    // persistent CTAs (8 fit an SM) so that the shared histograms are flushed ~1000 times, not per tile
-    uint64_t grid = (uint64_t)sm_count() * 8;
+    // persistent CTAs (4 fit an SM: 64 registers x 256 threads, 45 KB of shared memory each) so that the shared
+    // histograms are flushed ~600 times, not per tile
+    uint64_t grid = (uint64_t)sm_count() * 4;
     if (grid > n_tiles) grid = n_tiles;
     const int hp = d_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
     const FragOut fr = frag ? *frag : FragOut();
