@@ -137,19 +137,33 @@ frag_expand_kernel(const uint64_t *__restrict__ sstart, const unsigned long long
 {
     if (*descent || (*err & 6)) return;
     const uint64_t m = off[F];
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < m; o += stride) {
-        uint64_t lo = 0, hi = F;  // last fragment whose offset is <= o
+    // eight consecutive windows per thread: one binary search, then a walk (almost all windows lie in fragments
+    // of thousands -- the pieces of an N run)
+    constexpr int kPer = 8;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kPer;
+    for (uint64_t o0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPer; o0 < m; o0 += stride) {
+        uint64_t lo = 0, hi = F;  // last fragment whose offset is <= o0
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
-            if (o < off[mid]) hi = mid; else lo = mid + 1;
+            if (o0 < off[mid]) hi = mid; else lo = mid + 1;
         }
-        const uint64_t q = lo - 1;
-        const uint64_t i = o - off[q];
-        const uint64_t slot = slot0[q] + i;
-        if (slot < n) {
-            d_idx[slot] = (IdxT)(sstart[q] + i);
-            d_flags[slot] = kFlagAmb | ((i == 0 && whead[q]) ? kFlagHead : 0);
+        uint64_t q = lo - 1;
+        uint64_t q_off = off[q], q_end = off[q + 1], q_slot = slot0[q], q_start = sstart[q];
+        uint8_t q_head = whead[q];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const uint64_t o = o0 + u;
+            if (o >= m) break;
+            while (o >= q_end) {   // (fragments are never empty)
+                ++q;
+                q_off = q_end; q_end = off[q + 1]; q_slot = slot0[q]; q_start = sstart[q]; q_head = whead[q];
+            }
+            const uint64_t i = o - q_off;
+            const uint64_t slot = q_slot + i;
+            if (slot < n) {
+                d_idx[slot] = (IdxT)(q_start + i);
+                d_flags[slot] = kFlagAmb | ((i == 0 && q_head) ? kFlagHead : 0);
+            }
         }
     }
 }
@@ -204,7 +218,7 @@ int frag_expand_device(FragSorted &fs, const uint64_t *keys_sorted, uint64_t n, 
                                                        n, d_descent, d_n_amb_expected,
                                                        fs.slot0.as<unsigned long long>(), d_err);
     GK_LAUNCH_CHECK();
-    const int grid = frag_grid(n_amb_host ? n_amb_host : 1);
+    const int grid = frag_grid(n_amb_host ? (n_amb_host + 7) / 8 : 1);
     if (idx_bytes == 4)
         frag_expand_kernel<uint32_t><<<grid, 256, 0, st>>>(fs.sstart.as<uint64_t>(), fs.off.as<unsigned long long>(),
                                                            fs.slot0.as<unsigned long long>(), fs.whead.as<uint8_t>(),

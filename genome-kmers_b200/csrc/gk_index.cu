@@ -449,6 +449,8 @@ struct PackedPairs {
     cudaEvent_t e_producer = nullptr;   // recorded on the stream behind the producer of keys and fragments
     int start_bits = 32;
     unsigned long long *d_alpha = nullptr, *h_alpha = nullptr;   // alphabet counters still in flight (optional)
+    cudaEvent_t e_alpha = nullptr;      // ... on another stream: recorded behind the scan
+    SpectrumPending *spectrum = nullptr;   // optional: group-size spectrum of the final order, same synchronise
     const int *d_extra_err = nullptr;   // optional device int that must be zero at the end (partition look-back)
     // results
     uint64_t *keys_sorted = nullptr;
@@ -535,11 +537,15 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
         }
     }
     marks.fix1 = tm.mark();
+    if (pp.spectrum) GK_TRY(pp.spectrum->start(d_flags, n, st));
 
     // ---- the one synchronise: descents, repair status, fragment check, alphabet counters -----------------------
     int h_extra_err = 0;
     GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-    if (pp.d_alpha) GK_CUDA(cudaMemcpyAsync(pp.h_alpha, pp.d_alpha, 24, cudaMemcpyDeviceToHost, st));
+    if (pp.d_alpha) {
+        if (pp.e_alpha) GK_CUDA(cudaStreamWaitEvent(st, pp.e_alpha, 0));
+        GK_CUDA(cudaMemcpyAsync(pp.h_alpha, pp.d_alpha, 24, cudaMemcpyDeviceToHost, st));
+    }
     if (pp.d_extra_err) GK_CUDA(cudaMemcpyAsync(&h_extra_err, pp.d_extra_err, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     if (h_extra_err) {
@@ -601,6 +607,10 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
         marks.fix1 = tm.mark();
         marks.refine_flags |= 2u;
     }
+    if (pp.spectrum && (status || (marks.refine_flags & 2u))) {   // the order changed after the first spectrum
+        GK_TRY(pp.spectrum->start(d_flags, n, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+    }
     return GK_OK;
 }
 
@@ -611,10 +621,13 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
 // instead of every window of the byte array.
 static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int class_bit, uint64_t n,
                        Owned &out_idx, Owned &out_flags, StageMarks &marks, EventTimer &tm, cudaStream_t st,
-                       unsigned long long *d_alpha, unsigned long long *h_alpha, const void *d_list = nullptr)
+                       unsigned long long *d_alpha, unsigned long long *h_alpha, const void *d_list = nullptr,
+                       SpectrumPending *spectrum = nullptr, cudaEvent_t e_alpha = nullptr)
 {
     const int ib = ix->idx_bytes;
     PackedPairs pp;
+    pp.spectrum = spectrum;
+    pp.e_alpha = e_alpha;
     pp.n = n;
     pp.key_len = key_len;
     pp.class_bit = class_bit;
@@ -666,7 +679,9 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
     } else {
         // (more digit positions than the pack kernel has counters for -- plain LSD over a long key on a small
         // input: the sort counts its digits itself)
-        const bool count_digits = (pp.key_bits - begin_bit + 7) / 8 <= pack_hist_passes_max();
+        const char *nohist = getenv("GK_PACK_NOHIST");   // (tuning: what do the pack kernel's histograms cost?)
+        const bool count_digits = (pp.key_bits - begin_bit + 7) / 8 <= pack_hist_passes_max() &&
+                                  !(nohist && nohist[0] == '1');
         GK_TRY(pack_keys_device(ix->d_sba, ix->sba_len, (const uint64_t *)ix->d_segs.ptr,
                                 (uint32_t)ix->h_segs.size(), valid_len, key_len, class_bit, 0, ix->sba_len, 0,
                                 pp.keys_a, ib, out_idx.ptr, pp.d_counters, begin_bit, pp.key_bits,
@@ -946,9 +961,18 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     DeviceBuffer alpha;
     unsigned long long h_alpha[3] = {0, 0, 0};
     const bool alpha_async = one_word && !ix->alphabet_known;
+    ScopedEvent e_alpha0, e_alpha1;
     if (alpha_async) {
+        // on the second stream, beside the pack kernel and the radix passes
+        cudaStream_t side = nullptr;
+        GK_TRY(side_stream(&side));
         GK_TRY(alpha.alloc(24, st));
-        GK_TRY(scan_alphabet_async(ix->d_sba, ix->sba_len, alpha.as<unsigned long long>(), st));
+        GK_TRY(e_alpha0.create());
+        GK_TRY(e_alpha1.create());
+        GK_CUDA(cudaEventRecord(e_alpha0.ev, st));
+        GK_CUDA(cudaStreamWaitEvent(side, e_alpha0.ev, 0));
+        GK_TRY(scan_alphabet_async(ix->d_sba, ix->sba_len, alpha.as<unsigned long long>(), side));
+        GK_CUDA(cudaEventRecord(e_alpha1.ev, side));
     } else {
         GK_TRY(ensure_alphabet(ix, st));
     }
@@ -981,6 +1005,9 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     Owned new_idx, new_flags;
     bool new_mark_amb = false;
     int t_ref0 = -1, t_ref1 = -1;
+    // the group-size spectrum of the new order rides along with the sort's own synchronise
+    SpectrumPending spectrum;
+    SpectrumPending *spec = spectrum_enabled() ? &spectrum : nullptr;
     if (n_sort == 0) {
         // nothing to sort
     } else if (one_word) {
@@ -988,11 +1015,11 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         new_mark_amb = fixed;
         GK_TRY(sort_level1(ix, k, key_len, 1, n_sort, new_idx, new_flags, marks, tm, st,
                            alpha_async ? alpha.as<unsigned long long>() : nullptr, h_alpha,
-                           subset ? user_list.ptr : nullptr));
+                           subset ? user_list.ptr : nullptr, spec, alpha_async ? e_alpha1.ev : nullptr));
     } else if (fixed && k == 32 && ix->n_amb_letters == 0 && ix->n_bad == 0) {
         new_mark_amb = true;
         GK_TRY(sort_level1(ix, k, k, 0, n_sort, new_idx, new_flags, marks, tm, st, nullptr, nullptr,
-                           subset ? user_list.ptr : nullptr));
+                           subset ? user_list.ptr : nullptr, spec));
     } else {
         // Longer than one key word -- fixed k > 32, max_kmer_len > 31, or None (suffix order inside each
         // record).  Sort EVERY start of every record by its first 31 symbols, terminator-aware, so that
@@ -1028,9 +1055,8 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
         }
     }
     const int t1 = tm.mark();
-    // the group-size spectrum of the new order rides along with the final synchronise
-    SpectrumPending spectrum;
-    if (n_sort > 0 && spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_sort, st));
+    if (n_sort > 0 && spec && !spectrum.armed)   // (the multi-level path: its flags are final only now)
+        GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_sort, st));
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
@@ -1125,6 +1151,8 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     DeviceBuffer counters, frag_mem, frag_off;
     FragSorted fs;
     PackedPairs pp;
+    SpectrumPending spectrum;
+    if (spectrum_enabled()) pp.spectrum = &spectrum;
     if (n_local) {
         GK_TRY(new_idx.alloc((size_t)n_local * ib, st));
         GK_TRY(new_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
@@ -1175,8 +1203,6 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         GK_TRY(sort_packed_pairs(ix, pp, (uint8_t *)new_flags.ptr, marks, tm, st));
     }
     const int t1 = tm.mark();
-    SpectrumPending spectrum;
-    if (n_local > 0 && spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_local, st));
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
