@@ -21,6 +21,8 @@
 //
 // pack4_words_kernel / rank4_stream_kernel: terminator-aware 4-bit rank words for an arbitrary list of
 // starts (the refinement keys).
+#include <stdlib.h>
+
 #include "gk_common.cuh"
 
 namespace gk {
@@ -32,6 +34,34 @@ constexpr int kPackChunks = kPackTile / 16 + 2;           // 16-byte chunks stag
 constexpr int kPackHistPasses = 5;                        // digit positions counted on the fly (see pack_hist_passes_max)
 constexpr int kPackKeyRow = kPackThreads + 1;             // padded row of the key staging buffer (bank-conflict free)
 
+// ---- TMA bulk copy of the byte tile (cp.async.bulk + mbarrier, sm_90+/sm_100a) --------------------------------
+// A persistent CTA knows its next tile, so one thread asks the copy engine for the next 4128 bytes while the
+// CTA still works on the current tile; the bytes land in the other half of a double buffer and an mbarrier
+// counts them in.  The threads then read their 16-byte chunk from shared memory instead of global memory.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_global, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
 template <typename IdxT, int HP>
 __global__ void __launch_bounds__(kPackThreads)
 pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
@@ -40,9 +70,10 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                  uint64_t out_base, uint64_t *__restrict__ keys_out, IdxT *__restrict__ idx_out,
                  unsigned long long *__restrict__ n_amb_out, uint64_t n_tiles, int hist_begin_bit,
                  int hist_end_bit, unsigned long long *__restrict__ g_hist /* [passes][256] or null */,
-                 const FragOut frag /* frag.key == nullptr: no fragment list */)
+                 const FragOut frag /* frag.key == nullptr: no fragment list */, int use_bulk)
 {
-    __shared__ __align__(16) uint8_t s_bytes[kPackChunks * 16];
+    __shared__ __align__(128) uint8_t s_bytes2[2][kPackChunks * 16];   // double buffer of the staged bytes
+    __shared__ __align__(8) uint64_t s_mbar[2];
     __shared__ uint32_t s_codes[kPackChunks];
     __shared__ __align__(4) uint16_t s_amb[kPackChunks + 2];
     __shared__ __align__(4) uint16_t s_sep[kPackChunks + 2];
@@ -55,24 +86,56 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
     __shared__ uint32_t s_hist[kPackHistPasses][256];
     // keys of a whole tile, written by the thread that cuts 16 CONSECUTIVE windows out of three code words and
     // read back position by position for coalesced stores: s_keys[j * kPackKeyRow + t] = key of position 16 t + j
-    __shared__ uint64_t s_keys[kPackPerThread * kPackKeyRow];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);   // kPackPerThread * kPackKeyRow entries
 
     const uint32_t t = threadIdx.x;
     const int hist_passes = g_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
     if (g_hist)
         for (int i = t; i < kPackHistPasses * 256; i += kPackThreads) (&s_hist[0][0])[i] = 0;
     uint32_t n_amb = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(sba) & 15u) == 0;
+    const uint64_t tile_first = first_start / kPackTile;
+    // a tile whose staged range lies inside the array can come through the copy engine
+    auto bulk_ok = [&](uint64_t tile_) -> bool {
+        return use_bulk && aligned && tile_ < n_tiles &&
+               (tile_first + tile_) * (uint64_t)kPackTile + (uint64_t)kPackChunks * 16 <= sba_len;
+    };
+    if (use_bulk) {
+        if (t == 0) {
+            mbar_init(&s_mbar[0], 1);
+            mbar_init(&s_mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0 && bulk_ok(blockIdx.x))
+            bulk_load(s_bytes2[0], sba + (tile_first + blockIdx.x) * (uint64_t)kPackTile, kPackChunks * 16, &s_mbar[0]);
+    }
+    uint32_t iter = 0, phase_bits = 0;   // bit b of phase_bits: parity the next wait on buffer b expects
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
     // tiles are aligned to the byte array, not to first_start, so 128-bit loads stay aligned
-    const uint64_t tile0 = (first_start / kPackTile + tile) * (uint64_t)kPackTile;
+    const uint64_t tile0 = (tile_first + tile) * (uint64_t)kPackTile;
     uint32_t any_amb = 0;
+    const uint32_t buf = iter & 1u;
+    uint8_t *s_bytes = s_bytes2[buf];
+    const bool from_bulk = bulk_ok(tile);
+    // the other buffer was last read one iteration ago (every thread has passed that iteration's barriers)
+    if (t == 0 && bulk_ok(tile + gridDim.x))
+        bulk_load(s_bytes2[buf ^ 1u], sba + (tile0 + (uint64_t)gridDim.x * kPackTile), kPackChunks * 16,
+                  &s_mbar[buf ^ 1u]);
+    if (from_bulk) {
+        mbar_wait(&s_mbar[buf], (phase_bits >> buf) & 1u);
+        phase_bits ^= 1u << buf;
+    }
 
     // ---- stage bytes, convert to streams ----------------------------------------------------
-    const bool aligned = (reinterpret_cast<uintptr_t>(sba) & 15u) == 0;
     for (uint32_t c = t; c < kPackChunks; c += kPackThreads) {
         const uint64_t g = tile0 + 16ull * c;
         uint32_t w[4];
-        if (aligned && g + 16 <= sba_len) {
+        if (from_bulk) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(s_bytes + 16 * c);
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else if (aligned && g + 16 <= sba_len) {
             uint4 q = *reinterpret_cast<const uint4 *>(sba + g);
             w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
         } else {
@@ -88,7 +151,7 @@ pack_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len,
                 w[i] = x;
             }
         }
-        *reinterpret_cast<uint4 *>(s_bytes + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (!from_bulk) *reinterpret_cast<uint4 *>(s_bytes + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
         // four bytes at a time (the kernel is bound by integer issue, not by memory)
         uint32_t codes = 0, amb = 0, sep = 0;
 #pragma unroll
@@ -493,10 +556,18 @@ int pack_keys_device(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *d_s
     if (grid > n_tiles) grid = n_tiles;
     const int hp = d_hist ? (hist_end_bit - hist_begin_bit + 7) / 8 : 0;
     const FragOut fr = frag ? *frag : FragOut();
+    constexpr int kDynSmem = kPackPerThread * kPackKeyRow * 8;
+    const char *tma = getenv("GK_PACK_TMA");
+    const int use_bulk = (tma && tma[0] == '0') ? 0 : 1;
 #define GK_PACK_LAUNCH(IDX, HPV)                                                                       \
-    pack_keys_kernel<IDX, HPV><<<(unsigned)grid, kPackThreads, 0, st>>>(                               \
-        d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start, end_start,   \
-        out_base, d_keys_out, (IDX *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit, hist_end_bit, d_hist, fr)
+    do {                                                                                               \
+        GK_CUDA(cudaFuncSetAttribute(pack_keys_kernel<IDX, HPV>,                                       \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));          \
+        pack_keys_kernel<IDX, HPV><<<(unsigned)grid, kPackThreads, kDynSmem, st>>>(                    \
+            d_sba, sba_len, d_seg_starts, n_seg, valid_len, key_len, class_bit, first_start,           \
+            end_start, out_base, d_keys_out, (IDX *)d_idx_out, d_n_amb, n_tiles, hist_begin_bit,       \
+            hist_end_bit, d_hist, fr, use_bulk);                                                       \
+    } while (0)
     if (idx_bytes == 4) {
         if (hp == 0) GK_PACK_LAUNCH(uint32_t, 0);
         else if (hp == 4) GK_PACK_LAUNCH(uint32_t, 4);
