@@ -95,6 +95,8 @@ int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, ui
                         cudaStream_t);
 int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, const uint64_t *,
                          uint32_t, uint64_t, uint64_t *, cudaStream_t);
+int pair_keys_words_device(const uint32_t *, const uint32_t *, uint64_t, const uint8_t *, uint64_t, uint64_t, uint32_t,
+                           uint64_t *, cudaStream_t);
 int subset_rank_update_device(const uint32_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *,
                               cudaStream_t);
 int gather_u32_device(const uint32_t *, const uint32_t *, uint64_t, uint32_t *, cudaStream_t);
@@ -707,8 +709,10 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
 // half (the window ended) sorts first.  Only the O(n) set-up touches every k-mer: rank_h of every start
 // (= sorted position of the first member of its group) and the list of members of multi-element groups.
 // The rounds then work on that shrinking list only and scatter their results into the global order.
+// by_words (a multi-GPU shard: the index holds one key range, so the rank of start + h is not known here): the
+// second half of the pair is the next 8 symbols read from the bytes, h -> h + 8 per round, no rank table.
 static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint64_t n_cur, uint64_t h0,
-                           uint64_t target, int *levels, cudaStream_t st)
+                           uint64_t target, int *levels, cudaStream_t st, bool by_words = false)
 {
     if (h0 >= target || n_cur < 2) return GK_OK;
     uint32_t *d_idx = (uint32_t *)cur_idx.ptr;
@@ -724,7 +728,7 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
     GK_TRY(select_flagged(mflags.as<uint8_t>(), n_cur, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr,
                           &m, st));
     if (m == 0) return GK_OK;
-    GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
+    if (!by_words) GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
     GK_TRY(gid.alloc((size_t)n_cur * 4, st));
     GK_TRY(head_positions_device(d_flags, d_idx, n_cur, gid.as<uint32_t>(), rank.as<uint32_t>(), st));
     DeviceBuffer slots, sub_idx, sub_gid;
@@ -739,15 +743,20 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
     mflags.release();
     uint64_t h = h0;
     while (h < target && m > 0) {
-        const uint64_t h2 = (2 * h < target) ? 2 * h : target;
+        const uint64_t step = by_words ? 8 : h;
+        const uint64_t h2 = (h + step < target) ? h + step : target;
         const uint32_t delta = (uint32_t)(h2 - h);
         DeviceBuffer keys, keys_alt, idx_alt, hf, gsub, gslot, mf;
         GK_TRY(keys.alloc((size_t)m * 8, st));
         GK_TRY(keys_alt.alloc((size_t)m * 8, st));
         GK_TRY(idx_alt.alloc((size_t)m * 4, st));
-        GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, rank.as<uint32_t>(), delta,
-                                    (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->sba_len,
-                                    keys.as<uint64_t>(), st));
+        if (by_words)
+            GK_TRY(pair_keys_words_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, ix->d_sba, ix->sba_len, h,
+                                          delta, keys.as<uint64_t>(), st));
+        else
+            GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, rank.as<uint32_t>(), delta,
+                                        (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->sba_len,
+                                        keys.as<uint64_t>(), st));
         int in_alt = 0;
         GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr, idx_alt.ptr, 4, m,
                                        0, 64, &in_alt, st, nullptr));
@@ -1120,11 +1129,20 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         return GK_ERR_ARG;
     }
     const uint32_t k = ix->min_len;
-    if (!(ix->max_len == ix->min_len && (k <= 31 || (k == 32 && !class_bit)))) {
-        set_error("gk_index_sort_shard: only single-word k-mers (k <= 31, or 32 without ambiguous bases)");
+    if (ix->max_len != ix->min_len) {
+        set_error("gk_index_sort_shard: fixed-length k-mers only");
         return GK_ERR_UNSUPPORTED;
     }
-    const int full_bits = 2 * (int)k + (class_bit ? 2 : 0);
+    // k-mers longer than one key word: the pairs carry the first 31 symbols (gk_pack_slice), the rest is compared
+    // from the bytes in word rounds after the sort
+    const bool long_k = k > 31 && !(k == 32 && !class_bit);
+    if (long_k && (!class_bit || ix->idx_bytes != 4)) {
+        set_error("gk_index_sort_shard: k-mers longer than one key word need class-bit keys and 32-bit start "
+                  "indices (a byte array below 2^32 positions)");
+        return GK_ERR_UNSUPPORTED;
+    }
+    const uint32_t key_len = long_k ? 31u : k;
+    const int full_bits = 2 * (int)key_len + (class_bit ? 2 : 0);
     if (key_bits <= 0 || key_bits > full_bits) key_bits = full_bits;
     const bool with_frag = d_frag_gathered != nullptr && class_bit && n_sources > 0 && frag_capacity > 0;
     if (!with_frag && n_ambiguous) {
@@ -1152,14 +1170,14 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     FragSorted fs;
     PackedPairs pp;
     SpectrumPending spectrum;
-    if (spectrum_enabled()) pp.spectrum = &spectrum;
+    if (spectrum_enabled() && !long_k) pp.spectrum = &spectrum;
     if (n_local) {
         GK_TRY(new_idx.alloc((size_t)n_local * ib, st));
         GK_TRY(new_flags.alloc((size_t)((n_local + 15) & ~15ull), st));
         GK_TRY(counters.alloc(kCounterBytes, st));
         GK_CUDA(cudaMemsetAsync(counters.ptr, 0, (size_t)kCounterWords * 8, st));
         pp.n = n_local;
-        pp.key_len = k;
+        pp.key_len = key_len;
         pp.key_bits = key_bits;
         pp.class_bit = class_bit;
         pp.keys_a = d_keys; pp.keys_b = d_keys_alt;
@@ -1202,6 +1220,14 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         pp.e_producer = e_ready.ev;
         GK_TRY(sort_packed_pairs(ix, pp, (uint8_t *)new_flags.ptr, marks, tm, st));
     }
+    int levels = 1;
+    int t_ref0 = -1, t_ref1 = -1;
+    if (long_k && n_local) {
+        t_ref0 = tm.mark();
+        GK_TRY(doubling_rounds(ix, new_idx, new_flags, n_local, key_len, k, &levels, st, /*by_words=*/true));
+        t_ref1 = tm.mark();
+        if (spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_local, st));
+    }
     const int t1 = tm.mark();
     int h_sort_err = 0;
     GK_CUDA(cudaMemcpyAsync(&h_sort_err, sort_err.ptr, 4, cudaMemcpyDeviceToHost, st));
@@ -1230,9 +1256,9 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     stats.hist_ms = marks.main_sort.hist_ms;
     stats.sort_ms = marks.main_sort.passes_ms;
     stats.sort_passes = marks.main_sort.passes;
-    stats.fixup_ms = tm.ms(marks.fix0, marks.fix1);
+    stats.fixup_ms = tm.ms(marks.fix0, marks.fix1) + tm.ms(t_ref0, t_ref1);
     stats.key_bits = key_bits;
-    stats.levels = 1;
+    stats.levels = levels;
     stats.n_windows = n_local;
     stats.n_ambiguous = marks.n_amb;
     stats.n_fragments = marks.n_frag;

@@ -662,8 +662,8 @@ check_starts_kernel(const IdxT *__restrict__ idx, uint64_t n, const uint64_t *__
 // init_indices_kernel, its key from the same definition as pack_keys_kernel.
 __global__ void __launch_bounds__(256)
 sample_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const uint64_t *__restrict__ seg_starts,
-                   uint32_t n_seg, uint32_t k, int class_bit, uint64_t base, uint64_t n_slice, uint32_t n_samples,
-                   uint64_t *__restrict__ keys_out)
+                   uint32_t n_seg, uint32_t k, uint32_t key_len, int class_bit, uint64_t base, uint64_t n_slice,
+                   uint32_t n_samples, uint64_t *__restrict__ keys_out)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_samples) return;
@@ -676,12 +676,12 @@ sample_keys_kernel(const uint8_t *__restrict__ sba, uint64_t sba_len, const uint
     const uint64_t s = p + (uint64_t)(lo - 1) * k;
     uint64_t value = 0;
     bool pure = true;
-    for (uint32_t i = 0; i < k; ++i) {
+    for (uint32_t i = 0; i < key_len; ++i) {
         const uint32_t b = (s + i < sba_len) ? sba[s + i] : kSep;
         if (is_acgt(b)) {
             value = (value << 2) | code2(b);
         } else {
-            const uint32_t rem = 2u * (k - i);
+            const uint32_t rem = 2u * (key_len - i);
             value = ((rem >= 64) ? 0ull : (value << rem)) + ((uint64_t)acgt_below(b) << (rem - 2));
             pure = false;
             break;
@@ -836,7 +836,9 @@ extern "C" int gk_pack_slice(const uint8_t *d_sba, uint64_t sba_len, const uint6
         frag.counter = reinterpret_cast<unsigned long long *>(d_counters) + 2;
         frag.capacity = frag_capacity;
     }
-    GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, kmer_len, kmer_len, class_bit, first_start,
+    // k-mers longer than one key word: the key covers the first 31 symbols, the windows are still kmer_len long
+    const uint32_t key_len = (class_bit && kmer_len > 31) ? 31u : kmer_len;
+    GK_TRY(pack_keys_device(d_sba, sba_len, segs.as<uint64_t>(), n_seg, kmer_len, key_len, class_bit, first_start,
                             end_start, base, d_keys_out, idx_bytes, d_idx_out,
                             reinterpret_cast<unsigned long long *>(d_counters), 0, 0, nullptr, st,
                             frag.key ? &frag : nullptr));
@@ -850,11 +852,11 @@ extern "C" int gk_sample_keys(const uint8_t *d_sba, uint64_t sba_len, const uint
                               uint32_t kmer_len, int class_bit, uint64_t first_start, uint64_t end_start,
                               uint32_t n_samples, uint64_t *d_keys_out, uint32_t *h_n_out, void *stream)
 {
-    if (!d_sba || !h_seg_starts || !d_keys_out || n_seg == 0 || kmer_len < 1 || kmer_len > 32 ||
-        (class_bit && kmer_len > 31)) {
+    if (!d_sba || !h_seg_starts || !d_keys_out || n_seg == 0 || kmer_len < 1 || (!class_bit && kmer_len > 32)) {
         set_error("gk_sample_keys: bad argument");
         return GK_ERR_ARG;
     }
+    const uint32_t key_len = (class_bit && kmer_len > 31) ? 31u : kmer_len;   // as gk_pack_slice
     cudaStream_t st = as_stream(stream);
     if (end_start > sba_len) end_start = sba_len;
     const uint64_t base = windows_before(h_seg_starts, n_seg, sba_len, kmer_len, first_start);
@@ -867,7 +869,8 @@ extern "C" int gk_sample_keys(const uint8_t *d_sba, uint64_t sba_len, const uint
     GK_TRY(segs.alloc((size_t)n_seg * 8, st));
     GK_CUDA(cudaMemcpyAsync(segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
     sample_keys_kernel<<<(n_samples + 255) / 256, 256, 0, st>>>(d_sba, sba_len, segs.as<uint64_t>(), n_seg, kmer_len,
-                                                                class_bit, base, n_slice, n_samples, d_keys_out);
+                                                                key_len, class_bit, base, n_slice, n_samples,
+                                                                d_keys_out);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

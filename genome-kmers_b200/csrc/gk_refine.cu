@@ -209,6 +209,27 @@ pair_keys_var_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__res
     }
 }
 
+// Word rounds (multi-GPU shards: the ranks of other starts live on other GPUs): the second half of the pair
+// is read from the bytes instead -- the 4-bit ranks of the `span` <= 8 symbols from start + h on, most
+// significant first; a '$' / the end of the array ends the k-mer (all later symbols 0, kmers.py:360-378).
+__global__ void __launch_bounds__(256)
+pair_keys_words_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__restrict__ sub_gid, uint64_t m,
+                       const uint8_t *__restrict__ sba, uint64_t sba_len, uint64_t h, uint32_t span,
+                       uint64_t *__restrict__ keys)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const uint64_t q = (uint64_t)sub_idx[r] + h;
+        uint32_t second = 0;
+        for (uint32_t j = 0; j < span; ++j) {
+            const uint32_t code = (q + j < sba_len) ? rank4(sba[q + j]) : 0u;
+            if (code == 0) break;
+            second |= code << (4u * (7u - j));
+        }
+        keys[r] = ((uint64_t)sub_gid[r] << 32) | second;
+    }
+}
+
 // the re-sorted subset goes back to its slots with fresh head flags
 __global__ void __launch_bounds__(256)
 key2_scatter_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ sub_idx_sorted,
@@ -409,7 +430,7 @@ subset_rank_update_kernel(const uint32_t *__restrict__ slots, const uint32_t *__
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
         const uint32_t g = slots[gid_sub[r]];
         gid_slot[r] = g;
-        rank_of_start[idx_sorted[r]] = g;
+        if (rank_of_start) rank_of_start[idx_sorted[r]] = g;
     }
 }
 
@@ -567,6 +588,15 @@ int pair_keys_var_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, u
     if (m == 0) return GK_OK;
     pair_keys_var_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_rank_of_start, delta,
                                                       d_seg_starts, n_seg, sba_len, d_keys);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int pair_keys_words_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, uint64_t m, const uint8_t *d_sba,
+                           uint64_t sba_len, uint64_t h, uint32_t span, uint64_t *d_keys, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    pair_keys_words_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_sba, sba_len, h, span, d_keys);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -204,6 +204,20 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d)
     return peers;
 }
 
+#ifdef GK_PROBE
+// Tuning aid (tools/probe_onesweep.py builds a second library with -DGK_PROBE): cycles thread 0 of every tile
+// spends in each phase, and how far bin 0's look-back walks / how often it finds a status word unpublished.
+__device__ unsigned long long g_probe[16];
+#define GK_PROBE_MARK(i)                                                            \
+    if (t == 0) {                                                                   \
+        const long long probe_now = clock64();                                      \
+        atomicAdd(&g_probe[i], (unsigned long long)(probe_now - probe_t0));         \
+        probe_t0 = probe_now;                                                       \
+    }
+#else
+#define GK_PROBE_MARK(i)
+#endif
+
 // One pass.  Phases (profiles/r01_onesweep.md explains the choices):
 //   A  claim a tile, load its pairs, count digits per warp with shared-memory atomics
 //   B  bin threads: per-warp exclusive offsets, tile totals -> publish the tile-local counts EARLY
@@ -236,6 +250,9 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
     const uint32_t lane = t & 31u, warp = t >> 5;
 
     // ---- A ------------------------------------------------------------------------------------------
+#ifdef GK_PROBE
+    long long probe_t0 = clock64();
+#endif
     if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
     for (int i = t; i < kWarps * kRadix; i += THREADS) (&s.warp_cnt[0][0])[i] = 0;
     if (PARTITION && t < n_split) s.splitters[t] = splitters[t];
@@ -287,6 +304,7 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
 #pragma unroll
     for (int j = 0; j < IPT; ++j) atomicAdd(&my_cnt[digit_of(key[j])], 1u);
     __syncthreads();
+    GK_PROBE_MARK(0)
 
     // ---- B ------------------------------------------------------------------------------------------
     uint32_t bin_count = 0;
@@ -321,6 +339,7 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
         for (int w = 0; w < kWarps; ++w) s.warp_cnt[w][t] += excl_in_tile;  // -> running tile positions
     }
     __syncthreads();
+    GK_PROBE_MARK(1)
 
     // ---- C ------------------------------------------------------------------------------------------
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -337,8 +356,12 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
         s.keys[pos] = key[j];
         s.vals[pos] = val[j];
     }
+    GK_PROBE_MARK(2)
 
     // ---- D ------------------------------------------------------------------------------------------
+#ifdef GK_PROBE
+    uint32_t probe_walk = 0, probe_spin = 0;
+#endif
     if (t < kRadix) {
         // a tile completes chip-wide every few dozen cycles while one L2 round trip takes hundreds, so
         // a one-at-a-time walk never catches up with the inclusive frontier: batch the status loads
@@ -357,11 +380,17 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                 uint32_t spins = 0;
                 while ((sv[u] >> ST::kShift) == 0) {
                     if (++spins > kLookbackSpinLimit) { failed = true; break; }
+#ifdef GK_PROBE
+                    ++probe_spin;
+#endif
                     __nanosleep(64);
                     sv[u] = load_status(status + (uint64_t)(tp - u) * kRadix + t);
                 }
                 if (failed) { done = true; break; }
                 excl += (uint64_t)(sv[u] & ST::kMask);
+#ifdef GK_PROBE
+                ++probe_walk;
+#endif
                 if ((sv[u] >> ST::kShift) == 2) done = true;
             }
             tp -= kLookbackBatch;
@@ -373,7 +402,17 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
         s.global_off[t] = off;
         s.global_off32[t] = (uint32_t)off;
     }
+    GK_PROBE_MARK(3)
     __syncthreads();
+    GK_PROBE_MARK(4)
+#ifdef GK_PROBE
+    if (t == 0) {
+        atomicAdd(&g_probe[8], (unsigned long long)probe_walk);
+        atomicAdd(&g_probe[9], (unsigned long long)probe_spin);
+        atomicAdd(&g_probe[10], 1ull);
+        atomicMax(&g_probe[11], (unsigned long long)probe_walk);
+    }
+#endif
 
     // ---- E ------------------------------------------------------------------------------------------
     // 32-bit offsets when every destination index fits (StatusT is 32-bit exactly when n < 2^30)
@@ -406,6 +445,7 @@ onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
             __stcs(keys_out + dst, k);
             __stcs(vals_out + dst, s.vals[p]);
         }
+        GK_PROBE_MARK(5)
     } else {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -1418,3 +1458,14 @@ extern "C" int gk_partition_count_split(const uint64_t *d_keys, uint64_t n, cons
     return partition_count_split_device(d_keys, n, d_splitters, n_parts, class_bit,
                                         reinterpret_cast<unsigned long long *>(d_counts_out), as_stream(stream));
 }
+
+#ifdef GK_PROBE
+// tools/probe_onesweep.py: read (and clear) the phase counters of onesweep_kernel
+extern "C" int gk_probe_read(unsigned long long *h16)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(h16, gk::g_probe, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    unsigned long long zero[16] = {};
+    return cudaMemcpyToSymbol(gk::g_probe, zero, sizeof(zero)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -587,12 +587,14 @@ class ShardedKmers:
         k, world, rank = self.k, self.world, self.rank
         self._marks = []
         self._mark("start")
-        if k > 31:
-            raise NotImplementedError("the multi-GPU path handles single-word k-mers (k <= 31)")
+        if k > 31 and self.idx_bytes != 4:
+            raise NotImplementedError("k-mers longer than one key word (k > 31) on the multi-GPU path need 32-bit "
+                                      "start indices (a byte array below 2^32 positions)")
         # every key carries the class bit, so nothing waits for the alphabet scan: its counters travel with the
-        # destination counts
+        # destination counts.  k > 31: the key covers the first 31 symbols (a key range still holds whole groups);
+        # the local sort compares the remaining symbols from the bytes (gk_index_sort_shard, word rounds)
         class_bit = 1
-        full_bits = 2 * k + 2
+        full_bits = 2 * min(k, 31) + 2
         first, end = slice_bounds(self.total_len, world, rank)
         # (16-byte aligned cut points, so that the scan keeps its 128-bit loads)
         a16 = (first // 16) * 16 if rank > 0 else 0

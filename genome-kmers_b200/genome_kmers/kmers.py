@@ -532,8 +532,8 @@ class Kmers:
     def _sort_sharded(self):
         from genome_kmers.distributed import ShardedKmers
 
-        if self.max_kmer_len != self.min_kmer_len or self.min_kmer_len > 31:
-            raise NotImplementedError("the multi-GPU path sorts fixed-length k-mers of one key word (k <= 31)")
+        if self.max_kmer_len != self.min_kmer_len:
+            raise NotImplementedError("the multi-GPU path sorts fixed-length k-mers (min_kmer_len == max_kmer_len)")
         if self._host_idx_dirty:
             raise NotImplementedError("assigned start indices cannot be sorted on the multi-GPU path")
         sc = self.seq_coll

@@ -201,7 +201,11 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream);
 int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx,
                         void *d_idx_alt, uint64_t n_local, int class_bit, gk_sort_stats *stats_out,
                         void *stream);
-/* The same with everything the sharded driver knows: key_bits = width of the received keys when they are
+/* k-mers longer than one key word (min_kmer_len > 31, class-bit keys, 32-bit starts): the pairs carry the first 31
+ * symbols; after the sort the members of groups that are still tied are ordered by the remaining symbols, read
+ * from the bytes eight at a time (the prefix doubling of gk_index_sort needs the ranks of other starts, which
+ * live on other GPUs).
+ * The same with everything the sharded driver knows: key_bits = width of the received keys when they are
  * relative to the start of this rank's key range (0: full width); d_frag_gathered: the all-gathered fragment
  * lists of all n_sources ranks (gk_pack_slice layout, frag_capacity entries each, d_frag_counts[s] used), from
  * which the n_ambiguous windows of the key range [key_lo, key_hi) (key_hi 0: unbounded) are generated behind
@@ -212,7 +216,8 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
                         const void *d_frag_gathered, const uint64_t *d_frag_counts, uint32_t n_sources,
                         uint64_t frag_capacity, uint64_t key_lo, uint64_t key_hi, const int *d_err,
                         gk_sort_stats *stats_out, void *stream);
-/* Multi-GPU producers (no synchronise).  gk_pack_slice: pack the windows whose start lies in
+/* Multi-GPU producers (no synchronise).  gk_pack_slice: pack the windows (kmer_len symbols; the key covers the
+ * first min(kmer_len, 31) of them when class_bit is set) whose start lies in
  * [first_start, end_start) and list the ambiguous-window fragments of that slice; d_frag: frag_capacity * 36
  * bytes laid out key[cap] w0[cap] w1[cap] start[cap] (u64) count[cap] (u32); d_counters: 4 x u64, zeroed by the
  * call: [0] ambiguous windows, [2] fragments found (above the capacity the list is incomplete).

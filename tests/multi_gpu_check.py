@@ -42,12 +42,21 @@ def main():
     world = dist.get_world_size()
     failures = []
     cases = [(31, 600_000, 6, 8, False), (21, 400_000, 3, 0, False), (12, 300_000, 2, 3, False),
-             (31, 500_000, 5, 6, True)]                      # last: 64-bit start indices (GK_FORCE_IDX64)
+             (31, 500_000, 5, 6, True),                      # 64-bit start indices (GK_FORCE_IDX64)
+             (40, 400_000, 4, 6, False), (64, 300_000, 3, 4, False), (33, 200_000, 2, 0, False)]   # k > one key word
     for k, n_bases, n_rec, runs, wide in cases:
         os.environ["GK_FORCE_IDX64"] = "1" if wide else "0"
         rng = np.random.default_rng(1000 + k)
         recs = gu.random_genome(rng, n_bases, n_rec, n_runs=runs, run_lo=50, run_hi=5000,
                                 n_scatter=20 if runs else 0)
+        if k > 31:
+            # copies of 35..400 symbols: k-mers that agree on the first 31 symbols (one key word) and differ
+            # later, or not at all
+            for _ in range(60):
+                seq = recs[int(rng.integers(0, len(recs)))][1]
+                ln = int(rng.integers(35, 400))
+                src, dst = (int(v) for v in rng.integers(0, len(seq) - ln, 2))
+                seq[dst:dst + ln] = seq[src:src + ln].copy()
         sba = np.concatenate([np.concatenate([seq, np.array([36], dtype=np.uint8)]) for _, seq in recs])[:-1]
         starts = np.cumsum([0] + [len(seq) + 1 for _, seq in recs[:-1]]).astype(np.uint64)
         both, both_starts = oracle.both_strands(sba, starts)

@@ -38,7 +38,8 @@ class NumpyEngine:
     def pack_slice(self, d_sba, seg_starts, k, class_bit, first, end, idx_bytes):
         raw = d_sba.numpy().tobytes()
         starts = self._slice_starts(d_sba, seg_starts, k, first, end)
-        keys = np.array([expected_key(raw[int(i):int(i) + k], class_bit) for i in starts], dtype=np.uint64)
+        kl = min(k, 31) if class_bit else k   # k > 31: the key covers the first 31 symbols
+        keys = np.array([expected_key(raw[int(i):int(i) + kl], class_bit) for i in starts], dtype=np.uint64)
         idx = starts.astype(np.uint32 if idx_bytes == 4 else np.uint64)
         n_amb = int((keys & np.uint64(1) == 0).sum()) if class_bit else 0
         return PackedSlice(torch.from_numpy(keys.view(np.int64).copy()),
@@ -50,7 +51,8 @@ class NumpyEngine:
         starts = self._slice_starts(d_sba, seg_starts, k, first, end)
         n = min(n_samples, len(starts))
         pick = [starts[(j * len(starts)) // n] for j in range(n)]
-        return np.array([expected_key(raw[int(i):int(i) + k], class_bit) for i in pick], dtype=np.uint64)
+        kl = min(k, 31) if class_bit else k
+        return np.array([expected_key(raw[int(i):int(i) + kl], class_bit) for i in pick], dtype=np.uint64)
 
     def splitters_to_device(self, splitters_host):
         return torch.from_numpy(np.ascontiguousarray(splitters_host).view(np.int64).copy())

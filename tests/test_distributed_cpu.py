@@ -65,7 +65,8 @@ def _worker(rank, world, port, strands, k, out_dir, kind="mixed"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,strands,k", [(2, "forward", 11), (2, "both", 21), (3, "both", 5)])
+@pytest.mark.parametrize("world,strands,k", [(2, "forward", 11), (2, "both", 21), (3, "both", 5),
+                                             (2, "both", 40)])      # 40: longer than one key word
 def test_sharded_sort_count_matches_oracle(tmp_path, world, strands, k):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, strands, k, str(tmp_path)), nprocs=world, join=True)

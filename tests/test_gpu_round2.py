@@ -316,3 +316,43 @@ def test_partition_to_destination_buffers_with_key_base_and_dropped_ambiguous_pa
     got_counts = d_counts.cpu().numpy()
     assert np.array_equal(got_counts[:4], np.bincount(dest[~amb], minlength=4))
     assert np.array_equal(got_counts[4:], np.bincount(dest[amb], minlength=4))
+
+
+@pytest.mark.parametrize("k,strands", [(33, "forward"), (40, "both"), (64, "both"), (100, "forward")])
+def test_shard_sort_of_kmers_longer_than_one_key_word(k, strands, tmp_path):
+    """gk_index_sort_shard with k > 31: the pairs carry the first 31 symbols, the rest is compared from the
+    bytes in word rounds (the doubling of the single-GPU path needs ranks that live on other GPUs).  One rank,
+    so the whole sharded path -- slice pack, staging partition, fragments, shard sort -- runs in this process."""
+    import torch.distributed as dist
+
+    from genome_kmers.distributed import ShardedKmers
+
+    rng = np.random.default_rng(k)
+    recs = gu.random_genome(rng, 300_000, 3, n_runs=5, run_lo=40, run_hi=3000, n_scatter=15)
+    for _ in range(80):   # copies: k-mers that agree on the first 31 symbols and differ later, or never
+        seq = recs[int(rng.integers(0, len(recs)))][1]
+        ln = int(rng.integers(33, 500))
+        src, dst = (int(v) for v in rng.integers(0, len(seq) - ln, 2))
+        seq[dst:dst + ln] = seq[src:src + ln].copy()
+    sba = np.concatenate([np.concatenate([seq, np.array([36], dtype=np.uint8)]) for _, seq in recs])[:-1]
+    starts = np.cumsum([0] + [len(seq) + 1 for _, seq in recs[:-1]]).astype(np.uint64)
+    full, full_starts = oracle.both_strands(sba, starts) if strands == "both" else (sba, starts)
+    want = oracle.sort_indices(full, oracle.init_indices(full_starts, len(full), k), k, k,
+                               threads=min(8, oracle.max_threads()))
+    hist_want, total_want = oracle.group_hist(full, want, k, max_bin=1000)
+    store = dist.FileStore(str(tmp_path / "store"), 1)
+    dist.init_process_group("gloo", store=store, rank=0, world_size=1)
+    try:
+        sk = ShardedKmers(sba, starts, k, strands)
+        sk.sort()
+        hist, total = sk.get_kmer_group_counts(k, max_counts_bin=1000)
+        got = sk.local_start_indices()
+        ver = sk.verify(hist, len(want))
+        levels = sk.stats["levels"]
+        sk.close()
+    finally:
+        dist.destroy_process_group()
+    assert np.array_equal(got.astype(np.uint64), want)
+    assert total == total_want and np.array_equal(hist, hist_want)
+    assert all(ver["checks"].values()), ver
+    assert levels > 1, "no word round ran: the input has no k-mers tied on 31 symbols?"
