@@ -170,11 +170,12 @@ frag_expand_kernel(const uint64_t *__restrict__ sstart, const unsigned long long
 
 // Order F fragments by (key, w0, w1, start); stable LSD, least significant word first.  Only small sorts:
 // no synchronise (the look-back error word of larger lists is the caller's deferred one).
-int frag_sort_device(const FragOut &frag, uint64_t F, uint32_t key_len, int key_bits, int start_bits,
-                     FragSorted &out, cudaStream_t st)
+// with_key = false: by (w0, w1, start) only.  That is the same order -- the words hold the window's symbols in
+// raw byte order and the radix key is a monotone function of the window -- and saves the key's digit passes.
+static int frag_sort_perm(const FragOut &frag, uint64_t F, uint32_t key_len, int key_bits, int start_bits,
+                          bool with_key, FragSorted &out, cudaStream_t st, uint32_t **perm_out,
+                          const uint64_t **last_word_out)
 {
-    out.F = F;
-    if (F == 0) return GK_OK;
     GK_TRY(out.reserve(F, st));
     const int grid = frag_grid(F);
     frag_iota_kernel<<<grid, 256, 0, st>>>(out.perm_a.as<uint32_t>(), F);
@@ -195,15 +196,154 @@ int frag_sort_device(const FragOut &frag, uint64_t F, uint32_t key_len, int key_
     GK_TRY(sort_word(frag.start, 0, start_bits));
     if (key_len > 16) GK_TRY(sort_word(frag.w1, 64 - 4 * ((int)key_len - 16), 64));
     GK_TRY(sort_word(frag.w0, 64 - 4 * ((int)key_len < 16 ? (int)key_len : 16), 64));
-    GK_TRY(sort_word(frag.key, 0, key_bits));
-    out.skey = sorted_word;
-    frag_finish_kernel<<<grid, 256, 0, st>>>(out.skey, frag.w0, frag.w1, frag.start, frag.count, cur, F,
-                                             out.sstart.as<uint64_t>(), out.off.as<unsigned long long>(),
-                                             out.whead.as<uint8_t>());
+    if (with_key) GK_TRY(sort_word(frag.key, 0, key_bits));
+    *perm_out = cur;
+    *last_word_out = sorted_word;
+    return GK_OK;
+}
+
+int frag_sort_device(const FragOut &frag, uint64_t F, uint32_t key_len, int key_bits, int start_bits,
+                     FragSorted &out, cudaStream_t st)
+{
+    out.F = F;
+    if (F == 0) return GK_OK;
+    uint32_t *perm = nullptr;
+    const uint64_t *sorted_key = nullptr;
+    GK_TRY(frag_sort_perm(frag, F, key_len, key_bits, start_bits, true, out, st, &perm, &sorted_key));
+    out.skey = sorted_key;
+    frag_finish_kernel<<<frag_grid(F), 256, 0, st>>>(out.skey, frag.w0, frag.w1, frag.start, frag.count, perm, F,
+                                                     out.sstart.as<uint64_t>(), out.off.as<unsigned long long>(),
+                                                     out.whead.as<uint8_t>());
     GK_LAUNCH_CHECK();
     frag_scan_kernel<<<1, 1024, 0, st>>>(out.off.as<unsigned long long>(), F);
     GK_LAUNCH_CHECK();
     return GK_OK;
+}
+
+// ---- multi-GPU: fragments are sorted where they are listed, and merged where they are used -----------------
+// A rank sorts the fragment list of its slice (a few ten thousand entries, beside the exchange); the owner of a
+// key range then MERGES the sorted lists of all ranks instead of sorting their union: the position of a
+// fragment is its index in its own list plus, for every other list, the number of fragments that go before it
+// (one binary search each).  Lists of lower ranks hold lower starts, so equal windows order by rank.
+__global__ void __launch_bounds__(256)
+frag_permute_kernel(FragOut in, const uint32_t *__restrict__ perm, uint64_t F, FragOut out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < F; q += stride) {
+        const uint32_t f = perm[q];
+        out.key[q] = in.key[f];
+        out.w0[q] = in.w0[f];
+        out.w1[q] = in.w1[f];
+        out.start[q] = in.start[f];
+        out.count[q] = in.count[f];
+    }
+}
+
+int frag_sort_copy_device(const FragOut &in, uint64_t F, uint32_t key_len, int start_bits, const FragOut &out,
+                          cudaStream_t st)
+{
+    if (F == 0) return GK_OK;
+    FragSorted scratch;
+    uint32_t *perm = nullptr;
+    const uint64_t *unused = nullptr;
+    GK_TRY(frag_sort_perm(in, F, key_len, 0, start_bits, false, scratch, st, &perm, &unused));
+    frag_permute_kernel<<<frag_grid(F), 256, 0, st>>>(in, perm, F, out);
+    GK_LAUNCH_CHECK();
+    return GK_OK;   // (scratch is released in stream order)
+}
+
+struct FragList {   // one rank's list inside the gathered buffer
+    const uint64_t *key, *w0, *w1, *start;
+    const uint32_t *count;
+};
+__device__ __forceinline__ FragList frag_list_of(const unsigned char *gathered, uint32_t src, uint64_t cap)
+{
+    const uint64_t *b = reinterpret_cast<const uint64_t *>(gathered + (size_t)src * cap * 36);
+    FragList l;
+    l.key = b; l.w0 = b + cap; l.w1 = b + 2 * cap; l.start = b + 3 * cap;
+    l.count = reinterpret_cast<const uint32_t *>(b + 4 * cap);
+    return l;
+}
+
+// range[2 s], range[2 s + 1]: the fragments of list s whose key lies in [key_lo, key_hi) -- contiguous, because
+// the key is monotone along a sorted list; *n_frag = their number over all lists.  One warp.
+__global__ void frag_ranges_kernel(const unsigned char *__restrict__ gathered,
+                                   const unsigned long long *__restrict__ counts, uint32_t world, uint64_t cap,
+                                   uint64_t key_lo, uint64_t key_hi, unsigned long long *__restrict__ range,
+                                   unsigned long long *__restrict__ n_frag)
+{
+    const uint32_t s = threadIdx.x;
+    unsigned long long len = 0;
+    if (s < world) {
+        const FragList l = frag_list_of(gathered, s, cap);
+        const uint64_t n_s = counts[s] < cap ? counts[s] : cap;
+        const uint64_t a = lower_bound_u64(l.key, n_s, key_lo);
+        const uint64_t b = key_hi ? lower_bound_u64(l.key, n_s, key_hi) : n_s;
+        range[2 * s] = a;
+        range[2 * s + 1] = b;
+        len = b - a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+    if (s == 0) *n_frag = len;
+}
+
+// fragments of [lo, hi) of list l that go before the words (x0, x1); with `or_equal` equal words count too
+__device__ __forceinline__ uint64_t frag_words_before(const FragList &l, uint64_t lo, uint64_t hi, uint64_t x0,
+                                                      uint64_t x1, bool or_equal)
+{
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const uint64_t m0 = l.w0[mid];
+        bool before = m0 < x0;
+        if (m0 == x0) {
+            const uint64_t m1 = l.w1[mid];
+            before = or_equal ? (m1 <= x1) : (m1 < x1);
+        }
+        if (before) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+frag_merge_kernel(const unsigned char *__restrict__ gathered, uint32_t world, uint64_t cap,
+                  const unsigned long long *__restrict__ range, uint64_t key_lo, uint64_t out_cap,
+                  uint64_t *__restrict__ skey, uint64_t *__restrict__ w0m, uint64_t *__restrict__ w1m,
+                  uint64_t *__restrict__ sstart, uint32_t *__restrict__ count)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total = (uint64_t)world * cap;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t src = (uint32_t)(t / cap);
+        const uint64_t j = t - (uint64_t)src * cap;
+        if (j < range[2 * src] || j >= range[2 * src + 1]) continue;
+        const FragList mine = frag_list_of(gathered, src, cap);
+        const uint64_t x0 = mine.w0[j], x1 = mine.w1[j];
+        uint64_t pos = j - range[2 * src];
+        for (uint32_t o = 0; o < world; ++o) {
+            if (o == src) continue;
+            const uint64_t a = range[2 * o], b = range[2 * o + 1];
+            if (a == b) continue;
+            pos += frag_words_before(frag_list_of(gathered, o, cap), a, b, x0, x1, o < src) - a;
+        }
+        if (pos < out_cap) {
+            skey[pos] = mine.key[j] - key_lo;
+            w0m[pos] = x0;
+            w1m[pos] = x1;
+            sstart[pos] = mine.start[j];
+            count[pos] = mine.count[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+frag_word_heads_kernel(const uint64_t *__restrict__ w0m, const uint64_t *__restrict__ w1m,
+                       const unsigned long long *__restrict__ n_frag, uint64_t cap, uint8_t *__restrict__ whead)
+{
+    const uint64_t F = *n_frag < cap ? *n_frag : cap;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < F; q += stride)
+        whead[q] = (q == 0 || w0m[q] != w0m[q - 1] || w1m[q] != w1m[q - 1]) ? 1 : 0;
 }
 
 // Write the fragments into the ambiguous slots of the sorted order.  keys_sorted: the fully sorted radix keys
@@ -340,6 +480,45 @@ int frag_placeholders_device(const FragOut &frag, unsigned long long *d_off, uin
         frag_placeholders_kernel<uint64_t><<<grid, 256, 0, st>>>(frag, d_off, n_pure, n_amb, d_keys, (uint64_t *)d_idx,
                                                                  d_err);
     GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// The sorted fragment list of a key range from the gathered, individually sorted lists of all ranks.  Leaves
+// `fs` as frag_sort_device would (fs.F is set by the caller once the count is known on the host), the number of
+// fragments in *d_n_frag, and a view of the merged list (key, start, count) for the placeholder pairs.
+int frag_merge_device(const void *d_gathered, const unsigned long long *d_counts, uint32_t world, uint64_t cap,
+                      uint64_t key_lo, uint64_t key_hi, uint64_t out_cap, unsigned long long *d_n_frag,
+                      FragSorted &fs, FragOut *view, cudaStream_t st)
+{
+    if (world == 0 || world > 32 || cap == 0) return GK_ERR_ARG;
+    GK_TRY(fs.reserve(out_cap, st));
+    DeviceBuffer range, w1m;
+    GK_TRY(range.alloc((size_t)world * 16, st));
+    GK_TRY(w1m.alloc((size_t)out_cap * 8, st));
+    frag_ranges_kernel<<<1, 32, 0, st>>>((const unsigned char *)d_gathered, d_counts, world, cap, key_lo, key_hi,
+                                         range.as<unsigned long long>(), d_n_frag);
+    GK_LAUNCH_CHECK();
+    uint64_t *skey = fs.skey_a.as<uint64_t>(), *w0m = fs.skey_b.as<uint64_t>();
+    uint32_t *count = fs.perm_a.as<uint32_t>();
+    frag_merge_kernel<<<frag_grid((uint64_t)world * cap), 256, 0, st>>>(
+        (const unsigned char *)d_gathered, world, cap, range.as<unsigned long long>(), key_lo, out_cap, skey, w0m,
+        w1m.as<uint64_t>(), fs.sstart.as<uint64_t>(), count);
+    GK_LAUNCH_CHECK();
+    frag_word_heads_kernel<<<frag_grid(out_cap), 256, 0, st>>>(w0m, w1m.as<uint64_t>(), d_n_frag, out_cap,
+                                                               fs.whead.as<uint8_t>());
+    GK_LAUNCH_CHECK();
+    frag_scan_counts_kernel<<<1, 1024, 0, st>>>(count, d_n_frag, out_cap, fs.off.as<unsigned long long>());
+    GK_LAUNCH_CHECK();
+    fs.skey = skey;
+    if (view) {
+        view->key = skey;
+        view->w0 = w0m;
+        view->w1 = nullptr;
+        view->start = fs.sstart.as<uint64_t>();
+        view->count = count;
+        view->counter = d_n_frag;
+        view->capacity = out_cap;
+    }
     return GK_OK;
 }
 

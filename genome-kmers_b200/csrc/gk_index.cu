@@ -36,6 +36,9 @@ int frag_expand_device(FragSorted &, const uint64_t *, uint64_t, int, void *, ui
                        const unsigned long long *, uint64_t, int *, cudaStream_t);
 int frag_filter_device(const void *, const unsigned long long *, uint32_t, uint64_t, uint64_t, uint64_t,
                        const FragOut &, cudaStream_t);
+int frag_sort_copy_device(const FragOut &, uint64_t, uint32_t, int, const FragOut &, cudaStream_t);
+int frag_merge_device(const void *, const unsigned long long *, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                      unsigned long long *, FragSorted &, FragOut *, cudaStream_t);
 int frag_placeholders_device(const FragOut &, unsigned long long *, uint64_t, uint64_t, uint64_t *, void *, int, int *,
                              cudaStream_t);
 int subset_rep_flags_device(const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint8_t *,
@@ -446,6 +449,7 @@ struct PackedPairs {
     FragOut frag;                  // fragment list of the ambiguous windows (counter = d_counters + 2)
     bool want_frag = false;
     FragSorted *fs = nullptr;
+    bool fs_ready = false;         // *fs already holds the sorted fragments (merged from sorted lists): only F is open
     unsigned long long *d_counters = nullptr;   // kCounterBytes, zeroed before the producer ran
     bool producer_counted_amb = true;   // d_counters[0] is final when e_producer fires (else the flags pass counts)
     cudaEvent_t e_producer = nullptr;   // recorded on the stream behind the producer of keys and fragments
@@ -529,9 +533,13 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
             if (begin_bit > 0)
                 GK_TRY(repair_big_ambiguous_buckets_on_device(keys_sorted, idx_sorted, ib, pp.class_bit, d_flags,
                                                               d_counters + 4, d_status, st));
-            GK_TRY(frag_sort_device(pp.frag, n_frag, pp.key_len, pp.key_bits, pp.start_bits, *pp.fs, side));
-            GK_CUDA(cudaEventRecord(e_frag.ev, side));
-            GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
+            if (pp.fs_ready) {
+                pp.fs->F = n_frag;
+            } else {
+                GK_TRY(frag_sort_device(pp.frag, n_frag, pp.key_len, pp.key_bits, pp.start_bits, *pp.fs, side));
+                GK_CUDA(cudaEventRecord(e_frag.ev, side));
+                GK_CUDA(cudaStreamWaitEvent(st, e_frag.ev, 0));
+            }
             GK_TRY(frag_expand_device(*pp.fs, keys_sorted, n, ib, idx_sorted, d_flags,
                                       reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb, d_frag_err,
                                       st));
@@ -1120,7 +1128,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
 int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
                         uint64_t n_pure, uint64_t n_ambiguous, int class_bit, int key_bits,
                         const void *d_frag_gathered, const uint64_t *d_frag_counts, uint32_t n_sources,
-                        uint64_t frag_capacity, uint64_t key_lo, uint64_t key_hi, const int *d_err,
+                        uint64_t frag_capacity, int frag_presorted, uint64_t key_lo, uint64_t key_hi, const int *d_err,
                         gk_sort_stats *stats_out, void *stream)
 {
     const uint64_t n_local = n_pure + n_ambiguous;
@@ -1196,17 +1204,26 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
             // placeholder pairs behind the received ones
             uint64_t cap = (uint64_t)n_sources * frag_capacity;
             if (cap > kFragCapacity) cap = kFragCapacity;
-            GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
             GK_TRY(frag_off.alloc((size_t)(cap + 1) * 8, st));
-            uint64_t *base = frag_mem.as<uint64_t>();
-            pp.frag.key = base; pp.frag.w0 = base + cap; pp.frag.w1 = base + 2 * cap; pp.frag.start = base + 3 * cap;
-            pp.frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
-            pp.frag.counter = pp.d_counters + 2;
-            pp.frag.capacity = cap;
             pp.want_frag = fragments_enabled() || n_ambiguous > 0;
-            GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
-            GK_TRY(frag_filter_device(d_frag_gathered, reinterpret_cast<const unsigned long long *>(d_frag_counts),
-                                      n_sources, frag_capacity, key_lo, key_hi, pp.frag, st));
+            if (frag_presorted) {
+                // every rank sorted its own list (gk_frag_sort_local): merge the lists instead of sorting their union
+                GK_TRY(frag_merge_device(d_frag_gathered, reinterpret_cast<const unsigned long long *>(d_frag_counts),
+                                         n_sources, frag_capacity, key_lo, key_hi, cap, pp.d_counters + 2, fs, &pp.frag,
+                                         st));
+                pp.fs_ready = true;
+            } else {
+                GK_TRY(frag_mem.alloc((size_t)cap * 36, st));
+                uint64_t *base = frag_mem.as<uint64_t>();
+                pp.frag.key = base; pp.frag.w0 = base + cap; pp.frag.w1 = base + 2 * cap;
+                pp.frag.start = base + 3 * cap;
+                pp.frag.count = reinterpret_cast<uint32_t *>(base + 4 * cap);
+                pp.frag.counter = pp.d_counters + 2;
+                pp.frag.capacity = cap;
+                GK_TRY(fs.reserve(cap < kFragReserve ? cap : kFragReserve, st));
+                GK_TRY(frag_filter_device(d_frag_gathered, reinterpret_cast<const unsigned long long *>(d_frag_counts),
+                                          n_sources, frag_capacity, key_lo, key_hi, pp.frag, st));
+            }
             GK_TRY(frag_placeholders_device(pp.frag, frag_off.as<unsigned long long>(), n_pure, n_ambiguous, d_keys,
                                             d_idx, ib, reinterpret_cast<int *>(pp.d_counters + 3), st));
             // d_counters[0] = ambiguous windows of the shard: known to the caller, the expand step checks it
@@ -1273,7 +1290,30 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
                         uint64_t n_local, int class_bit, gk_sort_stats *stats_out, void *stream)
 {
     return gk_index_sort_shard(ix, d_keys, d_keys_alt, d_idx, d_idx_alt, n_local, 0, class_bit, 0, nullptr, nullptr, 0,
-                               0, 0, 0, nullptr, stats_out, stream);
+                               0, 0, 0, 0, nullptr, stats_out, stream);
+}
+
+/* Sort a fragment list (gk_pack_slice layout, n_frag <= frag_capacity entries used) by window, ties by start,
+ * into d_frag_sorted (same layout and capacity).  No synchronise. */
+int gk_frag_sort_local(const void *d_frag, uint64_t frag_capacity, uint64_t n_frag, uint32_t kmer_len,
+                       uint64_t sba_len, void *d_frag_sorted, void *stream)
+{
+    if (!d_frag || !d_frag_sorted || frag_capacity == 0 || n_frag > frag_capacity || kmer_len < 1) {
+        set_error("gk_frag_sort_local: bad argument");
+        return GK_ERR_ARG;
+    }
+    auto view = [&](const void *p) {
+        FragOut f;
+        uint64_t *b = reinterpret_cast<uint64_t *>(const_cast<void *>(p));
+        f.key = b; f.w0 = b + frag_capacity; f.w1 = b + 2 * frag_capacity; f.start = b + 3 * frag_capacity;
+        f.count = reinterpret_cast<uint32_t *>(b + 4 * frag_capacity);
+        f.capacity = frag_capacity;
+        return f;
+    };
+    int start_bits = 1;
+    while (start_bits < 64 && (sba_len >> start_bits)) ++start_bits;
+    const uint32_t key_len = kmer_len > 31 ? 31u : kmer_len;   // as gk_pack_slice
+    return frag_sort_copy_device(view(d_frag), n_frag, key_len, start_bits, view(d_frag_sorted), as_stream(stream));
 }
 
 int gk_index_device_indices(gk_index *ix, const void **d_idx_out, void *stream)

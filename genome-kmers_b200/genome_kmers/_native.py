@@ -92,8 +92,9 @@ SIGNATURES = {
     "gk_index_set_indices": (_int, [_vp, _vp, _u64, _int, _int, _vp]),
     "gk_index_sort": (_int, [_vp, _p(GkSortStats), _vp]),
     "gk_index_sort_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _int, _p(GkSortStats), _vp]),
-    "gk_index_sort_shard": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _int, _int, _vp, _vp, _u32, _u64, _u64, _u64,
-                                   _vp, _p(GkSortStats), _vp]),
+    "gk_index_sort_shard": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _int, _int, _vp, _vp, _u32, _u64, _int, _u64,
+                                   _u64, _vp, _p(GkSortStats), _vp]),
+    "gk_frag_sort_local": (_int, [_vp, _u64, _u64, _u32, _u64, _vp, _vp]),
     "gk_pack_slice": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _u64, _u64, _vp, _int, _vp, _u64, _p(_u64), _vp, _u64,
                              _vp, _vp]),
     "gk_sample_keys": (_int, [_vp, _u64, _vp, _u32, _u32, _int, _u64, _u64, _u32, _vp, _p(_u32), _vp]),

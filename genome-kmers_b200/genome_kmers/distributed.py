@@ -168,21 +168,34 @@ class NativeEngine:
         self._partition(pk, splitters, n_parts, key_ptrs, idx_ptrs, offsets, key_base, skip_amb)
         return keys[:total], idx[:total]
 
-    def gather_fragments(self, pk, dist, group):
-        """All ranks' fragment lists, back to back, on the device; issued on the second stream so that it runs
-        beside the partition kernel.  Returns (tensor, event to wait for)."""
+    def gather_fragments(self, pk, dist, group, n_frag, k, sba_len):
+        """All ranks' fragment lists, each sorted by its own rank (gk_frag_sort_local), back to back on the device;
+        issued on the second stream so that sort and gather run beside the partition kernel.  The owner of a key
+        range merges the sorted lists.  Returns (tensor, event to wait for)."""
         torch = self.torch
         world = dist.get_world_size(group)
-        self.side.wait_stream(torch.cuda.current_stream())
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            if backend_is_nccl(dist, group):
-                out = torch.empty(world * pk.frag.numel(), dtype=torch.uint8, device=self.device)
-                dist.all_gather_into_tensor(out, pk.frag, group=group)
+            self.frag_presorted = os.environ.get("GK_FRAG_PRESORT", "1") != "0"   # (0: A/B switch, tests)
+            if self.frag_presorted:
+                mine = torch.empty_like(pk.frag)
+                _native.check(self.lib.gk_frag_sort_local(pk.frag.data_ptr(), FRAG_SHARE, int(n_frag), k, sba_len,
+                                                          mine.data_ptr(), self.stream()))
+            else:
+                mine = pk.frag
+            pk.frag.record_stream(self.side)
+            if world == 1:
+                out = mine
+            elif backend_is_nccl(dist, group):
+                out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(out, mine, group=group)
             else:   # gloo cannot gather CUDA tensors: through the host (tests with two ranks on one GPU)
-                mine = pk.frag.cpu()
-                host = torch.empty(world * mine.numel(), dtype=torch.uint8)
-                dist.all_gather_into_tensor(host, mine, group=group)
+                mine_host = mine.cpu()
+                host = torch.empty(world * mine_host.numel(), dtype=torch.uint8)
+                dist.all_gather_into_tensor(host, mine_host, group=group)
                 out = host.to(self.device)
+            out.record_stream(main)
             ev = torch.cuda.Event()
             ev.record(self.side)
         return out, ev
@@ -211,7 +224,8 @@ class NativeEngine:
                 handle, keys_ptr, k_alt.data_ptr(), idx_ptr, i_alt.data_ptr(), n_pure, n_amb, class_bit, key_bits,
                 frag_all.data_ptr() if frag_all is not None else None,
                 counts_dev.data_ptr() if counts_dev is not None else None,
-                len(frag_counts) if frag_all is not None else 0, FRAG_SHARE, int(key_lo), int(key_hi),
+                len(frag_counts) if frag_all is not None else 0, FRAG_SHARE,
+                int(getattr(self, "frag_presorted", False)), int(key_lo), int(key_hi),
                 self.err_word.data_ptr(), ctypes.byref(stats), self.stream()))
         except Exception:
             self.lib.gk_index_destroy(handle)
@@ -652,7 +666,7 @@ class ShardedKmers:
             # buffer over NVLink peer memory; the fragment lists are gathered beside it
             eng.partition_to_peers(pk, splitters, world, px, pure[:rank, :].sum(axis=0), key_lo, frag_ok)
             if frag_ok:
-                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group)
+                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group, n_frag_src[rank], k, self.total_len)
             self._order_after_peer_writes()
             keys_ptr, idx_ptr = px.my_keys, px.my_idx
             self._keep = None
@@ -661,10 +675,8 @@ class ShardedKmers:
             # several hosts, no peer access, or a single rank: the same kernel into a local staging buffer, then
             # one all-to-all per array
             keys_s, idx_s = eng.partition_to_staging(pk, splitters, world, pure[rank], key_lo, frag_ok)
-            if frag_ok and world > 1:
-                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group)
-            elif frag_ok:
-                frag_all = pk.frag
+            if frag_ok:
+                frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group, n_frag_src[rank], k, self.total_len)
             keys_r, idx_r = eng.recv_buffers(idx_s, n_pure + n_amb)
             if world > 1:
                 in_splits, out_splits = [int(c) for c in pure[rank]], [int(c) for c in pure[:, rank]]

@@ -209,13 +209,19 @@ int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
  * relative to the start of this rank's key range (0: full width); d_frag_gathered: the all-gathered fragment
  * lists of all n_sources ranks (gk_pack_slice layout, frag_capacity entries each, d_frag_counts[s] used), from
  * which the n_ambiguous windows of the key range [key_lo, key_hi) (key_hi 0: unbounded) are generated behind
- * the n_pure received pairs -- the four buffers hold n_pure + n_ambiguous pairs; d_err: the device word the
+ * the n_pure received pairs -- the four buffers hold n_pure + n_ambiguous pairs; frag_presorted: every list was
+ * sorted by gk_frag_sort_local; d_err: the device word the
  * partition step wrote its look-back verdict to (optional). */
 int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx, void *d_idx_alt,
                         uint64_t n_pure, uint64_t n_ambiguous, int class_bit, int key_bits,
                         const void *d_frag_gathered, const uint64_t *d_frag_counts, uint32_t n_sources,
-                        uint64_t frag_capacity, uint64_t key_lo, uint64_t key_hi, const int *d_err,
-                        gk_sort_stats *stats_out, void *stream);
+                        uint64_t frag_capacity, int frag_presorted, uint64_t key_lo, uint64_t key_hi,
+                        const int *d_err, gk_sort_stats *stats_out, void *stream);
+/* Sort one rank's fragment list (gk_pack_slice layout, n_frag entries used) by window and start into
+ * d_frag_sorted (same layout and capacity); no synchronise.  With frag_presorted = 1 gk_index_sort_shard merges
+ * the gathered lists (one binary search per fragment and list) instead of sorting their union. */
+int gk_frag_sort_local(const void *d_frag, uint64_t frag_capacity, uint64_t n_frag, uint32_t kmer_len,
+                       uint64_t sba_len, void *d_frag_sorted, void *stream);
 /* Multi-GPU producers (no synchronise).  gk_pack_slice: pack the windows (kmer_len symbols; the key covers the
  * first min(kmer_len, 31) of them when class_bit is set) whose start lies in
  * [first_start, end_start) and list the ambiguous-window fragments of that slice; d_frag: frag_capacity * 36
