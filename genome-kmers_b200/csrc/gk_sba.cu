@@ -252,6 +252,32 @@ int gk_sba_both_strands(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void 
     return gk_sba_revcomp(d_in, len, d_out + len + 1, stream);
 }
 
+/* Bytes [begin, end) of the both-strand layout only (a GPU's slice of the start positions first, the rest
+ * later on another stream).  The reverse-complement part of the range is the reverse complement of the
+ * mirrored part of the input, so this is gk_sba_revcomp on a sub-array. */
+int gk_sba_both_strands_range(const uint8_t *d_in, uint64_t len, uint8_t *d_out, uint64_t begin, uint64_t end,
+                              void *stream)
+{
+    if ((!d_in || !d_out) && len) {
+        set_error("gk_sba_both_strands_range: null pointer");
+        return GK_ERR_ARG;
+    }
+    const uint64_t total = 2 * len + 1;
+    if (end > total) end = total;
+    if (begin >= end) return GK_OK;
+    cudaStream_t st = as_stream(stream);
+    if (begin < len) {
+        const uint64_t e = end < len ? end : len;
+        GK_CUDA(cudaMemcpyAsync(d_out + begin, d_in + begin, e - begin, cudaMemcpyDeviceToDevice, st));
+    }
+    if (begin <= len && len < end) GK_CUDA(cudaMemsetAsync(d_out + len, kSep, 1, st));
+    if (end > len + 1) {
+        const uint64_t rb = begin > len + 1 ? begin - (len + 1) : 0, re = end - (len + 1);   // range inside revcomp
+        return gk_sba_revcomp(d_in + (len - re), re - rb, d_out + len + 1 + rb, stream);
+    }
+    return GK_OK;
+}
+
 int gk_kmer_count(const uint64_t *h_seg_starts, uint32_t n_seg, uint64_t sba_len,
                   uint32_t kmer_len, uint64_t *n_out)
 {

@@ -67,6 +67,7 @@ SIGNATURES = {
     "gk_sba_scan_alphabet_async": (_int, [_vp, _u64, _vp, _vp]),
     "gk_sba_revcomp": (_int, [_vp, _u64, _vp, _vp]),
     "gk_sba_both_strands": (_int, [_vp, _u64, _vp, _vp]),
+    "gk_sba_both_strands_range": (_int, [_vp, _u64, _vp, _u64, _u64, _vp]),
     "gk_kmer_count": (_int, [_vp, _u32, _u64, _u32, _p(_u64)]),
     "gk_kmer_init_indices": (_int, [_vp, _u32, _u64, _u32, _int, _vp, _vp]),
     "gk_pack_keys": (_int, [_vp, _u64, _vp, _u32, _u32, _u32, _int, _u64, _u64, _vp, _int, _vp,

@@ -89,6 +89,27 @@ class NativeEngine:
         _native.check(self.lib.gk_sba_both_strands(d_fwd.data_ptr(), d_fwd.numel(), out.data_ptr(), self.stream()))
         return out
 
+    def both_strands_sliced(self, d_fwd, begin, end):
+        """The same layout, bytes [begin, end) on the caller's stream now and the rest on the second stream.
+        Returns (tensor, event behind the rest)."""
+        torch = self.torch
+        n = d_fwd.numel()
+        out = torch.empty(2 * n + 1, dtype=torch.uint8, device=self.device)
+        main = torch.cuda.current_stream()
+        _native.check(self.lib.gk_sba_both_strands_range(d_fwd.data_ptr(), n, out.data_ptr(), begin, end,
+                                                         self.stream()))
+        self.side.wait_stream(main)          # d_fwd (and the allocation) are ready on the caller's stream
+        with torch.cuda.stream(self.side):
+            for b, e in ((0, begin), (end, 2 * n + 1)):
+                if e > b:
+                    _native.check(self.lib.gk_sba_both_strands_range(d_fwd.data_ptr(), n, out.data_ptr(), b, e,
+                                                                     self.stream()))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        d_fwd.record_stream(self.side)
+        out.record_stream(self.side)
+        return out, ev
+
     def alphabet_async(self, d_sba):
         """Device tensor int64[3] (bad bytes, '$', ambiguous letters); no synchronise."""
         counts = self.torch.empty(3, dtype=self.torch.int64, device=self.device)
@@ -554,12 +575,22 @@ class ShardedKmers:
             ends = np.concatenate([starts[1:].astype(np.int64) - 2, [n - 1]])
             rc = (n - 1 - ends[::-1]).astype(np.uint64) + np.uint64(n + 1)
             self.seg_starts = np.ascontiguousarray(np.concatenate([starts, rc]), dtype=np.uint64)
-            self.d_sba = eng.both_strands(d_fwd)
             self.total_len = 2 * n + 1
+            self._layout_ev = None
+            sliced = getattr(eng, "both_strands_sliced", None)
+            if sliced is not None and self.world > 1 and os.environ.get("GK_LAZY_LAYOUT", "1") != "0":
+                # this rank's slice of the start positions (plus one pack tile of look-ahead) first; the rest of
+                # the layout is built on the second stream and is waited for before the local sort
+                first, end = slice_bounds(self.total_len, self.world, self.rank)
+                self.d_sba, self._layout_ev = sliced(d_fwd, max(0, first - 64),
+                                                     min(self.total_len, end + 8192 + self.k))
+            else:
+                self.d_sba = eng.both_strands(d_fwd)
         else:
             self.seg_starts = starts
             self.d_sba = d_fwd
             self.total_len = n
+            self._layout_ev = None
         self.idx_bytes = 8 if self.total_len > 0xFFFFFFFF else 4
         if os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0"):   # tests: 64-bit starts on small inputs
             self.idx_bytes = 8
@@ -699,6 +730,9 @@ class ShardedKmers:
             eng.shard_free(self.shard)
         if frag_ev is not None:
             eng.wait_event(frag_ev)
+        if self._layout_ev is not None:     # the rest of the both-strand layout (second stream)
+            eng.wait_event(self._layout_ev)
+            self._layout_ev = None
         self.shard = eng.shard_sort(self.d_sba, self.seg_starts, k, keys_ptr, idx_ptr, self.idx_bytes, n_pure, n_amb,
                                     class_bit, key_bits, frag_all, n_frag_src if frag_all is not None else None,
                                     int(key_lo[rank]), int(key_hi[rank]))

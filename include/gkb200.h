@@ -99,6 +99,9 @@ int gk_sba_scan_alphabet_async(const uint8_t *d_sba, uint64_t len, uint64_t *d_c
 int gk_sba_revcomp(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream);
 /* out = in || '$' || revcomp(in), 2*len+1 bytes: this library's definition of both strands. */
 int gk_sba_both_strands(const uint8_t *d_in, uint64_t len, uint8_t *d_out, void *stream);
+/* Bytes [begin, end) of that layout only: a GPU of a multi-GPU sort first builds the slice it packs. */
+int gk_sba_both_strands_range(const uint8_t *d_in, uint64_t len, uint8_t *d_out, uint64_t begin, uint64_t end,
+                              void *stream);
 
 /* ---- k-mer start indices (row A3, kmers.py:789-835) --------------------------------------- */
 /* Number of windows of kmer_len bases that fit inside a record. */

@@ -356,3 +356,30 @@ def test_shard_sort_of_kmers_longer_than_one_key_word(k, strands, tmp_path):
     assert total == total_want and np.array_equal(hist, hist_want)
     assert all(ver["checks"].values()), ver
     assert levels > 1, "no word round ran: the input has no k-mers tied on 31 symbols?"
+
+
+@pytest.mark.parametrize("n", [1, 37, 4099, 300_001])
+def test_both_strand_layout_built_in_ranges_equals_the_whole(n):
+    """gk_sba_both_strands_range: any partition of [0, 2n + 1) into ranges gives the layout of
+    gk_sba_both_strands (the multi-GPU path builds a rank's own slice first, the rest on another stream)."""
+    torch = gu.torch_mod()
+    lib = _native.lib()
+    rng = np.random.default_rng(n)
+    sba = np.frombuffer(b"ACGTRYSWKMBDHVN$", dtype=np.uint8)[rng.integers(0, 16, n)].copy()
+    d_in = gu.dev(sba)
+    whole = torch.zeros(2 * n + 1, dtype=torch.uint8, device="cuda")
+    _native.check(lib.gk_sba_both_strands(d_in.data_ptr(), n, whole.data_ptr(), gu.stream()))
+    total = 2 * n + 1
+    for trial in range(6):
+        cuts = sorted({0, total, *(int(c) for c in rng.integers(0, total + 1, 4)), n, min(total, n + 1)})
+        out = torch.full((total,), 255, dtype=torch.uint8, device="cuda")
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            _native.check(lib.gk_sba_both_strands_range(d_in.data_ptr(), n, out.data_ptr(), b, e, gu.stream()))
+        assert torch.equal(out, whole), f"cuts {cuts}"
+    # a range writes nothing outside itself
+    out = torch.full((total,), 255, dtype=torch.uint8, device="cuda")
+    b, e = total // 3, (2 * total) // 3 + 1
+    _native.check(lib.gk_sba_both_strands_range(d_in.data_ptr(), n, out.data_ptr(), b, e, gu.stream()))
+    got = out.cpu().numpy()
+    assert np.array_equal(got[b:e], whole.cpu().numpy()[b:e])
+    assert (got[:b] == 255).all() and (got[e:] == 255).all()
