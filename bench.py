@@ -752,7 +752,8 @@ def run_multi_gpu(args, rank, world):
                       or os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0")) else 4
     last = per_step[-1][0]
     mine = [last.get("total_ms", 0.0), last.get("fixup_ms", 0.0), float(last.get("n_shard", 0)),
-            float(last.get("n_ambiguous", 0))]
+            float(last.get("n_ambiguous", 0)), float(last.get("n_fragments", 0)), float(last.get("refine_flags", 0)),
+            last.get("pack_ms", 0.0), last.get("hist_ms", 0.0), last.get("sort_ms", 0.0)]
     per_rank = [None] * world
     dist.all_gather_object(per_rank, mine)
     sent_all = torch.tensor([float(np.mean([s for _, s in per_step]))], dtype=torch.float64, device="cuda")
@@ -798,7 +799,11 @@ def run_multi_gpu(args, rank, world):
             "per_rank_local_sort": {"total_ms": [round(r[0], 3) for r in per_rank],
                                     "refine_ms": [round(r[1], 3) for r in per_rank],
                                     "pairs": [int(r[2]) for r in per_rank],
-                                    "ambiguous": [int(r[3]) for r in per_rank]},
+                                    "ambiguous": [int(r[3]) for r in per_rank],
+                                    "fragments": [int(r[4]) for r in per_rank],
+                                    "refine_flags": [int(r[5]) for r in per_rank],
+                                    "placeholders_hist_passes_ms": [[round(r[6], 3), round(r[7], 3), round(r[8], 3)]
+                                                                    for r in per_rank]},
             "local_sort_stats_rank0": {k_: v for k_, v in per_step[-1][0].items()},
             "result": {"kmers": int(n_total), "distinct_kmers": int(hist.sum())},
         }

@@ -137,11 +137,14 @@ frag_expand_kernel(const uint64_t *__restrict__ sstart, const unsigned long long
 {
     if (*descent || (*err & 6)) return;
     const uint64_t m = off[F];
-    // eight consecutive windows per thread: one binary search, then a walk (almost all windows lie in fragments
-    // of thousands -- the pieces of an N run)
+    // a warp writes 256 consecutive windows, lane-strided (coalesced stores): one binary search for the chunk's
+    // first window, then every lane walks forward on its own (almost all windows lie in fragments of thousands
+    // -- the pieces of an N run -- so the walk rarely moves)
     constexpr int kPer = 8;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kPer;
-    for (uint64_t o0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPer; o0 < m; o0 += stride) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t o0 = warp_id * (32 * kPer); o0 < m; o0 += n_warps * (32 * kPer)) {
         uint64_t lo = 0, hi = F;  // last fragment whose offset is <= o0
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
@@ -152,11 +155,15 @@ frag_expand_kernel(const uint64_t *__restrict__ sstart, const unsigned long long
         uint8_t q_head = whead[q];
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
-            const uint64_t o = o0 + u;
+            const uint64_t o = o0 + (uint64_t)u * 32 + lane;
             if (o >= m) break;
-            while (o >= q_end) {   // (fragments are never empty)
-                ++q;
-                q_off = q_end; q_end = off[q + 1]; q_slot = slot0[q]; q_start = sstart[q]; q_head = whead[q];
+            if (o >= q_end) {   // (fragments are never empty)
+                do {
+                    ++q;
+                    q_off = q_end;
+                    q_end = off[q + 1];
+                } while (o >= q_end);
+                q_slot = slot0[q]; q_start = sstart[q]; q_head = whead[q];
             }
             const uint64_t i = o - q_off;
             const uint64_t slot = q_slot + i;
@@ -443,17 +450,35 @@ frag_placeholders_kernel(FragOut frag, const unsigned long long *__restrict__ of
     const uint64_t m = off[F];
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid == 0 && (m != n_amb || *frag.counter > frag.capacity)) atomicOr(err, 8);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t lim = m < n_amb ? m : n_amb;
-    for (uint64_t o = tid; o < lim; o += stride) {
+    // as frag_expand_kernel: a warp writes 256 consecutive pairs, lane-strided, after one binary search
+    constexpr int kPer = 8;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_id = tid >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t o0 = warp_id * (32 * kPer); o0 < lim; o0 += n_warps * (32 * kPer)) {
         uint64_t lo = 0, hi = F;
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
-            if (o < off[mid]) hi = mid; else lo = mid + 1;
+            if (o0 < off[mid]) hi = mid; else lo = mid + 1;
         }
-        const uint64_t q = lo - 1;
-        keys[n_pure + o] = frag.key[q];
-        idx[n_pure + o] = (IdxT)(frag.start[q] + (o - off[q]));
+        uint64_t q = lo - 1;
+        uint64_t q_off = off[q], q_end = off[q + 1], q_key = frag.key[q], q_start = frag.start[q];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const uint64_t o = o0 + (uint64_t)u * 32 + lane;
+            if (o >= lim) break;
+            if (o >= q_end) {
+                do {
+                    ++q;
+                    q_off = q_end;
+                    q_end = off[q + 1];
+                } while (o >= q_end);
+                q_key = frag.key[q]; q_start = frag.start[q];
+            }
+            keys[n_pure + o] = q_key;
+            idx[n_pure + o] = (IdxT)(q_start + (o - q_off));
+        }
     }
 }
 
@@ -472,7 +497,7 @@ int frag_placeholders_device(const FragOut &frag, unsigned long long *d_off, uin
 {
     frag_scan_counts_kernel<<<1, 1024, 0, st>>>(frag.count, frag.counter, frag.capacity, d_off);
     GK_LAUNCH_CHECK();
-    const int grid = frag_grid(n_amb ? n_amb : 1);
+    const int grid = frag_grid(n_amb ? (n_amb + 7) / 8 : 1);
     if (idx_bytes == 4)
         frag_placeholders_kernel<uint32_t><<<grid, 256, 0, st>>>(frag, d_off, n_pure, n_amb, d_keys, (uint32_t *)d_idx,
                                                                  d_err);

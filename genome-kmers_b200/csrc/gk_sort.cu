@@ -76,10 +76,24 @@ digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit,
             }
         }
     };
+    // several 16-byte loads in flight per thread: with one, 2 x 512 threads per SM keep ~16 KB in flight, half of
+    // what the HBM latency-bandwidth product asks for
+    constexpr int kLoads = 4;
     if constexpr (sizeof(KeyT) == 8) {  // two keys per 16-byte load
         const uint64_t n2 = n / 2;
         const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys);
-        for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n2; i += stride) {
+        uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x;
+        for (; i + (kLoads - 1) * stride < n2; i += kLoads * stride) {
+            ulonglong2 v[kLoads];
+#pragma unroll
+            for (int u = 0; u < kLoads; ++u) v[u] = k2[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < kLoads; ++u) {
+                add(v[u].x);
+                add(v[u].y);
+            }
+        }
+        for (; i < n2; i += stride) {
             ulonglong2 v = k2[i];
             add(v.x);
             add(v.y);
@@ -88,12 +102,20 @@ digit_histogram_kernel(const KeyT *__restrict__ keys, uint64_t n, int begin_bit,
     } else {                            // four keys per 16-byte load
         const uint64_t n4 = n / 4;
         const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
-        for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n4; i += stride) {
+        uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x;
+        for (; i + (kLoads - 1) * stride < n4; i += kLoads * stride) {
+            uint4 v[kLoads];
+#pragma unroll
+            for (int u = 0; u < kLoads; ++u) v[u] = k4[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < kLoads; ++u) { add(v[u].x); add(v[u].y); add(v[u].z); add(v[u].w); }
+        }
+        for (; i < n4; i += stride) {
             const uint4 v = k4[i];
             add(v.x); add(v.y); add(v.z); add(v.w);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            for (uint64_t i = n4 * 4; i < n; ++i) add((uint64_t)keys[i]);
+            for (uint64_t j = n4 * 4; j < n; ++j) add((uint64_t)keys[j]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) {
@@ -848,7 +870,7 @@ static int run_onesweep(uint64_t *d_keys, uint64_t *d_keys_alt, void *d_vals, vo
     GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
 
     if (timing) GK_CUDA(cudaEventRecord(timing->ev[0], st));
-    int hist_grid = sm_count() * 2;
+    int hist_grid = sm_count() * 4;
     {
         uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
         if (need < 1) need = 1;
@@ -971,7 +993,7 @@ int radix_sort_pairs32_device(uint32_t *d_keys, uint32_t *d_keys_alt, void *d_va
     int *d_err = reinterpret_cast<int *>(d_ctr + kMaxPasses);
     void *d_status = reinterpret_cast<unsigned char *>(d_ctr) + ctr_bytes;
     GK_CUDA(cudaMemsetAsync(temp.ptr, 0, 2 * hist_bytes + ctr_bytes, st));
-    int hist_grid = sm_count() * 2;
+    int hist_grid = sm_count() * 4;
     {
         uint64_t need = (n / 4 + kHistThreads - 1) / kHistThreads;
         if (need < 1) need = 1;
@@ -1271,7 +1293,7 @@ int partition_count_device(const uint64_t *d_keys, uint64_t n, const uint64_t *d
     DeviceBuffer hist;
     GK_TRY(hist.alloc(kRadix * sizeof(unsigned long long), st));
     GK_CUDA(cudaMemsetAsync(hist.ptr, 0, hist.bytes, st));
-    int grid = sm_count() * 2;
+    int grid = sm_count() * 4;
     uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
     if (need < 1) need = 1;
     if ((uint64_t)grid > need) grid = (int)need;
@@ -1299,7 +1321,7 @@ int partition_count_split_device(const uint64_t *d_keys, uint64_t n, const uint6
     DeviceBuffer hist;
     GK_TRY(hist.alloc(kRadix * sizeof(unsigned long long), st));
     GK_CUDA(cudaMemsetAsync(hist.ptr, 0, hist.bytes, st));
-    int grid = sm_count() * 2;
+    int grid = sm_count() * 4;
     uint64_t need = (n / 2 + kHistThreads - 1) / kHistThreads;
     if (need < 1) need = 1;
     if ((uint64_t)grid > need) grid = (int)need;
