@@ -90,25 +90,31 @@ class NativeEngine:
         return out
 
     def both_strands_sliced(self, d_fwd, begin, end):
-        """The same layout, bytes [begin, end) on the caller's stream now and the rest on the second stream.
-        Returns (tensor, event behind the rest)."""
+        """The same layout, bytes [begin, end) on the caller's stream now.  Returns (tensor, finish): finish()
+        enqueues the rest on a third stream behind whatever the caller's stream holds at that moment (the pack
+        kernel: the rest then fills the gaps of the host-driven phases) and returns the event to wait for."""
         torch = self.torch
         n = d_fwd.numel()
         out = torch.empty(2 * n + 1, dtype=torch.uint8, device=self.device)
-        main = torch.cuda.current_stream()
         _native.check(self.lib.gk_sba_both_strands_range(d_fwd.data_ptr(), n, out.data_ptr(), begin, end,
                                                          self.stream()))
-        self.side.wait_stream(main)          # d_fwd (and the allocation) are ready on the caller's stream
-        with torch.cuda.stream(self.side):
-            for b, e in ((0, begin), (end, 2 * n + 1)):
-                if e > b:
-                    _native.check(self.lib.gk_sba_both_strands_range(d_fwd.data_ptr(), n, out.data_ptr(), b, e,
-                                                                     self.stream()))
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-        d_fwd.record_stream(self.side)
-        out.record_stream(self.side)
-        return out, ev
+        if getattr(self, "bg", None) is None:
+            self.bg = torch.cuda.Stream(device=self.device)
+
+        def finish():
+            self.bg.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.bg):
+                for b, e in ((0, begin), (end, 2 * n + 1)):
+                    if e > b:
+                        _native.check(self.lib.gk_sba_both_strands_range(d_fwd.data_ptr(), n, out.data_ptr(), b, e,
+                                                                         self.stream()))
+                ev = torch.cuda.Event()
+                ev.record(self.bg)
+            d_fwd.record_stream(self.bg)
+            out.record_stream(self.bg)
+            return ev
+
+        return out, finish
 
     def alphabet_async(self, d_sba):
         """Device tensor int64[3] (bad bytes, '$', ambiguous letters); no synchronise."""
@@ -576,21 +582,22 @@ class ShardedKmers:
             rc = (n - 1 - ends[::-1]).astype(np.uint64) + np.uint64(n + 1)
             self.seg_starts = np.ascontiguousarray(np.concatenate([starts, rc]), dtype=np.uint64)
             self.total_len = 2 * n + 1
-            self._layout_ev = None
+            self._layout_ev = self._layout_finish = None
             sliced = getattr(eng, "both_strands_sliced", None)
             if sliced is not None and self.world > 1 and os.environ.get("GK_LAZY_LAYOUT", "1") != "0":
-                # this rank's slice of the start positions (plus one pack tile of look-ahead) first; the rest of
-                # the layout is built on the second stream and is waited for before the local sort
+                # this rank's slice of the start positions first -- with two pack tiles either side: the pack kernel
+                # reads whole 4096-byte tiles (aligned down) and counts the '$' of a tile from its first byte; the
+                # rest of the layout is built behind the pack kernel and is waited for before the local sort
                 first, end = slice_bounds(self.total_len, self.world, self.rank)
-                self.d_sba, self._layout_ev = sliced(d_fwd, max(0, first - 64),
-                                                     min(self.total_len, end + 8192 + self.k))
+                self.d_sba, self._layout_finish = sliced(d_fwd, max(0, first - 8192),
+                                                         min(self.total_len, end + 8192 + self.k))
             else:
                 self.d_sba = eng.both_strands(d_fwd)
         else:
             self.seg_starts = starts
             self.d_sba = d_fwd
             self.total_len = n
-            self._layout_ev = None
+            self._layout_ev = self._layout_finish = None
         self.idx_bytes = 8 if self.total_len > 0xFFFFFFFF else 4
         if os.environ.get("GK_FORCE_IDX64", "0") not in ("", "0"):   # tests: 64-bit starts on small inputs
             self.idx_bytes = 8
@@ -647,6 +654,9 @@ class ShardedKmers:
         alpha = eng.alphabet_async(self.d_sba[a16:b16] if world > 1 else self.d_sba)
         pk = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
         self._mark("pack")
+        if self._layout_finish is not None:   # the rest of the both-strand layout: behind the pack kernel
+            self._layout_ev = self._layout_finish()
+            self._layout_finish = None
 
         # ---- splitters from evenly spaced samples (second stream: runs beside the pack kernel) --------------
         if world > 1:
@@ -696,6 +706,7 @@ class ShardedKmers:
             # fused: ONE kernel partitions and writes every pair straight into its destination rank's receive
             # buffer over NVLink peer memory; the fragment lists are gathered beside it
             eng.partition_to_peers(pk, splitters, world, px, pure[:rank, :].sum(axis=0), key_lo, frag_ok)
+            self._mark("partition_kernel")
             if frag_ok:
                 frag_all, frag_ev = eng.gather_fragments(pk, dist, self.group, n_frag_src[rank], k, self.total_len)
             self._order_after_peer_writes()

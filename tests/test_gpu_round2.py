@@ -383,3 +383,48 @@ def test_both_strand_layout_built_in_ranges_equals_the_whole(n):
     got = out.cpu().numpy()
     assert np.array_equal(got[b:e], whole.cpu().numpy()[b:e])
     assert (got[:b] == 255).all() and (got[e:] == 255).all()
+
+
+@pytest.mark.parametrize("k", [12, 31, 64])
+def test_pack_slice_reads_nothing_beyond_two_tiles_around_its_slice(k):
+    """The multi-GPU path builds bytes [first - 8192, end + 8192 + k) of the both-strand layout before it packs
+    the slice [first, end) and the rest later: whatever the other bytes hold then ('$' is the worst garbage: it
+    shifts the record count of a tile) must not change the pairs or the fragments of the slice."""
+    torch = gu.torch_mod()
+    lib = _native.lib()
+    rng = np.random.default_rng(k)
+    recs = gu.random_genome(rng, 400_000, 5, n_runs=6, run_lo=40, run_hi=6000, n_scatter=20)
+    sba = np.concatenate([np.concatenate([seq, np.array([36], dtype=np.uint8)]) for _, seq in recs])[:-1]
+    starts = np.cumsum([0] + [len(seq) + 1 for _, seq in recs[:-1]]).astype(np.uint64)
+    n = len(sba)
+    cap_frag = 1 << 14
+
+    def pack(d_bytes, first, end):
+        keys = torch.zeros(end - first, dtype=torch.int64, device="cuda")
+        idx = torch.zeros(end - first, dtype=torch.int32, device="cuda")
+        frag = torch.zeros(cap_frag * 36, dtype=torch.uint8, device="cuda")
+        counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+        n_out = ctypes.c_uint64(0)
+        _native.check(lib.gk_pack_slice(d_bytes.data_ptr(), n, _native.host_ptr(starts), len(starts), k, 1, first, end,
+                                        keys.data_ptr(), 4, idx.data_ptr(), end - first, ctypes.byref(n_out),
+                                        frag.data_ptr(), cap_frag, counters.data_ptr(), gu.stream()))
+        torch.cuda.synchronize()
+        m = n_out.value
+        c = counters.cpu().numpy()
+        f = frag.cpu().numpy()
+        nf = int(c[2])
+        words = f[:cap_frag * 32].view(np.uint64).reshape(4, cap_frag)[:, :nf]
+        cnt = f[cap_frag * 32:].view(np.uint32)[:nf]
+        order = np.argsort(words[3], kind="stable")          # fragments are listed in any order: by start
+        return keys[:m].cpu().numpy(), idx[:m].cpu().numpy(), int(c[0]), words[:, order], cnt[order]
+
+    full = gu.dev(sba)
+    for first, end in ((0, 100_000), (100_001, 233_333), (n - 90_000, n), (4096 * 30, 4096 * 40)):
+        poisoned = np.full(n, 36, dtype=np.uint8)
+        lo, hi = max(0, first - 8192), min(n, end + 8192 + k)
+        poisoned[lo:hi] = sba[lo:hi]
+        want = pack(full, first, end)
+        got = pack(gu.dev(poisoned), first, end)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (first, end)
+        assert len(want[0]) > 0 and want[2] > 0
