@@ -143,13 +143,21 @@ class NativeEngine:
         torch = self.torch
         out = torch.empty(max(1, n_samples), dtype=torch.int64, device=self.device)
         n_out = ctypes.c_uint32(0)
-        self.side.wait_stream(torch.cuda.current_stream())      # d_sba was produced on the caller's stream
+        if after is not None:
+            self.side.wait_event(after)      # d_sba was produced on the caller's stream, before this event
+        else:
+            self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             _native.check(self.lib.gk_sample_keys(d_sba.data_ptr(), d_sba.numel(), _native.host_ptr(seg_starts),
                                                   len(seg_starts), k, class_bit, first, end, n_samples,
                                                   out.data_ptr(), ctypes.byref(n_out), self.stream()))
             host = out[:n_out.value].cpu()
         return host.numpy().view(np.uint64)
+
+    def side_context(self):
+        """Work issued inside runs on the second stream (small collectives that must not queue behind the bulk
+        kernel the caller's stream is busy with)."""
+        return self.torch.cuda.stream(self.side)
 
     def splitters_to_device(self, splitters_host):
         return self.torch.from_numpy(np.ascontiguousarray(splitters_host).view(np.int64).copy()).to(self.device)
@@ -652,6 +660,7 @@ class ShardedKmers:
         a16 = (first // 16) * 16 if rank > 0 else 0
         b16 = (end // 16) * 16 if rank < world - 1 else self.total_len
         alpha = eng.alphabet_async(self.d_sba[a16:b16] if world > 1 else self.d_sba)
+        bytes_ready = eng.mark() if world > 1 and hasattr(eng, "mark") else None   # (before the pack kernel)
         pk = eng.pack_slice(self.d_sba, self.seg_starts, k, class_bit, first, end, self.idx_bytes)
         self._mark("pack")
         if self._layout_finish is not None:   # the rest of the both-strand layout: behind the pack kernel
@@ -660,11 +669,17 @@ class ShardedKmers:
 
         # ---- splitters from evenly spaced samples (second stream: runs beside the pack kernel) --------------
         if world > 1:
-            sample = eng.sample_keys_host(self.d_sba, self.seg_starts, k, class_bit, first, end, SAMPLES_PER_RANK)
+            sample = eng.sample_keys_host(self.d_sba, self.seg_starts, k, class_bit, first, end, SAMPLES_PER_RANK,
+                                          **({"after": bytes_ready} if bytes_ready is not None else {}))
             padded = np.zeros(SAMPLES_PER_RANK + 1, dtype=np.uint64)
             padded[0] = len(sample)
             padded[1:1 + len(sample)] = sample
-            table = self._gather(padded)
+            side = getattr(eng, "side_context", None)
+            if side is not None:      # beside the pack kernel, not behind it
+                with side():
+                    table = self._gather(padded)
+            else:
+                table = self._gather(padded)
             pooled = np.sort(np.concatenate([row[1:1 + int(row[0])] for row in table]))
             # even splitters: a key range then starts at an even key, so subtracting it keeps the class bit
             splitters_host = choose_splitters(pooled, world, class_bit) & ~np.uint64(1)
