@@ -419,6 +419,12 @@ class Kmers:
     def _ensure_device(self) -> None:
         """Upload the byte array (once) and create the native index.  Fails without a GPU."""
         if self._ix is not None:
+            # every later call allocates and launches on the current device: it must be the one that holds
+            # the byte array and the index
+            current = _torch().cuda.current_device()
+            if current != self._device_index:
+                raise RuntimeError(f"this Kmers object lives on cuda:{self._device_index} but the current CUDA device "
+                                   f"is cuda:{current}; call torch.cuda.set_device({self._device_index}) first")
             return
         torch = _torch()
         lib = _native.lib()
@@ -426,6 +432,7 @@ class Kmers:
             raise RuntimeError("genome_kmers needs a CUDA device: the k-mer hot path has no CPU fallback")
         if self._device is not None:
             torch.cuda.set_device(self._device)
+        self._device_index = torch.cuda.current_device()
         host_sba, starts, total = self._strand_layout()
         stream = self._stream()
         if host_sba is not None:
@@ -495,14 +502,15 @@ class Kmers:
             self._n_kmers = len(self._host_idx)
 
     def device_start_indices(self):
-        """The (sorted) start indices as a torch tensor that aliases the index's device buffer."""
+        """The (sorted) start indices as a torch tensor on the device: a copy, so it stays valid when a later
+        sort() or load() replaces the index's own buffer."""
         self._ensure_device()
         self._push_host_indices()
         torch, lib = _torch(), _native.lib()
         ptr = ctypes.c_void_p()
         _native.check(lib.gk_index_device_indices(self._ix, ctypes.byref(ptr), self._stream()))
         nbytes = lib.gk_index_idx_bytes(self._ix)
-        return _tensor_from_ptr(torch, ptr.value, self._n_kmers, nbytes)
+        return _tensor_from_ptr(torch, ptr.value, self._n_kmers, nbytes).clone()
 
     def __len__(self):
         if self._host_idx is not None:

@@ -515,7 +515,7 @@ def _fasta_block(data: np.ndarray):
     hdr_lines = np.flatnonzero(is_hdr)
     cuts = line_off[np.searchsorted(seq_lines, hdr_lines)]
     names = [SequenceCollection._get_fasta_record_name(
-        data[line_start[i]:line_end[i]].tobytes().decode("utf-8", errors="replace")) for i in hdr_lines]
+        data[line_start[i]:line_end[i]].tobytes().decode("utf-8")) for i in hdr_lines]
     return names, kept, cuts
 
 
@@ -601,7 +601,7 @@ def _read_fasta(path) -> Tuple[List[str], np.ndarray, np.ndarray]:
                     end = text.find(b"\n", hdr)
                     end = len(text) if end < 0 else end
                     names.append(SequenceCollection._get_fasta_record_name(
-                        text[hdr:end].decode("utf-8", errors="replace")))
+                        text[hdr:end].decode("utf-8")))
                     starts_in_seq.append(total)
                     pos = min(end + 1, len(text))
                     if text.startswith(b">", pos):

@@ -387,6 +387,11 @@ def test_fasta_reader_errors(tmp_path):
         load(">a x\nAC\n>a y\nGT\n")
     with pytest.raises(AssertionError, match="we expect sba to be full"):
         load("ACGT\n>a\nAC\n")                   # text before the first header (ref :555-569)
+    # a header that is not valid UTF-8: the reference reads the file in text mode and raises
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">chr\xff1\nACGT\n")
+    with pytest.raises(UnicodeDecodeError):
+        SequenceCollection(fasta_file_path=bad)
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference is only mounted in the build container")
