@@ -14,6 +14,8 @@ def child(n):
     import torch
     from genome_kmers import _native
 
+    if os.environ.get("GK_BENCH_LIB"):   # a second build of the library (an experiment compiled with -D...)
+        _native.LIB_PATH = os.environ["GK_BENCH_LIB"]
     lib = _native.lib()
     g = torch.Generator(device="cuda").manual_seed(1)
     keys = torch.randint(-(1 << 62), 1 << 62, (n,), dtype=torch.int64, device="cuda", generator=g)
