@@ -56,6 +56,8 @@ void count_launch(int n = 1);
 // All scratch comes from the device's default mempool (cudaMallocAsync); the release threshold
 // is raised once so repeated sorts reuse the same pages instead of going back to the driver.
 int ensure_pool_configured();
+int pool_alloc(void **out, size_t n, cudaStream_t s);   // block cache in front of cudaMallocAsync (gk_core.cu)
+void pool_free(void *ptr, size_t n, cudaStream_t s);
 void trace_alloc(double ms, size_t bytes);  // GK_TRACE=1: allocation time accounting (gk_core.cu)
 
 double trace_now_ms();
@@ -74,15 +76,14 @@ struct DeviceBuffer {
         stream = s;
         bytes = n;
         if (n == 0) return GK_OK;
-        GK_TRY(ensure_pool_configured());
         const double t0 = trace_now_ms();
-        GK_CUDA(cudaMallocAsync(&ptr, n, s));
+        GK_TRY(pool_alloc(&ptr, n, s));
         trace_alloc(trace_now_ms() - t0, n);
         return GK_OK;
     }
     void release()
     {
-        if (ptr) cudaFreeAsync(ptr, stream);
+        if (ptr) pool_free(ptr, bytes, stream);
         ptr = nullptr;
         bytes = 0;
     }

@@ -14,6 +14,7 @@
 namespace gk {
 
 void trace_report(const char *what);
+void trace_point(const char *name);
 void set_deferred_sort_error_word(int *d_err);
 // kernels / device drivers from the other translation units
 int kmer_count_host(const uint64_t *, uint32_t, uint64_t, uint32_t, uint64_t *);
@@ -117,7 +118,7 @@ struct Owned {
     ~Owned() { reset(); }
     void reset()
     {
-        if (ptr) cudaFreeAsync(ptr, stream);
+        if (ptr) pool_free(ptr, bytes, stream);
         ptr = nullptr;
         bytes = 0;
     }
@@ -126,9 +127,8 @@ struct Owned {
         reset();
         stream = st;
         if (n == 0) return GK_OK;
-        GK_TRY(ensure_pool_configured());
         const double t0 = trace_now_ms();
-        GK_CUDA(cudaMallocAsync(&ptr, n, st));
+        GK_TRY(pool_alloc(&ptr, n, st));
         trace_alloc(trace_now_ms() - t0, n);
         bytes = n;
         return GK_OK;
@@ -486,10 +486,12 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
 
     int in_alt = 0;
     bool amb_counted = false;
+    trace_point("pairs_ready");
     // (inlined sort_pairs_and_flag: the third start buffer needs the passes' own bookkeeping)
     GK_CUDA(cudaMemsetAsync(d_descent, 0, 4, st));
     GK_TRY(radix_sort_pairs_device(pp.keys_a, pp.keys_b, pp.idx_a, pp.idx_b, ib, n, begin_bit, pp.key_bits, &in_alt, st,
                                    &marks.main_sort, pp.d_pre_hist, pp.idx_final));
+    trace_point("passes_enqueued");
     uint64_t *keys_sorted = in_alt ? pp.keys_b : pp.keys_a;
     uint64_t *keys_other = in_alt ? pp.keys_a : pp.keys_b;
     void *idx_sorted = pp.idx_final ? pp.idx_final : (in_alt ? pp.idx_b : pp.idx_a);
@@ -521,9 +523,11 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
         cudaStream_t side = nullptr;
         GK_TRY(side_stream(&side));
         GK_TRY(e_frag.create());
+        trace_point("repair_enqueued");
         GK_CUDA(cudaStreamWaitEvent(side, pp.e_producer, 0));
         GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, side));
         GK_CUDA(cudaStreamSynchronize(side));
+        trace_point("side_sync");
         n_amb = h_counters[0];
         n_frag = h_counters[2];
         use_frag = n_amb > 0 && n_frag > 0 && n_frag <= pp.frag.capacity;
@@ -548,6 +552,7 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
     }
     marks.fix1 = tm.mark();
     if (pp.spectrum) GK_TRY(pp.spectrum->start(d_flags, n, st));
+    trace_point("all_enqueued");
 
     // ---- the one synchronise: descents, repair status, fragment check, alphabet counters -----------------------
     int h_extra_err = 0;
@@ -558,6 +563,7 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
     }
     if (pp.d_extra_err) GK_CUDA(cudaMemcpyAsync(&h_extra_err, pp.d_extra_err, 4, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
+    trace_point("final_sync");
     if (h_extra_err) {
         set_error("partition: decoupled look-back timed out");
         return GK_ERR_INTERNAL;
@@ -957,6 +963,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     gk_sort_stats stats;
     memset(&stats, 0, sizeof(stats));
     const uint64_t launches0 = gk_launch_count(0);
+    trace_point("begin");
     EventTimer tm(st);
     StageMarks marks;
     const int t0 = tm.mark();
@@ -1115,6 +1122,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
     stats.total_ms = tm.ms(t0, t1);
     stats.gpu_launches = (int32_t)(gk_launch_count(0) - launches0);
     if (stats_out) *stats_out = stats;
+    trace_point("end");
     trace_report("gk_index_sort");
     return GK_OK;
 }
