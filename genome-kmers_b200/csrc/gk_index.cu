@@ -101,6 +101,8 @@ int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uin
                          uint32_t, uint64_t, uint64_t *, cudaStream_t);
 int pair_keys_words_device(const uint32_t *, const uint32_t *, uint64_t, const uint8_t *, uint64_t, uint64_t, uint32_t,
                            uint64_t *, cudaStream_t);
+int scatter_sorted_subset_device(const void *, const uint64_t *, const void *, uint64_t, int, int, uint64_t *, void *,
+                                 uint8_t *, cudaStream_t);
 int subset_rank_update_device(const uint32_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *,
                               cudaStream_t);
 int gather_u32_device(const uint32_t *, const uint32_t *, uint64_t, uint32_t *, cudaStream_t);
@@ -413,6 +415,36 @@ static int refine_subset(gk_index *ix, const uint64_t *keys_sorted, void *d_idx,
     return GK_OK;  // the scratch above is released in stream order (cudaFreeAsync): no synchronise needed
 }
 
+// Too many out-of-order long prefix runs for the bucket-wise repair (a repeat-rich genome: millions of k-mers
+// that agree on their first 16 symbols): every member of every long run is taken out, the set is sorted by the
+// full key (the members come out in prefix order, so a stable sort puts every run's members back into the
+// run's own slots) and written back with fresh flags -- keys too, so that the fragments can be expanded
+// afterwards.  Cost: one ordered select, 8 radix passes over the set, one scatter.  No synchronise.
+static int repair_long_runs(uint64_t *keys_sorted, void *d_idx, uint8_t *d_flags, uint64_t n, int ib, int class_bit,
+                            int key_bits, uint64_t *m_out, cudaStream_t st)
+{
+    uint64_t m = 0;
+    DeviceBuffer sel_temp;
+    GK_TRY(select_pairs_count(d_flags, n, kFlagLong, sel_temp, &m, st));
+    if (m_out) *m_out = m;
+    if (m == 0) return GK_OK;
+    DeviceBuffer pos, key, key_alt, idx, idx_alt;
+    GK_TRY(pos.alloc((size_t)m * ib, st));
+    GK_TRY(key.alloc((size_t)m * 8, st));
+    GK_TRY(key_alt.alloc((size_t)m * 8, st));
+    GK_TRY(idx.alloc((size_t)m * ib, st));
+    GK_TRY(idx_alt.alloc((size_t)m * ib, st));
+    GK_TRY(select_pairs_write(d_flags, n, kFlagLong, sel_temp, ib, pos.ptr, keys_sorted, key.as<uint64_t>(), d_idx,
+                              idx.ptr, st));
+    int in_alt = 0;
+    GK_TRY(radix_sort_pairs_device(key.as<uint64_t>(), key_alt.as<uint64_t>(), idx.ptr, idx_alt.ptr, ib, m, 0, key_bits,
+                                   &in_alt, st, nullptr));
+    GK_TRY(scatter_sorted_subset_device(pos.ptr, in_alt ? key_alt.as<uint64_t>() : key.as<uint64_t>(),
+                                        in_alt ? idx_alt.ptr : idx.ptr, m, class_bit, ib, keys_sorted, d_idx, d_flags,
+                                        st));
+    return GK_OK;
+}
+
 // Out-of-order prefix buckets that were too long for the device-side repair (one CTA per bucket): sort each
 // by its low key bits with the radix passes, in place, and recompute its flags.  h_ranges: n_ranges (lo, hi)
 // slot ranges as listed by repair_buckets_kernel.  No synchronise.
@@ -603,6 +635,19 @@ static int sort_packed_pairs(gk_index *ix, PackedPairs &pp, uint8_t *d_flags, St
                                           reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb,
                                           d_frag_err, st));
             }
+            GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaStreamSynchronize(st));
+            frag_err = (int)(h_counters[3] & 0xffffffffull);
+        } else if (use_frag && !frag_err) {
+            // more out-of-order long runs than the device list holds: re-sort all long runs by their keys, then
+            // let the fragments write the ambiguous slots (they did nothing while the keys were out of order)
+            uint64_t m_long = 0;
+            GK_TRY(repair_long_runs(keys_sorted, idx_sorted, d_flags, n, ib, pp.class_bit, pp.key_bits, &m_long, st));
+            marks.refine_flags |= 64u;
+            GK_CUDA(cudaMemsetAsync(d_status, 0, 4, st));
+            GK_TRY(frag_expand_device(*pp.fs, keys_sorted, n, ib, idx_sorted, d_flags,
+                                      reinterpret_cast<const unsigned int *>(d_status), d_counters, n_amb, d_frag_err,
+                                      st));
             GK_CUDA(cudaMemcpyAsync(h_counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
             GK_CUDA(cudaStreamSynchronize(st));
             frag_err = (int)(h_counters[3] & 0xffffffffull);

@@ -419,6 +419,27 @@ subset_expand_kernel(const T *__restrict__ pos, const T *__restrict__ idx_sel, c
     }
 }
 
+// Long prefix runs re-sorted by their full keys (gk_index.cu: repair_long_runs): the sorted members go back to
+// the slots of the set, in order, with fresh flags; the sorted keys are written back too, so that the fragment
+// expansion can look its keys up afterwards.
+template <typename T>
+__global__ void __launch_bounds__(256)
+scatter_sorted_subset_kernel(const T *__restrict__ pos, const uint64_t *__restrict__ keys_sorted,
+                             const T *__restrict__ idx_sorted, uint64_t m, int class_bit,
+                             uint64_t *__restrict__ keys, T *__restrict__ idx, uint8_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const uint64_t k = keys_sorted[r];
+        const bool head = (r == 0) || keys_sorted[r - 1] != k;
+        const bool amb = class_bit && !(k & 1ull);
+        const uint64_t p = (uint64_t)pos[r];
+        keys[p] = k;
+        idx[p] = idx_sorted[r];
+        flags[p] = amb ? kFlagAmb : (head ? kFlagHead : 0);
+    }
+}
+
 // subset bookkeeping of the doubling rounds: global slot of every member's group head, and the new rank of
 // every member's start (rank = sorted position of the first member of its group)
 __global__ void __launch_bounds__(256)
@@ -597,6 +618,23 @@ int pair_keys_words_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid,
 {
     if (m == 0) return GK_OK;
     pair_keys_words_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_sba, sba_len, h, span, d_keys);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+int scatter_sorted_subset_device(const void *d_pos, const uint64_t *d_keys_sorted, const void *d_idx_sorted, uint64_t m,
+                                 int class_bit, int t_bytes, uint64_t *d_keys, void *d_idx, uint8_t *d_flags,
+                                 cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    if (t_bytes == 4)
+        scatter_sorted_subset_kernel<uint32_t><<<grid_for(m), 256, 0, st>>>(
+            (const uint32_t *)d_pos, d_keys_sorted, (const uint32_t *)d_idx_sorted, m, class_bit, d_keys,
+            (uint32_t *)d_idx, d_flags);
+    else
+        scatter_sorted_subset_kernel<uint64_t><<<grid_for(m), 256, 0, st>>>(
+            (const uint64_t *)d_pos, d_keys_sorted, (const uint64_t *)d_idx_sorted, m, class_bit, d_keys,
+            (uint64_t *)d_idx, d_flags);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }

@@ -75,7 +75,9 @@ typedef struct {
     uint64_t n_ambiguous; /* windows holding a non-ACGT symbol within the key */
     uint64_t n_fragments; /* blocks of identical ambiguous windows listed by the pack kernel (0: not used) */
     uint64_t refine_flags; /* 1 fragment path used, 2 element-wise repair ran, 4 a long prefix run was out of
-                              order, fragment consistency error bits << 8 */
+                              order, 16 repaired bucket-wise on the device, 32 big buckets re-sorted from the host,
+                              64 all long runs re-sorted by key (too many were out of order for the bucket list),
+                              fragment consistency error bits << 8 */
 } gk_sort_stats;
 
 typedef struct gk_index gk_index;

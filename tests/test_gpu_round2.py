@@ -220,6 +220,35 @@ def test_repeat_rich_input_is_repaired_without_the_elementwise_path():
     assert total == o_total and np.array_equal(hist, o_hist)
 
 
+def test_many_out_of_order_long_runs_are_resorted_by_key_and_fragments_still_apply():
+    """Hundreds of diverged copies of a long unit: far more out-of-order members of long prefix runs than the
+    device-side bucket list holds.  All long runs are then re-sorted by key (refine_flags bit 64) and the
+    ambiguous windows still come from the fragments -- no element-wise repair (bit 2)."""
+    rng = np.random.default_rng(79)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, 2500)]
+    parts = []
+    for c_i in range(300):
+        c = unit.copy()
+        c[rng.integers(0, len(unit), 60)] = acgt[rng.integers(0, 4, 60)]
+        parts += [c, acgt[rng.integers(0, 4, int(rng.integers(10, 200)))]]
+        if c_i % 40 == 0:
+            parts.append(np.full(int(rng.integers(50, 3000)), ord("N"), dtype=np.uint8))
+    seq = np.concatenate(parts)
+    seq[rng.integers(0, len(seq), 12)] = ord("R")
+    cut = len(seq) // 2
+    sc, sba, seg, want = _oracle_sorted([("chr0", seq[:cut]), ("chr1", seq[cut:])], 31, "both")
+    km = Kmers(sc, 31, 31, source_strand="both")
+    km.sort()
+    st = km.last_sort_stats
+    assert np.array_equal(km.kmer_sba_start_indices.astype(np.uint64), want)
+    assert st["refine_flags"] & 64 and st["refine_flags"] & 1 and not st["refine_flags"] & 2, st
+    assert km.verify_order(31)["ok"]
+    hist, total = km.get_kmer_group_counts(31, max_counts_bin=700)
+    o_hist, o_total = oracle.group_hist(sba, want, 31, max_bin=700)
+    assert total == o_total and np.array_equal(hist, o_hist)
+
+
 @pytest.mark.parametrize("strands", ["forward", "both"])
 def test_stranger_in_the_all_n_bucket_is_moved_without_sorting_the_bucket(strands):
     """A bucket of more than 65536 equal ambiguous keys (one long N run) with pure k-mers that share its 32-bit
