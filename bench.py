@@ -360,14 +360,18 @@ def run_reference_arm(args, rank, world):
     if ref is not None:
         # every sort() / count call of the reference compiles a fresh numba closure (kmers.py:1641-1645, :1156):
         # the warm-up steps run the same calls on a 200-bp collection and measure exactly that
-        sample_bases = args.ref_sample_bases or 150_000
-        jit = [reference_run(ref, 0, seed=50 + s)[1] for s in range(max(1, args.warmup))]
-        jit_s = float(np.median(jit))
+        # (at least three calibration calls, the fastest counts: the first also compiles the module-level
+        # functions once per process, which no later call pays)
+        sample_bases = args.ref_sample_bases or 1_000_000
+        jit = [reference_run(ref, 0, seed=50 + s)[1] for s in range(max(3, args.warmup))]
+        jit_s = float(min(jit))
         raw, n = [], 0
         for s in range(args.steps):
             n, dt = reference_run(ref, sample_bases, seed=100 + s)
             raw.append(dt)
-        net_total = max(sum(raw) - jit_s * args.steps, 0.05 * sum(raw))   # (a noisy JIT estimate cannot zero it)
+        net_total = sum(raw) - jit_s * args.steps
+        jit_clamped = net_total < 0.05 * sum(raw)     # (cannot happen at the default sample size: ~1.5 s of sorting)
+        net_total = max(net_total, 0.05 * sum(raw))
         value = n * args.steps / net_total / 1e9
         cores, kind = 1, "reference"
         ms_per_step = 1e3 * net_total / args.steps
@@ -376,7 +380,8 @@ def run_reference_arm(args, rank, world):
                   f"reverse-complemented records = both strands, {n} k-mers per step, single-threaded like the "
                   f"reference; numba compile time ({jit_s:.1f} s per step, measured on a 200-bp collection) is "
                   f"subtracted; with it the value is {n * args.steps / sum(raw) / 1e9:.6f} {UNIT}")
-        extra = {"jit_s_per_step": jit_s, "raw_s_per_step": float(np.mean(raw))}
+        extra = {"jit_s_per_step": jit_s, "raw_s_per_step": float(np.mean(raw)), "jit_estimate_clamped": bool(jit_clamped),
+                 "jit_calibration_s": [round(t, 3) for t in jit]}
     else:
         threads = max(1, min(PORT_THREADS, os.cpu_count() or 1))
         sample_bases = args.ref_sample_bases or 4_000_000
@@ -831,9 +836,9 @@ def main():
     ap.add_argument("--records", type=int, default=N_RECORDS, help="records per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-bases", type=int, default=0,
-                    help="sample size of the cpu_baseline leg (0: 500 kbp for the reference, 2 Mbp for the port)")
+                    help="sample size of the cpu_baseline leg (0: 4 Mbp for the reference, 2 Mbp for the port)")
     ap.add_argument("--ref-sample-bases", type=int, default=0,
-                    help="sample size per step of --impl reference (0: 150 kbp for the reference, 4 Mbp for the port)")
+                    help="sample size per step of --impl reference (0: 1 Mbp for the reference, 4 Mbp for the port)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "port"],
                     help="auto: the real reference from oracle/_ref when numba imports, else the C port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -851,7 +856,7 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if args.cpu_sample_bases == 0:
-        args.cpu_sample_bases = 500_000 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "genome_kmers")) \
+        args.cpu_sample_bases = 4_000_000 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "genome_kmers")) \
             else 2_000_000
     if args.config == "c3":
         n = max(world, args.gpus)
