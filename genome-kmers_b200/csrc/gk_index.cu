@@ -99,8 +99,10 @@ int key2_scatter_device(const uint64_t *, const uint32_t *, const uint32_t *, ui
                         cudaStream_t);
 int pair_keys_var_device(const uint32_t *, const uint32_t *, uint64_t, const uint32_t *, uint32_t, const uint64_t *,
                          uint32_t, uint64_t, uint64_t *, cudaStream_t);
-int pair_keys_words_device(const uint32_t *, const uint32_t *, uint64_t, const uint8_t *, uint64_t, uint64_t, uint32_t,
+int pair_keys_words_device(const void *, int, const uint32_t *, uint64_t, const uint8_t *, uint64_t, uint64_t, uint32_t,
                            uint64_t *, cudaStream_t);
+int key2_scatter_any_device(const uint64_t *, const void *, const uint32_t *, uint64_t, int, void *, uint8_t *,
+                            cudaStream_t);
 int scatter_sorted_subset_device(const void *, const uint64_t *, const void *, uint64_t, int, int, uint64_t *, void *,
                                  uint8_t *, cudaStream_t);
 int subset_rank_update_device(const uint32_t *, const uint32_t *, const uint32_t *, uint64_t, uint32_t *, uint32_t *,
@@ -768,10 +770,8 @@ static int sort_level1(gk_index *ix, uint32_t valid_len, uint32_t key_len, int c
 // half (the window ended) sorts first.  Only the O(n) set-up touches every k-mer: rank_h of every start
 // (= sorted position of the first member of its group) and the list of members of multi-element groups.
 // The rounds then work on that shrinking list only and scatter their results into the global order.
-// by_words (a multi-GPU shard: the index holds one key range, so the rank of start + h is not known here): the
-// second half of the pair is the next 8 symbols read from the bytes, h -> h + 8 per round, no rank table.
 static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint64_t n_cur, uint64_t h0,
-                           uint64_t target, int *levels, cudaStream_t st, bool by_words = false)
+                           uint64_t target, int *levels, cudaStream_t st)
 {
     if (h0 >= target || n_cur < 2) return GK_OK;
     uint32_t *d_idx = (uint32_t *)cur_idx.ptr;
@@ -787,7 +787,7 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
     GK_TRY(select_flagged(mflags.as<uint8_t>(), n_cur, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr,
                           &m, st));
     if (m == 0) return GK_OK;
-    if (!by_words) GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
+    GK_TRY(rank.alloc((size_t)ix->sba_len * 4, st));
     GK_TRY(gid.alloc((size_t)n_cur * 4, st));
     GK_TRY(head_positions_device(d_flags, d_idx, n_cur, gid.as<uint32_t>(), rank.as<uint32_t>(), st));
     DeviceBuffer slots, sub_idx, sub_gid;
@@ -802,20 +802,15 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
     mflags.release();
     uint64_t h = h0;
     while (h < target && m > 0) {
-        const uint64_t step = by_words ? 8 : h;
-        const uint64_t h2 = (h + step < target) ? h + step : target;
+        const uint64_t h2 = (2 * h < target) ? 2 * h : target;
         const uint32_t delta = (uint32_t)(h2 - h);
         DeviceBuffer keys, keys_alt, idx_alt, hf, gsub, gslot, mf;
         GK_TRY(keys.alloc((size_t)m * 8, st));
         GK_TRY(keys_alt.alloc((size_t)m * 8, st));
         GK_TRY(idx_alt.alloc((size_t)m * 4, st));
-        if (by_words)
-            GK_TRY(pair_keys_words_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, ix->d_sba, ix->sba_len, h,
-                                          delta, keys.as<uint64_t>(), st));
-        else
-            GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, rank.as<uint32_t>(), delta,
-                                        (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->sba_len,
-                                        keys.as<uint64_t>(), st));
+        GK_TRY(pair_keys_var_device(sub_idx.as<uint32_t>(), sub_gid.as<uint32_t>(), m, rank.as<uint32_t>(), delta,
+                                    (const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(), ix->sba_len,
+                                    keys.as<uint64_t>(), st));
         int in_alt = 0;
         GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr, idx_alt.ptr, 4, m,
                                        0, 64, &in_alt, st, nullptr));
@@ -851,6 +846,94 @@ static int doubling_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint6
         slots.release(); sub_idx.release(); sub_gid.release();
         if (m2) {
             // adopt the new lists (move the pointers: DeviceBuffer has no move assignment)
+            slots.ptr = new_slots.ptr; slots.bytes = new_slots.bytes; slots.stream = st; new_slots.ptr = nullptr;
+            sub_idx.ptr = new_idx.ptr; sub_idx.bytes = new_idx.bytes; sub_idx.stream = st; new_idx.ptr = nullptr;
+            sub_gid.ptr = new_gid.ptr; sub_gid.bytes = new_gid.bytes; sub_gid.stream = st; new_gid.ptr = nullptr;
+        }
+        m = m2;
+        h = h2;
+        if (levels) ++*levels;
+    }
+    return GK_OK;
+}
+
+// Word rounds: fixed-length k-mers longer than one key word where the ranks of other starts are not at hand -- a
+// multi-GPU shard (the index holds one key range) -- or do not fit 32 bits (a byte array of 2^32 positions or
+// more).  In: the windows sorted by their first h0 symbols, flags = groups of equal h0-prefixes.  The members of
+// groups that are still tied are ordered by (group, 4-bit ranks of the next 8 symbols), read from the bytes, 8
+// symbols per round, on the shrinking list of tied members.  Start indices of either width; positions inside the
+// index are 32-bit (n < 2^32).
+static int word_rounds(gk_index *ix, Owned &cur_idx, Owned &cur_flags, uint64_t n, uint64_t h0, uint64_t target,
+                       int *levels, cudaStream_t st)
+{
+    if (h0 >= target || n < 2) return GK_OK;
+    if (n >= (1ull << 32)) {
+        set_error("k-mers longer than one key word: %llu windows in one index (limit 2^32 - 1)", (unsigned long long)n);
+        return GK_ERR_UNSUPPORTED;
+    }
+    const int ib = ix->idx_bytes;
+    void *d_idx = cur_idx.ptr;
+    uint8_t *d_flags = (uint8_t *)cur_flags.ptr;
+    DeviceBuffer gid, mflags;
+    GK_TRY(mflags.alloc((size_t)((n + 15) & ~15ull), st));
+    GK_TRY(multi_flags_device(d_flags, n, mflags.as<uint8_t>(), st));
+    uint64_t m = 0;
+    GK_TRY(select_flagged(mflags.as<uint8_t>(), n, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr, &m, st));
+    if (m == 0) return GK_OK;
+    GK_TRY(gid.alloc((size_t)n * 4, st));
+    GK_TRY(head_positions_device(d_flags, nullptr, n, gid.as<uint32_t>(), nullptr, st));
+    DeviceBuffer slots, sub_idx, sub_gid;
+    GK_TRY(slots.alloc((size_t)m * 4, st));
+    GK_TRY(sub_idx.alloc((size_t)m * ib, st));
+    GK_TRY(sub_gid.alloc((size_t)m * 4, st));
+    GK_TRY(select_flagged(mflags.as<uint8_t>(), n, kFlagMulti, 4, slots.ptr, gid.ptr, sub_gid.ptr, nullptr, nullptr,
+                          nullptr, st));
+    GK_TRY(select_flagged(mflags.as<uint8_t>(), n, kFlagMulti, ib, nullptr, d_idx, sub_idx.ptr, nullptr, nullptr,
+                          nullptr, st));
+    gid.release();
+    mflags.release();
+    uint64_t h = h0;
+    while (h < target && m > 0) {
+        const uint64_t h2 = (h + 8 < target) ? h + 8 : target;
+        DeviceBuffer keys, keys_alt, idx_alt, hf, gsub, gslot, mf;
+        GK_TRY(keys.alloc((size_t)m * 8, st));
+        GK_TRY(keys_alt.alloc((size_t)m * 8, st));
+        GK_TRY(idx_alt.alloc((size_t)m * ib, st));
+        GK_TRY(pair_keys_words_device(sub_idx.ptr, ib, sub_gid.as<uint32_t>(), m, ix->d_sba, ix->sba_len, h,
+                                      (uint32_t)(h2 - h), keys.as<uint64_t>(), st));
+        int in_alt = 0;
+        GK_TRY(radix_sort_pairs_device(keys.as<uint64_t>(), keys_alt.as<uint64_t>(), sub_idx.ptr, idx_alt.ptr, ib, m, 0,
+                                       64, &in_alt, st, nullptr));
+        const uint64_t *K = in_alt ? keys_alt.as<uint64_t>() : keys.as<uint64_t>();
+        const void *I = in_alt ? idx_alt.ptr : sub_idx.ptr;
+        GK_TRY(key2_scatter_any_device(K, I, slots.as<uint32_t>(), m, ib, d_idx, d_flags, st));
+        // the groups inside the list after this round and the members that are still tied
+        GK_TRY(hf.alloc((size_t)((m + 15) & ~15ull), st));
+        GK_TRY(key_flags_device(K, m, 0, hf.as<uint8_t>(), st));
+        GK_TRY(gsub.alloc((size_t)m * 4, st));
+        GK_TRY(head_positions_device(hf.as<uint8_t>(), nullptr, m, gsub.as<uint32_t>(), nullptr, st));
+        GK_TRY(gslot.alloc((size_t)m * 4, st));
+        GK_TRY(subset_rank_update_device(slots.as<uint32_t>(), gsub.as<uint32_t>(), nullptr, m, gslot.as<uint32_t>(),
+                                         nullptr, st));
+        GK_TRY(mf.alloc((size_t)((m + 15) & ~15ull), st));
+        GK_TRY(gid_flags_device(gsub.as<uint32_t>(), m, mf.as<uint8_t>(), st));
+        uint64_t m2 = 0;
+        GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, 4, nullptr, nullptr, nullptr, nullptr, nullptr, &m2, st));
+        DeviceBuffer pos, new_slots, new_idx, new_gid;
+        if (m2 && h2 < target) {
+            GK_TRY(pos.alloc((size_t)m2 * 4, st));
+            GK_TRY(new_slots.alloc((size_t)m2 * 4, st));
+            GK_TRY(new_idx.alloc((size_t)m2 * ib, st));
+            GK_TRY(new_gid.alloc((size_t)m2 * 4, st));
+            GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, 4, pos.ptr, gslot.ptr, new_gid.ptr, nullptr, nullptr,
+                                  nullptr, st));
+            GK_TRY(select_flagged(mf.as<uint8_t>(), m, kFlagMulti, ib, nullptr, I, new_idx.ptr, nullptr, nullptr,
+                                  nullptr, st));
+            GK_TRY(gather_u32_device(slots.as<uint32_t>(), pos.as<uint32_t>(), m2, new_slots.as<uint32_t>(), st));
+        }
+        GK_CUDA(cudaStreamSynchronize(st));  // the round's scratch is released in stream order after this
+        slots.release(); sub_idx.release(); sub_gid.release();
+        if (m2 && h2 < target) {
             slots.ptr = new_slots.ptr; slots.bytes = new_slots.bytes; slots.stream = st; new_slots.ptr = nullptr;
             sub_idx.ptr = new_idx.ptr; sub_idx.bytes = new_idx.bytes; sub_idx.stream = st; new_idx.ptr = nullptr;
             sub_gid.ptr = new_gid.ptr; sub_gid.bytes = new_gid.bytes; sub_gid.stream = st; new_gid.ptr = nullptr;
@@ -1099,11 +1182,19 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
                       "(max_kmer_len <= 31) only");
             return GK_ERR_UNSUPPORTED;
         }
-        if (ix->idx_bytes != 4) {
-            set_error("k-mers longer than one key word on a byte array of 2^32 or more positions are not "
-                      "available yet");
+        if (ix->idx_bytes != 4 && !fixed) {
+            set_error("the variable-length mode on a byte array of 2^32 or more positions is not available");
             return GK_ERR_UNSUPPORTED;
         }
+        if (ix->idx_bytes != 4) {
+            // fixed k > one key word with 64-bit start indices: the rank table of the doubling is 32-bit, so the
+            // windows are sorted by their first 31 symbols and the tied ones by the following symbols, read from
+            // the bytes (word_rounds)
+            GK_TRY(sort_level1(ix, k, 31, 1, n_sort, new_idx, new_flags, marks, tm, st, nullptr, nullptr));
+            t_ref0 = tm.mark();
+            GK_TRY(word_rounds(ix, new_idx, new_flags, n_sort, 31, k, &marks.levels, st));
+            t_ref1 = tm.mark();
+        } else {
         uint64_t longest = 0;
         for (size_t r = 0; r < ix->h_segs.size(); ++r) {
             const uint64_t e = (r + 1 < ix->h_segs.size()) ? ix->h_segs[r + 1] - 1 : ix->sba_len;
@@ -1121,6 +1212,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
             set_error("doubling kept %llu windows, expected %llu", (unsigned long long)n_cur,
                       (unsigned long long)n_sort);
             return GK_ERR_INTERNAL;
+        }
         }
     }
     const int t1 = tm.mark();
@@ -1197,9 +1289,8 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     // k-mers longer than one key word: the pairs carry the first 31 symbols (gk_pack_slice), the rest is compared
     // from the bytes in word rounds after the sort
     const bool long_k = k > 31 && !(k == 32 && !class_bit);
-    if (long_k && (!class_bit || ix->idx_bytes != 4)) {
-        set_error("gk_index_sort_shard: k-mers longer than one key word need class-bit keys and 32-bit start "
-                  "indices (a byte array below 2^32 positions)");
+    if (long_k && !class_bit) {
+        set_error("gk_index_sort_shard: k-mers longer than one key word need class-bit keys");
         return GK_ERR_UNSUPPORTED;
     }
     const uint32_t key_len = long_k ? 31u : k;
@@ -1294,7 +1385,7 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
     int t_ref0 = -1, t_ref1 = -1;
     if (long_k && n_local) {
         t_ref0 = tm.mark();
-        GK_TRY(doubling_rounds(ix, new_idx, new_flags, n_local, key_len, k, &levels, st, /*by_words=*/true));
+        GK_TRY(word_rounds(ix, new_idx, new_flags, n_local, key_len, k, &levels, st));
         t_ref1 = tm.mark();
         if (spectrum_enabled()) GK_TRY(spectrum.start((const uint8_t *)new_flags.ptr, n_local, st));
     }

@@ -212,8 +212,9 @@ pair_keys_var_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__res
 // Word rounds (multi-GPU shards: the ranks of other starts live on other GPUs): the second half of the pair
 // is read from the bytes instead -- the 4-bit ranks of the `span` <= 8 symbols from start + h on, most
 // significant first; a '$' / the end of the array ends the k-mer (all later symbols 0, kmers.py:360-378).
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pair_keys_words_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__restrict__ sub_gid, uint64_t m,
+pair_keys_words_kernel(const IdxT *__restrict__ sub_idx, const uint32_t *__restrict__ sub_gid, uint64_t m,
                        const uint8_t *__restrict__ sba, uint64_t sba_len, uint64_t h, uint32_t span,
                        uint64_t *__restrict__ keys)
 {
@@ -231,9 +232,10 @@ pair_keys_words_kernel(const uint32_t *__restrict__ sub_idx, const uint32_t *__r
 }
 
 // the re-sorted subset goes back to its slots with fresh head flags
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
-key2_scatter_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ sub_idx_sorted,
-                    const uint32_t *__restrict__ slots, uint64_t m, uint32_t *__restrict__ idx,
+key2_scatter_kernel(const uint64_t *__restrict__ keys_sorted, const IdxT *__restrict__ sub_idx_sorted,
+                    const uint32_t *__restrict__ slots, uint64_t m, IdxT *__restrict__ idx,
                     uint8_t *__restrict__ flags)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -613,11 +615,32 @@ int pair_keys_var_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, u
     return GK_OK;
 }
 
-int pair_keys_words_device(const uint32_t *d_sub_idx, const uint32_t *d_sub_gid, uint64_t m, const uint8_t *d_sba,
-                           uint64_t sba_len, uint64_t h, uint32_t span, uint64_t *d_keys, cudaStream_t st)
+int pair_keys_words_device(const void *d_sub_idx, int idx_bytes, const uint32_t *d_sub_gid, uint64_t m,
+                           const uint8_t *d_sba, uint64_t sba_len, uint64_t h, uint32_t span, uint64_t *d_keys,
+                           cudaStream_t st)
 {
     if (m == 0) return GK_OK;
-    pair_keys_words_kernel<<<grid_for(m), 256, 0, st>>>(d_sub_idx, d_sub_gid, m, d_sba, sba_len, h, span, d_keys);
+    if (idx_bytes == 4)
+        pair_keys_words_kernel<uint32_t><<<grid_for(m), 256, 0, st>>>((const uint32_t *)d_sub_idx, d_sub_gid, m, d_sba,
+                                                                      sba_len, h, span, d_keys);
+    else
+        pair_keys_words_kernel<uint64_t><<<grid_for(m), 256, 0, st>>>((const uint64_t *)d_sub_idx, d_sub_gid, m, d_sba,
+                                                                      sba_len, h, span, d_keys);
+    GK_LAUNCH_CHECK();
+    return GK_OK;
+}
+
+// key2_scatter for either width of start index (the word rounds run on 64-bit starts too)
+int key2_scatter_any_device(const uint64_t *d_keys_sorted, const void *d_sub_idx_sorted, const uint32_t *d_slots,
+                            uint64_t m, int idx_bytes, void *d_idx, uint8_t *d_flags, cudaStream_t st)
+{
+    if (m == 0) return GK_OK;
+    if (idx_bytes == 4)
+        key2_scatter_kernel<uint32_t><<<grid_for(m), 256, 0, st>>>(d_keys_sorted, (const uint32_t *)d_sub_idx_sorted,
+                                                                   d_slots, m, (uint32_t *)d_idx, d_flags);
+    else
+        key2_scatter_kernel<uint64_t><<<grid_for(m), 256, 0, st>>>(d_keys_sorted, (const uint64_t *)d_sub_idx_sorted,
+                                                                   d_slots, m, (uint64_t *)d_idx, d_flags);
     GK_LAUNCH_CHECK();
     return GK_OK;
 }
@@ -697,7 +720,7 @@ int key2_scatter_device(const uint64_t *d_keys_sorted, const uint32_t *d_sub_idx
                         cudaStream_t st)
 {
     if (m == 0) return GK_OK;
-    key2_scatter_kernel<<<grid_for(m), 256, 0, st>>>(d_keys_sorted, d_sub_idx_sorted, d_slots, m, d_idx,
+    key2_scatter_kernel<uint32_t><<<grid_for(m), 256, 0, st>>>(d_keys_sorted, d_sub_idx_sorted, d_slots, m, d_idx,
                                                      d_flags);
     GK_LAUNCH_CHECK();
     return GK_OK;

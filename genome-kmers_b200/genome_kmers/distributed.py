@@ -647,9 +647,6 @@ class ShardedKmers:
         k, world, rank = self.k, self.world, self.rank
         self._marks = []
         self._mark("start")
-        if k > 31 and self.idx_bytes != 4:
-            raise NotImplementedError("k-mers longer than one key word (k > 31) on the multi-GPU path need 32-bit "
-                                      "start indices (a byte array below 2^32 positions)")
         # every key carries the class bit, so nothing waits for the alphabet scan: its counters travel with the
         # destination counts.  k > 31: the key covers the first 31 symbols (a key range still holds whole groups);
         # the local sort compares the remaining symbols from the bytes (gk_index_sort_shard, word rounds)

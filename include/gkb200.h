@@ -206,7 +206,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream);
 int gk_index_sort_pairs(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, void *d_idx,
                         void *d_idx_alt, uint64_t n_local, int class_bit, gk_sort_stats *stats_out,
                         void *stream);
-/* k-mers longer than one key word (min_kmer_len > 31, class-bit keys, 32-bit starts): the pairs carry the first 31
+/* k-mers longer than one key word (min_kmer_len > 31, class-bit keys, starts of either width): the pairs carry the first 31
  * symbols; after the sort the members of groups that are still tied are ordered by the remaining symbols, read
  * from the bytes eight at a time (the prefix doubling of gk_index_sort needs the ranks of other starts, which
  * live on other GPUs).

@@ -43,7 +43,8 @@ def main():
     failures = []
     cases = [(31, 600_000, 6, 8, False), (21, 400_000, 3, 0, False), (12, 300_000, 2, 3, False),
              (31, 500_000, 5, 6, True),                      # 64-bit start indices (GK_FORCE_IDX64)
-             (40, 400_000, 4, 6, False), (64, 300_000, 3, 4, False), (33, 200_000, 2, 0, False)]   # k > one key word
+             (40, 400_000, 4, 6, False), (64, 300_000, 3, 4, False), (33, 200_000, 2, 0, False),   # k > one key word
+             (47, 250_000, 3, 3, True)]                      # ... with 64-bit start indices
     for k, n_bases, n_rec, runs, wide in cases:
         os.environ["GK_FORCE_IDX64"] = "1" if wide else "0"
         rng = np.random.default_rng(1000 + k)

@@ -130,6 +130,21 @@ def test_seeded_random_with_64bit_start_indices(monkeypatch):
     _oracle_compare(recs, 31, "both")
 
 
+@pytest.mark.parametrize("k", [33, 40, 64, 100])
+def test_long_kmers_with_64bit_start_indices(k, monkeypatch):
+    """k-mers longer than one key word on a byte array of 2^32 or more positions: the rank table of the prefix
+    doubling is 32-bit, so the tied members are ordered by the symbols read from the bytes (word rounds)."""
+    monkeypatch.setenv("GK_FORCE_IDX64", "1")
+    rng = np.random.default_rng(640 + k)
+    recs = gu.random_genome(rng, 300_000, 3, n_runs=4, run_lo=50, run_hi=3000, n_scatter=15)
+    for _ in range(80):   # copies: k-mers that agree on the first 31 symbols and differ later, or never
+        seq = recs[int(rng.integers(0, len(recs)))][1]
+        ln = int(rng.integers(33, 500))
+        src, dst = (int(v) for v in rng.integers(0, len(seq) - ln, 2))
+        seq[dst:dst + ln] = seq[src:src + ln].copy()
+    _oracle_compare(recs, k, "both")
+
+
 @pytest.mark.parametrize("name", VARIABLE)
 def test_golden_variable_length_modes(name):
     """sort() with min_kmer_len != max_kmer_len."""

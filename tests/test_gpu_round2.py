@@ -347,8 +347,9 @@ def test_partition_to_destination_buffers_with_key_base_and_dropped_ambiguous_pa
     assert np.array_equal(got_counts[4:], np.bincount(dest[amb], minlength=4))
 
 
-@pytest.mark.parametrize("k,strands", [(33, "forward"), (40, "both"), (64, "both"), (100, "forward")])
-def test_shard_sort_of_kmers_longer_than_one_key_word(k, strands, tmp_path):
+@pytest.mark.parametrize("k,strands,wide", [(33, "forward", False), (40, "both", False), (64, "both", False),
+                                            (100, "forward", False), (40, "both", True)])
+def test_shard_sort_of_kmers_longer_than_one_key_word(k, strands, wide, tmp_path, monkeypatch):
     """gk_index_sort_shard with k > 31: the pairs carry the first 31 symbols, the rest is compared from the
     bytes in word rounds (the doubling of the single-GPU path needs ranks that live on other GPUs).  One rank,
     so the whole sharded path -- slice pack, staging partition, fragments, shard sort -- runs in this process."""
@@ -356,6 +357,8 @@ def test_shard_sort_of_kmers_longer_than_one_key_word(k, strands, tmp_path):
 
     from genome_kmers.distributed import ShardedKmers
 
+    if wide:
+        monkeypatch.setenv("GK_FORCE_IDX64", "1")     # 64-bit start indices on a small input
     rng = np.random.default_rng(k)
     recs = gu.random_genome(rng, 300_000, 3, n_runs=5, run_lo=40, run_hi=3000, n_scatter=15)
     for _ in range(80):   # copies: k-mers that agree on the first 31 symbols and differ later, or never

@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -x -q -m gpu -k "long_runs or repeat or Repeat" 2>&1 | tail -8
-timeout 300 python bench.py --workload repeats --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > /tmp/bench_dbg.log 2>/dev/null
-tail -1 /tmp/bench_dbg.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],2), d['verified'], [round(x,1) for x in d['step_wall_ms']], d['roofline']['stage_ms'], d['result'])"
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -m gpu -k "64bit or longer_than_one_key_word or long_k or k64 or C4" 2>&1 | tail -12
+timeout 800 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -12
