@@ -89,7 +89,8 @@ constexpr int kTieHalo = kTieMaxRun;                   // keys staged either sid
 //      first slot of a short run -> queue the run
 //   3  queued runs: rank the run by the full key in registers, write keys, values and flags in place
 template <typename ValT, typename PreT, int kTiePerThread>
-__global__ void __launch_bounds__(kTieThreads)
+// (five CTAs per SM: 51 registers instead of 54, no spills; 7.48 -> 7.42 ms per bench step.  Six spills.)
+__global__ void __launch_bounds__(kTieThreads, 5)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent,
                      unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */,

@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -m gpu -k "64bit or longer_than_one_key_word or long_k or k64 or C4" 2>&1 | tail -12
-timeout 800 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -12
+L=genome-kmers_b200/lib
+for rep in 1 2; do for v in base t5 t6; do
+cp $L/libgkb200_$v.so $L/libgkb200.so
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-verify --clock-mode off > /tmp/b.log 2>/dev/null
+tail -1 /tmp/b.log | python -c "import sys,json,statistics; d=json.loads(sys.stdin.read()); print('$v', round(d['ms_per_step'],3), round(statistics.median(d['step_wall_ms']),3))"
+done; done
+cp $L/libgkb200_base.so $L/libgkb200.so
