@@ -41,6 +41,10 @@ SAMPLES_PER_RANK = 2048
 HIST_PAIRS_PER_MESSAGE = 512   # occupied histogram bins per rank in the first all-gather round
 FRAG_SHARE = 1 << 16           # fragments per rank that the fixed-size fragment all-gather carries
 FRAG_BYTES = 36                # key, w0, w1, start (u64) + count (u32)
+# weight of an ambiguous window against a pure one when the splitters balance the ranks: its pair does not cross
+# NVLink, but the owner generates it, carries it through the passes and rewrites its slot (measured at 8 GPUs:
+# the owner of the 70 M-window all-N group took 0.7 ms longer than the others at weight 1)
+AMBIGUOUS_COST = float(os.environ.get("GK_AMBIGUOUS_COST", "1.3"))
 
 
 def _torch():
@@ -172,6 +176,20 @@ class NativeEngine:
                                                         counts.data_ptr(), self.stream()))
         parts = [counts, pk.counters[2:3], pk.counters[0:1]] + [e for e in extra]
         return torch.cat(parts).cpu().numpy()
+
+    def partition_counts_gathered(self, pk, splitters, n_parts, class_bit, dist, group, extra=()):
+        """The same header from every rank, [world, ...] on the host: under NCCL the header is gathered on the
+        device and crosses to the host once (no round trip in between)."""
+        torch = self.torch
+        counts = torch.empty(2 * n_parts, dtype=torch.int64, device=self.device)
+        sp = splitters.data_ptr() if splitters is not None and splitters.numel() else None
+        _native.check(self.lib.gk_partition_count_split(pk.keys.data_ptr(), pk.n, sp, n_parts, class_bit,
+                                                        counts.data_ptr(), self.stream()))
+        mine = torch.cat([counts, pk.counters[2:3], pk.counters[0:1]] + [e for e in extra])
+        world = dist.get_world_size(group)
+        out = torch.empty(world * mine.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out.cpu().numpy().reshape(world, mine.numel())
 
     def peer_exchange(self, dist, group, capacity, idx_bytes):
         return PeerExchange.get(self, dist, group, capacity, idx_bytes)
@@ -679,7 +697,7 @@ class ShardedKmers:
                 table = self._gather(padded)
             pooled = np.sort(np.concatenate([row[1:1 + int(row[0])] for row in table]))
             # even splitters: a key range then starts at an even key, so subtracting it keeps the class bit
-            splitters_host = choose_splitters(pooled, world, class_bit) & ~np.uint64(1)
+            splitters_host = choose_splitters(pooled, world, class_bit, AMBIGUOUS_COST) & ~np.uint64(1)
             splitters = eng.splitters_to_device(splitters_host)
         else:
             splitters_host, splitters = np.zeros(0, dtype=np.uint64), None
@@ -687,8 +705,11 @@ class ShardedKmers:
         self._mark("splitters")
 
         # ---- ONE small all-gather: destination counts, fragment count, ambiguous windows, alphabet counters -----
-        header = eng.partition_counts_host(pk, splitters, world, class_bit, extra=(alpha,))
-        table = self._gather(header.astype(np.int64))
+        if world > 1 and hasattr(eng, "partition_counts_gathered") and backend_is_nccl(dist, self.group):
+            table = eng.partition_counts_gathered(pk, splitters, world, class_bit, dist, self.group, extra=(alpha,))
+        else:
+            header = eng.partition_counts_host(pk, splitters, world, class_bit, extra=(alpha,))
+            table = self._gather(header.astype(np.int64))
         alpha_all = table[:, 2 * world + 2:].sum(axis=0)
         if int(alpha_all[1]) != len(self.seg_starts) - 1:
             raise AssertionError("kmers compared were less than min_kmer_len: '$' inside a record")
