@@ -460,3 +460,37 @@ def test_pack_slice_reads_nothing_beyond_two_tiles_around_its_slice(k):
         for a, b in zip(got, want):
             assert np.array_equal(a, b), (first, end)
         assert len(want[0]) > 0 and want[2] > 0
+
+
+@pytest.mark.parametrize("presort", ["1", "0"])
+def test_sharded_path_with_merged_and_with_resorted_fragment_lists(presort, tmp_path, monkeypatch):
+    """GK_FRAG_PRESORT=1 (default): every rank sorts its own fragment list and the owner of a key range merges the
+    lists; 0: the owner sorts the gathered lists itself.  Same order either way (one rank here; two ranks on one
+    GPU in test_gpu_multi.py)."""
+    import torch.distributed as dist
+
+    from genome_kmers.distributed import ShardedKmers
+
+    monkeypatch.setenv("GK_FRAG_PRESORT", presort)
+    rng = np.random.default_rng(31)
+    recs = gu.random_genome(rng, 400_000, 4, n_runs=12, run_lo=31, run_hi=9000, n_scatter=40)
+    sba = np.concatenate([np.concatenate([seq, np.array([36], dtype=np.uint8)]) for _, seq in recs])[:-1]
+    starts = np.cumsum([0] + [len(seq) + 1 for _, seq in recs[:-1]]).astype(np.uint64)
+    full, full_starts = oracle.both_strands(sba, starts)
+    want = oracle.sort_indices(full, oracle.init_indices(full_starts, len(full), 31), 31, 31,
+                               threads=min(8, oracle.max_threads()))
+    store = dist.FileStore(str(tmp_path / "store"), 1)
+    dist.init_process_group("gloo", store=store, rank=0, world_size=1)
+    try:
+        sk = ShardedKmers(sba, starts, 31, "both")
+        sk.sort()
+        got = sk.local_start_indices()
+        stats = dict(sk.stats)
+        hist, total = sk.get_kmer_group_counts(31)
+        ver = sk.verify(hist, len(want))
+        sk.close()
+    finally:
+        dist.destroy_process_group()
+    assert np.array_equal(got.astype(np.uint64), want)
+    assert stats["n_fragments"] > 0 and stats["refine_flags"] & 1 and not stats["refine_flags"] & 2, stats
+    assert all(ver["checks"].values()), ver
