@@ -175,7 +175,10 @@ struct gk_index {
     const uint8_t *d_sba = nullptr;
     uint64_t sba_len = 0;
     std::vector<uint64_t> h_segs;
-    Owned d_segs;
+    Owned d_segs;                       // device copy of h_segs, uploaded by the first call that has a stream
+    cudaStream_t segs_stream = nullptr;
+    cudaEvent_t segs_ev = nullptr;
+    ~gk_index() { if (segs_ev) cudaEventDestroy(segs_ev); }
     uint32_t min_len = 1, max_len = 0;  // max_len 0 == None
     int idx_bytes = 4;
     uint64_t n = 0;
@@ -193,6 +196,24 @@ struct gk_index {
     std::vector<std::pair<uint64_t, uint64_t>> spectrum;
     bool spectrum_valid = false;
 };
+
+// The segment table on the device.  gk_index_create has no stream, and a synchronous copy there would wait for
+// whatever the caller has queued (the both-strand layout) before the sort could be enqueued; the first call that
+// brings a stream uploads it there (a few hundred bytes, staged at once), later calls on another stream wait for
+// that upload's event.
+static int ensure_segs(gk_index *ix, cudaStream_t st)
+{
+    if (!ix->d_segs.ptr) {
+        GK_TRY(ix->d_segs.alloc(ix->h_segs.size() * 8, st));
+        GK_CUDA(cudaMemcpyAsync(ix->d_segs.ptr, ix->h_segs.data(), ix->h_segs.size() * 8, cudaMemcpyHostToDevice, st));
+        GK_CUDA(cudaEventCreateWithFlags(&ix->segs_ev, cudaEventDisableTiming));
+        GK_CUDA(cudaEventRecord(ix->segs_ev, st));
+        ix->segs_stream = st;
+    } else if (st != ix->segs_stream && ix->segs_ev) {
+        GK_CUDA(cudaStreamWaitEvent(st, ix->segs_ev, 0));
+    }
+    return GK_OK;
+}
 
 // Group-size spectrum behind a sort: kernels and the device-to-host copy are enqueued (no synchronise); finish()
 // turns the copy into ix->spectrum after the caller's own synchronise.
@@ -247,6 +268,7 @@ static int ensure_alphabet(gk_index *ix, cudaStream_t st)
 
 static int ensure_indices(gk_index *ix, cudaStream_t st)
 {
+    GK_TRY(ensure_segs(ix, st));
     if (ix->idx_ready) return GK_OK;
     GK_TRY(ix->d_idx.alloc((size_t)ix->n * ix->idx_bytes, st));
     GK_TRY(init_indices_device((const uint64_t *)ix->d_segs.ptr, (uint32_t)ix->h_segs.size(),
@@ -1001,19 +1023,7 @@ int gk_index_create(const uint8_t *d_sba, uint64_t sba_len, const uint64_t *h_se
         const char *f = getenv("GK_FORCE_IDX64");
         if (f && *f && *f != '0') ix->idx_bytes = 8;
     }
-    int rc = ix->d_segs.alloc((size_t)n_seg * 8);
-    if (rc == GK_OK) {
-        cudaError_t e = cudaMemcpy(ix->d_segs.ptr, h_seg_starts, (size_t)n_seg * 8, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            set_error("segment table upload failed: %s", cudaGetErrorString(e));
-            rc = GK_ERR_CUDA;
-        }
-    }
-    if (rc != GK_OK) {
-        delete ix;
-        return rc;
-    }
-    *out = ix;
+    *out = ix;   // (the segment table goes to the device with the first call that brings a stream: ensure_segs)
     return GK_OK;
 }
 
@@ -1088,6 +1098,7 @@ int gk_index_sort(gk_index *ix, gk_sort_stats *stats_out, void *stream)
 {
     if (!ix) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     gk_sort_stats stats;
     memset(&stats, 0, sizeof(stats));
     const uint64_t launches0 = gk_launch_count(0);
@@ -1302,6 +1313,7 @@ int gk_index_sort_shard(gk_index *ix, uint64_t *d_keys, uint64_t *d_keys_alt, vo
         return GK_ERR_ARG;
     }
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     gk_sort_stats stats;
     memset(&stats, 0, sizeof(stats));
     const uint64_t launches0 = gk_launch_count(0);
@@ -1502,6 +1514,7 @@ static int index_group_counts(gk_index *ix, uint32_t kmer_len, const gk_filter *
 {
     if (!ix) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     gk_filter keep_all = {GK_FILTER_KEEP_ALL, 0, 0, 0};
     const gk_filter f = filter ? *filter : keep_all;
     if (h_total_out) *h_total_out = 0;
@@ -1625,6 +1638,7 @@ int gk_index_groups(gk_index *ix, uint32_t kmer_len, uint64_t *h_n_groups, uint6
         return GK_ERR_STATE;
     }
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     *h_n_groups = 0;
     if (ix->n == 0) return GK_OK;
     const uint64_t n = ix->n;
@@ -1656,6 +1670,7 @@ int gk_index_groups_filtered(gk_index *ix, uint32_t kmer_len, const gk_filter *f
 {
     if (!ix || !filter || !h_n_kept || !h_n_groups) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     *h_n_kept = *h_n_groups = 0;
     if (ix->n == 0) return GK_OK;
     GK_TRY(ensure_indices(ix, st));
@@ -1707,6 +1722,7 @@ int gk_index_verify(gk_index *ix, uint32_t kmer_len, uint64_t *h_report8, uint32
 {
     if (!ix || !h_report8) return GK_ERR_ARG;
     cudaStream_t st = as_stream(stream);
+    GK_TRY(ensure_segs(ix, st));
     GK_TRY(ensure_indices(ix, st));
     const bool cached = ix->sorted && ix->flags_valid && ix->flags_kmer_len == kmer_len && kmer_len != 0;
     return verify_order_device(ix->d_sba, ix->sba_len, ix->d_idx.ptr, ix->idx_bytes, ix->n, kmer_len,
