@@ -89,8 +89,9 @@ constexpr int kTieHalo = kTieMaxRun;                   // keys staged either sid
 //      first slot of a short run -> queue the run
 //   3  queued runs: rank the run by the full key in registers, write keys, values and flags in place
 template <typename ValT, typename PreT, int kTiePerThread>
-// (five CTAs per SM: 51 registers instead of 54, no spills; 7.48 -> 7.42 ms per bench step.  Six spills.)
-__global__ void __launch_bounds__(kTieThreads, 5)
+// (five CTAs per SM with 32-bit start indices: 48 registers instead of 54, no spills; 7.48 -> 7.42 ms per bench
+// step.  Six spill, and so do five with 64-bit starts: four there.)
+__global__ void __launch_bounds__(kTieThreads, sizeof(ValT) == 8 ? 4 : 5)
 tie_fix_flags_kernel(uint64_t *__restrict__ keys, ValT *__restrict__ vals, uint64_t n, int lo_bits,
                      int class_bit, uint8_t *__restrict__ flags, unsigned int *__restrict__ descent,
                      unsigned long long *__restrict__ n_amb_out /* nullable: count of ambiguous slots */,
